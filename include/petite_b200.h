@@ -1,0 +1,141 @@
+/* petite_b200 C ABI - the drop-in boundary of the B200 shower engine.
+ *
+ * PETITE (the reference) has no FFI of its own: its boundary is the Python class API
+ *   Shower.generate_shower          reference src/PETITE/shower.py:603-708
+ *   DarkShower.generate_dark_shower reference src/PETITE/dark_shower.py:806-849
+ * and the methods they call.  The entry points below are what a ctypes binding inside those two
+ * classes would call (INTEGRATION.md shows the stub); each comment names the reference lines the
+ * call replaces.  Plain C types only; no torch types cross this boundary.
+ *
+ * Conventions: every function returns 0 on success and a negative pb_status otherwise;
+ * pb_last_error() returns a static, per-engine message.  An engine is bound to one CUDA device and is
+ * not thread-safe; distinct engines are independent.  All kernels are enqueued on the stream passed
+ * in (a cudaStream_t cast to void*, NULL = default stream).  Pointers marked [host] are host memory,
+ * [dev] device memory owned by the caller (e.g. torch.Tensor.data_ptr()); the library never frees
+ * caller memory.
+ */
+#ifndef PETITE_B200_H
+#define PETITE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_engine_s* pb_engine;
+
+enum pb_status {
+  PB_OK = 0,
+  PB_ERR_CUDA = -1,
+  PB_ERR_ARG = -2,
+  PB_ERR_CAPACITY = -3,   /* particle stack too small for the showers requested */
+  PB_ERR_STATE = -4,      /* tables missing */
+  PB_ERR_NO_SAMPLE = -5   /* a sampler exhausted max_n_integrators sweeps (shower.py:460-461) */
+};
+
+/* process codes (generation_process); 0-7 follow shower.py:36 process_code */
+enum pb_process {
+  PB_BREM = 0, PB_ANN = 1, PB_PAIRPROD = 2, PB_COMP = 3, PB_MOLLER = 4, PB_BHABHA = 5, PB_MUONE = 6,
+  PB_MUONBREM = 7, PB_DARKBREM = 8, PB_DARKANN = 9, PB_DARKCOMP = 10, PB_DARKMUONBREM = 11,
+  PB_SMDECAY = 12, PB_BSMDECAY = 13, PB_NONE = 14, PB_INPUT = 15, PB_NPROC_SAMPLED = 12
+};
+
+/* Shower / DarkShower constructor state that the kernels need (shower.py:100-142, 189-208;
+ * dark_shower.py:69-129).  All energies GeV, lengths m unless noted. */
+typedef struct pb_config {
+  double Z_T, A_T, rho;          /* physical_constants.py:49-55 */
+  double dEdx_GeV_per_m;         /* 0.1 * dEdx[MeV/cm]  (shower.py:649) */
+  double mT_sampler;             /* event_info['mT'] at sampling time = A_T (SURVEY Q-19) */
+  double min_energy;             /* Shower(min_energy) */
+  double Eg_min, Ee_min;         /* shower.py:214-215 */
+  double maxF_fudge;             /* maxF_fudge_global */
+  double rescale_MCS;            /* rescale_MCS */
+  double min_calc[5];            /* shower.py:242-246 for e-, e+, gamma, mu-, mu+ (in that order) */
+  int64_t max_sweeps;            /* max_n_integrators */
+  /* dark sector (ignored by pb_run_showers) */
+  double mV, g_e, kinetic_mixing, Zeff;
+  double E_res_ann, E_thr_comp;  /* dark_shower.py:234-235 */
+  int32_t bound_electron;
+  int32_t reserved;
+} pb_config;
+
+/* Structure-of-arrays particle stack in HBM (the Particle list of shower.py:621, particle.py:50-175).
+ * One record = 4 x double4 + 32 bytes of ids = 160 B.  Records [0, n_primaries) are the primaries, daughters
+ * are appended wave by wave; record order within a wave is not the reference's creation order (host
+ * side restores it from parent/child links, see petite_b200/shower.py). */
+typedef struct pb_stack {
+  double* p0;      /* [dev] capacity x 4 : E, px, py, pz at creation            (particle._p0) */
+  double* r0w;     /* [dev] capacity x 4 : x, y, z at creation, weight          (particle._r0, ids['weight']) */
+  double* pf;      /* [dev] capacity x 4 : four-momentum after propagation      (particle._pf) */
+  double* rf;      /* [dev] capacity x 4 : position after propagation, 4th = 0  (particle._rf) */
+  uint32_t* key;   /* [dev] capacity x 2 : Philox particle key */
+  int32_t* meta;   /* [dev] capacity x 4 : pid, parent slot (-1 primary), gen<<16 | child_bit<<15 | flags<<8 | process, shower id */
+  int32_t* aux;    /* [dev] capacity x 2 : accept/reject trials used, dE/dx sub-steps taken */
+  int64_t capacity;
+} pb_stack;
+
+#define PB_FLAG_SHORT_LIVED 1   /* ids['stability'] == 'short-lived' */
+#define PB_FLAG_NO_SAMPLE 2     /* sampler exhausted */
+
+/* Primaries (host SoA): what the caller's loop over Particle objects feeds generate_shower with. */
+typedef struct pb_primaries {
+  const double* p;        /* [host] n x 4 */
+  const double* r;        /* [host] n x 3 */
+  const double* weight;   /* [host] n */
+  const double* mass;     /* [host] n   ids['mass'] (particle.py:125-131 back-computed value if absent) */
+  const int32_t* pid;     /* [host] n */
+  const int32_t* flags;   /* [host] n   PB_FLAG_SHORT_LIVED for pi0 etc. */
+  int64_t n;
+} pb_primaries;
+
+typedef struct pb_counters {
+  int64_t n_particles;     /* records written (primaries + daughters) */
+  int64_t n_waves;
+  int64_t n_steps;         /* propagate_particle calls that actually stepped */
+  int64_t n_substeps;      /* dE/dx + MCS sub-steps */
+  int64_t n_samples;       /* accepted draw_sample calls */
+  int64_t n_trials;        /* integrand evaluations */
+  int64_t n_no_sample;     /* samplers that gave up */
+  int64_t n_launches;      /* kernels launched by the engine for this call */
+  int64_t max_wave;        /* widest wave */
+} pb_counters;
+
+const char* pb_version(void);
+const char* pb_last_error(pb_engine e);
+
+/* Shower.__init__ (shower.py:100-142) minus the table reads, which stay in Python. */
+int pb_create(pb_engine* out, int device, const pb_config* cfg);
+void pb_destroy(pb_engine e);
+int pb_set_config(pb_engine e, const pb_config* cfg);
+
+/* One n*sigma(E) interpolant of set_NSigmas (shower.py:273-295) / set_dark_NSigmas; table_id = pb_process
+ * for the 8 SM processes.  Linear in (E, n*sigma) with 0 outside, evaluated like scipy interp1d. */
+int pb_upload_nsigma(pb_engine e, int table_id, const double* E /*[host]*/, const double* nsigma /*[host]*/, int n);
+
+/* All trained maps of one process (set_samples, shower.py:210-215; set_dark_samples, dark_shower.py:196-201):
+ * grid = n_energy rows of sum_d(ninc[d]+1) fp64 node positions (axes concatenated), E_inc and max_F per row. */
+int pb_upload_maps(pb_engine e, int process, const double* grid /*[host]*/, int n_energy, int dim,
+                   const int32_t* ninc /*[host]*/, const double* E_inc /*[host]*/,
+                   const double* max_F /*[host]*/, int neval);
+
+/* generate_shower (shower.py:603-708) for a batch of independent primaries.  Shower i of this call uses the
+ * Philox root key (seed, first_shower_id + i).  global_ms mirrors the GlobalMS argument. */
+int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t seed, uint64_t first_shower_id,
+                   int global_ms, pb_stack* stack, pb_counters* counters /*[host] out*/, void* stream);
+
+/* Deterministic-piece probes used by the parity tests (all arrays [host]). what: */
+enum pb_probe {
+  PB_PROBE_DSIGMA = 0,   /* in: n x (1 + dim): E_inc, x[dim];            out: n     dsigma (integrands of all_processes.py) */
+  PB_PROBE_NSIGMA = 1,   /* in: n x 1: E;  process = table id;           out: n     n*sigma(E) */
+  PB_PROBE_MAP = 2,      /* in: n x (1 + dim): energy row index, y[dim]; out: n x (dim+1): x[dim], jac */
+  PB_PROBE_MCS = 3,      /* in: n x 9: p4[4], dist_m, m_lepton, u_sign, z1, z2 ... see tests; out: n x 4 */
+  PB_PROBE_KIN = 4,      /* in: n x 8: E, mass, x[4], u_az, pad;          out: n x 8 two four-vectors (parent along z) */
+  PB_PROBE_PHILOX = 5    /* in: n x 6 (as doubles): key0,key1,c0,stream,c2,c3; out: n x 2 doubles */
+};
+int pb_probe(pb_engine e, int what, int process, const double* in, int64_t n, int in_stride, double* out, int out_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,838 @@
+// petite_b200 shower engine: wavefront stepping of independent EM showers on a B200 (sm_100a).
+//
+// One "wave" = every particle created by the previous wave, across all showers of the batch.  Per wave:
+//   k_propagate   one thread / particle: free path or dE/dx + multiple-scattering sub-steps, process choice,
+//                 threshold + map look-up key -> bucket (process, energy row); bucket histogram
+//   k_bucket_scan one CTA: exclusive scan of the histogram, tile table (<= TILE samples of one bucket per tile)
+//   k_bucket_fill counting-sort scatter of the wave's particles into bucket order
+//   k_sample      persistent CTAs pull tiles; the bucket's VEGAS node grid is staged in shared memory by a TMA
+//                 bulk copy; lane groups run counter-indexed accept/reject trials (first accepted trial wins)
+//   k_emit        one thread / particle in bucket order: kinematics, rotation to the lab, daughter records
+//                 appended with one warp-aggregated atomic per warp
+// The host loop only needs the new tail of the stack after each wave.
+// Reference behaviour reproduced: src/PETITE/shower.py:401-708 (see include/petite_b200.h and DESIGN.md).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/petite_b200.h"
+#include "physics.cuh"
+
+namespace pb {
+
+constexpr int LU_MAX = 256;                 // energy rows per process (100 in data/, 150 in data_400GeV/)
+constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
+constexpr int TILE = 256;                   // samples per tile
+constexpr int SAMPLE_THREADS = 128;
+constexpr int GRID_SMEM_DOUBLES = 4096;     // >= padded stride of a 4-D map row (3964 -> 3968)
+
+struct NSigmaTable { const double* E; const double* y; int n; int pad; };
+struct MapInfo {
+  const double* grid;   // nE rows, `stride` doubles each (padded to a multiple of 16 doubles)
+  const double* E;
+  const double* maxF;
+  int nE, dim, stride, B;
+  int ninc[4];
+  int off[4];
+};
+struct Tables {
+  NSigmaTable ns[16];
+  MapInfo map[N_SAMPLED];
+};
+
+struct Stack {
+  double* p0; double* r0w; double* pf; double* rf;
+  uint2* key; int4* meta; int2* aux;
+  long long capacity;
+};
+
+struct Work {            // per-wave scratch, sized to the widest wave seen so far
+  int* bucket;           // [n] bucket of particle (begin + i)
+  int* sorted;           // [n] wave-local indices in bucket order
+  double* xs;            // [n x 4] accepted sample (map variables)
+  int* hist;             // [NBUCKET]
+  int* offsets;          // [NBUCKET + 1]
+  int* cursor;           // [NBUCKET]
+  int* tile_bucket;      // [max_tiles]
+  int* tile_start;
+  int* tile_count;
+  int* ctrl;             // [0] n_tiles, [1] tile cursor, [2] n sampled entries (bucket < NONE)
+  unsigned long long* tail;      // stack tail (next free record)
+  unsigned long long* counters;  // [8]: steps, substeps, samples, trials, no_sample, overflow
+};
+
+enum { CNT_STEPS = 0, CNT_SUBSTEPS, CNT_SAMPLES, CNT_TRIALS, CNT_NOSAMPLE, CNT_OVERFLOW, CNT_N };
+
+__device__ __forceinline__ int pack_info(int gen, int child_bit, int flags, int process) {
+  return (gen << 16) | (child_bit << 15) | ((flags & 0x7f) << 8) | (process & 0xff);
+}
+
+// ------------------------------------------------------------------------------------------ n*sigma(E)
+// scipy interp1d (linear, bounds_error=False, fill_value=0) as used by shower.py:280-295
+__device__ __forceinline__ double nsigma_eval(const NSigmaTable& T, double E) {
+  int n = T.n;
+  if (n < 2) return 0.0;
+  const double* __restrict__ x = T.E;
+  if (!(E >= __ldg(x) && E <= __ldg(x + n - 1))) return (E == E) ? 0.0 : E;
+  int lo = 0, hi = n;
+  while (lo < hi) {                       // searchsorted(side='left')
+    int mid = (lo + hi) >> 1;
+    if (__ldg(x + mid) < E) lo = mid + 1; else hi = mid;
+  }
+  hi = min(max(lo, 1), n - 1);
+  lo = hi - 1;
+  double xl = __ldg(x + lo), xh = __ldg(x + hi), yl = __ldg(T.y + lo), yh = __ldg(T.y + hi);
+  double slope = (yh - yl) / (xh - xl);
+  return __dadd_rn(__dmul_rn(slope, E - xl), yl);
+}
+
+__device__ __forceinline__ double nsigma_total(const Tables& T, int pid, double E) {   // shower.py:357-368
+  switch (pid) {
+    case 22: return nsigma_eval(T.ns[P_PAIRPROD], E) + nsigma_eval(T.ns[P_COMP], E);
+    case 11: return nsigma_eval(T.ns[P_BREM], E) + nsigma_eval(T.ns[P_MOLLER], E);
+    case -11: return nsigma_eval(T.ns[P_BREM], E) + nsigma_eval(T.ns[P_BHABHA], E) + nsigma_eval(T.ns[P_ANN], E);
+    default: return nsigma_eval(T.ns[P_MUONBREM], E) + nsigma_eval(T.ns[P_MUONE], E);
+  }
+}
+__device__ __forceinline__ double mfp_of(const Tables& T, int pid, double E) {          // shower.py:370-389
+  double ns = nsigma_total(T, pid, E);
+  return (ns <= 0.0) ? 1.0e12 : kCmToM / ns;
+}
+
+// SURVEY Q-1: argmin |E_i - E| + 1, clamped to the last row (shower.py:416-426)
+__device__ __forceinline__ int lookup_row(const MapInfo& m, double E) {
+  int lo = 0, hi = m.nE;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(m.E + mid) < E) lo = mid + 1; else hi = mid;
+  }
+  int best;                                  // lo = first row with E_row >= E
+  if (lo <= 0) best = 0;
+  else if (lo >= m.nE) best = m.nE - 1;
+  else best = (fabs(__ldg(m.E + lo - 1) - E) <= fabs(__ldg(m.E + lo) - E)) ? lo - 1 : lo;   // argmin keeps the first minimum
+  int lu = best + 1;
+  return lu >= m.nE ? m.nE - 1 : lu;
+}
+
+// ------------------------------------------------------------------------------------------ wave kernels
+__global__ void __launch_bounds__(128)
+k_propagate(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
+            long long begin, int n, const double* __restrict__ prim_mass, int ms_e) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long c_steps = 0, c_sub = 0;
+  if (i < n) {
+    long long s = begin + i;
+    const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
+    const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
+    double2 a0 = p0p[0], a1 = p0p[1], b0 = r0p[0], b1 = r0p[1];
+    V4 p{a0.x, a0.y, a1.x, a1.y};
+    double rx = b0.x, ry = b0.y, rz = b1.x;
+    int4 meta = S.meta[s];
+    uint2 key = S.key[s];
+    int pid = meta.x;
+    int flags = (meta.z >> 8) & 0x7f;
+    double mass = (meta.y < 0) ? prim_mass[s] : pid_mass(pid);
+    int bucket = P_NONE * LU_MAX;
+    int nsub = 0;
+    if (flags & PB_FLAG_SHORT_LIVED) {
+      bucket = P_SMDECAY * LU_MAX;                                       // particle.py:391-409, decays in k_emit
+    } else {
+      int cls = pid_class(pid);
+      if (cls >= 0) {
+        double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);    // shower.py:532-533
+        if (!(p.E < pmin)) {
+          c_steps = 1;
+          if (pid == 22) {                                                // shower.py:538-553 (MS_g is always False)
+            double mfp = mfp_of(T, pid, p.E);
+            double distC = draw2(key, 0, ST_FINAL).a;
+            double dist = mfp * log(1.0 / (1.0 - distC));
+            double pn = norm3_nofma(p.x, p.y, p.z);
+            rx += p.x / pn * dist; ry += p.y / pn * dist; rz += p.z / pn * dist;
+          } else {                                                        // shower.py:555-598
+            const double losses = M.dEdx;
+            const double ml = pid_mass(pid);
+            double delta_z = 0.0;
+            bool hard = false;
+            uint32_t it = 0;
+            while (!hard && p.E >= pmin) {
+              double mfp = mfp_of(T, pid, p.E);
+              D2 u = draw2(key, it, ST_SUBSTEP);
+              delta_z = mfp / (6.0 + 14.0 * u.b);
+              if (u.a > exp(-delta_z / mfp)) {
+                hard = true;
+              } else {
+                p = lose_energy(p, mass, losses * delta_z);
+                double pn = norm3_nofma(p.x, p.y, p.z);
+                if (pn > 0.0) { rx += p.x / pn * delta_z; ry += p.y / pn * delta_z; rz += p.z / pn * delta_z; }
+                if (ms_e && pn > 0.0) {
+                  McsDraw d = mcs_draw(key, it, 0);
+                  p = mcs_scatter(M, p, M.rho * (delta_z / kCmToM), ml, d.sign, d.z1, d.z2, d.uphi);
+                }
+                ++nsub;
+              }
+              ++it;
+            }
+            double distC = draw2(key, 0, ST_FINAL).a;
+            double last;
+            if (p.E < pmin) last = distC * delta_z;
+            else {
+              double mfp = mfp_of(T, pid, p.E);
+              last = mfp * log(1.0 / (1.0 + (exp(-delta_z / mfp) - 1) * distC));
+            }
+            p = lose_energy(p, mass, losses * last);
+            double pn = norm3_nofma(p.x, p.y, p.z);
+            if (pn > 0.0) { rx += p.x / pn * last; ry += p.y / pn * last; rz += p.z / pn * last; }
+            if (ms_e && pn > 0.0) {                                       // SURVEY Q-12: electron mass here
+              McsDraw d = mcs_draw(key, MCS_FINAL_INDEX, 0);
+              p = mcs_scatter(M, p, M.rho * (last / kCmToM), kMe, d.sign, d.z1, d.z2, d.uphi);
+            }
+          }
+        }
+        // process choice (shower.py:665-698) and the sample_scattering threshold (shower.py:469)
+        double Ef = p.E;
+        int cand[3]; double c[3]; int nc;
+        if (pid == 11) { cand[0] = P_BREM; cand[1] = P_MOLLER; nc = 2; }
+        else if (pid == -11) { cand[0] = P_BREM; cand[1] = P_ANN; cand[2] = P_BHABHA; nc = 3; }
+        else if (pid == 22) { cand[0] = P_PAIRPROD; cand[1] = P_COMP; nc = 2; }
+        else { cand[0] = P_MUONE; cand[1] = P_MUONBREM; nc = 2; }
+        double SC = 0.0;
+        for (int k = 0; k < nc; ++k) { c[k] = nsigma_eval(T.ns[cand[k]], Ef); SC += c[k]; }
+        if (!(SC == 0.0 || SC != SC)) {
+          double u = draw2(key, 0, ST_CHOICE).a;
+          // np.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
+          double cdf[3]; double acc = 0.0;
+          for (int k = 0; k < nc; ++k) { acc += c[k] / SC; cdf[k] = acc; }
+          int pick = nc - 1;
+          for (int k = nc - 1; k >= 0; --k) if (u < cdf[k] / acc) pick = k;
+          int proc = cand[pick];
+          double thr = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
+          if (!(Ef <= thr)) bucket = proc * LU_MAX + lookup_row(T.map[proc], Ef);
+        }
+      }
+    }
+    double2* pfp = reinterpret_cast<double2*>(S.pf + 4 * s);
+    double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * s);
+    pfp[0] = make_double2(p.E, p.x); pfp[1] = make_double2(p.y, p.z);
+    rfp[0] = make_double2(rx, ry);   rfp[1] = make_double2(rz, mass);
+    S.aux[s] = make_int2(0, nsub);
+    W.bucket[i] = bucket;
+    atomicAdd(&W.hist[bucket], 1);
+    c_sub = nsub;
+  }
+  // block-level counter reduction: one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    c_steps += __shfl_down_sync(0xffffffffu, c_steps, o);
+    c_sub += __shfl_down_sync(0xffffffffu, c_sub, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c_steps) atomicAdd(&W.counters[CNT_STEPS], c_steps);
+    if (c_sub) atomicAdd(&W.counters[CNT_SUBSTEPS], c_sub);
+  }
+}
+
+// Exclusive scan over NBUCKET bins + tile table; one CTA of 1024 threads, NBUCKET/1024 bins per thread.
+__global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
+  constexpr int PER = NBUCKET / 1024;
+  __shared__ int s_cnt[1024], s_til[1024];
+  int t = threadIdx.x;
+  int cnt[PER], til[PER];
+  int csum = 0, tsum = 0;
+  for (int k = 0; k < PER; ++k) {
+    int b = t * PER + k;
+    int c = W.hist[b];
+    cnt[k] = c;
+    til[k] = (b < N_SAMPLED * LU_MAX) ? (c + TILE - 1) / TILE : 0;
+    csum += c; tsum += til[k];
+    W.hist[b] = 0;
+    W.cursor[b] = 0;
+  }
+  s_cnt[t] = csum; s_til[t] = tsum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {           // Hillis-Steele inclusive scan
+    int a = (t >= o) ? s_cnt[t - o] : 0, b = (t >= o) ? s_til[t - o] : 0;
+    __syncthreads();
+    s_cnt[t] += a; s_til[t] += b;
+    __syncthreads();
+  }
+  int cbase = s_cnt[t] - csum, tbase = s_til[t] - tsum;
+  for (int k = 0; k < PER; ++k) {
+    int b = t * PER + k;
+    W.offsets[b] = cbase;
+    for (int j = 0; j < til[k]; ++j) {
+      W.tile_bucket[tbase + j] = b;
+      W.tile_start[tbase + j] = cbase + j * TILE;
+      W.tile_count[tbase + j] = min(TILE, cnt[k] - j * TILE);
+    }
+    cbase += cnt[k]; tbase += til[k];
+  }
+  if (t == 1023) { W.offsets[NBUCKET] = cbase; W.ctrl[0] = tbase; W.ctrl[1] = 0; }
+  if (t == 0) W.ctrl[2] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_bucket_fill(Work W, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int b = W.bucket[i];
+  int pos = W.offsets[b] + atomicAdd(&W.cursor[b], 1);
+  W.sorted[pos] = i;
+}
+
+// ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+// One accept/reject trial: Philox doubles D[0..dim] = y_0..y_{dim-1}, u_accept; map y -> x through the staged
+// grid (vegas AdaptiveMap: x = g[i] + (g[i+1]-g[i]) * (y*ninc - i), jac = prod ninc*(g[i+1]-g[i])); accept iff
+// max_F * u < (jac / B) * f(x)  (shower.py:453-459).
+template <int DIM>
+__device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, const double* __restrict__ g, int proc,
+                                      double E, double maxF, uint2 key, uint32_t t, double* x) {
+  double D[DIM + 2];
+#pragma unroll
+  for (int j = 0; j < (DIM + 2) / 2; ++j) {
+    D2 d = draw2(key, t, ST_VEGAS, j, proc);
+    D[2 * j] = d.a; D[2 * j + 1] = d.b;
+  }
+  double jac = 1.0;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    int ninc = mi.ninc[d];
+    double yn = D[d] * ninc;
+    int iy = min((int)yn, ninc - 1);
+    const double* gd = g + mi.off[d];
+    double g0 = gd[iy], g1 = gd[iy + 1];
+    double inc = g1 - g0;
+    x[d] = __dadd_rn(g0, __dmul_rn(inc, yn - iy));
+    jac *= inc * ninc;
+  }
+  double f = dsigma(M, proc, E, x);
+  return maxF * D[DIM] < (jac / mi.B) * f;
+}
+
+// Persistent sampling kernel.  G lanes cooperate on one sample: lane l of the group evaluates trial r*G + l in
+// round r and the lowest accepted trial wins - identical to the reference's sequential first-accept rule because
+// every trial's uniforms are a pure function of (particle key, trial index).  Groups pull the next sample of the
+// tile from a shared cursor as soon as they finish.
+template <int G>
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, long long begin) {
+  __shared__ __align__(128) double s_grid[GRID_SMEM_DOUBLES];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_tile, s_cursor;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % G;
+  const int gbase = lane - sub;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+  uint32_t phase = 0;
+  unsigned long long c_trials = 0, c_samples = 0, c_fail = 0;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  for (;;) {
+    if (threadIdx.x == 0) { s_tile = atomicAdd(&W.ctrl[1], 1); s_cursor = 0; }
+    __syncthreads();
+    int tile = s_tile;
+    if (tile >= W.ctrl[0]) break;
+    int bucket = W.tile_bucket[tile], tstart = W.tile_start[tile], tcount = W.tile_count[tile];
+    int proc = bucket / LU_MAX, lu = bucket % LU_MAX;
+    const MapInfo& mi = T.map[proc];
+    if (threadIdx.x == 0) {
+      uint32_t bytes = (uint32_t)mi.stride * 8u;
+      mbar_expect_tx(&s_bar, bytes);
+      tma_bulk_g2s(s_grid, mi.grid + (size_t)lu * mi.stride, bytes, &s_bar);
+    }
+    double maxF = __ldg(mi.maxF + lu) * M.fudge;
+    mbar_wait(&s_bar, phase);
+    phase ^= 1;
+    const long long max_trials = M.max_trials;
+    // group state
+    int cur = -1;          // wave-local particle index, -1 = need a new one, -2 = tile exhausted
+    long long slot = 0;
+    double E = 0.0; uint2 key = make_uint2(0, 0);
+    uint32_t round = 0;
+    for (;;) {
+      if (cur == -1) {
+        int j = 0;
+        if (sub == 0) j = atomicAdd(&s_cursor, 1);
+        j = __shfl_sync(gmask, j, gbase);
+        if (j < tcount) {
+          cur = W.sorted[tstart + j];
+          slot = begin + cur;
+          E = S.pf[4 * slot];
+          key = S.key[slot];
+          round = 0;
+        } else cur = -2;
+      }
+      if (__all_sync(0xffffffffu, cur == -2)) break;
+      double x[4] = {0.0, 0.0, 0.0, 0.0};
+      bool acc = false;
+      uint32_t t = round * G + sub;
+      if (cur >= 0 && (long long)t < max_trials) {
+        switch (mi.dim) {
+          case 4: acc = trial<4>(M, mi, s_grid, proc, E, maxF, key, t, x); break;
+          case 3: acc = trial<3>(M, mi, s_grid, proc, E, maxF, key, t, x); break;
+          default: acc = trial<1>(M, mi, s_grid, proc, E, maxF, key, t, x); break;
+        }
+      }
+      unsigned ball = __ballot_sync(0xffffffffu, acc);
+      unsigned gb = ball & gmask;
+      if (cur >= 0) {
+        if (gb) {
+          int win = __ffs(gb) - 1;                       // absolute lane of the first accepted trial
+          if (lane == win) {
+            double2* xo = reinterpret_cast<double2*>(W.xs + 4 * (size_t)cur);
+            xo[0] = make_double2(x[0], x[1]); xo[1] = make_double2(x[2], x[3]);
+            int ntr = (int)(round * G + sub + 1);
+            S.aux[slot].x = ntr;
+            c_trials += ntr; c_samples += 1;
+          }
+          cur = -1;
+        } else {
+          ++round;
+          if ((long long)round * G >= max_trials) {      // "No Sample Found" (shower.py:460-461)
+            if (sub == 0) {
+              S.meta[slot].z |= (PB_FLAG_NO_SAMPLE << 8);
+              W.bucket[cur] = P_NONE * LU_MAX;
+              c_trials += (unsigned long long)max_trials; c_fail += 1;
+            }
+            cur = -1;
+          }
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with s_grid before the next tile overwrites it
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c_trials += __shfl_down_sync(0xffffffffu, c_trials, o);
+    c_samples += __shfl_down_sync(0xffffffffu, c_samples, o);
+    c_fail += __shfl_down_sync(0xffffffffu, c_fail, o);
+  }
+  if (lane == 0) {
+    if (c_trials) atomicAdd(&W.counters[CNT_TRIALS], c_trials);
+    if (c_samples) atomicAdd(&W.counters[CNT_SAMPLES], c_samples);
+    if (c_fail) atomicAdd(&W.counters[CNT_NOSAMPLE], c_fail);
+  }
+}
+
+// Kinematics + rotation + daughter append, in bucket order (warps are process-coherent).
+__global__ void __launch_bounds__(128)
+k_emit(const __grid_constant__ Material M, Stack S, Work W, long long begin, int n) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  V4 da{0, 0, 0, 0}, db{0, 0, 0, 0};
+  int pid_a = 0, pid_b = 0, proc = P_NONE;
+  bool keep_a = false, keep_b = false;
+  long long slot = 0;
+  int4 meta = make_int4(0, 0, 0, 0);
+  uint2 key = make_uint2(0, 0);
+  double wgt = 0.0, rx = 0, ry = 0, rz = 0;
+  if (j < n) {
+    int i = W.sorted[j];
+    int bucket = W.bucket[i];
+    proc = bucket / LU_MAX;
+    if (proc != P_NONE) {
+      slot = begin + i;
+      const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * slot);
+      const double2* rfp = reinterpret_cast<const double2*>(S.rf + 4 * slot);
+      double2 a0 = pfp[0], a1 = pfp[1], b0 = rfp[0], b1 = rfp[1];
+      V4 pf{a0.x, a0.y, a1.x, a1.y};
+      rx = b0.x; ry = b0.y; rz = b1.x;
+      double mass = b1.y;
+      meta = S.meta[slot];
+      key = S.key[slot];
+      wgt = S.r0w[4 * slot + 3];
+      int pid = meta.x;
+      if (proc == P_SMDECAY) {                                     // pi0 -> gamma gamma (particle.py:391-409)
+        D2 u = draw2(key, 0, ST_DECAY, 0, P_SMDECAY);
+        two_body_decay(pf, mass, 0.0, 0.0, u.a, u.b, &da, &db);
+        pid_a = 22; pid_b = 22;
+        wgt *= 0.98823;                                            // particle.py:40 meson_decay_dict[111]
+      } else {
+        const double2* xp = reinterpret_cast<const double2*>(W.xs + 4 * (size_t)i);
+        double2 x01 = xp[0], x23 = xp[1];
+        double x[4] = {x01.x, x01.y, x23.x, x23.y};
+        double u_az = draw2(key, 0, ST_KIN, 0, proc).a;
+        double E0 = pf.E;
+        switch (proc) {                                            // shower.py:77-96
+          case P_BREM: case P_MUONBREM: kin_brem(E0, mass, x, u_az, &da, &db); pid_a = pid; pid_b = 22; break;
+          case P_PAIRPROD: kin_pairprod(E0, x, u_az, &da, &db); pid_a = -11; pid_b = 11; break;
+          case P_COMP: kin_compton(E0, 0.0, x[0], u_az, &da, &db); pid_a = 11; pid_b = 22; break;
+          case P_ANN: kin_annihilation(E0, 0.0, x[0], u_az, &da, &db); pid_a = 22; pid_b = 22; break;
+          case P_MOLLER: case P_BHABHA: kin_ee(E0, x[0], u_az, &da, &db); pid_a = pid; pid_b = 11; break;
+          case P_MUONE: kin_mue(E0, x[0], u_az, &da, &db); pid_a = pid; pid_b = 11; break;
+        }
+        Rot R = rotation_to(pf);                                   // shower.py:471,479-480
+        da = rotate(R, da); db = rotate(R, db);
+      }
+      keep_a = da.E > M.min_energy;                                // shower.py:704-706
+      keep_b = db.E > M.min_energy;
+    }
+  }
+  // warp-aggregated append: one atomic on the stack tail per warp
+  int cnt = (keep_a ? 1 : 0) + (keep_b ? 1 : 0);
+  int incl = cnt;
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  int total = __shfl_sync(0xffffffffu, incl, 31);
+  unsigned long long base = 0;
+  if (lane == 31 && total > 0) base = atomicAdd(W.tail, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (cnt) {
+    long long dst = (long long)base + (incl - cnt);
+    int gen = ((meta.z >> 16) & 0xffff) + 1;
+    for (int bit = 0; bit < 2; ++bit) {
+      bool keep = bit ? keep_b : keep_a;
+      if (!keep) continue;
+      if (dst >= S.capacity) { atomicAdd(&W.counters[CNT_OVERFLOW], 1ull); break; }
+      V4 d = bit ? db : da;
+      double2* p0p = reinterpret_cast<double2*>(S.p0 + 4 * dst);
+      double2* r0p = reinterpret_cast<double2*>(S.r0w + 4 * dst);
+      p0p[0] = make_double2(d.E, d.x); p0p[1] = make_double2(d.y, d.z);
+      r0p[0] = make_double2(rx, ry);   r0p[1] = make_double2(rz, wgt);
+      S.key[dst] = child_key(key, bit);
+      S.meta[dst] = make_int4(bit ? pid_b : pid_a, (int)slot, pack_info(gen, bit, 0, proc), meta.w);
+      ++dst;
+    }
+  }
+}
+
+__global__ void k_init_primaries(Stack S, const double* __restrict__ p, const double* __restrict__ r,
+                                 const double* __restrict__ w, const int* __restrict__ pid, const int* __restrict__ flags,
+                                 long long n, unsigned long long seed, unsigned long long first_id) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < 4; ++k) S.p0[4 * i + k] = p[4 * i + k];
+  for (int k = 0; k < 3; ++k) S.r0w[4 * i + k] = r[3 * i + k];
+  S.r0w[4 * i + 3] = w[i];
+  S.key[i] = root_key(seed, first_id + (unsigned long long)i);
+  S.meta[i] = make_int4(pid[i], -1, pack_info(0, 0, flags[i], P_INPUT), (int)i);
+}
+
+// ------------------------------------------------------------------------------------------ probes (tests)
+__global__ void k_probe(const __grid_constant__ Material M, const __grid_constant__ Tables T, int what, int process,
+                        const double* __restrict__ in, long long n, int is, double* __restrict__ out, int os) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* a = in + i * is;
+  double* o = out + i * os;
+  switch (what) {
+    case PB_PROBE_DSIGMA: o[0] = dsigma(M, process, a[0], a + 1); break;
+    case PB_PROBE_NSIGMA: o[0] = nsigma_eval(T.ns[process], a[0]); break;
+    case PB_PROBE_MAP: {
+      const MapInfo& mi = T.map[process];
+      const double* g = mi.grid + (size_t)((int)a[0]) * mi.stride;
+      double jac = 1.0;
+      for (int d = 0; d < mi.dim; ++d) {
+        int ninc = mi.ninc[d];
+        double yn = a[1 + d] * ninc;
+        int iy = min((int)yn, ninc - 1);
+        double g0 = g[mi.off[d] + iy], g1 = g[mi.off[d] + iy + 1];
+        double inc = g1 - g0;
+        o[d] = __dadd_rn(g0, __dmul_rn(inc, yn - iy));
+        jac *= inc * ninc;
+      }
+      o[mi.dim] = jac;
+    } break;
+    case PB_PROBE_MCS: {   // in: p4[4], dist_m, m_lepton, sign, z1, z2, u_phi
+      V4 p{a[0], a[1], a[2], a[3]};
+      V4 q = mcs_scatter(M, p, M.rho * (a[4] / kCmToM), a[5], a[6], a[7], a[8], a[9]);
+      o[0] = q.E; o[1] = q.x; o[2] = q.y; o[3] = q.z;
+    } break;
+    case PB_PROBE_KIN: {   // in: E, mass, x[4], u_az, u2 ; out: two four-vectors
+      V4 va{0, 0, 0, 0}, vb{0, 0, 0, 0};
+      switch (process) {
+        case P_BREM: case P_MUONBREM: kin_brem(a[0], a[1], a + 2, a[6], &va, &vb); break;
+        case P_PAIRPROD: kin_pairprod(a[0], a + 2, a[6], &va, &vb); break;
+        case P_COMP: kin_compton(a[0], 0.0, a[2], a[6], &va, &vb); break;
+        case P_ANN: kin_annihilation(a[0], 0.0, a[2], a[6], &va, &vb); break;
+        case P_MOLLER: case P_BHABHA: kin_ee(a[0], a[2], a[6], &va, &vb); break;
+        case P_MUONE: kin_mue(a[0], a[2], a[6], &va, &vb); break;
+        case P_SMDECAY: two_body_decay(V4{a[0], a[2], a[3], a[4]}, a[1], 0.0, 0.0, a[6], a[7], &va, &vb); break;
+      }
+      o[0] = va.E; o[1] = va.x; o[2] = va.y; o[3] = va.z; o[4] = vb.E; o[5] = vb.x; o[6] = vb.y; o[7] = vb.z;
+    } break;
+    case PB_PROBE_PHILOX: {
+      D2 d = draw2(make_uint2((uint32_t)a[0], (uint32_t)a[1]), (uint32_t)a[2], (uint32_t)a[3], (uint32_t)a[4], (uint32_t)a[5]);
+      o[0] = d.a; o[1] = d.b;
+    } break;
+  }
+}
+
+}  // namespace pb
+
+// =============================================================================================== host side
+using namespace pb;
+
+struct pb_engine_s {
+  int device = 0;
+  pb_config cfg{};
+  Material mat{};
+  Tables tab{};
+  std::vector<void*> owned;      // device allocations for tables
+  Work work{};
+  long long work_n = 0;          // capacity of per-wave scratch
+  void* work_blob = nullptr;
+  void* fixed_blob = nullptr;    // hist/offsets/cursor/ctrl/tail/counters
+  double* prim_mass = nullptr; long long prim_cap = 0;
+  void* prim_stage = nullptr; size_t prim_stage_bytes = 0;
+  int n_sm = 148;
+  std::string err;
+};
+
+#define PB_CUDA(e, call)                                                                         \
+  do {                                                                                           \
+    cudaError_t _c = (call);                                                                     \
+    if (_c != cudaSuccess) {                                                                     \
+      (e)->err = std::string(#call) + ": " + cudaGetErrorString(_c);                             \
+      return PB_ERR_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+static void derive_material(pb_engine e) {
+  const pb_config& c = e->cfg;
+  Material& m = e->mat;
+  memset(&m, 0, sizeof(m));
+  m.Z = c.Z_T; m.A = c.A_T; m.rho = c.rho; m.dEdx = c.dEdx_GeV_per_m; m.mT = c.mT_sampler;
+  m.min_energy = c.min_energy; m.Eg_min = c.Eg_min; m.Ee_min = c.Ee_min;
+  m.fudge = c.maxF_fudge; m.rescale_mcs = c.rescale_MCS;
+  for (int i = 0; i < 5; ++i) m.min_calc[i] = c.min_calc[i];
+  // all_processes.py:92-103 ; host libm pow, as CPython's float ** float
+  double a0 = 184.15 * pow(2.718, -0.5) * pow(c.Z_T, -1.0 / 3.0) / kMe;
+  m.ff_a0sq = a0 * a0;
+  m.ff_Z2a04 = (c.Z_T * c.Z_T) * pow(a0, 4);
+  // all_processes.py:123-133
+  double c1 = pow(111 * pow(c.Z_T, -1.0 / 3) / kMe, 2);
+  m.dff_c1 = c1;
+  m.dff_c2 = 0.164 * pow(c.A_T, -2.0 / 3);
+  m.dff_ap2 = pow(773.0 * pow(c.Z_T, -2.0 / 3) / kMe, 2);
+  m.dff_inel_pref = c.Z_T / (c1 * c1 * (c.Z_T * c.Z_T));
+  m.dff_pref = (c.Z_T * c.Z_T) * (c1 * c1);
+  m.Z23 = pow(c.Z_T, 2.0 / 3.0);
+  m.mV = c.mV; m.g_e = c.g_e; m.eps = c.kinetic_mixing; m.Zeff = c.Zeff;
+  m.E_res_ann = c.E_res_ann; m.E_thr_comp = c.E_thr_comp; m.bound_electron = c.bound_electron;
+  m.max_trials = 0;
+}
+
+extern "C" const char* pb_version(void) { return "petite_b200 0.1 (sm_100a)"; }
+extern "C" const char* pb_last_error(pb_engine e) { return e ? e->err.c_str() : "null engine"; }
+
+extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
+  if (!out || !cfg) return PB_ERR_ARG;
+  pb_engine e = new pb_engine_s();
+  e->device = device;
+  cudaError_t c = cudaSetDevice(device);
+  if (c != cudaSuccess) { delete e; return PB_ERR_CUDA; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->n_sm = prop.multiProcessorCount;
+  e->cfg = *cfg;
+  derive_material(e);
+  size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * 16;
+  if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
+  cudaMemset(e->fixed_blob, 0, fixed);
+  char* p = (char*)e->fixed_blob;
+  e->work.tail = (unsigned long long*)p; p += 8 * sizeof(unsigned long long);
+  e->work.counters = (unsigned long long*)p; p += 8 * sizeof(unsigned long long);
+  e->work.hist = (int*)p; p += NBUCKET * sizeof(int);
+  e->work.offsets = (int*)p; p += (NBUCKET + 1) * sizeof(int);
+  e->work.cursor = (int*)p; p += NBUCKET * sizeof(int);
+  e->work.ctrl = (int*)p;
+  *out = e;
+  return PB_OK;
+}
+
+extern "C" int pb_set_config(pb_engine e, const pb_config* cfg) {
+  if (!e || !cfg) return PB_ERR_ARG;
+  e->cfg = *cfg;
+  derive_material(e);
+  return PB_OK;
+}
+
+extern "C" void pb_destroy(pb_engine e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (void* p : e->owned) cudaFree(p);
+  if (e->work_blob) cudaFree(e->work_blob);
+  if (e->fixed_blob) cudaFree(e->fixed_blob);
+  if (e->prim_mass) cudaFree(e->prim_mass);
+  if (e->prim_stage) cudaFree(e->prim_stage);
+  delete e;
+}
+
+extern "C" int pb_upload_nsigma(pb_engine e, int id, const double* E, const double* y, int n) {
+  if (!e || id < 0 || id >= 16 || n < 0) return PB_ERR_ARG;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  double* d = nullptr;
+  PB_CUDA(e, cudaMalloc(&d, sizeof(double) * 2 * (size_t)std::max(n, 1)));
+  e->owned.push_back(d);
+  PB_CUDA(e, cudaMemcpy(d, E, sizeof(double) * n, cudaMemcpyHostToDevice));
+  PB_CUDA(e, cudaMemcpy(d + n, y, sizeof(double) * n, cudaMemcpyHostToDevice));
+  e->tab.ns[id] = NSigmaTable{d, d + n, n, 0};
+  return PB_OK;
+}
+
+extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int nE, int dim, const int32_t* ninc,
+                              const double* E_inc, const double* max_F, int neval) {
+  if (!e || process < 0 || process >= N_SAMPLED || dim < 1 || dim > 4 || nE < 1 || nE > LU_MAX) return PB_ERR_ARG;
+  if (dim != proc_dim(process)) { e->err = "map dimension does not match process"; return PB_ERR_ARG; }
+  PB_CUDA(e, cudaSetDevice(e->device));
+  MapInfo mi{};
+  int stride = 0;
+  for (int d = 0; d < dim; ++d) { mi.ninc[d] = ninc[d]; mi.off[d] = stride; stride += ninc[d] + 1; }
+  int padded = (stride + 15) / 16 * 16;          // rows start 128-byte aligned; TMA bulk size multiple of 16 B
+  if (padded > GRID_SMEM_DOUBLES) { e->err = "map row larger than the shared-memory staging buffer"; return PB_ERR_ARG; }
+  std::vector<double> host((size_t)padded * nE, 0.0);
+  for (int r = 0; r < nE; ++r) memcpy(&host[(size_t)r * padded], grid + (size_t)r * stride, sizeof(double) * stride);
+  double* d = nullptr;
+  PB_CUDA(e, cudaMalloc(&d, sizeof(double) * ((size_t)padded * nE + 2 * (size_t)nE)));
+  e->owned.push_back(d);
+  PB_CUDA(e, cudaMemcpy(d, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
+  double* dE = d + (size_t)padded * nE;
+  PB_CUDA(e, cudaMemcpy(dE, E_inc, sizeof(double) * nE, cudaMemcpyHostToDevice));
+  PB_CUDA(e, cudaMemcpy(dE + nE, max_F, sizeof(double) * nE, cudaMemcpyHostToDevice));
+  mi.grid = d; mi.E = dE; mi.maxF = dE + nE; mi.nE = nE; mi.dim = dim; mi.stride = padded; mi.B = neval;
+  e->tab.map[process] = mi;
+  return PB_OK;
+}
+
+static int ensure_work(pb_engine e, long long n) {
+  if (n <= e->work_n) return PB_OK;
+  long long cap = std::max<long long>(n * 5 / 4, 1 << 16);
+  if (e->work_blob) { cudaFree(e->work_blob); e->work_blob = nullptr; }
+  long long max_tiles = cap / TILE + N_SAMPLED * LU_MAX + 1;
+  size_t bytes = (size_t)cap * (4 + 4 + 32) + (size_t)max_tiles * 12 + 256;
+  PB_CUDA(e, cudaMalloc(&e->work_blob, bytes));
+  char* p = (char*)e->work_blob;
+  e->work.xs = (double*)p; p += (size_t)cap * 32;
+  e->work.bucket = (int*)p; p += (size_t)cap * 4;
+  e->work.sorted = (int*)p; p += (size_t)cap * 4;
+  e->work.tile_bucket = (int*)p; p += (size_t)max_tiles * 4;
+  e->work.tile_start = (int*)p; p += (size_t)max_tiles * 4;
+  e->work.tile_count = (int*)p;
+  e->work_n = cap;
+  return PB_OK;
+}
+
+extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t seed, uint64_t first_id, int global_ms,
+                              pb_stack* st, pb_counters* out, void* stream_) {
+  if (!e || !prim || !st) return PB_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  long long n0 = prim->n;
+  if (n0 <= 0 || n0 > st->capacity) { e->err = "primaries exceed stack capacity"; return PB_ERR_CAPACITY; }
+  for (int p = 0; p < 8; ++p)
+    if (e->tab.map[p].grid == nullptr || e->tab.ns[p].n == 0) { e->err = "tables not uploaded"; return PB_ERR_STATE; }
+  int B = e->tab.map[P_BREM].B;
+  e->mat.max_trials = (long long)std::min<double>((double)e->cfg.max_sweeps * (double)B, 4.0e9);
+  Stack S{st->p0, st->r0w, st->pf, st->rf, (uint2*)st->key, (int4*)st->meta, (int2*)st->aux, st->capacity};
+  long long launches = 0;
+  // ---- primaries: host SoA -> device staging -> stack records [0, n0)
+  size_t stage_bytes = (size_t)n0 * (sizeof(double) * (4 + 3 + 1 + 1) + sizeof(int) * 2);
+  if (stage_bytes > e->prim_stage_bytes) {
+    if (e->prim_stage) cudaFree(e->prim_stage);
+    PB_CUDA(e, cudaMalloc(&e->prim_stage, stage_bytes));
+    e->prim_stage_bytes = stage_bytes;
+  }
+  if (n0 > e->prim_cap) {
+    if (e->prim_mass) cudaFree(e->prim_mass);
+    PB_CUDA(e, cudaMalloc(&e->prim_mass, sizeof(double) * n0));
+    e->prim_cap = n0;
+  }
+  char* sp = (char*)e->prim_stage;
+  double* d_p = (double*)sp; sp += sizeof(double) * 4 * n0;
+  double* d_r = (double*)sp; sp += sizeof(double) * 3 * n0;
+  double* d_w = (double*)sp; sp += sizeof(double) * n0;
+  int* d_pid = (int*)sp; sp += sizeof(int) * n0;
+  int* d_fl = (int*)sp;
+  PB_CUDA(e, cudaMemcpyAsync(d_p, prim->p, sizeof(double) * 4 * n0, cudaMemcpyHostToDevice, stream));
+  PB_CUDA(e, cudaMemcpyAsync(d_r, prim->r, sizeof(double) * 3 * n0, cudaMemcpyHostToDevice, stream));
+  PB_CUDA(e, cudaMemcpyAsync(d_w, prim->weight, sizeof(double) * n0, cudaMemcpyHostToDevice, stream));
+  PB_CUDA(e, cudaMemcpyAsync(e->prim_mass, prim->mass, sizeof(double) * n0, cudaMemcpyHostToDevice, stream));
+  PB_CUDA(e, cudaMemcpyAsync(d_pid, prim->pid, sizeof(int) * n0, cudaMemcpyHostToDevice, stream));
+  PB_CUDA(e, cudaMemcpyAsync(d_fl, prim->flags, sizeof(int) * n0, cudaMemcpyHostToDevice, stream));
+  k_init_primaries<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(S, d_p, d_r, d_w, d_pid, d_fl, n0, seed, first_id);
+  ++launches;
+  unsigned long long tail0 = (unsigned long long)n0;
+  PB_CUDA(e, cudaMemcpyAsync(e->work.tail, &tail0, sizeof(tail0), cudaMemcpyHostToDevice, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.counters, 0, sizeof(unsigned long long) * CNT_N, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.hist, 0, sizeof(int) * NBUCKET, stream));
+
+  long long begin = 0, end = n0, waves = 0, max_wave = 0;
+  const int sample_grid = e->n_sm * 4;
+  while (begin < end) {
+    long long n = end - begin;
+    if (n > 0x7fffffffLL) { e->err = "wave wider than 2^31"; return PB_ERR_CAPACITY; }
+    if (end + 2 * n > st->capacity) {
+      e->err = "particle stack capacity exhausted (wave " + std::to_string(waves) + ")";
+      return PB_ERR_CAPACITY;
+    }
+    int rc = ensure_work(e, n);
+    if (rc != PB_OK) return rc;
+    max_wave = std::max(max_wave, n);
+    k_propagate<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, e->tab, S, e->work, begin, (int)n, e->prim_mass,
+                                                                  global_ms ? 1 : 0);
+    k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
+    k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, (int)n);
+    int sg = (int)std::min<long long>(sample_grid, (n + 31) / 32 + 1);
+    k_sample<8><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin);
+    k_emit<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, S, e->work, begin, (int)n);
+    launches += 5;
+    unsigned long long tail = 0;
+    PB_CUDA(e, cudaMemcpyAsync(&tail, e->work.tail, sizeof(tail), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(e, cudaStreamSynchronize(stream));
+    begin = end;
+    end = (long long)std::min<unsigned long long>(tail, (unsigned long long)st->capacity);
+    ++waves;
+  }
+  unsigned long long cnt[CNT_N];
+  PB_CUDA(e, cudaMemcpyAsync(cnt, e->work.counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+  PB_CUDA(e, cudaStreamSynchronize(stream));
+  if (out) {
+    out->n_particles = end; out->n_waves = waves; out->n_steps = (int64_t)cnt[CNT_STEPS];
+    out->n_substeps = (int64_t)cnt[CNT_SUBSTEPS]; out->n_samples = (int64_t)cnt[CNT_SAMPLES];
+    out->n_trials = (int64_t)cnt[CNT_TRIALS]; out->n_no_sample = (int64_t)cnt[CNT_NOSAMPLE];
+    out->n_launches = launches; out->max_wave = max_wave;
+  }
+  if (cnt[CNT_OVERFLOW]) { e->err = "particle stack overflow"; return PB_ERR_CAPACITY; }
+  if (cnt[CNT_NOSAMPLE]) { e->err = "No Sample Found for " + std::to_string(cnt[CNT_NOSAMPLE]) + " particle(s)"; return PB_ERR_NO_SAMPLE; }
+  return PB_OK;
+}
+
+extern "C" int pb_probe(pb_engine e, int what, int process, const double* in, int64_t n, int is, double* out, int os) {
+  if (!e || !in || !out || n <= 0) return PB_ERR_ARG;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  double *din = nullptr, *dout = nullptr;
+  PB_CUDA(e, cudaMalloc(&din, sizeof(double) * n * is));
+  PB_CUDA(e, cudaMalloc(&dout, sizeof(double) * n * os));
+  PB_CUDA(e, cudaMemcpy(din, in, sizeof(double) * n * is, cudaMemcpyHostToDevice));
+  PB_CUDA(e, cudaMemset(dout, 0, sizeof(double) * n * os));
+  k_probe<<<(unsigned)((n + 127) / 128), 128>>>(e->mat, e->tab, what, process, din, n, is, dout, os);
+  cudaError_t c = cudaDeviceSynchronize();
+  if (c == cudaSuccess) c = cudaMemcpy(out, dout, sizeof(double) * n * os, cudaMemcpyDeviceToHost);
+  cudaFree(din); cudaFree(dout);
+  if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
+  return PB_OK;
+}

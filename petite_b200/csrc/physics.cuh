@@ -1,0 +1,579 @@
+// Device physics for the shower hot path: differential cross-sections in VEGAS-map variables, form factors,
+// Lynch-Dahl multiple scattering, two-body kinematics.  fp64 throughout.  Each function cites the reference
+// lines whose RESULTS it must reproduce (<=1e-12 relative away from cancellation points); the arithmetic is
+// arranged for the GPU (shared sub-expressions, reciprocal reuse), not transliterated.
+#pragma once
+#include <math.h>
+#include "rng.cuh"
+
+namespace pb {
+
+// physical_constants.py:19-30 (same literal expressions, so the doubles are bit-identical)
+constexpr double kAlpha = 1.0 / 137.035999;
+constexpr double kMe = 510.998950 * 1e-6;
+constexpr double kMmu = 105.6583755 * 1e-3;
+constexpr double kMp = 938.272088 * 1e-3;
+constexpr double kMpi0 = 134.9768 * 1e-3;
+constexpr double kPi = 3.141592653589793;
+constexpr double kTwoPi = 2.0 * 3.141592653589793;
+constexpr double kCmToM = 0.01;
+constexpr double EGAMMA_MIN_KIN = 0.001;  // kinematics.py:9 (SURVEY Q-6)
+
+enum Proc : int {
+  P_BREM = 0, P_ANN = 1, P_PAIRPROD = 2, P_COMP = 3, P_MOLLER = 4, P_BHABHA = 5, P_MUONE = 6, P_MUONBREM = 7,
+  P_DARKBREM = 8, P_DARKANN = 9, P_DARKCOMP = 10, P_DARKMUONBREM = 11, P_SMDECAY = 12, P_BSMDECAY = 13,
+  P_NONE = 14, P_INPUT = 15, N_SAMPLED = 12
+};
+
+__host__ __device__ constexpr int proc_dim(int p) {
+  return (p == P_BREM || p == P_PAIRPROD || p == P_MUONBREM) ? 4 : ((p == P_DARKBREM || p == P_DARKMUONBREM) ? 3 : 1);
+}
+
+// Per-engine constants derived on the host (glibc pow, as CPython uses) from Z, A, mV ... ; lives in __constant__.
+struct Material {
+  double Z, A, rho, dEdx;         // dEdx in GeV/m
+  double mT;                      // sampler-time event_info['mT'] (= A, SURVEY Q-19)
+  double min_energy, Eg_min, Ee_min;
+  double fudge, rescale_mcs;
+  double min_calc[5];             // e-, e+, gamma, mu-, mu+
+  double ff_a0sq;                 // (184.15 * 2.718^-0.5 * Z^(-1/3) / m_e)^2        all_processes.py:92-103
+  double ff_Z2a04;                // Z^2 * a0^4
+  double dff_c1, dff_c2, dff_ap2; // all_processes.py:123-126
+  double dff_inel_pref;           // Z / (c1^2 Z^2)
+  double dff_pref;                // Z^2 c1^2
+  double Z23;                     // Z^(2/3)   moliere.py:218
+  long long max_trials;           // max_n_integrators * B
+  // dark sector
+  double mV, g_e, eps, Zeff, E_res_ann, E_thr_comp;
+  int bound_electron, pad;
+};
+
+__device__ __forceinline__ int pid_class(int pid) {  // index into min_calc; -1 if not a stepping species
+  switch (pid) { case 11: return 0; case -11: return 1; case 22: return 2; case 13: return 3; case -13: return 4; }
+  return -1;
+}
+__host__ __device__ __forceinline__ double pid_mass(int pid) {  // particle.py:4-14 (mass_dict)
+  switch (pid) {
+    case 11: case -11: return kMe;
+    case 13: case -13: return kMmu;
+    case 111: return kMpi0;
+    default: return 0.0;
+  }
+}
+
+// numpy evaluates px**2 + py**2 + pz**2 left to right without contraction; keep the same roundings where the
+// result feeds an ill-conditioned acos (particle.py:181).
+__device__ __forceinline__ double norm3_nofma(double x, double y, double z) {
+  return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+}
+
+// ---------------------------------------------------------------- form factors
+__device__ __forceinline__ double ff_elastic(const Material& M, double t) {  // all_processes.py:99-103
+  double den = 1.0 + M.ff_a0sq * t;
+  return M.ff_Z2a04 * t * t / (den * den);
+}
+
+__device__ __forceinline__ double ff_el_inel_over_t2(const Material& M, double t) {  // all_processes.py:112-133
+  const double mu_p = 2.79;
+  double a = 1.0 / (1.0 + M.dff_c1 * t);
+  double b = 1.0 + t / M.dff_c2;
+  double Gel = a * a / (b * b);
+  double r = M.dff_ap2 / (1.0 + M.dff_ap2 * t);
+  double d = 1.0 + t / 0.71;
+  double d2 = d * d;
+  double Ginel = M.dff_inel_pref * (r * r) * ((1.0 + (mu_p * mu_p - 1.0) * t / (4.0 * kMp * kMp)) / (d2 * d2));
+  return M.dff_pref * (Gel + Ginel);
+}
+
+// ---------------------------------------------------------------- differential cross-sections
+// Each takes the sampled point x (map variables), the incoming energy and returns dsigma per unit map volume.
+
+// all_processes.py:140-206 (dsigma_brem_dimensionless); ml = m_e (Brem) or m_mu (MuonBrem, SURVEY Q-5).
+__device__ __forceinline__ double ds_brem(const Material& M, double ep, double ml, const double* x) {
+  const double Egmin = M.Eg_min;
+  double span = ep - ml - Egmin;
+  double w = Egmin + x[0] * span;
+  double k = ep / (2 * ml);
+  double d = k * (x[1] + x[2]);
+  double dp = k * (x[1] - x[2]);
+  double ph = (x[3] - 0.5) * 2 * kPi;
+  double epp = ep - w;
+  bool ok = (Egmin < w) && (w < ep - ml) && (ml < epp) && (epp < ep) && (d > 0.0) && (dp > 0.0);
+  double cph = cos(ph);
+  double d2 = d * d, dp2 = dp * dp;
+  double ml2 = ml * ml;
+  double u = (1 + d2) / (2 * ep) - (1 + dp2) / (2 * epp);
+  double qsq = ml2 * ((d2 + dp2 - 2 * d * dp * cph) + ml2 * u * u);
+  double aem = kAlpha / ml;
+  double PF = 8.0 / kPi * kAlpha * (aem * aem) * (epp * ml2 * ml2) / (w * ep * qsq * qsq) * d * dp;
+  double jac = kPi * ep * ep * span / ml2;
+  double FF = ff_elastic(M, qsq);
+  double od = 1 + d2, odp = 1 + dp2;
+  double T1 = d2 / (od * od);
+  double T2 = dp2 / (odp * odp);
+  double T3 = w * w / (2 * ep * epp) * (d2 + dp2) / (od * odp);
+  double T4 = -(epp / ep + ep / epp) * (d * dp * cph) / (od * odp);
+  // SURVEY Q-22: the reference multiplies by the boolean mask, so NaN*0 stays NaN (and is then rejected)
+  return (ok ? 1.0 : 0.0) * PF * (T1 + T2 + T3 + T4) * jac * FF;
+}
+
+// all_processes.py:532-622 (dsigma_pairprod_dimensionless)
+__device__ __forceinline__ double ds_pairprod(const Material& M, double w, const double* x) {
+  const double me = kMe, me2 = kMe * kMe;
+  double epp = me + x[0] * (w - 2 * me);
+  double k = w / (2 * me);
+  double dp = k * (x[1] + x[2]);
+  double dm = k * (x[1] - x[2]);
+  double ph = x[3] * 2 * kPi;
+  double epm = w - epp;
+  bool ok = (me < epm) && (epm < w) && (me < epp) && (epp < w) && (dm > 0.0) && (dp > 0.0);
+  if (!ok) return 0.0;
+  double cph = cos(ph);
+  double dp2 = dp * dp, dm2 = dm * dm;
+  double u = (1.0 + dp2) / (2.0 * epp) + (1.0 + dm2) / (2.0 * epm);
+  double q2r = (dp2 + dm2 + 2.0 * dp * dm * cph) + me2 * u * u;
+  double aem = kAlpha / me;
+  double PF = 8.0 / kPi * kAlpha * (aem * aem) * epp * epm / (w * w * w * q2r * q2r) * dp * dm;
+  double jac = kPi * w * w * (w - 2 * me) / me2;
+  double FF = ff_elastic(M, me2 * q2r);
+  double op = 1.0 + dp2, om = 1.0 + dm2;
+  double T1 = -1.0 * dp2 / (op * op);
+  double T2 = -1.0 * dm2 / (om * om);
+  double T3 = w * w / (2.0 * epp * epm) * (dp2 + dm2) / (op * om);
+  double T4 = (epp / epm + epm / epp) * (dp * dm * cph) / (op * om);
+  return PF * (T1 + T2 + T3 + T4) * jac * FF;
+}
+
+// all_processes.py:625-742 (dsigma_compton_dCT); mV > 0 is DarkComp.
+__device__ __forceinline__ double ds_compton(double Eg, double mV, double ct) {
+  const double me = kMe, me2 = kMe * kMe, me4 = me2 * me2;
+  double s = me2 + 2 * Eg * me;
+  double smv = me + mV;
+  if (s < smv * smv) return 0.0;
+  double mV2 = mV * mV;
+  double lam = sqrt((s - mV2) * (s - mV2) - 2 * me2 * (s + mV2) + me4);
+  double jac = (s - me2) / (2 * s) * lam;
+  double lam2 = sqrt(me4 + (mV2 - s) * (mV2 - s) - 2 * me2 * (mV2 + s));
+  double t = -0.5 * (me4 + s * (-mV2 + s + ct * lam2) - me2 * (mV2 + 2 * s + ct * lam2)) / s;
+  double sm = s - me2;
+  double PF = 2.0 * kPi * kAlpha * kAlpha / (sm * sm);
+  double T1, T2, T3;
+  if (mV == 0.0) {
+    T1 = (6.0 * me2 * s + 3.0 * me4 - s * s) / ((me2 - s) * (-me2 + s + t));
+    double a = s + t - me2;
+    T2 = 4 * me4 / (a * a);
+    T3 = (t * sm + (s + me2) * (s + me2)) / (sm * sm);
+  } else {
+    double a = me2 + mV2 - s - t;
+    T1 = (2.0 * me2 * (mV2 - 3 * s) - 3 * me4 - 2 * mV2 * s + 2 * mV2 * mV2 + s * s) / ((me2 - s) * a);
+    T2 = (2 * me2 * (2 * me2 + mV2)) / (a * a);
+    T3 = ((me2 + s) * (me2 + mV2 + s) + t * sm) / ((me2 - s) * (me2 - s));
+  }
+  return PF * jac * (T1 + T2 + T3);
+}
+
+// all_processes.py:469-529 (dsigma_annihilation_dCT)
+__device__ __forceinline__ double ds_annihilation(double Ee, double mV, double EgMin, double ct) {
+  const double me = kMe;
+  double s = 2.0 * me * (Ee + me);
+  double mV2 = mV * mV;
+  double ctMax = sqrt((Ee + me) / (Ee - me)) * (2 * me * (Ee - 2 * EgMin + me) - mV2) / (2 * me * (Ee + me) - mV2);
+  if (s < mV2) return 0.0;
+  if (ct > ctMax) return 0.0;
+  double b2 = 1.0 - 4.0 * me * me / s;   // b = sqrt(b2); only b^2 is used
+  double bb = sqrt(b2);
+  bb = bb * bb;
+  return 4.0 * kPi * kAlpha * kAlpha / (s * (1 - bb * ct * ct)) * ((s - mV2) / (2 * s) * (1 + ct * ct) + 2.0 * mV2 / (s - mV2));
+}
+
+// all_processes.py:787-840 (dsigma_moller_dCT)
+__device__ __forceinline__ double ds_moller(double Ee, double DE, double ct) {
+  const double me = kMe, me2 = kMe * kMe;
+  double lim = 2.0 * DE / (Ee - me);
+  if (!((ct > -1 + lim) && (ct < 1.0 - lim))) return 0.0;
+  double s = me2 + 2 * Ee * me;
+  double c2 = ct * ct, c4 = c2 * c2;
+  double num = s * s * (3 + c2) * (3 + c2) - 8 * me2 * s * (7 + c4) + 16 * me2 * me2 * (6 - 3 * c2 + c4);
+  double a = s - 4 * me2;
+  return 16 * kPi * kPi * kAlpha * kAlpha * num / (8 * kPi * s * a * a * (1 - ct) * (1 - ct) * (1 + ct) * (1 + ct));
+}
+
+// all_processes.py:948-1007 (dsigma_bhabha_dCT)
+__device__ __forceinline__ double ds_bhabha(double Ee, double DE, double ct) {
+  const double m = kMe;
+  double lim = 2.0 * DE / (Ee - m);
+  if (!((ct > -1 + lim) && (ct < 1.0 - lim))) return 0.0;
+  double m2 = m * m, m4 = m2 * m2, m6 = m4 * m2, m8 = m4 * m4;
+  double s = m2 + 2 * Ee * m;
+  double s2 = s * s, s3 = s2 * s, s4 = s2 * s2;
+  double c1 = -1 + ct;
+  double num = 256 * c1 * c1 * ct * ct * m8
+             - 128 * c1 * (1 + ct * (1 + ct) * (-3 + 2 * ct)) * m6 * s
+             + 16 * (7 + ct * (2 + ct * (-5 + 6 * c1 * ct))) * m4 * s2
+             - 8 * (7 + ct * (-3 + ct * (3 + ct * (-1 + 2 * ct)))) * m2 * s3
+             + (3 + ct * ct) * (3 + ct * ct) * s4;
+  double a = -4 * m2 + s;
+  return (kAlpha * kAlpha * kPi * num) / (2 * c1 * c1 * s3 * a * a);
+}
+
+// all_processes.py:843-886 (dsigma_muonelectron_dCT)
+__device__ __forceinline__ double ds_muone(double Emu, double DE, double ct) {
+  const double me = kMe, me2 = kMe * kMe, mm2 = kMmu * kMmu;
+  double s = me2 + mm2 + 2 * me * Emu;
+  double t_limit = 2.0 * me * (me - DE);
+  double a = s + me2 - mm2;
+  double t = -2.0 * (1 - ct) * (a * a / (4.0 * s) - me2);
+  if (!(t < t_limit)) return 0.0;
+  double b = s + t - 4 * me2;
+  return 16 * kPi * kPi * kAlpha * kAlpha * (s * s + 2 * (me2 + mm2) * (2 * t + mm2 - 3 * me2) + b * b) / (16 * kPi * s * t * t);
+}
+
+// all_processes.py:208-372 (dsig_dx_dcostheta_dark_brem_exact_tree_level, Method "Log")
+__device__ __forceinline__ double ds_darkbrem(const Material& M, double Eb, double ml, const double* xx) {
+  const double mV = M.mV, MT = M.mT;
+  const double LN10 = 2.302585092994046;
+  double x = xx[0];
+  double omc = pow(10.0, xx[1]);
+  double cth = 1.0 - omc;
+  double ttilde = pow(10.0, xx[2]);
+  double Jac = omc * ttilde * (LN10 * LN10);
+  double xE = x * Eb;
+  double mV2 = mV * mV, ml2 = ml * ml;
+  double k = sqrt(fabs(xE * xE - mV2));
+  double p = sqrt(Eb * Eb - ml2);
+  double V2 = p * p + k * k - 2 * p * k * cth;
+  double V = sqrt(V2);
+  double utilde = -2 * (x * Eb * Eb - k * p * cth) + mV2;
+  double Er = (1 - x) * Eb + MT;
+  double discr = utilde * utilde + 4 * MT * utilde * Er + 4 * MT * MT * (V * V);
+  double sq = sqrt(fabs(discr));
+  double den = 2 * Er * Er - 2 * (V * V);
+  double cmn = V * (utilde + 2 * MT * Er);
+  double Qp = fabs((cmn + Er * sq) / den);
+  double Qm = fabs((cmn - Er * sq) / den);
+  double tplus = 2 * MT * (sqrt(MT * MT + Qp * Qp) - MT);
+  double tminus = 2 * MT * (sqrt(MT * MT + Qm * Qm) - MT);
+  double tc = 2 * MT * (MT + Eb) * sqrt(Eb * Eb + ml2) / (MT * (MT + 2 * Eb) + ml2);
+  double tconv = tc * tc;
+  double t = ttilde * tconv;
+  double q0 = -t / (2 * MT);
+  double q = sqrt(t * t / (4 * MT * MT) + t);
+  double e3 = Eb + q0 - xE;
+  double cthq = -((V * V) + q * q + ml2 - e3 * e3) / (2 * V * q);
+  double mm = mV2 + 2 * ml2;
+  double Y = -t + 2 * q0 * Eb - 2 * q * p * (p - k * cth) * cthq / V;
+  double W = fabs(Y * Y - 4 * q * q * p * p * k * k * (1 - cth * cth) * (1 - cthq * cthq) / (V * V));
+  bool ok = (xE >= mV) && (discr >= 0) && (tplus > tminus) && (t > tminus) && (t < tplus) && (fabs(cthq) <= 1.0) && (W > 0);
+  if (!ok) return 0.0;
+  double Am2 = -8 * MT * (4 * Eb * Eb * MT - t * (2 * Eb + MT)) * mm;
+  double A1 = 8 * MT * MT / utilde;
+  double Am1 = (8 / utilde) * (MT * MT * (2 * t * utilde + utilde * utilde
+                                          + 4 * Eb * Eb * (2 * (x - 1) * mm - t * ((x - 2) * x + 2))
+                                          + 2 * t * (-mV2 + 2 * ml2 + t))
+                               - 2 * Eb * MT * t * ((1 - x) * utilde + (x - 2) * (mm + t))
+                               + t * t * (utilde - mV2));
+  double A0 = (8 / (utilde * utilde)) * (MT * MT * (2 * t * utilde + (t - 4 * Eb * Eb * (x - 1) * (x - 1)) * mm)
+                                         + 2 * Eb * MT * t * (utilde - (x - 1) * mm));
+  double sW = sqrt(W);
+  double phi_int = (A0 + Y * A1 + Am1 / sW + Y * Am2 / (W * sW)) / (8 * MT * MT);
+  double FF = ff_el_inel_over_t2(M, t);
+  double ans = FF * (kAlpha * kAlpha * kAlpha) * k * Eb * phi_int / (p * sqrt(k * k + p * p - 2 * p * k * cth));
+  return ans * tconv * Jac;
+}
+
+// radiative_return.py:26-79 + all_processes.py:400-466 (dsigma_radiative_return_du)
+__device__ __forceinline__ double kf_beta(double s) { return (2.0 * kAlpha / kPi) * (log(s / (kMe * kMe)) - 1.0); }
+__device__ __forceinline__ double fl_kf(double x, double beta) {
+  if (x >= 1.0) x = 1.0 - 1e-10;
+  return (beta / 16.0) * ((8.0 + 3.0 * beta) * pow(1.0 - x, beta / 2.0 - 1.0) - 4.0 * (1.0 + x));
+}
+__device__ __forceinline__ double fl_kf_scaled(double x, double beta) {
+  return (beta / 16.0) * ((8.0 + 3.0 * beta) - 4.0 * (1.0 + x) * pow(1.0 - x, 1.0 - beta / 2.0));
+}
+__device__ __forceinline__ double ds_darkann(const Material& M, double Ee, double u0) {
+  const double me = kMe;
+  double mV2 = M.mV * M.mV;
+  double s = 2.0 * me * (Ee + me);
+  if (s < mV2) return 0.0;
+  double beta = kf_beta(s);
+  double umax = pow(1.0 - mV2 / s, beta / 2.0);
+  double betaf = sqrt(1.0 - 4.0 * me * me / mV2);
+  double prefac = (4.0 * kPi * kPi) * kAlpha * betaf * (3.0 / 2.0 - betaf * betaf / 2.0) / s * umax;
+  double u = u0 * umax;
+  double x1 = 1.0 - pow(u, 2.0 / beta);
+  double x2 = mV2 / (x1 * s);
+  if (!((x2 < 1.0) && (x1 > 0.0) && (u0 < 1.0))) return 0.0;
+  double y = mV2 / s;
+  double lumi = fl_kf(y / x1, beta) * fl_kf_scaled(x1, beta) * (1.0 / x1) * (2.0 / beta);
+  return 2.0 * prefac * lumi;
+}
+
+__device__ __forceinline__ double dsigma(const Material& M, int proc, double E, const double* x) {
+  switch (proc) {
+    case P_BREM: return ds_brem(M, E, kMe, x);
+    case P_MUONBREM: return ds_brem(M, E, kMmu, x);
+    case P_PAIRPROD: return ds_pairprod(M, E, x);
+    case P_COMP: return ds_compton(E, 0.0, x[0]);
+    case P_ANN: return ds_annihilation(E, 0.0, M.Eg_min, x[0]);
+    case P_MOLLER: return ds_moller(E, M.Ee_min, x[0]);
+    case P_BHABHA: return ds_bhabha(E, M.Ee_min, x[0]);
+    case P_MUONE: return ds_muone(E, M.Ee_min, x[0]);
+    case P_DARKBREM: return ds_darkbrem(M, E, kMe, x);
+    case P_DARKMUONBREM: return ds_darkbrem(M, E, kMmu, x);
+    case P_DARKANN: return ds_darkann(M, E, x[0]);
+    case P_DARKCOMP: return ds_compton(E, M.mV, x[0]);
+  }
+  return 0.0;
+}
+
+// ---------------------------------------------------------------- energy loss, rotations, multiple scattering
+struct V4 { double E, x, y, z; };
+
+// particle.py:143-153
+__device__ __forceinline__ V4 lose_energy(V4 p, double mass, double value) {
+  double p30 = norm3_nofma(p.x, p.y, p.z);
+  double Eu = p.E - value;
+  if (Eu <= mass) Eu = mass;
+  double p3f = sqrt(Eu * Eu - mass * mass);
+  if (p3f > 0.0) return V4{Eu, p.x / p30 * p3f, p.y / p30 * p3f, p.z / p30 * p3f};
+  return V4{mass, 0.0, 0.0, 0.0};
+}
+
+// moliere.py:196-219, 265-281: Lynch-Dahl width of the Gaussian core, F = 0.98, z = 1
+__device__ __forceinline__ double mcs_theta0(const Material& M, double t, double beta, double m_lepton) {
+  const double F = 0.98;
+  double p = (m_lepton / 1e-3) * beta / sqrt(1.0 - beta * beta);
+  double pb = 1.0 / (p * beta);
+  double chic2 = 0.157 * M.Z * (M.Z + 1) * (t / M.A) * (pb * pb);
+  double za = M.Z * kAlpha / beta;
+  double chia2 = 2.007e-5 * M.Z23 * (1.0 + 3.34 * (za * za)) / (p * p);
+  double omega = chic2 / chia2;
+  double v = 0.5 * omega / (1.0 - F);
+  return sqrt(chic2 * ((1.0 + v) * log(1.0 + v) / v - 1) / (1.0 + F * F));
+}
+
+// moliere.py:287-348 (get_rotation_matrix incl. the duplicated branch, SURVEY Q-13) and :350-400
+// (get_scattered_momentum_fast).  sign in {-1,+1}; z1, z2 standard normals; u_phi in [0,1).
+__device__ __forceinline__ V4 mcs_scatter(const Material& M, V4 p4, double t, double m_lepton, double sign, double z1,
+                                          double z2, double u_phi) {
+  double vx = p4.x, vy = p4.y, vz = p4.z;
+  double pn = norm3_nofma(vx, vy, vz);
+  if (!(pn > 0)) return p4;
+  double beta = pn / p4.E;
+  double ca, sa;
+  if (fabs(vx) > 0.0 && fabs(vy) > 0.0) {
+    double a = atan(fabs(vy / vx));
+    if (vx > 0.0 && vy > 0.0) a = -a;
+    if (vx < 0.0 && vy > 0.0) a = -(kPi - a);
+    if (vx < 0.0 && vy < 0.0) a = -(kPi + a);
+    if (vx > 0.0 && vy < 0.0) a = -(2.0 * kPi - a);
+    sincos(a, &sa, &ca);
+  } else if (fabs(vy) > 0.0) { ca = 0.0; sa = 1.0; }
+  else { ca = 1.0; sa = 0.0; }
+  double vxp = vx * ca - vy * sa;
+  double cb, sb;
+  if (fabs(vz) > 0.0 && fabs(vxp) > 0.0) {
+    double b = atan(fabs(vxp / vz));
+    if (vz > 0.0 && vxp > 0.0) b = -b;
+    if (vz < 0.0 && vxp > 0.0) b = -(kPi - b);
+    if (vz < 0.0 && vxp < 0.0) b = -(kPi + b);
+    if (vz > 0.0 && vxp > 0.0) b = -(2.0 * kPi - b);
+    sincos(b, &sb, &cb);
+  } else if (vxp > 0.0) { cb = 0.0; sb = -1.0; }
+  else if (vxp < 0.0) { cb = 0.0; sb = 1.0; }
+  else { cb = 1.0; sb = 0.0; }
+  double th0 = mcs_theta0(M, t, beta, m_lepton);
+  double g1 = z1 * th0, g2 = z2 * th0;
+  double theta = sign * sqrt(g1 * g1 + g2 * g2) * M.rescale_mcs;
+  double phi = kTwoPi * u_phi;
+  double cth, sth, cph, sph;
+  sincos(theta, &sth, &cth);
+  sincos(phi, &sph, &cph);
+  double q0 = pn * (sph * sth), q1 = pn * (-cph * sth), q2 = pn * cth;
+  // R = Rb Ra = [[cb ca, -cb sa, sb], [sa, ca, 0], [-sb ca, sb sa, cb]] ; lab = R^T q
+  V4 o;
+  o.E = p4.E;
+  o.x = (cb * ca) * q0 + sa * q1 + (-sb * ca) * q2;
+  o.y = (-cb * sa) * q0 + ca * q1 + (sb * sa) * q2;
+  o.z = sb * q0 + cb * q2;
+  return o;
+}
+
+// CPython random.gauss pair from two uniforms (oracle/physics.py normals_from_uniforms)
+__device__ __forceinline__ void normals_from_uniforms(double ua, double ur, double* z1, double* z2) {
+  double s, c;
+  sincos(ua * kTwoPi, &s, &c);
+  double g = sqrt(-2.0 * log(1.0 - ur));
+  *z1 = c * g;
+  *z2 = s * g;
+}
+
+struct McsDraw { double sign, z1, z2, uphi; };
+__device__ __forceinline__ McsDraw mcs_draw(uint2 key, uint32_t index, uint32_t pc) {
+  D2 a = draw2(key, index, ST_MCS, 0, pc);
+  D2 b = draw2(key, index, ST_MCS, 1, pc);
+  McsDraw d;
+  d.sign = a.a < 0.5 ? -1.0 : 1.0;
+  d.uphi = a.b;
+  normals_from_uniforms(b.a, b.b, &d.z1, &d.z2);
+  return d;
+}
+
+// particle.py:176-185: rows of Rz(phi) Ry(theta) taking z-hat onto pf; applied as lab = R v
+struct Rot { double r00, r01, r02, r10, r11, r12, r20, r22; };
+__device__ __forceinline__ Rot rotation_to(V4 pf) {
+  double th = acos(pf.z / norm3_nofma(pf.x, pf.y, pf.z));
+  double ph = atan2(pf.y, pf.x);
+  double ct, st, cp, sp;
+  sincos(th, &st, &ct);
+  sincos(ph, &sp, &cp);
+  return Rot{ct * cp, -sp, st * cp, ct * sp, cp, st * sp, -st, ct};
+}
+__device__ __forceinline__ V4 rotate(const Rot& R, V4 v) {
+  return V4{v.E, R.r00 * v.x + R.r01 * v.y + R.r02 * v.z, R.r10 * v.x + R.r11 * v.y + R.r12 * v.z, R.r20 * v.x + R.r22 * v.z};
+}
+
+// ---------------------------------------------------------------- kinematics (parent along +z)
+__device__ __forceinline__ double sq(double v) { return v * v; }
+
+// kinematics.py:10-41 (e_to_egamma_fourvecs): a = outgoing lepton, b = photon
+__device__ __forceinline__ void kin_brem(double ep, double ml, const double* x, double u_az, V4* a, V4* b) {
+  double w = EGAMMA_MIN_KIN + x[0] * (ep - ml - EGAMMA_MIN_KIN);
+  double ct = cos((x[1] + x[2]) / 2);
+  double ctp = cos((x[1] - x[2]) * ep / (2 * (ep - w)));
+  double ph = (x[3] - 0.5) * 2.0 * kPi;
+  double epp = ep - w;
+  double pp = sqrt(epp * epp - ml * ml);
+  double sal, cal, sp, cp;
+  sincos(u_az * kTwoPi, &sal, &cal);
+  sincos(ph, &sp, &cp);
+  double st = sqrt(1.0 - ct * ct), stp = sqrt(1.0 - ctp * ctp);
+  *b = V4{w, w * cal * st, w * sal * st, w * ct};
+  *a = V4{epp, pp * (sal * sp * stp + cal * (ctp * st - cp * ct * stp)), pp * (ctp * sal * st - (cp * ct * sal + cal * sp) * stp),
+          pp * (ct * ctp + cp * st * stp)};
+}
+
+// kinematics.py:70-102 (gamma_to_epem_fourvecs): a = positron, b = electron
+__device__ __forceinline__ void kin_pairprod(double w, const double* x, double u_az, V4* a, V4* b) {
+  const double me = kMe;
+  double epp = me + x[0] * (w - 2 * me);
+  double ctp = cos(w * (x[1] + x[2]) / (2 * epp));
+  double ctm = cos(w * (x[1] - x[2]) / (2 * (w - epp)));
+  double ph = x[3] * 2 * kPi;
+  double epm = w - epp;
+  double pm = sqrt(epm * epm - me * me), pp = sqrt(epp * epp - me * me);
+  double al = u_az * kTwoPi;
+  double sal, cal, spal, cpal;
+  sincos(al, &sal, &cal);
+  sincos(ph + al, &spal, &cpal);
+  double stp = sqrt(1.0 - ctp * ctp), stm = sqrt(1.0 - ctm * ctm);
+  *a = V4{epp, pp * stp * cal, pp * stp * sal, pp * ctp};
+  *b = V4{epm, pm * stm * cpal, pm * stm * spal, pm * ctm};
+}
+
+// kinematics.py:104-132 (compton_fourvecs): a = electron, b = photon / V
+__device__ __forceinline__ void kin_compton(double Eg, double mV, double ct, double u_az, V4* a, V4* b) {
+  const double me = kMe;
+  double s = me * me + 2 * Eg * me;
+  double rs = sqrt(s);
+  double Ee0 = (s + me * me) / (2.0 * rs);
+  double Ee = (s - mV * mV + me * me) / (2 * rs);
+  double EV = (s + mV * mV - me * me) / (2 * rs);
+  double pF = sqrt(Ee * Ee - me * me);
+  double g0 = Ee0 / me;
+  double b0 = 1.0 / g0 * sqrt(g0 * g0 - 1.0);
+  double sp, cp;
+  sincos(u_az * kTwoPi, &sp, &cp);
+  double st = sqrt(1 - ct * ct);
+  *a = V4{g0 * Ee + b0 * g0 * pF * ct, -pF * st * sp, -pF * st * cp, b0 * g0 * Ee + g0 * pF * ct};
+  *b = V4{g0 * EV - b0 * g0 * pF * ct, pF * st * sp, pF * st * cp, b0 * g0 * EV - g0 * pF * ct};
+}
+
+// kinematics.py:301-334 (annihilation_fourvecs): a = photon, b = photon / V
+__device__ __forceinline__ void kin_annihilation(double Ee, double mV, double ct, double u_az, V4* a, V4* b) {
+  const double me = kMe;
+  double s = 2 * me * (Ee + me);
+  double rs = sqrt(s);
+  double EeCM = rs / 2.0;
+  double Eg = (s - mV * mV) / (2 * rs);
+  double EV = (s + mV * mV) / (2 * rs);
+  double pF = Eg;
+  double g0 = EeCM / me;
+  double b0 = 1.0 / g0 * sqrt(g0 * g0 - 1.0);
+  double sp, cp;
+  sincos(u_az * kTwoPi, &sp, &cp);
+  double st = sqrt(1 - ct * ct);
+  *a = V4{g0 * Eg - b0 * g0 * pF * ct, -pF * st * sp, -pF * st * cp, b0 * g0 * Eg - g0 * pF * ct};
+  *b = V4{g0 * EV + b0 * g0 * pF * ct, pF * st * sp, pF * st * cp, b0 * g0 * EV + g0 * pF * ct};
+}
+
+// kinematics.py:213-237 (ee_to_ee_fourvecs): a = scattered e+-, b = struck electron
+__device__ __forceinline__ void kin_ee(double Einc, double ct, double u_az, V4* a, V4* b) {
+  const double me = kMe;
+  double s = 2 * me * me + 2 * Einc * me;
+  double Ee0 = sqrt(s) / 2.0;
+  double pF = sqrt(Ee0 * Ee0 - me * me);
+  double g0 = Ee0 / me;
+  double b0 = 1.0 / g0 * sqrt(g0 * g0 - 1.0);
+  double sp, cp;
+  sincos(u_az * kTwoPi, &sp, &cp);
+  double st = sqrt(1 - ct * ct);
+  *a = V4{g0 * Ee0 + b0 * g0 * pF * ct, -pF * st * sp, -pF * st * cp, b0 * g0 * Ee0 + g0 * pF * ct};
+  *b = V4{g0 * Ee0 - b0 * g0 * pF * ct, pF * st * sp, pF * st * cp, b0 * g0 * Ee0 - g0 * pF * ct};
+}
+
+// kinematics.py:239-265 (mue_to_mue_fourvecs): a = muon, b = electron
+__device__ __forceinline__ void kin_mue(double Einc, double ct, double u_az, V4* a, V4* b) {
+  const double me = kMe, mm = kMmu;
+  double s = me * me + mm * mm + 2 * Einc * me;
+  double rs = sqrt(s);
+  double Ee0 = (s + me * me - mm * mm) / (2.0 * rs);
+  double Em0 = (s + mm * mm - me * me) / (2.0 * rs);
+  double pe = sqrt(Ee0 * Ee0 - me * me);
+  double pm = sqrt(Em0 * Em0 - mm * mm);
+  double g0 = Ee0 / me;
+  double b0 = 1.0 / g0 * sqrt(g0 * g0 - 1.0);
+  double sp, cp;
+  sincos(u_az * kTwoPi, &sp, &cp);
+  double st = sqrt(1 - ct * ct);
+  *a = V4{g0 * Em0 + b0 * g0 * pm * ct, pm * st * sp, pm * st * cp, b0 * g0 * Em0 + g0 * pm * ct};
+  *b = V4{g0 * Ee0 - b0 * g0 * pe * ct, -pe * st * sp, -pe * st * cp, b0 * g0 * Ee0 - g0 * pe * ct};
+}
+
+// particle.py:187-256 (boost_matrix, two_body_decay, isotropic)
+__device__ __forceinline__ void two_body_decay(V4 pf, double mX, double m1, double m2, double u_cos, double u_phi, V4* a, V4* b) {
+  double E1 = (mX * mX - m2 * m2 + m1 * m1) / (2 * mX);
+  double E2 = (mX * mX - m1 * m1 + m2 * m2) / (2 * mX);
+  double pF = sqrt(E1 * E1 - m1 * m1);
+  double c = -1.0 + 2.0 * u_cos;
+  double sphi, cphi;
+  sincos(kTwoPi * u_phi, &sphi, &cphi);
+  double sth = sqrt(1 - c * c);
+  double v1[4] = {E1, -pF * sth * sphi, -pF * sth * cphi, -pF * c};
+  double v2[4] = {E2, pF * sth * sphi, pF * sth * cphi, pF * c};
+  double gamma = pf.E / mX;
+  double beta = (gamma == 1.0) ? 1.0 : sqrt(1.0 - 1.0 / (gamma * gamma));
+  double pmag = norm3_nofma(pf.x, pf.y, pf.z);
+  if (pmag == 0.0) {
+    *a = V4{v1[0], v1[1], v1[2], v1[3]};
+    *b = V4{v2[0], v2[1], v2[2], v2[3]};
+    return;
+  }
+  double bv[3] = {beta * pf.x / pmag, beta * pf.y / pmag, beta * pf.z / pmag};
+  double g1 = gamma - 1, b2 = beta * beta;
+  double B[4][4];
+  B[0][0] = gamma;
+  for (int i = 0; i < 3; ++i) {
+    B[0][i + 1] = B[i + 1][0] = gamma * bv[i];
+    for (int j = 0; j < 3; ++j) B[i + 1][j + 1] = (i == j ? 1.0 : 0.0) + g1 * bv[i] * bv[j] / b2;
+  }
+  double o1[4], o2[4];
+  for (int i = 0; i < 4; ++i) {
+    o1[i] = B[i][0] * v1[0] + B[i][1] * v1[1] + B[i][2] * v1[2] + B[i][3] * v1[3];
+    o2[i] = B[i][0] * v2[0] + B[i][1] * v2[1] + B[i][2] * v2[2] + B[i][3] * v2[3];
+  }
+  *a = V4{o1[0], o1[1], o1[2], o1[3]};
+  *b = V4{o2[0], o2[1], o2[2], o2[3]};
+}
+
+}  // namespace pb

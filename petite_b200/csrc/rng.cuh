@@ -1,0 +1,64 @@
+// Counter-based Philox4x32-10 draws, keyed by a path-derived particle key.
+// The addressing scheme (streams, counter layout) is specified in DESIGN.md section 4 and mirrored by the
+// CPU oracle (oracle/philox.py) so that both consume identical uniforms.
+#pragma once
+#include <stdint.h>
+
+namespace pb {
+
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+
+enum Stream : uint32_t {
+  ST_SUBSTEP = 1, ST_FINAL = 2, ST_MCS = 3, ST_CHOICE = 4, ST_VEGAS = 5, ST_KIN = 6, ST_DECAY = 7,
+  ST_DBIN = 8, ST_PE = 11, ST_C0 = 12, ST_KEY_ROOT = 0xA0, ST_KEY_CHILD = 0xA1
+};
+constexpr uint32_t MCS_FINAL_INDEX = 0xFFFFFFFFu;
+
+struct U4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mulhi32(PHILOX_M0, c.x), lo0 = PHILOX_M0 * c.x;
+    uint32_t hi1 = mulhi32(PHILOX_M1, c.z), lo1 = PHILOX_M1 * c.z;
+    c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+    k0 += PHILOX_W0;
+    k1 += PHILOX_W1;
+  }
+  return c;
+}
+
+// 53-bit uniform in [0,1): ((hi>>5)*2^26 + (lo>>6)) * 2^-53
+__host__ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+  uint64_t m = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
+  return (double)m * (1.0 / 9007199254740992.0);
+}
+
+struct D2 { double a, b; };
+
+__host__ __device__ __forceinline__ D2 draw2(uint2 key, uint32_t c0, uint32_t stream, uint32_t c2 = 0, uint32_t c3 = 0) {
+  U4 o = philox4x32_10(U4{c0, stream, c2, c3}, key.x, key.y);
+  return D2{u53(o.x, o.y), u53(o.z, o.w)};
+}
+
+__host__ __device__ __forceinline__ uint2 root_key(uint64_t seed, uint64_t shower) {
+  U4 o = philox4x32_10(U4{(uint32_t)shower, (uint32_t)(shower >> 32), 0u, (uint32_t)ST_KEY_ROOT},
+                       (uint32_t)seed, (uint32_t)(seed >> 32));
+  return make_uint2(o.x, o.y);
+}
+
+__host__ __device__ __forceinline__ uint2 child_key(uint2 key, uint32_t bit) {
+  U4 o = philox4x32_10(U4{bit, (uint32_t)ST_KEY_CHILD, 0u, 0u}, key.x, key.y);
+  return make_uint2(o.x, o.y);
+}
+
+}  // namespace pb

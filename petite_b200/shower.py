@@ -1,0 +1,459 @@
+"""``Shower``: PETITE's SM shower API in front of the B200 engine.
+
+Constructor arguments, attribute names and the per-primary ``generate_shower`` follow the reference
+(src/PETITE/shower.py:98-142, 603-708) so existing scripts keep working; the stepping itself runs as CUDA
+kernels behind the C ABI of ``include/petite_b200.h`` (there is no CPU path).  What stays on the host is the
+one-off set-up the reference also does in Python: reading the tables and tabulating n*sigma(E)
+(shower.py:202-295).
+
+New, batched entry point: :meth:`Shower.generate_showers` steps many independent primaries at once and
+returns a :class:`ShowerBatch` (structure-of-arrays view of the device stack).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from . import constants as K
+from . import tables as tb
+from . import totals
+from .particle import Particle, mass_dict
+
+process_code = {"Brem": 0, "Ann": 1, "PairProd": 2, "Comp": 3, "Moller": 4, "Bhabha": 5, "MuonE": 6, "MuonBrem": 7}
+dimensionalities = {p: tb.PROC_DIM[p] for p in process_code}
+process_PIDS = {"PairProd": [-11, 11], "Brem": [0, 22], "MuonBrem": [0, 22], "Comp": [11, 22], "Ann": [22, 22],
+                "Moller": [0, 11], "Bhabha": [0, 11], "MuonE": [0, 11]}
+_STEPPING_PIDS = (22, 11, -11, 13, -13)
+
+
+class LinearTable:
+    """1-D table evaluated like ``scipy.interpolate.interp1d(x, y, fill_value=0.0, bounds_error=False)``.
+
+    This is the host-side twin of the device interpolant (``nsigma_eval`` in csrc/engine.cu); the ``x``/``y``
+    arrays are exactly what ``pb_upload_nsigma`` ships.
+    """
+
+    def __init__(self, x, y, fill_value=0.0):
+        self.x = np.ascontiguousarray(x, dtype=np.float64)
+        self.y = np.ascontiguousarray(y, dtype=np.float64)
+        self.fill_value = fill_value
+
+    def __call__(self, xn):
+        xn_arr = np.asarray(xn, dtype=np.float64)
+        x, y = self.x, self.y
+        hi = np.clip(np.searchsorted(x, xn_arr), 1, len(x) - 1)
+        lo = hi - 1
+        slope = (y[hi] - y[lo]) / (x[hi] - x[lo])
+        out = slope * (xn_arr - x[lo]) + y[lo]
+        out = np.where((xn_arr < x[0]) | (xn_arr > x[-1]), self.fill_value, out)
+        return out if out.ndim else np.float64(out)
+
+
+class ShowerBatch:
+    """Result of a batched run: the filled part of the particle stack, still on the GPU (torch tensors).
+
+    Columns: ``p0`` (n,4), ``r0`` (n,3), ``weight`` (n,), ``pf`` (n,4), ``rf`` (n,3), ``pid``, ``parent`` (slot of the
+    parent record, -1 for primaries), ``generation``, ``child_bit``, ``process`` (pb_process code), ``flags``,
+    ``shower`` (index of the primary within the call), ``ntrials``, ``nsub``.
+    """
+
+    def __init__(self, owner, tensors, n, counters, n_primaries, first_shower_id):
+        self._owner = owner
+        self._t = tensors
+        self.n = int(n)
+        self.counters = counters
+        self.n_primaries = int(n_primaries)
+        self.first_shower_id = int(first_shower_id)
+        self._host = None
+
+    def device(self, name):
+        """Raw device column (torch tensor view over the first ``n`` records)."""
+        t = self._t[name]
+        return t[: self.n]
+
+    def to_host(self):
+        if self._host is None:
+            n = self.n
+            t = {k: v[:n].cpu().numpy() for k, v in self._t.items()}
+            meta = t["meta"]
+            info = meta[:, 2]
+            self._host = dict(
+                p0=t["p0"], r0=t["r0w"][:, :3], weight=t["r0w"][:, 3], pf=t["pf"], rf=t["rf"][:, :3], mass=t["rf"][:, 3],
+                pid=meta[:, 0], parent=meta[:, 1], generation=(info >> 16) & 0xFFFF, child_bit=(info >> 15) & 1,
+                flags=(info >> 8) & 0x7F, process=info & 0xFF, shower=meta[:, 3],
+                ntrials=t["aux"][:, 0], nsub=t["aux"][:, 1])
+        return self._host
+
+    def reference_order(self):
+        """Permutation of record slots into the reference's creation order, shower by shower.
+
+        ``generate_shower`` appends daughters while iterating over the growing list (shower.py:634-706), so its
+        output is ordered by wave, then by the parent's position, then first/second daughter.  Records are stored
+        wave by wave on the GPU but unordered inside a wave; this rebuilds the order from (parent, child_bit).
+        Returns ``(order, shower_offsets)``: ``order[shower_offsets[i]:shower_offsets[i+1]]`` are shower i's slots.
+        """
+        h = self.to_host()
+        n = self.n
+        gen = h["generation"].astype(np.int64)
+        gen0 = gen[: self.n_primaries]
+        depth = gen - gen0[h["shower"]]
+        rank = np.zeros(n, dtype=np.int64)
+        rank[: self.n_primaries] = np.arange(self.n_primaries)
+        wave_order = [np.arange(self.n_primaries)]
+        # slots are appended wave by wave, so depth is non-decreasing along the stack
+        bounds = np.searchsorted(depth, np.arange(1, int(depth.max()) + 2 if n else 1))
+        b = self.n_primaries
+        for e in bounds:
+            if e <= b:
+                continue
+            sl = np.arange(b, e)
+            key = rank[h["parent"][sl]] * 2 + h["child_bit"][sl]
+            o = np.argsort(key, kind="stable")
+            rank[sl[o]] = np.arange(len(sl))
+            wave_order.append(sl[o])
+            b = e
+        allslots = np.concatenate(wave_order)
+        o = np.argsort(h["shower"][allslots], kind="stable")
+        order = allslots[o]
+        counts = np.bincount(h["shower"][order], minlength=self.n_primaries)
+        return order, np.concatenate([[0], np.cumsum(counts)])
+
+    def to_particles(self, primaries=None):
+        """-> list (one per primary) of lists of :class:`Particle` in the reference's order and conventions."""
+        h = self.to_host()
+        order, offs = self.reference_order()
+        ref_ids = {}
+        out = []
+        for i in range(self.n_primaries):
+            plist = []
+            for s in order[offs[i]:offs[i + 1]]:
+                s = int(s)
+                pid = int(h["pid"][s])
+                par = int(h["parent"][s])
+                proc = K.PROCESS_NAMES[int(h["process"][s])]
+                if par < 0:
+                    src = primaries[i].get_ids() if primaries is not None else {}
+                    ids = dict(src)
+                    ids.setdefault("PID", pid)
+                    ids.setdefault("ID", 1)
+                    ids["mass"] = float(h["mass"][s])
+                else:
+                    pids = ref_ids[par]
+                    ids = {"PID": pid, "ID": 2 * pids["ID"] + int(h["child_bit"][s]),
+                           "generation_number": pids["generation_number"] + 1, "generation_process": proc,
+                           "weight": float(h["weight"][s]), "mass": mass_dict[pid]}
+                    if proc == "SMDecay":
+                        # decay daughters keep the default parent ids (particle.py:407-408; SURVEY Q-10)
+                        ids["production_time"] = pids.get("decay_time", 0.0)
+                    else:
+                        ids["parent_PID"] = pids["PID"]
+                        ids["parent_ID"] = pids["ID"]
+                p = Particle(np.array(h["p0"][s]), np.array(h["r0"][s]), ids)
+                p.set_pf(np.array(h["pf"][s]))
+                p.set_rf(np.array(h["rf"][s]))
+                p.set_ended(True)
+                ref_ids[s] = p.get_ids()
+                plist.append(p)
+            out.append(plist)
+        return out
+
+
+class Shower:
+    """Representation of a shower (GPU-backed).  Same constructor as the reference (shower.py:100-110)."""
+
+    def __init__(self, dict_dir, target_material, min_energy, maxF_fudge_global=1, max_n_integrators=int(1e4),
+                 fast_MCS_mode=True, seed=None, rescale_MCS=1, device=None):
+        if not fast_MCS_mode:
+            raise NotImplementedError("Bethe-Moliere multiple scattering is outside the accelerated path "
+                                      "(and raises TypeError in the reference, moliere.py:244)")
+        import torch  # device memory + streams only
+        if not torch.cuda.is_available():
+            raise RuntimeError("petite_b200 needs a CUDA device: the shower path has no CPU fallback")
+        self._torch = torch
+        self._device = torch.cuda.current_device() if device is None else int(device)
+        self._seed = 0 if seed is None else int(seed)
+        self._next_shower_id = 0
+        self.set_dict_dir(dict_dir)
+        self.set_target_material(target_material)
+        self.min_energy = min_energy
+        self.set_material_properties()
+        self.set_n_targets()
+        self.set_cross_sections()
+        self.set_samples()
+        self.set_NSigmas()
+        self._MCS_rescale_factor = rescale_MCS
+        self._maxF_fudge_global = maxF_fudge_global
+        self._max_n_integrators = max_n_integrators
+        self._engine = capi.pb_engine()
+        self._stack_tensors = None
+        self._stack_capacity = 0
+        self._create_engine()
+
+    # ------------------------------------------------------------------ reference-compatible set-up
+    def set_dict_dir(self, value):
+        self._dict_dir = value
+
+    def get_dict_dir(self):
+        return self._dict_dir
+
+    def set_target_material(self, value):
+        self._target_material = value
+
+    def get_target_material(self):
+        return self._target_material
+
+    def set_material_properties(self):
+        info = K.target_information[self.get_target_material()]
+        self._ZTarget, self._ATarget, self._rhoTarget, self._dEdx = info["Z_T"], info["A_T"], info["rho"], info["dEdx"]
+
+    def get_material_properties(self):
+        return self._ZTarget, self._ATarget, self._rhoTarget, self._dEdx
+
+    def set_n_targets(self):
+        ZT, AT, rhoT, _ = self.get_material_properties()
+        self._nTarget = rhoT / K.m_proton_grams / AT
+        self._nElecs = self._nTarget * ZT
+
+    def get_n_targets(self):
+        return self._nTarget, self._nElecs
+
+    def set_cross_sections(self):
+        xs = tb.load_sm_xsec(self._dict_dir, self._target_material)
+        mue = xs["MuonE"]
+        while mue[0][1] == 0.0:          # leading zero rows are dropped (shower.py:238-239)
+            mue = mue[1:]
+        xs["MuonE"] = mue
+        self._xsec = xs
+        self._brem_cross_section, self._pair_production_cross_section = xs["Brem"], xs["PairProd"]
+        self._annihilation_cross_section, self._compton_cross_section = xs["Ann"], xs["Comp"]
+        self._moller_cross_section, self._bhabha_cross_section = xs["Moller"], xs["Bhabha"]
+        self._muonbrem_cross_section, self._muone_cross_section = xs["MuonBrem"], xs["MuonE"]
+        lo = {p: xs[p][0][0] for p in xs}
+        mu_lo = max(min(lo["MuonBrem"], lo["MuonE"]), 0.120)
+        self._minimum_calculable_energy = {11: min(lo["Brem"], lo["Moller"]),
+                                           -11: min(lo["Brem"], lo["Bhabha"], lo["Ann"]),
+                                           13: mu_lo, -13: mu_lo, 22: min(lo["PairProd"], lo["Comp"])}
+
+    def get_brem_cross_section(self):
+        return self._brem_cross_section
+
+    def get_pairprod_cross_section(self):
+        return self._pair_production_cross_section
+
+    def get_annihilation_cross_section(self):
+        return self._annihilation_cross_section
+
+    def get_compton_cross_section(self):
+        return self._compton_cross_section
+
+    def get_moller_cross_section(self):
+        return self._moller_cross_section
+
+    def get_bhabha_cross_section(self):
+        return self._bhabha_cross_section
+
+    def get_muonbrem_cross_section(self):
+        return self._muonbrem_cross_section
+
+    def get_muone_cross_section(self):
+        return self._muone_cross_section
+
+    def set_samples(self):
+        self._maps = tb.load_sm_maps(self._dict_dir, self._target_material)
+        for P, ms in self._maps.items():
+            if np.any(np.isnan(ms.max_F)):
+                raise Exception(f"no max_F table for process {P} / material {self._target_material} in {self._dict_dir}")
+        # reference-shaped view: _loaded_samples[process][i] = [E_inc, {...}] (shower.py:210-215)
+        self._loaded_samples = {
+            P: [[float(ms.E[i]), {"neval": ms.neval, "max_F": {self._target_material: float(ms.max_F[i])},
+                                  "adaptive_map": [ms.axis_nodes(i, d) for d in range(ms.dim)],
+                                  "Eg_min": ms.Eg_min, "Ee_min": ms.Ee_min}] for i in range(len(ms.E))]
+            for P, ms in self._maps.items()}
+        self._Egamma_min = self._maps["Brem"].Eg_min
+        self._Ee_min = self._maps["Brem"].Ee_min
+
+    def set_NSigmas(self):
+        """n*sigma(E) in 1/cm for the 8 processes (shower.py:273-295): tables for Brem/PairProd/Ann/Comp/MuonBrem,
+        closed forms on a geometric grid for Moller/Bhabha/MuonE."""
+        X = self._xsec
+        nZ, ne = self.get_n_targets()
+        G = K.GeVsqcm2
+        t = {}
+        for P, n in (("Brem", nZ), ("PairProd", nZ), ("Ann", ne), ("Comp", ne), ("MuonBrem", nZ)):
+            t[P] = LinearTable(X[P][:, 0], n * G * X[P][:, 1])
+        BS = X["Brem"]
+        ee_grid = np.geomspace(3.0 * K.m_electron + self._Ee_min, BS[-1][0], len(BS))
+        t["Moller"] = LinearTable(ee_grid, ne * G * totals.sigma_moller(ee_grid, self._Ee_min))
+        t["Bhabha"] = LinearTable(ee_grid, ne * G * totals.sigma_bhabha(ee_grid, self._Ee_min))
+        self._muon_e_minimum = max(float(totals.muone_threshold(self._Ee_min)), X["MuonE"][0][0])
+        mu_grid = np.geomspace(self._muon_e_minimum, ee_grid[-1], len(BS))
+        t["MuonE"] = LinearTable(mu_grid, ne * G * totals.sigma_muone(mu_grid, self._Ee_min))
+        self._nsigma_tables = t
+        self._NSigmaBrem, self._NSigmaPP, self._NSigmaAnn, self._NSigmaComp = t["Brem"], t["PairProd"], t["Ann"], t["Comp"]
+        self._NSigmaMoller, self._NSigmaBhabha = t["Moller"], t["Bhabha"]
+        self._NSigmaMuonE, self._NSigmaMuonBrem = t["MuonE"], t["MuonBrem"]
+
+    def _NSigmaElectron(self, E):
+        return self._NSigmaBrem(E) + self._NSigmaMoller(E)
+
+    def _NSigmaPhoton(self, E):
+        return self._NSigmaPP(E) + self._NSigmaComp(E)
+
+    def _NSigmaPositron(self, E):
+        return self._NSigmaBrem(E) + self._NSigmaBhabha(E) + self._NSigmaAnn(E)
+
+    def _NSigmaMuon(self, E):
+        return self._NSigmaMuonBrem(E) + self._NSigmaMuonE(E)
+
+    def get_mfp(self, particle):
+        """Mean free path in metres (shower.py:370-389)."""
+        if not isinstance(particle, Particle) and isinstance(particle, (list, np.ndarray)):
+            PID, Energy = particle
+        else:
+            PID, Energy = particle.get_ids()["PID"], particle.get_pf()[0]
+        if PID == 22:
+            ns = self._NSigmaPhoton(Energy)
+        elif PID == 11:
+            ns = self._NSigmaElectron(Energy)
+        elif PID == -11:
+            ns = self._NSigmaPositron(Energy)
+        elif abs(PID) == 13:
+            ns = self._NSigmaMuon(Energy)
+        if ns <= 0.0:
+            return 1.0e12
+        return K.cmtom / ns
+
+    def BF_positron_brem(self, Energy):
+        b0, b1 = self._NSigmaBrem(Energy), self._NSigmaAnn(Energy)
+        return b0 / (b0 + b1)
+
+    def BF_photon_pairprod(self, Energy):
+        b0, b1 = self._NSigmaPP(Energy), self._NSigmaComp(Energy)
+        return b0 / (b0 + b1)
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _config(self):
+        c = capi.pb_config()
+        c.Z_T, c.A_T, c.rho = float(self._ZTarget), float(self._ATarget), float(self._rhoTarget)
+        c.dEdx_GeV_per_m = self._dEdx * 0.1
+        c.mT_sampler = float(self._ATarget)          # event_info['mT'] = A_T at sampling time (shower.py:435)
+        c.min_energy = float(self.min_energy)
+        c.Eg_min, c.Ee_min = float(self._Egamma_min), float(self._Ee_min)
+        c.maxF_fudge = float(self._maxF_fudge_global)
+        c.rescale_MCS = float(self._MCS_rescale_factor)
+        for i, pid in enumerate((11, -11, 22, 13, -13)):
+            c.min_calc[i] = float(self._minimum_calculable_energy[pid])
+        c.max_sweeps = int(self._max_n_integrators)
+        return c
+
+    def _create_engine(self):
+        cfg = self._config()
+        rc = capi.lib.pb_create(C.byref(self._engine), self._device, C.byref(cfg))
+        if rc != capi.PB_OK:
+            raise capi.EngineError(rc, "pb_create failed (is a CUDA device visible?)")
+        for P, code in process_code.items():
+            t = self._nsigma_tables[P]
+            capi.check(self._engine, capi.lib.pb_upload_nsigma(self._engine, code, capi.dptr(t.x), capi.dptr(t.y), len(t.x)))
+            self._upload_maps(code, self._maps[P])
+
+    def _upload_maps(self, code, ms):
+        grid = np.ascontiguousarray(ms.grid, dtype=np.float64)
+        ninc = np.ascontiguousarray(ms.ninc, dtype=np.int32)
+        E = np.ascontiguousarray(ms.E, dtype=np.float64)
+        mf = np.ascontiguousarray(ms.max_F, dtype=np.float64)
+        capi.check(self._engine, capi.lib.pb_upload_maps(self._engine, code, capi.dptr(grid), len(E), ms.dim, capi.iptr(ninc),
+                                                         capi.dptr(E), capi.dptr(mf), int(ms.neval)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_engine", None):
+                capi.lib.pb_destroy(self._engine)
+                self._engine = None
+        except Exception:
+            pass
+
+    def _ensure_stack(self, capacity):
+        if capacity <= self._stack_capacity:
+            return
+        torch = self._torch
+        dev = torch.device("cuda", self._device)
+        self._stack_tensors = None   # release before allocating the bigger one
+        self._stack_tensors = {
+            "p0": torch.empty((capacity, 4), dtype=torch.float64, device=dev),
+            "r0w": torch.empty((capacity, 4), dtype=torch.float64, device=dev),
+            "pf": torch.empty((capacity, 4), dtype=torch.float64, device=dev),
+            "rf": torch.empty((capacity, 4), dtype=torch.float64, device=dev),
+            "key": torch.empty((capacity, 2), dtype=torch.int32, device=dev),
+            "meta": torch.empty((capacity, 4), dtype=torch.int32, device=dev),
+            "aux": torch.zeros((capacity, 2), dtype=torch.int32, device=dev),
+        }
+        self._stack_capacity = capacity
+
+    def estimate_records(self, energies, pids):
+        """Rough upper estimate of stack records for a batch (used to size HBM; the run fails loudly if exceeded)."""
+        E = np.asarray(energies, dtype=np.float64)
+        per = 64 + 4.0 * E / max(self.min_energy, 1e-4)
+        return int(np.sum(per) * 1.5) + 1024
+
+    @staticmethod
+    def _pack_primaries(plist):
+        n = len(plist)
+        p = np.empty((n, 4)); r = np.empty((n, 3)); w = np.empty(n); m = np.empty(n)
+        pid = np.empty(n, dtype=np.int32); fl = np.zeros(n, dtype=np.int32)
+        for i, q in enumerate(plist):
+            ids = q.get_ids()
+            p[i] = np.asarray(q.get_p0(), dtype=np.float64)
+            r[i] = np.asarray(q.get_r0(), dtype=np.float64)
+            w[i] = ids["weight"]; m[i] = ids["mass"]; pid[i] = ids["PID"]
+            st = ids["stability"]
+            if st in ("short-lived", "long-lived"):
+                if st == "long-lived" or ids["PID"] != 111:
+                    raise ValueError("only short-lived pi0 -> gamma gamma decays are handled on the GPU path")
+                fl[i] = capi.PB_FLAG_SHORT_LIVED
+            elif ids["PID"] not in _STEPPING_PIDS and abs(ids["PID"]) != 14:
+                # the reference never ends such a particle and loops forever (SURVEY Q-20)
+                raise ValueError(f"stable PID {ids['PID']} cannot be showered")
+        return p, r, w, m, pid, fl
+
+    def run_arrays(self, p, r, w, m, pid, flags, GlobalMS=True, capacity=None, first_shower_id=None):
+        """Lowest-level entry: host SoA primaries -> :class:`ShowerBatch` (one ``pb_run_showers`` call)."""
+        n = len(pid)
+        p = np.ascontiguousarray(p, dtype=np.float64); r = np.ascontiguousarray(r, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64); m = np.ascontiguousarray(m, dtype=np.float64)
+        pid = np.ascontiguousarray(pid, dtype=np.int32); flags = np.ascontiguousarray(flags, dtype=np.int32)
+        if capacity is None:
+            capacity = self.estimate_records(p[:, 0], pid)
+        self._ensure_stack(int(capacity))
+        if first_shower_id is None:
+            first_shower_id = self._next_shower_id
+            self._next_shower_id += n
+        t = self._stack_tensors
+        st = capi.pb_stack(t["p0"].data_ptr(), t["r0w"].data_ptr(), t["pf"].data_ptr(), t["rf"].data_ptr(),
+                           t["key"].data_ptr(), t["meta"].data_ptr(), t["aux"].data_ptr(), self._stack_capacity)
+        prim = capi.pb_primaries(capi.dptr(p), capi.dptr(r), capi.dptr(w), capi.dptr(m), capi.iptr(pid), capi.iptr(flags), n)
+        cnt = capi.pb_counters()
+        stream = self._torch.cuda.current_stream(self._device).cuda_stream
+        rc = capi.lib.pb_run_showers(self._engine, C.byref(prim), self._seed, int(first_shower_id), 1 if GlobalMS else 0,
+                                     C.byref(st), C.byref(cnt), C.c_void_p(stream))
+        capi.check(self._engine, rc)
+        return ShowerBatch(self, t, cnt.n_particles, cnt.as_dict(), n, first_shower_id)
+
+    # ------------------------------------------------------------------ public stepping API
+    def generate_showers(self, primaries, GlobalMS=True, capacity=None, first_shower_id=None):
+        """Step many independent primaries (list of :class:`Particle`) at once -> :class:`ShowerBatch`."""
+        return self.run_arrays(*self._pack_primaries(primaries), GlobalMS=GlobalMS, capacity=capacity,
+                               first_shower_id=first_shower_id)
+
+    def generate_shower(self, p0, VB=False, GlobalMS=True):
+        """One primary -> list of all particles of its shower, primary first (shower.py:603-708)."""
+        if VB:
+            print("Starting shower, initial particle with ID Info")
+            print(p0.get_ids())
+            print("Initial four-momenta:")
+            print(p0.get_p0())
+        p0.set_ended(False)
+        if p0.get_p0()[0] < self.min_energy:
+            p0.set_ended(True)
+            return [p0.copy()]
+        batch = self.generate_showers([p0], GlobalMS=GlobalMS)
+        return batch.to_particles([p0])[0]
