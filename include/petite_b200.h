@@ -87,6 +87,7 @@ typedef struct pb_primaries {
   const int32_t* pid;     /* [host] n */
   const int32_t* flags;   /* [host] n   PB_FLAG_SHORT_LIVED for pi0 etc. */
   int64_t n;
+  int64_t on_device;      /* 0: the six arrays are host memory (copied inside the call); 1: they are [dev] already */
 } pb_primaries;
 
 typedef struct pb_counters {
@@ -99,7 +100,31 @@ typedef struct pb_counters {
   int64_t n_no_sample;     /* samplers that gave up */
   int64_t n_launches;      /* kernels launched by the engine for this call */
   int64_t max_wave;        /* widest wave */
+  int64_t n_charged;       /* records that went through the dE/dx sub-step loop (e+-, mu+-) */
 } pb_counters;
+
+/* Per-kernel device times (CUDA events on the launching stream) and per-process sampler counts of the LAST
+ * pb_run_showers / pb_run_dark call; filled only while profiling is on (it adds two events per launch). */
+enum pb_kernel { PB_K_INIT = 0, PB_K_PROPAGATE = 1 /* k_loop */, PB_K_SCAN = 2, PB_K_FILL = 3, PB_K_SAMPLE = 4, PB_K_EMIT = 5,
+                 PB_K_FINALIZE = 6, PB_K_N = 7 };
+typedef struct pb_profile {
+  double ms[8];            /* summed device time per pb_kernel */
+  int64_t launches[8];
+  int64_t trials[16];      /* integrand evaluations per pb_process */
+  int64_t samples[16];     /* accepted samples per pb_process */
+} pb_profile;
+
+/* Tally layout (doubles) written by pb_tally: see PB_TALLY_* ; counts are exact integers stored as fp64 so that one
+ * NCCL all-reduce(sum) over the buffer combines ranks. Species order: e-, e+, gamma, mu-, mu+, V(4900022), other. */
+#define PB_TALLY_NSPECIES 7
+#define PB_TALLY_EBINS 64        /* log10(E/GeV) in [-3, 3) */
+#define PB_TALLY_TBINS 32        /* log10(theta) in [-7, 1) */
+#define PB_TALLY_COUNT 0                                   /* [7] records per species (creation)            */
+#define PB_TALLY_WSUM 8                                    /* [7] sum of weights per species                */
+#define PB_TALLY_WESUM 16                                  /* [7] sum of weight * E0 per species            */
+#define PB_TALLY_EHIST 32                                  /* [7][64] weighted spectrum of creation energy  */
+#define PB_TALLY_THIST (32 + 7 * 64)                       /* [7][32] weighted polar-angle spectrum         */
+#define PB_TALLY_SIZE 1024
 
 const char* pb_version(void);
 const char* pb_last_error(pb_engine e);
@@ -123,6 +148,15 @@ int pb_upload_maps(pb_engine e, int process, const double* grid /*[host]*/, int 
  * Philox root key (seed, first_shower_id + i).  global_ms mirrors the GlobalMS argument. */
 int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t seed, uint64_t first_shower_id,
                    int global_ms, pb_stack* stack, pb_counters* counters /*[host] out*/, void* stream);
+
+/* Histogram / yield tallies over records [first, first+n) of a stack, ACCUMULATED into tally[PB_TALLY_SIZE] [dev]. */
+int pb_tally(pb_engine e, const pb_stack* stack, int64_t first, int64_t n, double* tally /*[dev]*/, void* stream);
+
+int pb_set_profiling(pb_engine e, int on);
+int pb_get_profile(pb_engine e, pb_profile* out /*[host]*/);
+
+/* FP64 FMA-chain microbenchmark on the engine's device: the measured FP64 roofline denominator (TFLOP/s). */
+int pb_measure_fp64_peak(pb_engine e, double* tflops /*[host] out*/);
 
 /* Deterministic-piece probes used by the parity tests (all arrays [host]). what: */
 enum pb_probe {

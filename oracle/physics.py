@@ -105,7 +105,9 @@ def mcs_scatter(p4, t, A, Z, rescale, m_lepton, sign, z1, z2, u_phi):
     ``sign`` in {-1,+1}, ``z1, z2`` standard normals, ``u_phi`` uniform in [0,1).
     """
     p3 = p4[1:]
-    pn = norm3(p3)
+    # np.linalg.norm as in the reference: beta feeds sqrt(1 - beta^2), which amplifies a last-bit difference of the
+    # norm by gamma^2 (up to ~1e8 for 10 GeV electrons), so the summation order matters here
+    pn = float(np.linalg.norm(np.asarray(p3, dtype=np.float64)))
     if not pn > 0:
         return list(p4)
     beta = pn / p4[0]

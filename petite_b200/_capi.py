@@ -38,16 +38,24 @@ class pb_stack(C.Structure):
 
 class pb_primaries(C.Structure):
     _fields_ = [("p", c_double_p), ("r", c_double_p), ("weight", c_double_p), ("mass", c_double_p),
-                ("pid", c_int32_p), ("flags", c_int32_p), ("n", C.c_int64)]
+                ("pid", c_int32_p), ("flags", c_int32_p), ("n", C.c_int64), ("on_device", C.c_int64)]
 
 
 class pb_counters(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("n_particles", "n_waves", "n_steps", "n_substeps", "n_samples", "n_trials",
-                                         "n_no_sample", "n_launches", "max_wave")]
+                                         "n_no_sample", "n_launches", "max_wave", "n_charged")]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
+
+class pb_profile(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8), ("trials", C.c_int64 * 16), ("samples", C.c_int64 * 16)]
+
+
+KERNEL_NAMES = ["k_init_primaries", "k_loop", "k_bucket_scan", "k_bucket_fill", "k_sample", "k_emit", "k_finalize"]
+TALLY_SIZE, TALLY_NSPECIES, TALLY_EBINS, TALLY_TBINS = 1024, 7, 64, 32
+TALLY_COUNT, TALLY_WSUM, TALLY_WESUM, TALLY_EHIST, TALLY_THIST = 0, 8, 16, 32, 32 + 7 * 64
 
 pb_engine = C.c_void_p
 
@@ -62,6 +70,10 @@ SIGNATURES = {
     "pb_upload_maps": (C.c_int, [pb_engine, C.c_int, c_double_p, C.c_int, C.c_int, c_int32_p, c_double_p, c_double_p, C.c_int]),
     "pb_run_showers": (C.c_int, [pb_engine, C.POINTER(pb_primaries), C.c_uint64, C.c_uint64, C.c_int,
                                  C.POINTER(pb_stack), C.POINTER(pb_counters), C.c_void_p]),
+    "pb_tally": (C.c_int, [pb_engine, C.POINTER(pb_stack), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pb_set_profiling": (C.c_int, [pb_engine, C.c_int]),
+    "pb_get_profile": (C.c_int, [pb_engine, C.POINTER(pb_profile)]),
+    "pb_measure_fp64_peak": (C.c_int, [pb_engine, c_double_p]),
     "pb_probe": (C.c_int, [pb_engine, C.c_int, C.c_int, c_double_p, C.c_int64, C.c_int, c_double_p, C.c_int]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

@@ -31,7 +31,7 @@ constexpr int TILE = 256;                   // samples per tile
 constexpr int SAMPLE_THREADS = 128;
 constexpr int GRID_SMEM_DOUBLES = 4096;     // >= padded stride of a 4-D map row (3964 -> 3968)
 
-struct NSigmaTable { const double* E; const double* y; int n; int pad; };
+struct NSigmaTable { const double4* node; double xmin, xmax; int n; int pad; };   // node = (x, y, slope to next, 0)
 struct MapInfo {
   const double* grid;   // nE rows, `stride` doubles each (padded to a multiple of 16 doubles)
   const double* E;
@@ -61,47 +61,74 @@ struct Work {            // per-wave scratch, sized to the widest wave seen so f
   int* tile_bucket;      // [max_tiles]
   int* tile_start;
   int* tile_count;
-  int* ctrl;             // [0] n_tiles, [1] tile cursor, [2] n sampled entries (bucket < NONE)
-  unsigned long long* tail;      // stack tail (next free record)
-  unsigned long long* counters;  // [8]: steps, substeps, samples, trials, no_sample, overflow
+  int* ctrl;             // [0] n_tiles, [1] tile cursor, [2] k_loop chunk cursor
+  int* order_c;          // [n] wave-local indices of the wave's charged (dE/dx-stepping) particles
+  int* order_n;          // [n] ... of everything else (photons, decaying mesons, neutrinos)
+  int* next_c;           // same two lists being built for the next wave by k_emit
+  int* next_n;
+  unsigned long long* tail;      // [0] stack tail (next free record); [1] = (n_neutral_next << 32) | n_charged_next
+  unsigned long long* counters;  // [CNT_N]: steps, substeps, samples, trials, no_sample, overflow, per-process trials/samples
 };
 
-enum { CNT_STEPS = 0, CNT_SUBSTEPS, CNT_SAMPLES, CNT_TRIALS, CNT_NOSAMPLE, CNT_OVERFLOW, CNT_N };
+enum { CNT_STEPS = 0, CNT_SUBSTEPS, CNT_SAMPLES, CNT_TRIALS, CNT_NOSAMPLE, CNT_OVERFLOW, CNT_PROC_TRIALS = 8,
+       CNT_PROC_SAMPLES = 24, CNT_N = 40 };
 
+__device__ __forceinline__ bool is_charged(int pid) { return pid == 11 || pid == -11 || pid == 13 || pid == -13; }
 __device__ __forceinline__ int pack_info(int gen, int child_bit, int flags, int process) {
   return (gen << 16) | (child_bit << 15) | ((flags & 0x7f) << 8) | (process & 0xff);
 }
 
 // ------------------------------------------------------------------------------------------ n*sigma(E)
-// scipy interp1d (linear, bounds_error=False, fill_value=0) as used by shower.py:280-295
-__device__ __forceinline__ double nsigma_eval(const NSigmaTable& T, double E) {
-  int n = T.n;
-  if (n < 2) return 0.0;
-  const double* __restrict__ x = T.E;
-  if (!(E >= __ldg(x) && E <= __ldg(x + n - 1))) return (E == E) ? 0.0 : E;
-  int lo = 0, hi = n;
+// scipy interp1d (linear, bounds_error=False, fill_value=0) as used by shower.py:280-295.  Nodes are packed as
+// (x_i, y_i, slope_i = (y_{i+1}-y_i)/(x_{i+1}-x_i), 0): one 32-byte sector per evaluation, no division.
+// `hi` follows scipy: hi = clip(searchsorted_left(x, E), 1, n-1), lo = hi - 1, y = slope_lo * (E - x_lo) + y_lo.
+__device__ __forceinline__ double4 ld_node(const double4* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  double2 a = __ldg(q), b = __ldg(q + 1);
+  return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ int nsigma_locate(const NSigmaTable& T, double E) {
+  int lo = 0, hi = T.n;
   while (lo < hi) {                       // searchsorted(side='left')
     int mid = (lo + hi) >> 1;
-    if (__ldg(x + mid) < E) lo = mid + 1; else hi = mid;
+    if (__ldg(reinterpret_cast<const double*>(&T.node[mid])) < E) lo = mid + 1; else hi = mid;
   }
-  hi = min(max(lo, 1), n - 1);
-  lo = hi - 1;
-  double xl = __ldg(x + lo), xh = __ldg(x + hi), yl = __ldg(T.y + lo), yh = __ldg(T.y + hi);
-  double slope = (yh - yl) / (xh - xl);
-  return __dadd_rn(__dmul_rn(slope, E - xl), yl);
+  return min(max(lo, 1), T.n - 1);
+}
+__device__ __forceinline__ double nsigma_at(const NSigmaTable& T, int hi, double E) {
+  if (T.n < 2) return 0.0;
+  if (!(E >= T.xmin && E <= T.xmax)) return (E == E) ? 0.0 : E;
+  double4 nd = ld_node(&T.node[hi - 1]);
+  return __dadd_rn(__dmul_rn(nd.z, E - nd.x), nd.y);
+}
+__device__ __forceinline__ double nsigma_eval(const NSigmaTable& T, double E) {
+  if (T.n < 2) return 0.0;
+  return nsigma_at(T, nsigma_locate(T, E), E);
+}
+// energy only ever decreases along a track: walk the hint down instead of searching again
+__device__ __forceinline__ double nsigma_hinted(const NSigmaTable& T, int& hi, double E) {
+  if (T.n < 2) return 0.0;
+  if (!(E >= T.xmin && E <= T.xmax)) return (E == E) ? 0.0 : E;
+  double4 nd = ld_node(&T.node[hi - 1]);
+  while (hi > 1 && !(nd.x < E)) { --hi; nd = ld_node(&T.node[hi - 1]); }
+  return __dadd_rn(__dmul_rn(nd.z, E - nd.x), nd.y);
 }
 
-__device__ __forceinline__ double nsigma_total(const Tables& T, int pid, double E) {   // shower.py:357-368
-  switch (pid) {
-    case 22: return nsigma_eval(T.ns[P_PAIRPROD], E) + nsigma_eval(T.ns[P_COMP], E);
-    case 11: return nsigma_eval(T.ns[P_BREM], E) + nsigma_eval(T.ns[P_MOLLER], E);
-    case -11: return nsigma_eval(T.ns[P_BREM], E) + nsigma_eval(T.ns[P_BHABHA], E) + nsigma_eval(T.ns[P_ANN], E);
-    default: return nsigma_eval(T.ns[P_MUONBREM], E) + nsigma_eval(T.ns[P_MUONE], E);
-  }
+// tables entering the mean free path of a charged species, in the reference's summation order (shower.py:357-368)
+__device__ __forceinline__ void species_tables(int pid, int* t) {
+  if (pid == 11) { t[0] = P_BREM; t[1] = P_MOLLER; t[2] = -1; }
+  else if (pid == -11) { t[0] = P_BREM; t[1] = P_BHABHA; t[2] = P_ANN; }
+  else { t[0] = P_MUONBREM; t[1] = P_MUONE; t[2] = -1; }
 }
-__device__ __forceinline__ double mfp_of(const Tables& T, int pid, double E) {          // shower.py:370-389
-  double ns = nsigma_total(T, pid, E);
-  return (ns <= 0.0) ? 1.0e12 : kCmToM / ns;
+__device__ __forceinline__ double mfp_from(double ns) { return (ns <= 0.0) ? 1.0e12 : kCmToM / ns; }   // shower.py:386-389
+
+__device__ __forceinline__ double mfp_photon(const Tables& T, double E) {
+  return mfp_from(nsigma_eval(T.ns[P_PAIRPROD], E) + nsigma_eval(T.ns[P_COMP], E));
+}
+__device__ __forceinline__ double mfp_charged(const Tables& T, const int* tb, double E) {
+  double ns = nsigma_eval(T.ns[tb[0]], E) + nsigma_eval(T.ns[tb[1]], E);
+  if (tb[2] >= 0) ns += nsigma_eval(T.ns[tb[2]], E);
+  return mfp_from(ns);
 }
 
 // SURVEY Q-1: argmin |E_i - E| + 1, clamped to the last row (shower.py:416-426)
@@ -120,99 +147,198 @@ __device__ __forceinline__ int lookup_row(const MapInfo& m, double E) {
 }
 
 // ------------------------------------------------------------------------------------------ wave kernels
+// One dE/dx + multiple-scattering sub-step state of a charged track (shower.py:559-581)
+struct Track {
+  V4 p; double rx, ry, rz;
+  double mass, ml, pmin, delta_z;
+  uint2 key;
+  int tb[3], hint[3];
+  int it;          // loop iterations done == accepted sub-steps while the loop is alive
+};
+
+// Sub-step loop of propagate_particle, charged species only.  Persistent warps pull chunks of the wave's charged
+// list; a lane that finishes its track (hard scatter drawn, or energy below threshold) stores it and immediately
+// takes the next entry of the chunk, so the warp stays converged on the loop body whatever the per-track sub-step
+// count (geometric, mean ~7, tail > 50).  The final partial step and the process choice are done by k_finalize.
+constexpr int LOOP_CHUNK = 64;
 __global__ void __launch_bounds__(128)
-k_propagate(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
-            long long begin, int n, const double* __restrict__ prim_mass, int ms_e) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long c_steps = 0, c_sub = 0;
-  if (i < n) {
+k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, long long begin,
+       int n_charged, const double* __restrict__ prim_mass, int ms_e) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int next = 0, chunk_end = 0;       // warp-uniform cursor into the charged list
+  int cur = -1;                       // -1: needs a track, -2: no more work
+  Track t;
+  unsigned long long c_sub = 0;
+  for (;;) {
+    // ---- refill
+    unsigned need = __ballot_sync(0xffffffffu, cur == -1);
+    while (need) {
+      if (next >= chunk_end) {
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&W.ctrl[2], LOOP_CHUNK);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        next = c; chunk_end = min(c + LOOP_CHUNK, n_charged);
+        if (next >= chunk_end) { if (cur == -1) cur = -2; break; }
+      }
+      int avail = chunk_end - next;
+      int rank = __popc(need & lt_mask);
+      bool take = (cur == -1) && rank < avail;
+      if (take) {
+        cur = W.order_c[next + rank];
+        long long s = begin + cur;
+        const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
+        const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
+        double2 a0 = p0p[0], a1 = p0p[1], b0 = r0p[0], b1 = r0p[1];
+        t.p = V4{a0.x, a0.y, a1.x, a1.y};
+        t.rx = b0.x; t.ry = b0.y; t.rz = b1.x;
+        int4 meta = S.meta[s];
+        t.key = S.key[s];
+        int pid = meta.x;
+        t.mass = (meta.y < 0) ? prim_mass[s] : pid_mass(pid);
+        t.ml = pid_mass(pid);
+        t.pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), t.mass);   // shower.py:532-533
+        species_tables(pid, t.tb);
+        for (int k = 0; k < 3; ++k) t.hint[k] = (t.tb[k] >= 0) ? nsigma_locate(T.ns[t.tb[k]], t.p.E) : 1;
+        t.delta_z = 0.0; t.it = 0;
+      }
+      next += min(__popc(need), avail);
+      need = __ballot_sync(0xffffffffu, cur == -1);
+    }
+    if (__all_sync(0xffffffffu, cur == -2)) break;
+    // ---- one sub-step for every live lane
+    bool done = false;
+    if (cur >= 0) {
+      if (!(t.p.E >= t.pmin)) done = true;                               // loop condition (shower.py:559)
+      else {
+        double ns = nsigma_hinted(T.ns[t.tb[0]], t.hint[0], t.p.E) + nsigma_hinted(T.ns[t.tb[1]], t.hint[1], t.p.E);
+        if (t.tb[2] >= 0) ns += nsigma_hinted(T.ns[t.tb[2]], t.hint[2], t.p.E);
+        double mfp = mfp_from(ns);
+        D2 u = draw2(t.key, (uint32_t)t.it, ST_SUBSTEP);
+        t.delta_z = mfp / (6.0 + 14.0 * u.b);
+        if (u.a > exp(-t.delta_z / mfp)) done = true;                    // hard scatter (shower.py:564)
+        else {
+          t.p = lose_energy(t.p, t.mass, M.dEdx * t.delta_z);
+          double pn = norm3_nofma(t.p.x, t.p.y, t.p.z);
+          if (pn > 0.0) {
+            double s = t.delta_z / pn;
+            t.rx += t.p.x * s; t.ry += t.p.y * s; t.rz += t.p.z * s;
+            if (ms_e) {
+              McsDraw d = mcs_draw(t.key, (uint32_t)t.it, 0);
+              t.p = mcs_scatter(M, t.p, pn, M.rho * (t.delta_z / kCmToM), t.ml, t.mass, d);
+            }
+          }
+          ++t.it; ++c_sub;
+        }
+      }
+    }
+    if (done) {
+      long long s = begin + cur;
+      double2* pfp = reinterpret_cast<double2*>(S.pf + 4 * s);
+      double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * s);
+      pfp[0] = make_double2(t.p.E, t.p.x); pfp[1] = make_double2(t.p.y, t.p.z);
+      rfp[0] = make_double2(t.rx, t.ry);   rfp[1] = make_double2(t.rz, t.delta_z);
+      S.aux[s] = make_int2(0, t.it);
+      cur = -1;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) c_sub += __shfl_down_sync(0xffffffffu, c_sub, o);
+  if (lane == 0 && c_sub) atomicAdd(&W.counters[CNT_SUBSTEPS], c_sub);
+}
+
+// Per particle of the wave (charged list first, then the rest): final partial step of a charged track or the
+// photon's free path, process choice, sample_scattering threshold and map look-up key -> bucket + histogram.
+__global__ void __launch_bounds__(128)
+k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
+           long long begin, int n_charged, int n, const double* __restrict__ prim_mass, int ms_e) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long c_steps = 0;
+  if (j < n) {
+    const bool charged = j < n_charged;
+    int i = charged ? W.order_c[j] : W.order_n[j - n_charged];
     long long s = begin + i;
-    const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
-    const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
-    double2 a0 = p0p[0], a1 = p0p[1], b0 = r0p[0], b1 = r0p[1];
-    V4 p{a0.x, a0.y, a1.x, a1.y};
-    double rx = b0.x, ry = b0.y, rz = b1.x;
     int4 meta = S.meta[s];
     uint2 key = S.key[s];
     int pid = meta.x;
     int flags = (meta.z >> 8) & 0x7f;
     double mass = (meta.y < 0) ? prim_mass[s] : pid_mass(pid);
     int bucket = P_NONE * LU_MAX;
+    int cls = pid_class(pid);
+    V4 p; double rx, ry, rz;
     int nsub = 0;
-    if (flags & PB_FLAG_SHORT_LIVED) {
-      bucket = P_SMDECAY * LU_MAX;                                       // particle.py:391-409, decays in k_emit
-    } else {
-      int cls = pid_class(pid);
-      if (cls >= 0) {
-        double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);    // shower.py:532-533
-        if (!(p.E < pmin)) {
-          c_steps = 1;
-          if (pid == 22) {                                                // shower.py:538-553 (MS_g is always False)
-            double mfp = mfp_of(T, pid, p.E);
-            double distC = draw2(key, 0, ST_FINAL).a;
-            double dist = mfp * log(1.0 / (1.0 - distC));
-            double pn = norm3_nofma(p.x, p.y, p.z);
-            rx += p.x / pn * dist; ry += p.y / pn * dist; rz += p.z / pn * dist;
-          } else {                                                        // shower.py:555-598
-            const double losses = M.dEdx;
-            const double ml = pid_mass(pid);
-            double delta_z = 0.0;
-            bool hard = false;
-            uint32_t it = 0;
-            while (!hard && p.E >= pmin) {
-              double mfp = mfp_of(T, pid, p.E);
-              D2 u = draw2(key, it, ST_SUBSTEP);
-              delta_z = mfp / (6.0 + 14.0 * u.b);
-              if (u.a > exp(-delta_z / mfp)) {
-                hard = true;
-              } else {
-                p = lose_energy(p, mass, losses * delta_z);
-                double pn = norm3_nofma(p.x, p.y, p.z);
-                if (pn > 0.0) { rx += p.x / pn * delta_z; ry += p.y / pn * delta_z; rz += p.z / pn * delta_z; }
-                if (ms_e && pn > 0.0) {
-                  McsDraw d = mcs_draw(key, it, 0);
-                  p = mcs_scatter(M, p, M.rho * (delta_z / kCmToM), ml, d.sign, d.z1, d.z2, d.uphi);
-                }
-                ++nsub;
-              }
-              ++it;
-            }
-            double distC = draw2(key, 0, ST_FINAL).a;
-            double last;
-            if (p.E < pmin) last = distC * delta_z;
-            else {
-              double mfp = mfp_of(T, pid, p.E);
-              last = mfp * log(1.0 / (1.0 + (exp(-delta_z / mfp) - 1) * distC));
-            }
-            p = lose_energy(p, mass, losses * last);
-            double pn = norm3_nofma(p.x, p.y, p.z);
-            if (pn > 0.0) { rx += p.x / pn * last; ry += p.y / pn * last; rz += p.z / pn * last; }
-            if (ms_e && pn > 0.0) {                                       // SURVEY Q-12: electron mass here
-              McsDraw d = mcs_draw(key, MCS_FINAL_INDEX, 0);
-              p = mcs_scatter(M, p, M.rho * (last / kCmToM), kMe, d.sign, d.z1, d.z2, d.uphi);
-            }
+    if (charged) {
+      const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * s);
+      const double2* rfp = reinterpret_cast<const double2*>(S.rf + 4 * s);
+      double2 a0 = pfp[0], a1 = pfp[1], b0 = rfp[0], b1 = rfp[1];
+      p = V4{a0.x, a0.y, a1.x, a1.y};
+      rx = b0.x; ry = b0.y; rz = b1.x;
+      double delta_z = b1.y;
+      nsub = S.aux[s].y;
+      const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
+      double E_start = p0p[0].x;
+      double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
+      if (!(E_start < pmin)) {                                            // shower.py:534-536: otherwise untouched
+        c_steps = 1;
+        int tb[3];
+        species_tables(pid, tb);
+        double distC = draw2(key, 0, ST_FINAL).a;                         // shower.py:583-598
+        double last;
+        if (p.E < pmin) last = distC * delta_z;
+        else {
+          double mfp = mfp_charged(T, tb, p.E);
+          last = mfp * log(1.0 / (1.0 + (exp(-delta_z / mfp) - 1) * distC));
+        }
+        p = lose_energy(p, mass, M.dEdx * last);
+        double pn = norm3_nofma(p.x, p.y, p.z);
+        if (pn > 0.0) {
+          double sc = last / pn;
+          rx += p.x * sc; ry += p.y * sc; rz += p.z * sc;
+          if (ms_e) {                                                     // SURVEY Q-12: electron mass here
+            McsDraw d = mcs_draw(key, MCS_FINAL_INDEX, 0);
+            p = mcs_scatter(M, p, pn, M.rho * (last / kCmToM), kMe, mass, d);
           }
         }
-        // process choice (shower.py:665-698) and the sample_scattering threshold (shower.py:469)
-        double Ef = p.E;
-        int cand[3]; double c[3]; int nc;
-        if (pid == 11) { cand[0] = P_BREM; cand[1] = P_MOLLER; nc = 2; }
-        else if (pid == -11) { cand[0] = P_BREM; cand[1] = P_ANN; cand[2] = P_BHABHA; nc = 3; }
-        else if (pid == 22) { cand[0] = P_PAIRPROD; cand[1] = P_COMP; nc = 2; }
-        else { cand[0] = P_MUONE; cand[1] = P_MUONBREM; nc = 2; }
-        double SC = 0.0;
-        for (int k = 0; k < nc; ++k) { c[k] = nsigma_eval(T.ns[cand[k]], Ef); SC += c[k]; }
-        if (!(SC == 0.0 || SC != SC)) {
-          double u = draw2(key, 0, ST_CHOICE).a;
-          // np.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
-          double cdf[3]; double acc = 0.0;
-          for (int k = 0; k < nc; ++k) { acc += c[k] / SC; cdf[k] = acc; }
-          int pick = nc - 1;
-          for (int k = nc - 1; k >= 0; --k) if (u < cdf[k] / acc) pick = k;
-          int proc = cand[pick];
-          double thr = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
-          if (!(Ef <= thr)) bucket = proc * LU_MAX + lookup_row(T.map[proc], Ef);
+      }
+    } else {
+      const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
+      const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
+      double2 a0 = p0p[0], a1 = p0p[1], b0 = r0p[0], b1 = r0p[1];
+      p = V4{a0.x, a0.y, a1.x, a1.y};
+      rx = b0.x; ry = b0.y; rz = b1.x;
+      if (flags & PB_FLAG_SHORT_LIVED) {
+        bucket = P_SMDECAY * LU_MAX;                                      // particle.py:391-409, decays in k_emit
+      } else if (pid == 22) {
+        double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
+        if (!(p.E < pmin)) {                                              // shower.py:538-553 (MS_g is always False)
+          c_steps = 1;
+          double mfp = mfp_photon(T, p.E);
+          double distC = draw2(key, 0, ST_FINAL).a;
+          double dist = mfp * log(1.0 / (1.0 - distC));
+          double pn = norm3_nofma(p.x, p.y, p.z);
+          rx += p.x / pn * dist; ry += p.y / pn * dist; rz += p.z / pn * dist;
         }
+      }
+    }
+    if (cls >= 0 && !(flags & PB_FLAG_SHORT_LIVED)) {
+      // process choice (shower.py:665-698) and the sample_scattering threshold (shower.py:469)
+      double Ef = p.E;
+      int cand[3]; double c[3]; int nc;
+      if (pid == 11) { cand[0] = P_BREM; cand[1] = P_MOLLER; nc = 2; }
+      else if (pid == -11) { cand[0] = P_BREM; cand[1] = P_ANN; cand[2] = P_BHABHA; nc = 3; }
+      else if (pid == 22) { cand[0] = P_PAIRPROD; cand[1] = P_COMP; nc = 2; }
+      else { cand[0] = P_MUONE; cand[1] = P_MUONBREM; nc = 2; }
+      double SC = 0.0;
+      for (int k = 0; k < nc; ++k) { c[k] = nsigma_eval(T.ns[cand[k]], Ef); SC += c[k]; }
+      if (!(SC == 0.0 || SC != SC)) {
+        double u = draw2(key, 0, ST_CHOICE).a;
+        // np.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
+        double cdf[3]; double acc = 0.0;
+        for (int k = 0; k < nc; ++k) { acc += c[k] / SC; cdf[k] = acc; }
+        int pick = nc - 1;
+        for (int k = nc - 1; k >= 0; --k) if (u < cdf[k] / acc) pick = k;
+        int proc = cand[pick];
+        double thr = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
+        if (!(Ef <= thr)) bucket = proc * LU_MAX + lookup_row(T.map[proc], Ef);
       }
     }
     double2* pfp = reinterpret_cast<double2*>(S.pf + 4 * s);
@@ -221,18 +347,12 @@ k_propagate(const __grid_constant__ Material M, const __grid_constant__ Tables T
     rfp[0] = make_double2(rx, ry);   rfp[1] = make_double2(rz, mass);
     S.aux[s] = make_int2(0, nsub);
     W.bucket[i] = bucket;
-    atomicAdd(&W.hist[bucket], 1);
-    c_sub = nsub;
+    // warp-aggregated histogram: one atomic per distinct bucket in the warp
+    unsigned peers = __match_any_sync(__activemask(), bucket);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&W.hist[bucket], __popc(peers));
   }
-  // block-level counter reduction: one atomic per warp
-  for (int o = 16; o > 0; o >>= 1) {
-    c_steps += __shfl_down_sync(0xffffffffu, c_steps, o);
-    c_sub += __shfl_down_sync(0xffffffffu, c_sub, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (c_steps) atomicAdd(&W.counters[CNT_STEPS], c_steps);
-    if (c_sub) atomicAdd(&W.counters[CNT_SUBSTEPS], c_sub);
-  }
+  for (int o = 16; o > 0; o >>= 1) c_steps += __shfl_down_sync(0xffffffffu, c_steps, o);
+  if ((threadIdx.x & 31) == 0 && c_steps) atomicAdd(&W.counters[CNT_STEPS], c_steps);
 }
 
 // Exclusive scan over NBUCKET bins + tile table; one CTA of 1024 threads, NBUCKET/1024 bins per thread.
@@ -278,8 +398,13 @@ __global__ void __launch_bounds__(256) k_bucket_fill(Work W, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int b = W.bucket[i];
-  int pos = W.offsets[b] + atomicAdd(&W.cursor[b], 1);
-  W.sorted[pos] = i;
+  const int lane = threadIdx.x & 31;
+  unsigned peers = __match_any_sync(__activemask(), b);        // lanes of this warp that share the bucket
+  int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&W.cursor[b], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  W.sorted[W.offsets[b] + base + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
 // ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier
@@ -351,7 +476,8 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
   uint32_t phase = 0;
   unsigned long long c_trials = 0, c_samples = 0, c_fail = 0;
-  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __shared__ unsigned long long s_ptrials, s_psamples;
+  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_ptrials = 0; s_psamples = 0; }
   __syncthreads();
   for (;;) {
     if (threadIdx.x == 0) { s_tile = atomicAdd(&W.ctrl[1], 1); s_cursor = 0; }
@@ -425,17 +551,24 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
         }
       }
     }
-    __syncthreads();   // everyone is done with s_grid before the next tile overwrites it
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    c_trials += __shfl_down_sync(0xffffffffu, c_trials, o);
-    c_samples += __shfl_down_sync(0xffffffffu, c_samples, o);
-    c_fail += __shfl_down_sync(0xffffffffu, c_fail, o);
-  }
-  if (lane == 0) {
-    if (c_trials) atomicAdd(&W.counters[CNT_TRIALS], c_trials);
-    if (c_samples) atomicAdd(&W.counters[CNT_SAMPLES], c_samples);
-    if (c_fail) atomicAdd(&W.counters[CNT_NOSAMPLE], c_fail);
+    // per-tile counter flush (a tile is one process): warp reduce -> shared -> one global atomic per CTA
+    for (int o = 16; o > 0; o >>= 1) {
+      c_trials += __shfl_down_sync(0xffffffffu, c_trials, o);
+      c_samples += __shfl_down_sync(0xffffffffu, c_samples, o);
+      c_fail += __shfl_down_sync(0xffffffffu, c_fail, o);
+    }
+    if (lane == 0) {
+      if (c_trials) atomicAdd(&s_ptrials, c_trials);
+      if (c_samples) atomicAdd(&s_psamples, c_samples);
+      if (c_fail) atomicAdd(&W.counters[CNT_NOSAMPLE], c_fail);
+    }
+    c_trials = 0; c_samples = 0; c_fail = 0;
+    __syncthreads();   // everyone is done with s_grid (and the counters) before the next tile overwrites it
+    if (threadIdx.x == 0) {
+      if (s_ptrials) { atomicAdd(&W.counters[CNT_TRIALS], s_ptrials); atomicAdd(&W.counters[CNT_PROC_TRIALS + proc], s_ptrials); }
+      if (s_psamples) { atomicAdd(&W.counters[CNT_SAMPLES], s_psamples); atomicAdd(&W.counters[CNT_PROC_SAMPLES + proc], s_psamples); }
+      s_ptrials = 0; s_psamples = 0;
+    }
   }
 }
 
@@ -493,16 +626,28 @@ k_emit(const __grid_constant__ Material M, Stack S, Work W, long long begin, int
       keep_b = db.E > M.min_energy;
     }
   }
-  // warp-aggregated append: one atomic on the stack tail per warp
+  // warp-aggregated append: one atomic on the stack tail and one on the packed (neutral, charged) list counters per warp
+  const bool ch_a = keep_a && is_charged(pid_a), ch_b = keep_b && is_charged(pid_b);
   int cnt = (keep_a ? 1 : 0) + (keep_b ? 1 : 0);
-  int incl = cnt;
-  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-  int total = __shfl_sync(0xffffffffu, incl, 31);
-  unsigned long long base = 0;
-  if (lane == 31 && total > 0) base = atomicAdd(W.tail, (unsigned long long)total);
+  int cch = (ch_a ? 1 : 0) + (ch_b ? 1 : 0);
+  int incl = cnt, inch = cch;
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o), w = __shfl_up_sync(0xffffffffu, inch, o);
+    if (lane >= o) { incl += v; inch += w; }
+  }
+  int total = __shfl_sync(0xffffffffu, incl, 31), total_ch = __shfl_sync(0xffffffffu, inch, 31);
+  unsigned long long base = 0, lbase = 0;
+  if (lane == 31 && total > 0) {
+    base = atomicAdd(&W.tail[0], (unsigned long long)total);
+    lbase = atomicAdd(&W.tail[1], ((unsigned long long)(total - total_ch) << 32) | (unsigned long long)total_ch);
+  }
   base = __shfl_sync(0xffffffffu, base, 31);
+  lbase = __shfl_sync(0xffffffffu, lbase, 31);
   if (cnt) {
     long long dst = (long long)base + (incl - cnt);
+    int ci = (int)(lbase & 0xffffffffu) + (inch - cch);
+    int ni = (int)(lbase >> 32) + ((incl - cnt) - (inch - cch));
+    const long long next_begin = begin + n;
     int gen = ((meta.z >> 16) & 0xffff) + 1;
     for (int bit = 0; bit < 2; ++bit) {
       bool keep = bit ? keep_b : keep_a;
@@ -515,12 +660,14 @@ k_emit(const __grid_constant__ Material M, Stack S, Work W, long long begin, int
       r0p[0] = make_double2(rx, ry);   r0p[1] = make_double2(rz, wgt);
       S.key[dst] = child_key(key, bit);
       S.meta[dst] = make_int4(bit ? pid_b : pid_a, (int)slot, pack_info(gen, bit, 0, proc), meta.w);
+      if (bit ? ch_b : ch_a) W.next_c[ci++] = (int)(dst - next_begin);
+      else W.next_n[ni++] = (int)(dst - next_begin);
       ++dst;
     }
   }
 }
 
-__global__ void k_init_primaries(Stack S, const double* __restrict__ p, const double* __restrict__ r,
+__global__ void k_init_primaries(Stack S, Work W, const double* __restrict__ p, const double* __restrict__ r,
                                  const double* __restrict__ w, const int* __restrict__ pid, const int* __restrict__ flags,
                                  long long n, unsigned long long seed, unsigned long long first_id) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -530,6 +677,52 @@ __global__ void k_init_primaries(Stack S, const double* __restrict__ p, const do
   S.r0w[4 * i + 3] = w[i];
   S.key[i] = root_key(seed, first_id + (unsigned long long)i);
   S.meta[i] = make_int4(pid[i], -1, pack_info(0, 0, flags[i], P_INPUT), (int)i);
+  const bool ch = is_charged(pid[i]) && !(flags[i] & PB_FLAG_SHORT_LIVED);
+  unsigned long long old = atomicAdd(&W.tail[1], ch ? 1ull : (1ull << 32));
+  if (ch) W.next_c[(int)(old & 0xffffffffu)] = (int)i; else W.next_n[(int)(old >> 32)] = (int)i;
+}
+
+// ------------------------------------------------------------------------------------------ tallies
+__device__ __forceinline__ int species_of(int pid) {
+  switch (pid) { case 11: return 0; case -11: return 1; case 22: return 2; case 13: return 3; case -13: return 4; case 4900022: return 5; }
+  return 6;
+}
+__global__ void __launch_bounds__(256) k_tally(Stack S, long long first, long long n, double* __restrict__ tally) {
+  __shared__ double s_t[PB_TALLY_SIZE];
+  for (int k = threadIdx.x; k < PB_TALLY_SIZE; k += blockDim.x) s_t[k] = 0.0;
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long s = first + i;
+    const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
+    double2 a0 = p0p[0], a1 = p0p[1];
+    double w = S.r0w[4 * s + 3];
+    int sp = species_of(S.meta[s].x);
+    atomicAdd(&s_t[PB_TALLY_COUNT + sp], 1.0);
+    atomicAdd(&s_t[PB_TALLY_WSUM + sp], w);
+    atomicAdd(&s_t[PB_TALLY_WESUM + sp], w * a0.x);
+    int eb = (int)floor((log10(a0.x) + 3.0) * (PB_TALLY_EBINS / 6.0));
+    eb = min(max(eb, 0), PB_TALLY_EBINS - 1);
+    atomicAdd(&s_t[PB_TALLY_EHIST + sp * PB_TALLY_EBINS + eb], w);
+    double pt = sqrt(a0.y * a0.y + a1.x * a1.x);
+    double th = atan2(pt, a1.y);
+    int tb = (th > 0) ? (int)floor((log10(th) + 7.0) * (PB_TALLY_TBINS / 8.0)) : 0;
+    tb = min(max(tb, 0), PB_TALLY_TBINS - 1);
+    atomicAdd(&s_t[PB_TALLY_THIST + sp * PB_TALLY_TBINS + tb], w);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < PB_TALLY_SIZE; k += blockDim.x)
+    if (s_t[k] != 0.0) atomicAdd(&tally[k], s_t[k]);
+}
+
+// FP64 roofline denominator: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (r == 12345.678) out[0] = r;
 }
 
 // ------------------------------------------------------------------------------------------ probes (tests)
@@ -559,7 +752,8 @@ __global__ void k_probe(const __grid_constant__ Material M, const __grid_constan
     } break;
     case PB_PROBE_MCS: {   // in: p4[4], dist_m, m_lepton, sign, z1, z2, u_phi
       V4 p{a[0], a[1], a[2], a[3]};
-      V4 q = mcs_scatter(M, p, M.rho * (a[4] / kCmToM), a[5], a[6], a[7], a[8], a[9]);
+      double pn = norm3_nofma(p.x, p.y, p.z);
+      V4 q = (pn > 0) ? mcs_apply(M, p, pn, M.rho * (a[4] / kCmToM), a[5], a[5], a[6], sqrt(a[7] * a[7] + a[8] * a[8]), a[9]) : p;
       o[0] = q.E; o[1] = q.x; o[2] = q.y; o[3] = q.z;
     } break;
     case PB_PROBE_KIN: {   // in: E, mass, x[4], u_az, u2 ; out: two four-vectors
@@ -597,9 +791,13 @@ struct pb_engine_s {
   long long work_n = 0;          // capacity of per-wave scratch
   void* work_blob = nullptr;
   void* fixed_blob = nullptr;    // hist/offsets/cursor/ctrl/tail/counters
+  int* order_blob = nullptr; long long order_cap = 0;
   double* prim_mass = nullptr; long long prim_cap = 0;
   void* prim_stage = nullptr; size_t prim_stage_bytes = 0;
   int n_sm = 148;
+  bool profiling = false;
+  cudaEvent_t ev[2 * 8] = {};
+  pb_profile prof{};
   std::string err;
 };
 
@@ -632,6 +830,8 @@ static void derive_material(pb_engine e) {
   m.dff_inel_pref = c.Z_T / (c1 * c1 * (c.Z_T * c.Z_T));
   m.dff_pref = (c.Z_T * c.Z_T) * (c1 * c1);
   m.Z23 = pow(c.Z_T, 2.0 / 3.0);
+  m.me4 = pow(kMe, 4);
+  m.mV4 = pow(c.mV, 4);
   m.mV = c.mV; m.g_e = c.g_e; m.eps = c.kinetic_mixing; m.Zeff = c.Zeff;
   m.E_res_ann = c.E_res_ann; m.E_thr_comp = c.E_thr_comp; m.bound_electron = c.bound_electron;
   m.max_trials = 0;
@@ -650,12 +850,13 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->n_sm = prop.multiProcessorCount;
   e->cfg = *cfg;
   derive_material(e);
-  size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * 16;
+  size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * (8 + CNT_N);
   if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
   cudaMemset(e->fixed_blob, 0, fixed);
+  for (int i = 0; i < 2 * 8; ++i) cudaEventCreate(&e->ev[i]);
   char* p = (char*)e->fixed_blob;
   e->work.tail = (unsigned long long*)p; p += 8 * sizeof(unsigned long long);
-  e->work.counters = (unsigned long long*)p; p += 8 * sizeof(unsigned long long);
+  e->work.counters = (unsigned long long*)p; p += CNT_N * sizeof(unsigned long long);
   e->work.hist = (int*)p; p += NBUCKET * sizeof(int);
   e->work.offsets = (int*)p; p += (NBUCKET + 1) * sizeof(int);
   e->work.cursor = (int*)p; p += NBUCKET * sizeof(int);
@@ -677,20 +878,26 @@ extern "C" void pb_destroy(pb_engine e) {
   for (void* p : e->owned) cudaFree(p);
   if (e->work_blob) cudaFree(e->work_blob);
   if (e->fixed_blob) cudaFree(e->fixed_blob);
+  if (e->order_blob) cudaFree(e->order_blob);
   if (e->prim_mass) cudaFree(e->prim_mass);
   if (e->prim_stage) cudaFree(e->prim_stage);
+  for (int i = 0; i < 2 * 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   delete e;
 }
 
 extern "C" int pb_upload_nsigma(pb_engine e, int id, const double* E, const double* y, int n) {
   if (!e || id < 0 || id >= 16 || n < 0) return PB_ERR_ARG;
   PB_CUDA(e, cudaSetDevice(e->device));
+  std::vector<double> node(4 * (size_t)std::max(n, 1), 0.0);
+  for (int i = 0; i < n; ++i) {
+    node[4 * i] = E[i]; node[4 * i + 1] = y[i];
+    node[4 * i + 2] = (i + 1 < n) ? (y[i + 1] - y[i]) / (E[i + 1] - E[i]) : 0.0;    // scipy's per-call slope, hoisted
+  }
   double* d = nullptr;
-  PB_CUDA(e, cudaMalloc(&d, sizeof(double) * 2 * (size_t)std::max(n, 1)));
+  PB_CUDA(e, cudaMalloc(&d, sizeof(double) * node.size()));
   e->owned.push_back(d);
-  PB_CUDA(e, cudaMemcpy(d, E, sizeof(double) * n, cudaMemcpyHostToDevice));
-  PB_CUDA(e, cudaMemcpy(d + n, y, sizeof(double) * n, cudaMemcpyHostToDevice));
-  e->tab.ns[id] = NSigmaTable{d, d + n, n, 0};
+  PB_CUDA(e, cudaMemcpy(d, node.data(), sizeof(double) * node.size(), cudaMemcpyHostToDevice));
+  e->tab.ns[id] = NSigmaTable{(const double4*)d, n ? E[0] : 0.0, n ? E[n - 1] : 0.0, n, 0};
   return PB_OK;
 }
 
@@ -715,6 +922,24 @@ extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int 
   PB_CUDA(e, cudaMemcpy(dE + nE, max_F, sizeof(double) * nE, cudaMemcpyHostToDevice));
   mi.grid = d; mi.E = dE; mi.maxF = dE + nE; mi.nE = nE; mi.dim = dim; mi.stride = padded; mi.B = neval;
   e->tab.map[process] = mi;
+  return PB_OK;
+}
+
+// order lists (current + next wave) live apart from the other scratch: growing them must keep the current lists
+static int ensure_order(pb_engine e, long long n_cur, long long n_next_max, cudaStream_t stream) {
+  if (n_next_max <= e->order_cap) return PB_OK;
+  long long cap = std::max<long long>(n_next_max * 5 / 4, 1 << 16);
+  int* blob = nullptr;
+  PB_CUDA(e, cudaMalloc(&blob, sizeof(int) * 4 * (size_t)cap));
+  if (e->order_blob && n_cur > 0) {
+    PB_CUDA(e, cudaMemcpyAsync(blob, e->work.order_c, sizeof(int) * n_cur, cudaMemcpyDeviceToDevice, stream));
+    PB_CUDA(e, cudaMemcpyAsync(blob + cap, e->work.order_n, sizeof(int) * n_cur, cudaMemcpyDeviceToDevice, stream));
+    PB_CUDA(e, cudaStreamSynchronize(stream));
+  }
+  if (e->order_blob) cudaFree(e->order_blob);
+  e->order_blob = blob;
+  e->work.order_c = blob; e->work.order_n = blob + cap; e->work.next_c = blob + 2 * cap; e->work.next_n = blob + 3 * cap;
+  e->order_cap = cap;
   return PB_OK;
 }
 
@@ -762,25 +987,51 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     e->prim_cap = n0;
   }
   char* sp = (char*)e->prim_stage;
-  double* d_p = (double*)sp; sp += sizeof(double) * 4 * n0;
-  double* d_r = (double*)sp; sp += sizeof(double) * 3 * n0;
-  double* d_w = (double*)sp; sp += sizeof(double) * n0;
-  int* d_pid = (int*)sp; sp += sizeof(int) * n0;
-  int* d_fl = (int*)sp;
-  PB_CUDA(e, cudaMemcpyAsync(d_p, prim->p, sizeof(double) * 4 * n0, cudaMemcpyHostToDevice, stream));
-  PB_CUDA(e, cudaMemcpyAsync(d_r, prim->r, sizeof(double) * 3 * n0, cudaMemcpyHostToDevice, stream));
-  PB_CUDA(e, cudaMemcpyAsync(d_w, prim->weight, sizeof(double) * n0, cudaMemcpyHostToDevice, stream));
-  PB_CUDA(e, cudaMemcpyAsync(e->prim_mass, prim->mass, sizeof(double) * n0, cudaMemcpyHostToDevice, stream));
-  PB_CUDA(e, cudaMemcpyAsync(d_pid, prim->pid, sizeof(int) * n0, cudaMemcpyHostToDevice, stream));
-  PB_CUDA(e, cudaMemcpyAsync(d_fl, prim->flags, sizeof(int) * n0, cudaMemcpyHostToDevice, stream));
-  k_init_primaries<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(S, d_p, d_r, d_w, d_pid, d_fl, n0, seed, first_id);
+  const double* d_p = (double*)sp; sp += sizeof(double) * 4 * n0;
+  const double* d_r = (double*)sp; sp += sizeof(double) * 3 * n0;
+  const double* d_w = (double*)sp; sp += sizeof(double) * n0;
+  const int* d_pid = (int*)sp; sp += sizeof(int) * n0;
+  const int* d_fl = (int*)sp;
+  const cudaMemcpyKind kind = prim->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  PB_CUDA(e, cudaMemcpyAsync(e->prim_mass, prim->mass, sizeof(double) * n0, kind, stream));
+  if (prim->on_device) {
+    d_p = prim->p; d_r = prim->r; d_w = prim->weight; d_pid = prim->pid; d_fl = prim->flags;
+  } else {
+    PB_CUDA(e, cudaMemcpyAsync((void*)d_p, prim->p, sizeof(double) * 4 * n0, kind, stream));
+    PB_CUDA(e, cudaMemcpyAsync((void*)d_r, prim->r, sizeof(double) * 3 * n0, kind, stream));
+    PB_CUDA(e, cudaMemcpyAsync((void*)d_w, prim->weight, sizeof(double) * n0, kind, stream));
+    PB_CUDA(e, cudaMemcpyAsync((void*)d_pid, prim->pid, sizeof(int) * n0, kind, stream));
+    PB_CUDA(e, cudaMemcpyAsync((void*)d_fl, prim->flags, sizeof(int) * n0, kind, stream));
+  }
+  const bool prof = e->profiling;
+  memset(&e->prof, 0, sizeof(e->prof));
+  bool recorded[8] = {false, false, false, false, false, false, false, false};
+  auto tick = [&](int k) { if (prof) { cudaEventRecord(e->ev[2 * k], stream); recorded[k] = true; } };
+  auto tock = [&](int k) { if (prof) cudaEventRecord(e->ev[2 * k + 1], stream); ++e->prof.launches[k]; };
+  auto collect = [&]() {     // after a stream synchronize: add up every kernel timed since the last collect
+    for (int k = 0; k < PB_K_N; ++k) {
+      if (!recorded[k]) continue;
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]) == cudaSuccess) e->prof.ms[k] += ms;
+      recorded[k] = false;
+    }
+  };
+  { int rc0 = ensure_order(e, 0, std::max<long long>(2 * n0, 1 << 16), stream); if (rc0 != PB_OK) return rc0; }
+  unsigned long long tail0[2] = {(unsigned long long)n0, 0ull};
+  PB_CUDA(e, cudaMemcpyAsync(e->work.tail, tail0, sizeof(tail0), cudaMemcpyHostToDevice, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.ctrl, 0, sizeof(int) * 8, stream));
+  tick(PB_K_INIT);
+  k_init_primaries<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(S, e->work, d_p, d_r, d_w, d_pid, d_fl, n0, seed, first_id);
+  tock(PB_K_INIT);
   ++launches;
-  unsigned long long tail0 = (unsigned long long)n0;
-  PB_CUDA(e, cudaMemcpyAsync(e->work.tail, &tail0, sizeof(tail0), cudaMemcpyHostToDevice, stream));
+  unsigned long long lists0[2] = {0, 0};
+  PB_CUDA(e, cudaMemcpyAsync(lists0, e->work.tail, sizeof(lists0), cudaMemcpyDeviceToHost, stream));
+  PB_CUDA(e, cudaStreamSynchronize(stream));
+  long long n_charged = (long long)(lists0[1] & 0xffffffffull);
   PB_CUDA(e, cudaMemsetAsync(e->work.counters, 0, sizeof(unsigned long long) * CNT_N, stream));
   PB_CUDA(e, cudaMemsetAsync(e->work.hist, 0, sizeof(int) * NBUCKET, stream));
 
-  long long begin = 0, end = n0, waves = 0, max_wave = 0;
+  long long begin = 0, end = n0, waves = 0, max_wave = 0, tot_charged = 0;
   const int sample_grid = e->n_sm * 4;
   while (begin < end) {
     long long n = end - begin;
@@ -791,18 +1042,40 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     }
     int rc = ensure_work(e, n);
     if (rc != PB_OK) return rc;
+    std::swap(e->work.order_c, e->work.next_c);          // lists built by the previous wave become current
+    std::swap(e->work.order_n, e->work.next_n);
+    rc = ensure_order(e, n, 2 * n, stream);
+    if (rc != PB_OK) return rc;
     max_wave = std::max(max_wave, n);
-    k_propagate<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, e->tab, S, e->work, begin, (int)n, e->prim_mass,
-                                                                  global_ms ? 1 : 0);
+    PB_CUDA(e, cudaMemsetAsync(e->work.tail + 1, 0, sizeof(unsigned long long), stream));
+    tot_charged += n_charged;
+    if (n_charged > 0) {
+      tick(PB_K_PROPAGATE);
+      int lg = (int)std::min<long long>((long long)e->n_sm * 8, (n_charged + 4 * LOOP_CHUNK - 1) / (4 * LOOP_CHUNK));
+      k_loop<<<lg, 128, 0, stream>>>(e->mat, e->tab, S, e->work, begin, (int)n_charged, e->prim_mass, global_ms ? 1 : 0);
+      tock(PB_K_PROPAGATE);
+      ++launches;
+    }
+    tick(PB_K_FINALIZE);
+    k_finalize<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, e->tab, S, e->work, begin, (int)n_charged, (int)n,
+                                                                 e->prim_mass, global_ms ? 1 : 0);
+    tock(PB_K_FINALIZE); tick(PB_K_SCAN);
     k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
+    tock(PB_K_SCAN); tick(PB_K_FILL);
     k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, (int)n);
+    tock(PB_K_FILL); tick(PB_K_SAMPLE);
     int sg = (int)std::min<long long>(sample_grid, (n + 31) / 32 + 1);
     k_sample<8><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin);
+    tock(PB_K_SAMPLE); tick(PB_K_EMIT);
     k_emit<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, S, e->work, begin, (int)n);
+    tock(PB_K_EMIT);
     launches += 5;
-    unsigned long long tail = 0;
-    PB_CUDA(e, cudaMemcpyAsync(&tail, e->work.tail, sizeof(tail), cudaMemcpyDeviceToHost, stream));
+    unsigned long long tl[2] = {0, 0};
+    PB_CUDA(e, cudaMemcpyAsync(tl, e->work.tail, sizeof(tl), cudaMemcpyDeviceToHost, stream));
     PB_CUDA(e, cudaStreamSynchronize(stream));
+    unsigned long long tail = tl[0];
+    collect();
+    n_charged = (long long)(tl[1] & 0xffffffffull);
     begin = end;
     end = (long long)std::min<unsigned long long>(tail, (unsigned long long)st->capacity);
     ++waves;
@@ -814,10 +1087,57 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     out->n_particles = end; out->n_waves = waves; out->n_steps = (int64_t)cnt[CNT_STEPS];
     out->n_substeps = (int64_t)cnt[CNT_SUBSTEPS]; out->n_samples = (int64_t)cnt[CNT_SAMPLES];
     out->n_trials = (int64_t)cnt[CNT_TRIALS]; out->n_no_sample = (int64_t)cnt[CNT_NOSAMPLE];
-    out->n_launches = launches; out->max_wave = max_wave;
+    out->n_launches = launches; out->max_wave = max_wave; out->n_charged = tot_charged;
   }
+  for (int p = 0; p < 16; ++p) { e->prof.trials[p] = (int64_t)cnt[CNT_PROC_TRIALS + p]; e->prof.samples[p] = (int64_t)cnt[CNT_PROC_SAMPLES + p]; }
   if (cnt[CNT_OVERFLOW]) { e->err = "particle stack overflow"; return PB_ERR_CAPACITY; }
   if (cnt[CNT_NOSAMPLE]) { e->err = "No Sample Found for " + std::to_string(cnt[CNT_NOSAMPLE]) + " particle(s)"; return PB_ERR_NO_SAMPLE; }
+  return PB_OK;
+}
+
+extern "C" int pb_set_profiling(pb_engine e, int on) {
+  if (!e) return PB_ERR_ARG;
+  e->profiling = on != 0;
+  return PB_OK;
+}
+extern "C" int pb_get_profile(pb_engine e, pb_profile* out) {
+  if (!e || !out) return PB_ERR_ARG;
+  *out = e->prof;
+  return PB_OK;
+}
+
+extern "C" int pb_tally(pb_engine e, const pb_stack* st, int64_t first, int64_t n, double* tally, void* stream_) {
+  if (!e || !st || !tally || n < 0 || first < 0 || first + n > st->capacity) return PB_ERR_ARG;
+  if (n == 0) return PB_OK;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  Stack S{st->p0, st->r0w, st->pf, st->rf, (uint2*)st->key, (int4*)st->meta, (int2*)st->aux, st->capacity};
+  int grid = (int)std::min<long long>((n + 255) / 256, (long long)e->n_sm * 8);
+  k_tally<<<grid, 256, 0, (cudaStream_t)stream_>>>(S, first, n, tally);
+  PB_CUDA(e, cudaGetLastError());
+  return PB_OK;
+}
+
+extern "C" int pb_measure_fp64_peak(pb_engine e, double* tflops) {
+  if (!e || !tflops) return PB_ERR_ARG;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  double* d = nullptr;
+  PB_CUDA(e, cudaMalloc(&d, 8));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  const int iters = 1 << 16, blocks = e->n_sm * 8, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(a);
+    k_fp64_peak<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0) best = std::max(best, tf);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+  *tflops = best;
   return PB_OK;
 }
 

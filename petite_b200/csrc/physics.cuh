@@ -42,6 +42,7 @@ struct Material {
   double dff_inel_pref;           // Z / (c1^2 Z^2)
   double dff_pref;                // Z^2 c1^2
   double Z23;                     // Z^(2/3)   moliere.py:218
+  double me4, mV4;                // m_e**4, mV**4 as CPython computes them (libm pow)
   long long max_trials;           // max_n_integrators * B
   // dark sector
   double mV, g_e, eps, Zeff, E_res_ann, E_thr_comp;
@@ -144,46 +145,65 @@ __device__ __forceinline__ double ds_pairprod(const Material& M, double w, const
   return PF * (T1 + T2 + T3 + T4) * jac * FF;
 }
 
+// The 1-D integrands below contain differences of nearly equal terms (s + t at backward angles, 1 - b^2 ct^2 at high
+// energy); they use only IEEE +,-,*,/,sqrt, so evaluating them in the reference's operation order WITHOUT fma
+// contraction reproduces its doubles exactly.  m_ = mul, a_ = add, s_ = sub, d_ = div (round-to-nearest, never fused).
+__device__ __forceinline__ double m_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double a_(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double s_(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double d_(double a, double b) { return __ddiv_rn(a, b); }
+
 // all_processes.py:625-742 (dsigma_compton_dCT); mV > 0 is DarkComp.
-__device__ __forceinline__ double ds_compton(double Eg, double mV, double ct) {
-  const double me = kMe, me2 = kMe * kMe, me4 = me2 * me2;
-  double s = me2 + 2 * Eg * me;
-  double smv = me + mV;
-  if (s < smv * smv) return 0.0;
-  double mV2 = mV * mV;
-  double lam = sqrt((s - mV2) * (s - mV2) - 2 * me2 * (s + mV2) + me4);
-  double jac = (s - me2) / (2 * s) * lam;
-  double lam2 = sqrt(me4 + (mV2 - s) * (mV2 - s) - 2 * me2 * (mV2 + s));
-  double t = -0.5 * (me4 + s * (-mV2 + s + ct * lam2) - me2 * (mV2 + 2 * s + ct * lam2)) / s;
-  double sm = s - me2;
-  double PF = 2.0 * kPi * kAlpha * kAlpha / (sm * sm);
+__device__ __forceinline__ double ds_compton(const Material& M, double Eg, double mV, double ct) {
+  const double me = kMe, me2 = kMe * kMe, me4 = M.me4;     // m**2 is an exact product; m**4 is libm pow (host)
+  double s = a_(me2, m_(m_(2, Eg), me));
+  double smv = a_(me, mV);
+  if (s < m_(smv, smv)) return 0.0;
+  double mV2 = m_(mV, mV);
+  double smm = s_(s, mV2);
+  double lam = sqrt(a_(s_(m_(smm, smm), m_(m_(2, me2), a_(s, mV2))), me4));
+  double jac = m_(d_(s_(s, me2), m_(2, s)), lam);
+  double mms = s_(mV2, s);
+  double lam2 = sqrt(s_(a_(me4, m_(mms, mms)), m_(m_(2, me2), a_(mV2, s))));
+  double ctl = m_(ct, lam2);
+  double inner = s_(a_(me4, m_(s, a_(a_(-mV2, s), ctl))), m_(me2, a_(a_(mV2, m_(2, s)), ctl)));
+  double t = d_(m_(-0.5, inner), s);
+  double sm = s_(s, me2);
+  double PF = d_(m_(m_(m_(2.0, kPi), kAlpha * kAlpha), 1.0), m_(sm, sm));
   double T1, T2, T3;
   if (mV == 0.0) {
-    T1 = (6.0 * me2 * s + 3.0 * me4 - s * s) / ((me2 - s) * (-me2 + s + t));
-    double a = s + t - me2;
-    T2 = 4 * me4 / (a * a);
-    T3 = (t * sm + (s + me2) * (s + me2)) / (sm * sm);
+    T1 = d_(s_(a_(m_(m_(6.0, me2), s), m_(3.0, me4)), m_(s, s)), m_(s_(me2, s), a_(a_(-me2, s), t)));
+    double a = s_(a_(s, t), me2);
+    T2 = d_(m_(4, me4), m_(a, a));
+    double b = a_(s, me2);
+    T3 = d_(a_(m_(t, sm), m_(b, b)), m_(sm, sm));
   } else {
-    double a = me2 + mV2 - s - t;
-    T1 = (2.0 * me2 * (mV2 - 3 * s) - 3 * me4 - 2 * mV2 * s + 2 * mV2 * mV2 + s * s) / ((me2 - s) * a);
-    T2 = (2 * me2 * (2 * me2 + mV2)) / (a * a);
-    T3 = ((me2 + s) * (me2 + mV2 + s) + t * sm) / ((me2 - s) * (me2 - s));
+    double mV4 = M.mV4;
+    double a = s_(s_(a_(me2, mV2), s), t);
+    double num = a_(a_(s_(s_(m_(m_(2.0, me2), s_(mV2, m_(3, s))), m_(3, me4)), m_(m_(2, mV2), s)), m_(2, mV4)), m_(s, s));
+    T1 = d_(num, m_(s_(me2, s), a));
+    T2 = d_(m_(m_(2, me2), a_(m_(2, me2), mV2)), m_(a, a));
+    double c = s_(me2, s);
+    T3 = d_(a_(m_(a_(me2, s), a_(a_(me2, mV2), s)), m_(t, sm)), m_(c, c));
   }
-  return PF * jac * (T1 + T2 + T3);
+  return m_(m_(PF, jac), a_(a_(T1, T2), T3));
 }
 
 // all_processes.py:469-529 (dsigma_annihilation_dCT)
 __device__ __forceinline__ double ds_annihilation(double Ee, double mV, double EgMin, double ct) {
   const double me = kMe;
-  double s = 2.0 * me * (Ee + me);
-  double mV2 = mV * mV;
-  double ctMax = sqrt((Ee + me) / (Ee - me)) * (2 * me * (Ee - 2 * EgMin + me) - mV2) / (2 * me * (Ee + me) - mV2);
+  double s = m_(m_(2.0, me), a_(Ee, me));
+  double mV2 = m_(mV, mV);
+  double ctMax = d_(m_(sqrt(d_(a_(Ee, me), s_(Ee, me))), s_(m_(m_(2, me), a_(s_(Ee, m_(2, EgMin)), me)), mV2)),
+                    s_(m_(m_(2, me), a_(Ee, me)), mV2));
   if (s < mV2) return 0.0;
   if (ct > ctMax) return 0.0;
-  double b2 = 1.0 - 4.0 * me * me / s;   // b = sqrt(b2); only b^2 is used
-  double bb = sqrt(b2);
-  bb = bb * bb;
-  return 4.0 * kPi * kAlpha * kAlpha / (s * (1 - bb * ct * ct)) * ((s - mV2) / (2 * s) * (1 + ct * ct) + 2.0 * mV2 / (s - mV2));
+  double b = sqrt(s_(1.0, d_(m_(4.0, m_(me, me)), s)));
+  double ct2 = m_(ct, ct);
+  double pre = d_(m_(m_(4.0, kPi), kAlpha * kAlpha), m_(s, s_(1, m_(m_(b, b), ct2))));
+  double smv = s_(s, mV2);
+  double br = a_(m_(d_(smv, m_(2, s)), a_(1, ct2)), d_(m_(2.0, mV2), smv));
+  return m_(pre, br);
 }
 
 // all_processes.py:787-840 (dsigma_moller_dCT)
@@ -313,7 +333,7 @@ __device__ __forceinline__ double dsigma(const Material& M, int proc, double E, 
     case P_BREM: return ds_brem(M, E, kMe, x);
     case P_MUONBREM: return ds_brem(M, E, kMmu, x);
     case P_PAIRPROD: return ds_pairprod(M, E, x);
-    case P_COMP: return ds_compton(E, 0.0, x[0]);
+    case P_COMP: return ds_compton(M, E, 0.0, x[0]);
     case P_ANN: return ds_annihilation(E, 0.0, M.Eg_min, x[0]);
     case P_MOLLER: return ds_moller(E, M.Ee_min, x[0]);
     case P_BHABHA: return ds_bhabha(E, M.Ee_min, x[0]);
@@ -321,7 +341,7 @@ __device__ __forceinline__ double dsigma(const Material& M, int proc, double E, 
     case P_DARKBREM: return ds_darkbrem(M, E, kMe, x);
     case P_DARKMUONBREM: return ds_darkbrem(M, E, kMmu, x);
     case P_DARKANN: return ds_darkann(M, E, x[0]);
-    case P_DARKCOMP: return ds_compton(E, M.mV, x[0]);
+    case P_DARKCOMP: return ds_compton(M, E, M.mV, x[0]);
   }
   return 0.0;
 }
@@ -334,61 +354,50 @@ __device__ __forceinline__ V4 lose_energy(V4 p, double mass, double value) {
   double p30 = norm3_nofma(p.x, p.y, p.z);
   double Eu = p.E - value;
   if (Eu <= mass) Eu = mass;
-  double p3f = sqrt(Eu * Eu - mass * mass);
-  if (p3f > 0.0) return V4{Eu, p.x / p30 * p3f, p.y / p30 * p3f, p.z / p30 * p3f};
+  // no fma contraction: at Eu == mass the reference gets exactly 0 here and stops the particle (particle.py:149-153)
+  double p3f = sqrt(__dsub_rn(__dmul_rn(Eu, Eu), __dmul_rn(mass, mass)));
+  if (p3f > 0.0) { double r = p3f / p30; return V4{Eu, p.x * r, p.y * r, p.z * r}; }
   return V4{mass, 0.0, 0.0, 0.0};
 }
 
-// moliere.py:196-219, 265-281: Lynch-Dahl width of the Gaussian core, F = 0.98, z = 1
-__device__ __forceinline__ double mcs_theta0(const Material& M, double t, double beta, double m_lepton) {
+// moliere.py:196-219, 265-281: Lynch-Dahl width of the Gaussian core, F = 0.98, z = 1.
+// The reference forms the momentum in MeV as m_lepton * beta / sqrt(1 - beta^2) with beta = |p|/E; that is
+// m_lepton * |p| / sqrt(E^2 - |p|^2) = m_lepton * |p| / mass, evaluated here without the gamma^2-amplified cancellation.
+__device__ __forceinline__ double mcs_theta0(const Material& M, double t, double beta, double p_MeV) {
   const double F = 0.98;
-  double p = (m_lepton / 1e-3) * beta / sqrt(1.0 - beta * beta);
-  double pb = 1.0 / (p * beta);
+  double pb = 1.0 / (p_MeV * beta);
   double chic2 = 0.157 * M.Z * (M.Z + 1) * (t / M.A) * (pb * pb);
   double za = M.Z * kAlpha / beta;
-  double chia2 = 2.007e-5 * M.Z23 * (1.0 + 3.34 * (za * za)) / (p * p);
+  double chia2 = 2.007e-5 * M.Z23 * (1.0 + 3.34 * (za * za)) / (p_MeV * p_MeV);
   double omega = chic2 / chia2;
   double v = 0.5 * omega / (1.0 - F);
   return sqrt(chic2 * ((1.0 + v) * log(1.0 + v) / v - 1) / (1.0 + F * F));
 }
 
-// moliere.py:287-348 (get_rotation_matrix incl. the duplicated branch, SURVEY Q-13) and :350-400
-// (get_scattered_momentum_fast).  sign in {-1,+1}; z1, z2 standard normals; u_phi in [0,1).
-__device__ __forceinline__ V4 mcs_scatter(const Material& M, V4 p4, double t, double m_lepton, double sign, double z1,
-                                          double z2, double u_phi) {
+// moliere.py:350-400 (get_scattered_momentum_fast) with the rotation of moliere.py:287-348 in closed form.
+// get_rotation_matrix builds Rb(b) Ra(a) from a = -/+atan|vy/vx| ..., b = ...atan|vx'/vz| with quadrant fix-ups (and a
+// duplicated branch, SURVEY Q-13); every branch reduces to cos a = vx/r, sin a = -vy/r (r = hypot(vx, vy), so vx' = r)
+// and cos b = vz/|v|, sin b = -vx'/|v|.  The axis-aligned special cases keep the reference's literal values.
+// sign in {-1,+1}; radial = sqrt(z1^2 + z2^2) for the two unit normals; u_phi in [0,1).
+__device__ __forceinline__ V4 mcs_apply(const Material& M, V4 p4, double pn, double t, double m_lepton, double mass,
+                                        double sign, double radial, double u_phi) {
   double vx = p4.x, vy = p4.y, vz = p4.z;
-  double pn = norm3_nofma(vx, vy, vz);
-  if (!(pn > 0)) return p4;
   double beta = pn / p4.E;
   double ca, sa;
-  if (fabs(vx) > 0.0 && fabs(vy) > 0.0) {
-    double a = atan(fabs(vy / vx));
-    if (vx > 0.0 && vy > 0.0) a = -a;
-    if (vx < 0.0 && vy > 0.0) a = -(kPi - a);
-    if (vx < 0.0 && vy < 0.0) a = -(kPi + a);
-    if (vx > 0.0 && vy < 0.0) a = -(2.0 * kPi - a);
-    sincos(a, &sa, &ca);
-  } else if (fabs(vy) > 0.0) { ca = 0.0; sa = 1.0; }
+  if (vx != 0.0 && vy != 0.0) { double r = 1.0 / sqrt(vx * vx + vy * vy); ca = vx * r; sa = -vy * r; }
+  else if (vy != 0.0) { ca = 0.0; sa = 1.0; }
   else { ca = 1.0; sa = 0.0; }
   double vxp = vx * ca - vy * sa;
   double cb, sb;
-  if (fabs(vz) > 0.0 && fabs(vxp) > 0.0) {
-    double b = atan(fabs(vxp / vz));
-    if (vz > 0.0 && vxp > 0.0) b = -b;
-    if (vz < 0.0 && vxp > 0.0) b = -(kPi - b);
-    if (vz < 0.0 && vxp < 0.0) b = -(kPi + b);
-    if (vz > 0.0 && vxp > 0.0) b = -(2.0 * kPi - b);
-    sincos(b, &sb, &cb);
-  } else if (vxp > 0.0) { cb = 0.0; sb = -1.0; }
+  if (vz != 0.0 && vxp != 0.0) { double r = 1.0 / sqrt(vxp * vxp + vz * vz); cb = vz * r; sb = -vxp * r; }
+  else if (vxp > 0.0) { cb = 0.0; sb = -1.0; }
   else if (vxp < 0.0) { cb = 0.0; sb = 1.0; }
   else { cb = 1.0; sb = 0.0; }
-  double th0 = mcs_theta0(M, t, beta, m_lepton);
-  double g1 = z1 * th0, g2 = z2 * th0;
-  double theta = sign * sqrt(g1 * g1 + g2 * g2) * M.rescale_mcs;
-  double phi = kTwoPi * u_phi;
+  double th0 = mcs_theta0(M, t, beta, (m_lepton * 1e3) * (pn / mass));
+  double theta = sign * (radial * th0) * M.rescale_mcs;
   double cth, sth, cph, sph;
   sincos(theta, &sth, &cth);
-  sincos(phi, &sph, &cph);
+  sincospi(2.0 * u_phi, &sph, &cph);
   double q0 = pn * (sph * sth), q1 = pn * (-cph * sth), q2 = pn * cth;
   // R = Rb Ra = [[cb ca, -cb sa, sb], [sa, ca, 0], [-sb ca, sb sa, cb]] ; lab = R^T q
   V4 o;
@@ -399,24 +408,21 @@ __device__ __forceinline__ V4 mcs_scatter(const Material& M, V4 p4, double t, do
   return o;
 }
 
-// CPython random.gauss pair from two uniforms (oracle/physics.py normals_from_uniforms)
-__device__ __forceinline__ void normals_from_uniforms(double ua, double ur, double* z1, double* z2) {
-  double s, c;
-  sincos(ua * kTwoPi, &s, &c);
-  double g = sqrt(-2.0 * log(1.0 - ur));
-  *z1 = c * g;
-  *z2 = s * g;
-}
-
-struct McsDraw { double sign, z1, z2, uphi; };
+// The MCS block's four draws: sign, two normals, azimuth.  CPython's gauss pair is
+// (cos, sin)(2 pi u_a) * sqrt(-2 ln(1 - u_r)), so sqrt(z1^2 + z2^2) = sqrt(-2 ln(1 - u_r)) and u_a drops out.
+struct McsDraw { double sign, radial, uphi; };
 __device__ __forceinline__ McsDraw mcs_draw(uint2 key, uint32_t index, uint32_t pc) {
   D2 a = draw2(key, index, ST_MCS, 0, pc);
   D2 b = draw2(key, index, ST_MCS, 1, pc);
   McsDraw d;
   d.sign = a.a < 0.5 ? -1.0 : 1.0;
   d.uphi = a.b;
-  normals_from_uniforms(b.a, b.b, &d.z1, &d.z2);
+  d.radial = sqrt(-2.0 * log(1.0 - b.b));
   return d;
+}
+__device__ __forceinline__ V4 mcs_scatter(const Material& M, V4 p4, double pn, double t, double m_lepton, double mass,
+                                          const McsDraw& d) {
+  return mcs_apply(M, p4, pn, t, m_lepton, mass, d.sign, d.radial, d.uphi);
 }
 
 // particle.py:176-185: rows of Rz(phi) Ry(theta) taking z-hat onto pf; applied as lab = R v

@@ -415,28 +415,73 @@ class Shower:
                 raise ValueError(f"stable PID {ids['PID']} cannot be showered")
         return p, r, w, m, pid, fl
 
+    def _stack_struct(self):
+        t = self._stack_tensors
+        return capi.pb_stack(t["p0"].data_ptr(), t["r0w"].data_ptr(), t["pf"].data_ptr(), t["rf"].data_ptr(),
+                             t["key"].data_ptr(), t["meta"].data_ptr(), t["aux"].data_ptr(), self._stack_capacity)
+
     def run_arrays(self, p, r, w, m, pid, flags, GlobalMS=True, capacity=None, first_shower_id=None):
-        """Lowest-level entry: host SoA primaries -> :class:`ShowerBatch` (one ``pb_run_showers`` call)."""
+        """Lowest-level entry: SoA primaries -> :class:`ShowerBatch` (one ``pb_run_showers`` call).
+
+        The six arrays are either all host NumPy arrays (copied to the GPU inside the call) or all torch CUDA
+        tensors already resident in HBM (float64 / int32, contiguous)."""
         n = len(pid)
-        p = np.ascontiguousarray(p, dtype=np.float64); r = np.ascontiguousarray(r, dtype=np.float64)
-        w = np.ascontiguousarray(w, dtype=np.float64); m = np.ascontiguousarray(m, dtype=np.float64)
-        pid = np.ascontiguousarray(pid, dtype=np.int32); flags = np.ascontiguousarray(flags, dtype=np.int32)
-        if capacity is None:
-            capacity = self.estimate_records(p[:, 0], pid)
+        on_device = not isinstance(p, np.ndarray)
+        if on_device:
+            arrs = [p, r, w, m, pid, flags]
+            assert all(a.is_cuda and a.is_contiguous() for a in arrs)
+            if capacity is None:
+                raise ValueError("capacity must be given for device-resident primaries")
+            cast = lambda a, ty: C.cast(C.c_void_p(a.data_ptr()), ty)
+            prim = capi.pb_primaries(cast(p, capi.c_double_p), cast(r, capi.c_double_p), cast(w, capi.c_double_p),
+                                     cast(m, capi.c_double_p), cast(pid, capi.c_int32_p), cast(flags, capi.c_int32_p), n, 1)
+        else:
+            p = np.ascontiguousarray(p, dtype=np.float64); r = np.ascontiguousarray(r, dtype=np.float64)
+            w = np.ascontiguousarray(w, dtype=np.float64); m = np.ascontiguousarray(m, dtype=np.float64)
+            pid = np.ascontiguousarray(pid, dtype=np.int32); flags = np.ascontiguousarray(flags, dtype=np.int32)
+            if capacity is None:
+                capacity = self.estimate_records(p[:, 0], pid)
+            prim = capi.pb_primaries(capi.dptr(p), capi.dptr(r), capi.dptr(w), capi.dptr(m), capi.iptr(pid), capi.iptr(flags), n, 0)
         self._ensure_stack(int(capacity))
         if first_shower_id is None:
             first_shower_id = self._next_shower_id
             self._next_shower_id += n
         t = self._stack_tensors
-        st = capi.pb_stack(t["p0"].data_ptr(), t["r0w"].data_ptr(), t["pf"].data_ptr(), t["rf"].data_ptr(),
-                           t["key"].data_ptr(), t["meta"].data_ptr(), t["aux"].data_ptr(), self._stack_capacity)
-        prim = capi.pb_primaries(capi.dptr(p), capi.dptr(r), capi.dptr(w), capi.dptr(m), capi.iptr(pid), capi.iptr(flags), n)
+        st = self._stack_struct()
         cnt = capi.pb_counters()
         stream = self._torch.cuda.current_stream(self._device).cuda_stream
         rc = capi.lib.pb_run_showers(self._engine, C.byref(prim), self._seed, int(first_shower_id), 1 if GlobalMS else 0,
                                      C.byref(st), C.byref(cnt), C.c_void_p(stream))
         capi.check(self._engine, rc)
         return ShowerBatch(self, t, cnt.n_particles, cnt.as_dict(), n, first_shower_id)
+
+    def tally(self, batch, out=None):
+        """Histogram / yield tallies of a batch (``pb_tally``), accumulated into ``out`` (torch float64[1024], CUDA)."""
+        torch = self._torch
+        if out is None:
+            out = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=torch.device("cuda", self._device))
+        st = self._stack_struct()
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        capi.check(self._engine, capi.lib.pb_tally(self._engine, C.byref(st), 0, batch.n, C.c_void_p(out.data_ptr()),
+                                                   C.c_void_p(stream)))
+        return out
+
+    def set_profiling(self, on=True):
+        capi.check(self._engine, capi.lib.pb_set_profiling(self._engine, 1 if on else 0))
+
+    def get_profile(self):
+        """Per-kernel device milliseconds / launches and per-process trial counts of the last run."""
+        pr = capi.pb_profile()
+        capi.check(self._engine, capi.lib.pb_get_profile(self._engine, C.byref(pr)))
+        return {"ms": {k: pr.ms[i] for i, k in enumerate(capi.KERNEL_NAMES)},
+                "launches": {k: int(pr.launches[i]) for i, k in enumerate(capi.KERNEL_NAMES)},
+                "trials": {K.PROCESS_NAMES[i]: int(pr.trials[i]) for i in range(12) if pr.trials[i]},
+                "samples": {K.PROCESS_NAMES[i]: int(pr.samples[i]) for i in range(12) if pr.samples[i]}}
+
+    def measure_fp64_peak(self):
+        v = (C.c_double * 1)(0.0)
+        capi.check(self._engine, capi.lib.pb_measure_fp64_peak(self._engine, v))
+        return float(v[0])
 
     # ------------------------------------------------------------------ public stepping API
     def generate_showers(self, primaries, GlobalMS=True, capacity=None, first_shower_id=None):

@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference; the GPU box does not have it):
+
+    python tests/golden/make_golden.py
+
+The reference is imported through ``_refstub`` (stub ``vegas``/``matplotlib`` modules, see its docstring).
+Everything recorded here is computed by the reference's own functions:
+
+    integrands.npz   dsigma_* classes of all_processes.py at points drawn through the shipped maps
+    kinematics.npz   *_fourvecs of kinematics.py (azimuth uniform recorded by re-seeding NumPy)
+    mcs.npz          moliere.get_scattered_momentum_fast with its ``random`` calls fed from a tape
+    particle.npz     Particle.lose_energy / rotation_matrix / two_body_decay
+    nsigma.npz       Shower._NSigma*, get_mfp, thresholds for graphite and lead
+    showers.npz      whole generate_shower runs (stream mode, seeded) - multiplicities, ids, four-vectors
+"""
+import os
+import pickle
+import random
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+import _refstub  # noqa: E402
+
+_refstub.import_reference()
+warnings.filterwarnings("ignore")
+
+import PETITE.all_processes as ap  # noqa: E402
+import PETITE.kinematics as kin  # noqa: E402
+import PETITE.moliere as mol  # noqa: E402
+from PETITE.particle import Particle  # noqa: E402
+from PETITE.physical_constants import m_electron, m_muon, alpha_em, m_pi0  # noqa: E402
+from oracle.vegasmap import AdaptiveMapStub, map_points  # noqa: E402
+from oracle.findmax import split_grid, MATERIALS  # noqa: E402
+from oracle.consts import SM_PROCESSES, DARK_PROCESSES, TARGETS  # noqa: E402
+
+DATA = os.path.join(HERE, "..", "..", "data", "")
+REFDIR = "/tmp/petite_refdata/"
+
+
+def build_reference_dict_dir():
+    """Reference-format dict_dir: shipped pickles + sm_maps.pkl / dark_maps.pkl rebuilt from data/*.npz."""
+    os.makedirs(REFDIR, exist_ok=True)
+    for f in ["sm_xsec.pkl", "dark_xsec.pkl", "dark_weights.pkl", "dark_drate.pkl"]:
+        if not os.path.exists(REFDIR + f):
+            os.symlink(os.path.join(_refstub.REF_ROOT, "data", f), REFDIR + f)
+
+    def mk(z, mf, procs, pre=""):
+        out = {}
+        for P in procs:
+            E, ninc, G, meta = z[f"{P}/E"], z[f"{P}/ninc"], z[f"{P}/grid"], z[f"{P}/meta"]
+            out[P] = [[float(E[i]), {"neval": int(meta[0]), "max_F": {m: float(mf[f"{pre}{P}/{m}"][i]) for m in MATERIALS},
+                                     "adaptive_map": AdaptiveMapStub(split_grid(G[i], ninc)),
+                                     "Eg_min": float(meta[1]), "Ee_min": float(meta[2])}] for i in range(len(E))]
+        return out
+    pickle.dump(mk(np.load(DATA + "sm_maps.npz"), np.load(DATA + "sm_maxF.npz"), SM_PROCESSES), open(REFDIR + "sm_maps.pkl", "wb"))
+    dmf = np.load(DATA + "dark_maxF.npz")
+    dm = {}
+    for f in sorted(os.listdir(DATA)):
+        if f.startswith("dark_maps_mV"):
+            tag = f[len("dark_maps_mV"):-4]
+            dm[float(tag)] = mk(np.load(DATA + f), dmf, DARK_PROCESSES, pre=tag + "/")
+    pickle.dump(dm, open(REFDIR + "dark_maps.pkl", "wb"))
+
+
+REF_DS = {"Brem": ap.dsigma_brem_dimensionless, "MuonBrem": ap.dsigma_brem_dimensionless,
+          "PairProd": ap.dsigma_pairprod_dimensionless, "Comp": ap.dsigma_compton_dCT, "Ann": ap.dsigma_annihilation_dCT,
+          "Moller": ap.dsigma_moller_dCT, "Bhabha": ap.dsigma_bhabha_dCT, "MuonE": ap.dsigma_muonelectron_dCT,
+          "DarkBrem": ap.dsig_dx_dcostheta_dark_brem_exact_tree_level,
+          "DarkMuonBrem": ap.dsig_dx_dcostheta_dark_brem_exact_tree_level,
+          "DarkAnn": ap.dsigma_radiative_return_du, "DarkComp": ap.dsigma_compton_dCT}
+
+
+def golden_integrands(rng):
+    out = {}
+    sm = np.load(DATA + "sm_maps.npz")
+    dk = np.load(DATA + "dark_maps_mV0.03.npz")
+    for material in ("graphite", "lead"):
+        t = TARGETS[material]
+        for P in SM_PROCESSES + DARK_PROCESSES:
+            z = sm if P in SM_PROCESSES else dk
+            E, ninc, G = z[f"{P}/E"], z[f"{P}/ninc"], z[f"{P}/grid"]
+            rows = [3, 20, 45, 70, 99]
+            Es, xs, fs = [], [], []
+            for ie in rows:
+                grid = split_grid(G[ie], ninc)
+                y = rng.random((24, len(grid)))
+                x, _ = map_points(grid, y)
+                # sampler-time event_info (shower.py:435-439, dark_shower.py:672-676): mT = A_T
+                for Einc in (float(E[ie]), float(E[ie]) * 0.93):
+                    ev = {"E_inc": Einc, "m_e": m_electron, "Z_T": t["Z_T"], "A_T": t["A_T"], "mT": t["A_T"],
+                          "alpha_FS": alpha_em, "mV": 0.0 if P in SM_PROCESSES else 0.03, "Eg_min": 0.001, "Ee_min": 0.005}
+                    if P in ("Brem", "DarkBrem"):
+                        ev["m_lepton"] = m_electron
+                    if P in ("MuonBrem", "DarkMuonBrem"):
+                        ev["m_lepton"] = m_muon
+                    f = REF_DS[P](event_info=ev, ndim=len(grid))
+                    for xi in x:
+                        Es.append(Einc)
+                        xs.append(np.pad(xi, (0, 4 - len(xi))))
+                        fs.append(float(np.asarray(f(xi))))
+            out[f"{material}/{P}/E"] = np.array(Es)
+            out[f"{material}/{P}/x"] = np.array(xs)
+            out[f"{material}/{P}/f"] = np.array(fs)
+    np.savez_compressed(os.path.join(HERE, "integrands.npz"), **out)
+
+
+def golden_kinematics(rng):
+    out = {}
+    sm = np.load(DATA + "sm_maps.npz")
+    cases = [("Brem", kin.e_to_egamma_fourvecs, 11, m_electron), ("MuonBrem", kin.e_to_egamma_fourvecs, 13, m_muon),
+             ("PairProd", kin.gamma_to_epem_fourvecs, 22, 0.0), ("Comp", kin.compton_fourvecs, 22, 0.0),
+             ("Ann", kin.annihilation_fourvecs, -11, m_electron), ("Moller", kin.ee_to_ee_fourvecs, 11, m_electron),
+             ("Bhabha", kin.ee_to_ee_fourvecs, -11, m_electron), ("MuonE", kin.mue_to_mue_fourvecs, 13, m_muon)]
+    for P, fn, pid, mass in cases:
+        E, ninc, G = sm[f"{P}/E"], sm[f"{P}/ninc"], sm[f"{P}/grid"]
+        inp, res = [], []
+        for ie in (25, 50, 75, 99):
+            grid = split_grid(G[ie], ninc)
+            x, _ = map_points(grid, rng.random((16, len(grid))))
+            for xi in x:
+                Einc = float(E[ie])
+                p = Particle([Einc, 0, 0, np.sqrt(Einc ** 2 - mass ** 2)], [0, 0, 0], {"PID": pid, "mass": mass})
+                seed = int(rng.integers(1 << 30))
+                np.random.seed(seed)
+                u = np.random.random()
+                np.random.seed(seed)
+                v = fn(p, xi)
+                inp.append([Einc, mass] + list(np.pad(xi, (0, 4 - len(xi)))) + [u, 0.0])
+                res.append(list(v[0]) + list(v[1]))
+        out[f"{P}/in"] = np.array(inp, dtype=float)
+        out[f"{P}/out"] = np.array(res, dtype=float)
+    # pi0 -> gamma gamma (particle.py:209-256)
+    inp, res = [], []
+    for _ in range(64):
+        pv = rng.normal(size=3) * rng.choice([0.05, 1.0, 30.0])
+        E = np.sqrt(m_pi0 ** 2 + pv @ pv)
+        p = Particle([E, *pv], [0.1, 0.2, 0.3], {"PID": 111, "mass": m_pi0, "stability": "short-lived"})
+        seed = int(rng.integers(1 << 30))
+        np.random.seed(seed)
+        u1, u2 = np.random.random(), np.random.random()
+        np.random.seed(seed)
+        d = p.decay_particle()
+        inp.append([E, m_pi0, pv[0], pv[1], pv[2], 0.0, u1, u2])
+        res.append(list(d[0].get_p0()) + list(d[1].get_p0()))
+    out["SMDecay/in"] = np.array(inp)
+    out["SMDecay/out"] = np.array(res)
+    np.savez_compressed(os.path.join(HERE, "kinematics.npz"), **out)
+
+
+class _Tape:
+    """Feeds moliere.py's ``random.choice / gauss / uniform`` from explicit values."""
+
+    def __init__(self, sign, z1, z2, uphi):
+        self.sign, self.z, self.uphi = sign, [z1, z2], uphi
+
+    def choice(self, seq):
+        return self.sign
+
+    def gauss(self, mu, sigma):
+        return mu + self.z.pop(0) * sigma
+
+    def uniform(self, a, b):
+        return a + (b - a) * self.uphi
+
+
+def golden_mcs(rng):
+    inp, res = [], []
+    real_random = mol.random
+    for material in ("graphite", "lead"):
+        t = TARGETS[material]
+        for _ in range(96):
+            m = rng.choice([m_electron, m_muon])
+            pmag = 10 ** rng.uniform(-2.5, 2)
+            d = rng.normal(size=3)
+            if rng.random() < 0.3:
+                d = np.array([rng.normal() * 1e-4, rng.normal() * 1e-4, rng.choice([-1.0, 1.0])])
+            if rng.random() < 0.1:
+                d[rng.integers(3)] = 0.0
+            d = d / np.linalg.norm(d) * pmag
+            p4 = np.array([np.sqrt(pmag ** 2 + m ** 2), *d])
+            dist = 10 ** rng.uniform(-5, -1)
+            sign, z1, z2, uphi = float(rng.choice([-1, 1])), rng.normal(), rng.normal(), rng.random()
+            mol.random = _Tape(sign, z1, z2, uphi)
+            q = mol.get_scattered_momentum_fast(p4, t["rho"] * (dist / 0.01), t["A_T"], t["Z_T"], 1, m_lepton=m)
+            inp.append(list(p4) + [dist, m, sign, z1, z2, uphi, t["Z_T"]])
+            res.append(list(q))
+    mol.random = real_random
+    np.savez_compressed(os.path.join(HERE, "mcs.npz"), inp=np.array(inp), out=np.array(res))
+
+
+def golden_particle(rng):
+    le_in, le_out, rm_in, rm_out = [], [], [], []
+    for _ in range(64):
+        m = rng.choice([m_electron, m_muon])
+        pv = rng.normal(size=3) * 10 ** rng.uniform(-3, 1)
+        E = np.sqrt(m ** 2 + pv @ pv)
+        p = Particle([E, *pv], [0, 0, 0], {"PID": 11, "mass": m})
+        loss = E * rng.choice([1e-3, 0.3, 2.0])
+        p.lose_energy(loss)
+        le_in.append([E, *pv, m, loss])
+        le_out.append(list(p.get_pf()))
+        q = Particle([E, *pv], [0, 0, 0], {"PID": 11, "mass": m})
+        rm_in.append([E, *pv])
+        rm_out.append(np.array(q.rotation_matrix(), dtype=float).ravel())
+    np.savez_compressed(os.path.join(HERE, "particle.npz"), lose_in=np.array(le_in), lose_out=np.array(le_out),
+                        rot_in=np.array(rm_in), rot_out=np.array(rm_out))
+
+
+def golden_nsigma():
+    from PETITE.shower import Shower
+    out = {}
+    names = ["Brem", "Ann", "PairProd", "Comp", "Moller", "Bhabha", "MuonE", "MuonBrem"]
+    attr = {"Brem": "_NSigmaBrem", "Ann": "_NSigmaAnn", "PairProd": "_NSigmaPP", "Comp": "_NSigmaComp",
+            "Moller": "_NSigmaMoller", "Bhabha": "_NSigmaBhabha", "MuonE": "_NSigmaMuonE", "MuonBrem": "_NSigmaMuonBrem"}
+    E = np.concatenate([np.geomspace(1e-3, 150.0, 400), [0.0016, 0.01, 1.0, 10.0, 100.0, 0.2, 0.25708651005470756]])
+    for material in ("graphite", "lead"):
+        s = Shower(REFDIR, material, 0.010)
+        out[f"{material}/E"] = E
+        for P in names:
+            out[f"{material}/{P}"] = np.array([float(getattr(s, attr[P])(e)) for e in E])
+            t = getattr(s, attr[P])
+            out[f"{material}/{P}/table_x"], out[f"{material}/{P}/table_y"] = np.asarray(t.x), np.asarray(t.y)
+        for pid in (22, 11, -11, 13):
+            out[f"{material}/mfp/{pid}"] = np.array([float(s.get_mfp([pid, e])) for e in E])
+        out[f"{material}/min_calc"] = np.array([s._minimum_calculable_energy[k] for k in (11, -11, 22, 13, -13)])
+        out[f"{material}/n"] = np.array(s.get_n_targets())
+    np.savez_compressed(os.path.join(HERE, "nsigma.npz"), **out)
+
+
+def golden_showers():
+    from PETITE.shower import Shower
+    out = {}
+    proc_code = {"Input": 15, "SMDecay": 12}
+    proc_code.update({p: i for i, p in enumerate(SM_PROCESSES)})
+    cases = [("graphite", 11, 10.0, 0.010, 101, None), ("graphite", 22, 10.0, 0.010, 102, None),
+             ("lead", 22, 5.0, 0.010, 103, None), ("lead", -11, 3.0, 0.010, 104, None),
+             ("graphite", 13, 20.0, 0.030, 105, m_muon), ("graphite", 111, 8.0, 0.010, 106, m_pi0),
+             ("graphite", 11, 1.0, 0.010, 107, None), ("lead", 11, 0.5, 0.010, 108, m_electron)]
+    for k, (mat, pid, E, Emin, seed, mass) in enumerate(cases):
+        s = Shower(REFDIR, mat, Emin)
+        m = {11: m_electron, -11: m_electron, 22: 0.0, 13: m_muon, -13: m_muon, 111: m_pi0}[pid]
+        ids = {"PID": pid, "ID": 1}
+        if mass is not None:
+            ids["mass"] = mass
+        if pid == 111:
+            ids["stability"] = "short-lived"
+        np.random.seed(seed)
+        random.seed(seed)
+        sh = s.generate_shower(Particle([E, 0, 0, np.sqrt(E ** 2 - m ** 2)], [0, 0, 0], ids))
+        out[f"{k}/case"] = np.array([pid, E, Emin, seed, -1.0 if mass is None else mass])
+        out[f"{k}/material"] = np.array(mat)
+        out[f"{k}/pid"] = np.array([p.get_ids()["PID"] for p in sh])
+        out[f"{k}/ID_mod"] = np.array([p.get_ids()["ID"] % (1 << 61) for p in sh], dtype=np.int64)
+        out[f"{k}/gen"] = np.array([p.get_ids()["generation_number"] for p in sh])
+        out[f"{k}/process"] = np.array([proc_code[p.get_ids()["generation_process"]] for p in sh])
+        out[f"{k}/weight"] = np.array([p.get_ids()["weight"] for p in sh])
+        out[f"{k}/mass"] = np.array([p.get_ids()["mass"] for p in sh], dtype=float)
+        out[f"{k}/p0"] = np.array([p.get_p0() for p in sh], dtype=float)
+        out[f"{k}/pf"] = np.array([p.get_pf() for p in sh], dtype=float)
+        out[f"{k}/r0"] = np.array([p.get_r0() for p in sh], dtype=float)
+        out[f"{k}/rf"] = np.array([p.get_rf() for p in sh], dtype=float)
+        print("shower case", k, mat, pid, E, "->", len(sh), "particles")
+    out["n_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "showers.npz"), **out)
+
+
+if __name__ == "__main__":
+    rng = np.random.default_rng(20261017)
+    build_reference_dict_dir()
+    golden_integrands(rng)
+    golden_kinematics(rng)
+    golden_mcs(rng)
+    golden_particle(rng)
+    golden_nsigma()
+    golden_showers()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

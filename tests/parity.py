@@ -46,5 +46,8 @@ def compare_with_oracle(batch, prims, material, min_energy, seed, **kw):
         for s, q in zip(sl, olist):
             rep["max_rel_p0"] = max(rep["max_rel_p0"], _relvec(q.p0, h["p0"][s]))
             rep["max_rel_pf"] = max(rep["max_rel_pf"], _relvec(q.pf, h["pf"][s]))
-            rep["max_abs_rf"] = max(rep["max_abs_rf"], float(np.max(np.abs(np.asarray(q.rf) - h["rf"][s]))))
+            # positions relative to their own scale (at least 1 m): a track with n*sigma = 0 gets the reference's 1e12 m
+            # mean free path (SURVEY Q-15) and ends ~1e10 m away
+            rf = np.asarray(q.rf)
+            rep["max_abs_rf"] = max(rep["max_abs_rf"], float(np.max(np.abs(rf - h["rf"][s])) / max(1.0, np.max(np.abs(rf)))))
     return rep

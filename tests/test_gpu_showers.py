@@ -1,0 +1,119 @@
+"""Whole showers on the GPU: replay parity with the CPU oracle, invariances, conservation, ensemble statistics."""
+import numpy as np
+import pytest
+
+from tests.gpu_util import shower, primaries
+from tests.parity import compare_with_oracle, oracle_showers
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # material, pid, E, Emin, n
+    ("graphite", 11, 10.0, 0.010, 3),       # BASELINE config 1 (README example)
+    ("lead", 22, 10.0, 0.010, 2),           # BASELINE config 2
+    ("lead", -11, 3.0, 0.010, 4),
+    ("graphite", 22, 1.0, 0.010, 16),
+    ("graphite", 13, 20.0, 0.030, 2),       # muons: MuonBrem/MuonE + Q-12
+    ("lead", -13, 5.0, 0.030, 2),
+]
+
+
+@pytest.mark.parametrize("material,pid,E,Emin,n", CASES)
+def test_replay_parity_with_oracle(material, pid, E, Emin, n):
+    """Counter-mode replay: same Philox draws on both sides -> identical multiplicities, PIDs, process choices,
+    accept/reject trial counts and sub-step counts; four-vectors agree up to amplified rounding."""
+    sh = shower(material, Emin, seed=11)
+    prims = primaries(pid, E, n)
+    batch = sh.generate_showers(prims, first_shower_id=1000)
+    rep = compare_with_oracle(batch, prims, material, Emin, seed=11)
+    assert rep["structure_mismatch"] == 0, rep
+    assert rep["particles"] == batch.n
+    assert rep["max_rel_p0"] < 1e-6 and rep["max_rel_pf"] < 1e-6 and rep["max_abs_rf"] < 1e-6, rep
+
+
+def test_pi0_primaries_and_q7_mass():
+    sh = shower("graphite", 0.010, seed=3)
+    from petite_b200 import Particle
+    from petite_b200.constants import m_pi0, m_electron
+    prims = [Particle([8.0, 0.3, -0.2, np.sqrt(64 - m_pi0 ** 2 - 0.13)], [0, 0, 0.1], {"PID": 111, "ID": 1, "mass": m_pi0, "stability": "short-lived"}),
+             Particle([2.0, 0, 0, np.sqrt(4 - m_electron ** 2)], [0, 0, 0], {"PID": 11, "ID": 0})]     # no mass -> 0.000511 (Q-7), ID 0 (Q-8)
+    batch = sh.generate_showers(prims, first_shower_id=0)
+    rep = compare_with_oracle(batch, prims, "graphite", 0.010, seed=3)
+    assert rep["structure_mismatch"] == 0, rep
+    out = batch.to_particles(prims)
+    assert out[0][1].get_ids()["generation_process"] == "SMDecay" and out[0][1].get_ids()["parent_ID"] == -1    # Q-10
+    assert abs(out[0][1].get_ids()["weight"] - 0.98823) < 1e-15
+    assert out[1][0].get_ids()["mass"] == 0.000511 and out[1][1].get_ids()["ID"] in (0, 1)
+
+
+def test_generate_shower_single_primary_api():
+    sh = shower("graphite", 0.010, seed=5)
+    p0 = primaries(11, 5.0, 1)[0]
+    sh._next_shower_id = 77
+    out = sh.generate_shower(p0)
+    ref = oracle_showers([p0], "graphite", 0.010, 5, first_shower_id=77)[0]
+    assert len(out) == len(ref)
+    assert [p.get_ids()["PID"] for p in out] == [q.PID for q in ref]
+    assert [p.get_ids()["ID"] for p in out] == [q.ID for q in ref]
+    assert [p.get_ids()["generation_process"] for p in out] == [q.process for q in ref]
+    assert all(p.get_ended() for p in out)
+    low = primaries(11, 0.005, 1)[0]
+    assert len(sh.generate_shower(low)) == 1
+
+
+def test_batch_split_and_determinism():
+    """A shower depends only on (seed, shower id): one call of 64 == two calls of 32, and reruns are identical."""
+    sh = shower("lead", 0.010, seed=9)
+    prims = primaries(22, 2.0, 64)
+
+    def signature(batch):
+        h = batch.to_host()
+        order, offs = batch.reference_order()
+        return [np.concatenate([h["p0"][order[offs[i]:offs[i + 1]]].ravel(), h["rf"][order[offs[i]:offs[i + 1]]].ravel()]) for i in range(batch.n_primaries)]
+    a = signature(sh.generate_showers(prims, first_shower_id=500))
+    b = signature(sh.generate_showers(prims, first_shower_id=500))
+    c1 = signature(sh.generate_showers(prims[:32], first_shower_id=500))
+    c2 = signature(sh.generate_showers(prims[32:], first_shower_id=532))
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    for x, y in zip(a, c1 + c2):
+        assert np.array_equal(x, y)
+
+
+def test_energy_accounting_full_size_property():
+    """Size-independent property at a BASELINE-like size: daughters never carry more energy than the parent had at
+    the vertex (up to the rest mass of the struck atomic electron), and weights are inherited."""
+    sh = shower("lead", 0.010, seed=2)
+    prims = primaries(22, 10.0, 2000)
+    batch = sh.generate_showers(prims)
+    h = batch.to_host()
+    par = h["parent"]
+    d = par >= 0
+    Ed = np.zeros(batch.n)
+    np.add.at(Ed, par[d], h["p0"][d][:, 0])
+    from petite_b200.constants import m_electron
+    assert np.all(Ed <= h["pf"][:, 0] + m_electron + 1e-9)
+    assert np.all(h["p0"][d][:, 0] > 0.010)
+    assert np.array_equal(h["weight"][d], h["weight"][par[d]])
+    assert batch.counters["n_steps"] <= batch.n and batch.counters["n_no_sample"] == 0
+    assert np.all(np.isfinite(h["pf"])) and np.all(np.isfinite(h["rf"]))
+
+
+def test_ensemble_statistics_vs_oracle():
+    """KS tests (p > 0.01) of GPU showers against an independent oracle sample (different shower ids)."""
+    from scipy.stats import ks_2samp
+    sh = shower("graphite", 0.010, seed=21)
+    n_gpu, n_orc = 4000, 150
+    prims = primaries(11, 1.0, n_gpu)
+    batch = sh.generate_showers(prims, first_shower_id=10_000)
+    h = batch.to_host()
+    mult_gpu = np.bincount(h["shower"], minlength=n_gpu)
+    ref = oracle_showers(prims[:n_orc], "graphite", 0.010, 21, first_shower_id=0)
+    mult_orc = np.array([len(r) for r in ref])
+    assert ks_2samp(mult_gpu, mult_orc).pvalue > 0.01
+    ph_gpu = h["p0"][(h["pid"] == 22) & (h["parent"] >= 0)][:, 0]
+    ph_orc = np.array([q.p0[0] for r in ref for q in r[1:] if q.PID == 22])
+    assert ks_2samp(ph_gpu, ph_orc).pvalue > 0.01
+    th = lambda p: np.arccos(np.clip(p[:, 3] / np.linalg.norm(p[:, 1:], axis=1), -1, 1))
+    el_gpu = th(h["p0"][(np.abs(h["pid"]) == 11) & (h["parent"] >= 0)])
+    el_orc = th(np.array([q.p0 for r in ref for q in r[1:] if abs(q.PID) == 11]))
+    assert ks_2samp(el_gpu, el_orc).pvalue > 0.01
