@@ -15,6 +15,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <string>
 #include <vector>
@@ -31,12 +32,13 @@ constexpr int TILE = 256;                   // samples per tile
 constexpr int SAMPLE_THREADS = 128;
 constexpr int GRID_SMEM_DOUBLES = 4096;     // >= padded stride of a 4-D map row (3964 -> 3968)
 
-struct NSigmaTable { const double4* node; double xmin, xmax; int n; int pad; };   // node = (x, y, slope to next, 0)
+struct NSigmaTable { const double4* node; double xmin, xmax; double log_x0, inv_dlog; int n; int pad; };   // node = (x, y, slope to next, 0)
 struct MapInfo {
   const double* grid;   // nE rows, `stride` doubles each (padded to a multiple of 16 doubles)
   const double* E;
   const double* maxF;
   int nE, dim, stride, B;
+  double log_E0, inv_dlog;   // geometric-grid guess for the row look-up
   int ninc[4];
   int off[4];
 };
@@ -95,6 +97,18 @@ __device__ __forceinline__ int nsigma_locate(const NSigmaTable& T, double E) {
   }
   return min(max(lo, 1), T.n - 1);
 }
+// same result as nsigma_locate, starting from the geometric-grid guess (all shipped tables are geomspace grids;
+// the two fix-up loops make it exact for any increasing grid)
+__device__ __forceinline__ int nsigma_locate_log(const NSigmaTable& T, double logE, double E) {
+  int n = T.n;
+  if (n < 2) return 1;
+  double g = (logE - T.log_x0) * T.inv_dlog;
+  int hi = (g > 0.0) ? ((g < (double)(n - 1)) ? (int)g + 1 : n - 1) : 1;
+  hi = min(max(hi, 1), n - 1);
+  while (hi < n - 1 && __ldg(reinterpret_cast<const double*>(&T.node[hi])) < E) ++hi;
+  while (hi > 1 && !(__ldg(reinterpret_cast<const double*>(&T.node[hi - 1])) < E)) --hi;
+  return hi;
+}
 __device__ __forceinline__ double nsigma_at(const NSigmaTable& T, int hi, double E) {
   if (T.n < 2) return 0.0;
   if (!(E >= T.xmin && E <= T.xmax)) return (E == E) ? 0.0 : E;
@@ -122,28 +136,26 @@ __device__ __forceinline__ void species_tables(int pid, int* t) {
 }
 __device__ __forceinline__ double mfp_from(double ns) { return (ns <= 0.0) ? 1.0e12 : kCmToM / ns; }   // shower.py:386-389
 
-__device__ __forceinline__ double mfp_photon(const Tables& T, double E) {
-  return mfp_from(nsigma_eval(T.ns[P_PAIRPROD], E) + nsigma_eval(T.ns[P_COMP], E));
-}
-__device__ __forceinline__ double mfp_charged(const Tables& T, const int* tb, double E) {
-  double ns = nsigma_eval(T.ns[tb[0]], E) + nsigma_eval(T.ns[tb[1]], E);
-  if (tb[2] >= 0) ns += nsigma_eval(T.ns[tb[2]], E);
-  return mfp_from(ns);
+__device__ __forceinline__ double nsigma_log(const NSigmaTable& T, double logE, double E) {
+  if (T.n < 2) return 0.0;
+  return nsigma_at(T, nsigma_locate_log(T, logE, E), E);
 }
 
-// SURVEY Q-1: argmin |E_i - E| + 1, clamped to the last row (shower.py:416-426)
-__device__ __forceinline__ int lookup_row(const MapInfo& m, double E) {
-  int lo = 0, hi = m.nE;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(m.E + mid) < E) lo = mid + 1; else hi = mid;
-  }
-  int best;                                  // lo = first row with E_row >= E
+// SURVEY Q-1: argmin |E_i - E| + 1, clamped to the last row (shower.py:416-426).  lo = first row with E_row >= E is
+// found from the geometric-grid guess plus exact fix-up loops.
+__device__ __forceinline__ int lookup_row(const MapInfo& m, double logE, double E) {
+  int n = m.nE;
+  double g = (logE - m.log_E0) * m.inv_dlog;
+  int lo = (g > 0.0) ? ((g < (double)n) ? (int)g + 1 : n) : 0;
+  lo = min(max(lo, 0), n);
+  while (lo < n && __ldg(m.E + lo) < E) ++lo;
+  while (lo > 0 && !(__ldg(m.E + lo - 1) < E)) --lo;
+  int best;
   if (lo <= 0) best = 0;
-  else if (lo >= m.nE) best = m.nE - 1;
+  else if (lo >= n) best = n - 1;
   else best = (fabs(__ldg(m.E + lo - 1) - E) <= fabs(__ldg(m.E + lo) - E)) ? lo - 1 : lo;   // argmin keeps the first minimum
   int lu = best + 1;
-  return lu >= m.nE ? m.nE - 1 : lu;
+  return lu >= n ? n - 1 : lu;
 }
 
 // ------------------------------------------------------------------------------------------ wave kernels
@@ -199,7 +211,8 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
         t.ml = pid_mass(pid);
         t.pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), t.mass);   // shower.py:532-533
         species_tables(pid, t.tb);
-        for (int k = 0; k < 3; ++k) t.hint[k] = (t.tb[k] >= 0) ? nsigma_locate(T.ns[t.tb[k]], t.p.E) : 1;
+        double logE = log(t.p.E);
+        for (int k = 0; k < 3; ++k) t.hint[k] = (t.tb[k] >= 0) ? nsigma_locate_log(T.ns[t.tb[k]], logE, t.p.E) : 1;
         t.delta_z = 0.0; t.it = 0;
       }
       next += min(__popc(need), avail);
@@ -285,7 +298,10 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
         double last;
         if (p.E < pmin) last = distC * delta_z;
         else {
-          double mfp = mfp_charged(T, tb, p.E);
+          double lE = log(p.E);
+          double ns = nsigma_log(T.ns[tb[0]], lE, p.E) + nsigma_log(T.ns[tb[1]], lE, p.E);
+          if (tb[2] >= 0) ns += nsigma_log(T.ns[tb[2]], lE, p.E);
+          double mfp = mfp_from(ns);
           last = mfp * log(1.0 / (1.0 + (exp(-delta_z / mfp) - 1) * distC));
         }
         p = lose_energy(p, mass, M.dEdx * last);
@@ -311,7 +327,8 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
         double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
         if (!(p.E < pmin)) {                                              // shower.py:538-553 (MS_g is always False)
           c_steps = 1;
-          double mfp = mfp_photon(T, p.E);
+          double lE = log(p.E);
+          double mfp = mfp_from(nsigma_log(T.ns[P_PAIRPROD], lE, p.E) + nsigma_log(T.ns[P_COMP], lE, p.E));
           double distC = draw2(key, 0, ST_FINAL).a;
           double dist = mfp * log(1.0 / (1.0 - distC));
           double pn = norm3_nofma(p.x, p.y, p.z);
@@ -328,7 +345,8 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
       else if (pid == 22) { cand[0] = P_PAIRPROD; cand[1] = P_COMP; nc = 2; }
       else { cand[0] = P_MUONE; cand[1] = P_MUONBREM; nc = 2; }
       double SC = 0.0;
-      for (int k = 0; k < nc; ++k) { c[k] = nsigma_eval(T.ns[cand[k]], Ef); SC += c[k]; }
+      const double lEf = log(Ef);
+      for (int k = 0; k < nc; ++k) { c[k] = nsigma_log(T.ns[cand[k]], lEf, Ef); SC += c[k]; }
       if (!(SC == 0.0 || SC != SC)) {
         double u = draw2(key, 0, ST_CHOICE).a;
         // np.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
@@ -338,7 +356,7 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
         for (int k = nc - 1; k >= 0; --k) if (u < cdf[k] / acc) pick = k;
         int proc = cand[pick];
         double thr = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
-        if (!(Ef <= thr)) bucket = proc * LU_MAX + lookup_row(T.map[proc], Ef);
+        if (!(Ef <= thr)) bucket = proc * LU_MAX + lookup_row(T.map[proc], lEf, Ef);
       }
     }
     double2* pfp = reinterpret_cast<double2*>(S.pf + 4 * s);
@@ -796,6 +814,7 @@ struct pb_engine_s {
   void* prim_stage = nullptr; size_t prim_stage_bytes = 0;
   int n_sm = 148;
   bool profiling = false;
+  int sample_group = 8;          // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
   cudaEvent_t ev[2 * 8] = {};
   pb_profile prof{};
   std::string err;
@@ -850,6 +869,7 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->n_sm = prop.multiProcessorCount;
   e->cfg = *cfg;
   derive_material(e);
+  if (const char* g = getenv("PB_SAMPLE_G")) e->sample_group = atoi(g);
   size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * (8 + CNT_N);
   if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
   cudaMemset(e->fixed_blob, 0, fixed);
@@ -897,7 +917,9 @@ extern "C" int pb_upload_nsigma(pb_engine e, int id, const double* E, const doub
   PB_CUDA(e, cudaMalloc(&d, sizeof(double) * node.size()));
   e->owned.push_back(d);
   PB_CUDA(e, cudaMemcpy(d, node.data(), sizeof(double) * node.size(), cudaMemcpyHostToDevice));
-  e->tab.ns[id] = NSigmaTable{(const double4*)d, n ? E[0] : 0.0, n ? E[n - 1] : 0.0, n, 0};
+  double lx0 = (n > 1 && E[0] > 0) ? log(E[0]) : 0.0;
+  double idl = (n > 1 && E[0] > 0 && E[n - 1] > E[0]) ? (double)(n - 1) / log(E[n - 1] / E[0]) : 0.0;
+  e->tab.ns[id] = NSigmaTable{(const double4*)d, n ? E[0] : 0.0, n ? E[n - 1] : 0.0, lx0, idl, n, 0};
   return PB_OK;
 }
 
@@ -921,6 +943,8 @@ extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int 
   PB_CUDA(e, cudaMemcpy(dE, E_inc, sizeof(double) * nE, cudaMemcpyHostToDevice));
   PB_CUDA(e, cudaMemcpy(dE + nE, max_F, sizeof(double) * nE, cudaMemcpyHostToDevice));
   mi.grid = d; mi.E = dE; mi.maxF = dE + nE; mi.nE = nE; mi.dim = dim; mi.stride = padded; mi.B = neval;
+  mi.log_E0 = (E_inc[0] > 0) ? log(E_inc[0]) : 0.0;
+  mi.inv_dlog = (nE > 1 && E_inc[0] > 0 && E_inc[nE - 1] > E_inc[0]) ? (double)(nE - 1) / log(E_inc[nE - 1] / E_inc[0]) : 0.0;
   e->tab.map[process] = mi;
   return PB_OK;
 }
@@ -1065,7 +1089,14 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, (int)n);
     tock(PB_K_FILL); tick(PB_K_SAMPLE);
     int sg = (int)std::min<long long>(sample_grid, (n + 31) / 32 + 1);
-    k_sample<8><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin);
+    switch (e->sample_group) {
+      case 1: k_sample<1><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
+      case 2: k_sample<2><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
+      case 4: k_sample<4><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
+      case 16: k_sample<16><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
+      case 32: k_sample<32><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
+      default: k_sample<8><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
+    }
     tock(PB_K_SAMPLE); tick(PB_K_EMIT);
     k_emit<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, S, e->work, begin, (int)n);
     tock(PB_K_EMIT);
