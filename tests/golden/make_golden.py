@@ -47,9 +47,16 @@ REFDIR = "/tmp/petite_refdata/"
 def build_reference_dict_dir():
     """Reference-format dict_dir: shipped pickles + sm_maps.pkl / dark_maps.pkl rebuilt from data/*.npz."""
     os.makedirs(REFDIR, exist_ok=True)
-    for f in ["sm_xsec.pkl", "dark_xsec.pkl", "dark_weights.pkl", "dark_drate.pkl"]:
+    import shutil
+    for f in ["sm_xsec.pkl", "dark_xsec.pkl"]:
         if not os.path.exists(REFDIR + f):
             os.symlink(os.path.join(_refstub.REF_ROOT, "data", f), REFDIR + f)
+    for f in ["dark_weights.pkl", "dark_drate.pkl"]:      # the constructors write into these (SURVEY Q-3): real copies
+        if not os.path.exists(REFDIR + f) or os.path.islink(REFDIR + f):
+            if os.path.islink(REFDIR + f):
+                os.unlink(REFDIR + f)
+            shutil.copy(os.path.join(_refstub.REF_ROOT, "data", f), REFDIR + f)
+            os.chmod(REFDIR + f, 0o644)
 
     def mk(z, mf, procs, pre=""):
         out = {}
@@ -66,6 +73,10 @@ def build_reference_dict_dir():
         if f.startswith("dark_maps_mV"):
             tag = f[len("dark_maps_mV"):-4]
             dm[float(tag)] = mk(np.load(DATA + f), dmf, DARK_PROCESSES, pre=tag + "/")
+            # the reference's default active_processes includes "TwoBody_BSMDecay" and set_dark_samples
+            # (dark_shower.py:196-201) looks every active process up in dark_maps.pkl: the lost pickle must have
+            # carried such a key.  An empty entry lets the unmodified constructor run.
+            dm[float(tag)]["TwoBody_BSMDecay"] = []
     pickle.dump(dm, open(REFDIR + "dark_maps.pkl", "wb"))
 
 
@@ -271,15 +282,86 @@ def golden_showers():
     np.savez_compressed(os.path.join(HERE, "showers.npz"), **out)
 
 
+DARK_CASES = [("graphite", 0.03), ("lead", 0.03), ("graphite", 0.003), ("graphite", 1.0)]
+
+
+def dump_dark_setup(d, material, mV):
+    """Constructor tables of a reference DarkShower -> data/dark_setup_<material>_mV<tag>.npz (set-up cache + oracle input)."""
+    out = {"meta": np.array([d._mV, d._mV_estimator, d._resonant_annihilation_energy, d._compton_threshold_energy, d.g_e,
+                             d.kinetic_mixing, d.Zeff, 1.0 if d.bound_electron else 0.0])}
+    pids, procs, Es = [], [], []
+    for pid, dd in d._minimum_calculable_dark_energy.items():
+        for pr, e in dd.items():
+            pids.append(pid); procs.append(pr); Es.append(float(e))
+    out["min_dark_pid"], out["min_dark_proc"], out["min_dark_E"] = np.array(pids), np.array(procs), np.array(Es)
+    for name, itp in (("brem_elec", d._brem_elec_numerical_weight), ("brem_positron", d._brem_positron_numerical_weight),
+                      ("muon_brem", d._muon_brem_numerical_weight), ("annihilation", d._annihilation_numerical_weight)):
+        out[f"weights/{name}"] = np.column_stack([np.asarray(itp.x), np.asarray(itp.y)])
+    for name, tab in (("brem_elec", d._d_rate_dict_elec_brem), ("brem_positron", d._d_rate_dict_positron_brem),
+                      ("muon_brem", d._d_rate_dict_muon_brem), ("annihilation", d._d_rate_dict_positron_ann)):
+        keys = list(tab.keys())
+        out[f"drate/{name}/E"] = np.array([float(k) for k in keys])
+        out[f"drate/{name}/table"] = np.stack([np.asarray(tab[k], dtype=float) for k in keys])
+    for P, itp in (("DarkBrem", d._NSigmaDarkBrem), ("DarkAnn", d._NSigmaDarkAnn), ("DarkComp", d._NSigmaDarkComp),
+                   ("DarkMuonBrem", d._NSigmaDarkMuonBrem)):
+        out[f"nsdark/{P}/x"], out[f"nsdark/{P}/y"] = np.asarray(itp.x), np.asarray(itp.y)
+    from petite_b200.tables import mv_tag
+    np.savez_compressed(os.path.join(DATA, f"dark_setup_{material}_mV{mv_tag(mV)}.npz"), **out)
+
+
+def golden_dark(rng):
+    from PETITE.dark_shower import DarkShower
+    out = {}
+    proc_code = {"DarkBrem": 8, "DarkAnn_bound": 9, "DarkComp_bound": 10, "DarkMuonBrem": 11, "TwoBody_BSMDecay": 13}
+    for ci, (material, mV) in enumerate(DARK_CASES):
+        d = DarkShower(REFDIR, material, 0.010, mV)
+        dump_dark_setup(d, material, mV)
+        # weight look-ups (GetBSMWeights)
+        E = np.geomspace(2e-3, 120.0, 60)
+        for pid, pr in ((11, "DarkBrem"), (-11, "DarkBrem"), (-11, "DarkAnn"), (22, "DarkComp"), (13, "DarkMuonBrem"), (11, "DarkAnn")):
+            out[f"{ci}/w/{pid}/{pr}"] = np.array([float(d.GetBSMWeights([pid, e], pr)) for e in E])
+        out[f"{ci}/w/E"] = E
+        pi0 = Particle([5.0, 0, 0, np.sqrt(25 - m_pi0 ** 2)], [0, 0, 0], {"PID": 111, "mass": m_pi0, "stability": "short-lived"})
+        out[f"{ci}/w/pi0"] = np.array([float(d.GetBSMWeights(pi0, "TwoBody_BSMDecay"))])
+        # whole dark pass on a stream-mode SM shower
+        for k, (pid, E0, seed) in enumerate(((11, 5.0, 201), (22, 8.0, 202), (-11, 2.0, 203), (13, 6.0, 204), (111, 6.0, 205))):
+            m = {11: m_electron, -11: m_electron, 22: 0.0, 13: m_muon, 111: m_pi0}[pid]
+            ids = {"PID": pid, "ID": 1, "mass": m}
+            if pid == 111:
+                ids["stability"] = "short-lived"
+            np.random.seed(seed)
+            random.seed(seed)
+            sm = d.generate_shower(Particle([E0, 0, 0, np.sqrt(E0 ** 2 - m ** 2)], [0, 0, 0], ids))
+            _, vs = d.generate_dark_shower(ExDir=list(sm))
+            pre = f"{ci}/sh{k}/"
+            out[pre + "case"] = np.array([pid, E0, seed, len(sm)])
+            out[pre + "p0"] = np.array([v.get_p0() for v in vs], dtype=float).reshape(-1, 4)
+            out[pre + "r0"] = np.array([v.get_r0() for v in vs], dtype=float).reshape(-1, 3)
+            out[pre + "weight"] = np.array([v.get_ids()["weight"] for v in vs], dtype=float)
+            out[pre + "mass"] = np.array([v.get_ids()["mass"] for v in vs], dtype=float)
+            out[pre + "process"] = np.array([proc_code[v.get_ids()["generation_process"]] for v in vs])
+            out[pre + "parent_ID_mod"] = np.array([v.get_ids()["parent_ID"] % (1 << 61) for v in vs], dtype=np.int64)
+            out[pre + "parent_PID"] = np.array([v.get_ids()["parent_PID"] for v in vs])
+            print("dark case", material, mV, pid, E0, "SM", len(sm), "V", len(vs))
+        out[f"{ci}/material"] = np.array(material)
+        out[f"{ci}/mV"] = np.array(mV)
+    out["n_cases"] = np.array(len(DARK_CASES))
+    np.savez_compressed(os.path.join(HERE, "dark.npz"), **out)
+
+
 if __name__ == "__main__":
     rng = np.random.default_rng(20261017)
     build_reference_dict_dir()
+    if "--dark-only" in sys.argv:
+        golden_dark(rng)
+        sys.exit(0)
     golden_integrands(rng)
     golden_kinematics(rng)
     golden_mcs(rng)
     golden_particle(rng)
     golden_nsigma()
     golden_showers()
+    golden_dark(rng)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
