@@ -149,6 +149,35 @@ int pb_upload_maps(pb_engine e, int process, const double* grid /*[host]*/, int 
 int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t seed, uint64_t first_shower_id,
                    int global_ms, pb_stack* stack, pb_counters* counters /*[host] out*/, void* stream);
 
+/* DarkShower constructor tables needed on the device (dark_shower.py:219-593), all [host]:
+ *   weights   _brem_elec_numerical_weight, _brem_positron_numerical_weight, _annihilation_numerical_weight,
+ *             _muon_brem_numerical_weight (dark_shower.py:447-452): linear, 0 outside
+ *   nsdark    _NSigmaDarkComp (dark_shower.py:306): log10 nodes, log-log interpolation, 1e-20 outside
+ *   drate     _d_rate_dict_{elec_brem, positron_brem, positron_ann, muon_brem} (dark_shower.py:590-593):
+ *             E[n] saved energies (ascending) and table[n][10][2] = (bin-centre energy, rate)
+ *   min_E     _minimum_calculable_dark_energy for DarkBrem, DarkAnn, DarkComp, DarkMuonBrem (dark_shower.py:236-245) */
+typedef struct pb_dark_tables {
+  const double* w_E[4];
+  const double* w_y[4];
+  int32_t w_n[4];
+  const double* nsdark_comp_lx;
+  const double* nsdark_comp_ly;
+  int32_t nsdark_comp_n;
+  int32_t pad;
+  const double* d_E[4];
+  const double* d_table[4];
+  int32_t d_n[4];
+  double min_E[4];
+} pb_dark_tables;
+int pb_upload_dark(pb_engine e, const pb_dark_tables* t);
+
+/* generate_dark_shower (dark_shower.py:806-849) over the first n_sm records of an SM stack (the output of
+ * pb_run_showers): for every record and every active process with a positive weight, one dark-vector record is
+ * appended to `dark` (pid 4900022, parent = SM slot, weight = wg * parent weight, r0 = parent's final position).
+ * active_mask: bit (1 << pb_process) for PB_DARKBREM, PB_DARKANN, PB_DARKCOMP, PB_DARKMUONBREM, PB_BSMDECAY. */
+int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32_t active_mask, pb_stack* dark,
+                pb_counters* counters /*[host] out*/, void* stream);
+
 /* Histogram / yield tallies over records [first, first+n) of a stack, ACCUMULATED into tally[PB_TALLY_SIZE] [dev]. */
 int pb_tally(pb_engine e, const pb_stack* stack, int64_t first, int64_t n, double* tally /*[dev]*/, void* stream);
 

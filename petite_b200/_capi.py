@@ -49,6 +49,12 @@ class pb_counters(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+class pb_dark_tables(C.Structure):
+    _fields_ = [("w_E", c_double_p * 4), ("w_y", c_double_p * 4), ("w_n", C.c_int32 * 4),
+                ("nsdark_comp_lx", c_double_p), ("nsdark_comp_ly", c_double_p), ("nsdark_comp_n", C.c_int32), ("pad", C.c_int32),
+                ("d_E", c_double_p * 4), ("d_table", c_double_p * 4), ("d_n", C.c_int32 * 4), ("min_E", C.c_double * 4)]
+
+
 class pb_profile(C.Structure):
     _fields_ = [("ms", C.c_double * 8), ("launches", C.c_int64 * 8), ("trials", C.c_int64 * 16), ("samples", C.c_int64 * 16)]
 
@@ -70,6 +76,9 @@ SIGNATURES = {
     "pb_upload_maps": (C.c_int, [pb_engine, C.c_int, c_double_p, C.c_int, C.c_int, c_int32_p, c_double_p, c_double_p, C.c_int]),
     "pb_run_showers": (C.c_int, [pb_engine, C.POINTER(pb_primaries), C.c_uint64, C.c_uint64, C.c_int,
                                  C.POINTER(pb_stack), C.POINTER(pb_counters), C.c_void_p]),
+    "pb_upload_dark": (C.c_int, [pb_engine, C.POINTER(pb_dark_tables)]),
+    "pb_run_dark": (C.c_int, [pb_engine, C.POINTER(pb_stack), C.c_int64, C.c_uint32, C.POINTER(pb_stack),
+                              C.POINTER(pb_counters), C.c_void_p]),
     "pb_tally": (C.c_int, [pb_engine, C.POINTER(pb_stack), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "pb_set_profiling": (C.c_int, [pb_engine, C.c_int]),
     "pb_get_profile": (C.c_int, [pb_engine, C.POINTER(pb_profile)]),

@@ -47,6 +47,23 @@ struct Tables {
   MapInfo map[N_SAMPLED];
 };
 
+struct DarkTables {
+  NSigmaTable w[4];          // brem_elec, brem_positron, annihilation, muon_brem
+  NSigmaTable nsdark_comp;   // log10 nodes
+  const double* dE[4];       // dRate/dE: saved energies ...
+  const double* dT[4];       // ... and [n][10][2] tables, same order as w
+  int dn[4];
+  double min_E[4];           // DarkBrem, DarkAnn, DarkComp, DarkMuonBrem
+};
+struct DarkCand {            // candidate dark emissions of one pb_run_dark call (capacity 2 x n_sm)
+  int* slot;                 // SM record
+  int* proc;
+  double* wg;                // GetBSMWeights value
+  double* pf;                // [4] parent four-momentum at the interaction point
+  int* ntr;
+  int* count;                // [1]
+};
+
 struct Stack {
   double* p0; double* r0w; double* pf; double* rf;
   uint2* key; int4* meta; int2* aux;
@@ -482,9 +499,19 @@ __device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, cons
 // round r and the lowest accepted trial wins - identical to the reference's sequential first-accept rule because
 // every trial's uniforms are a pure function of (particle key, trial index).  Groups pull the next sample of the
 // tile from a shared cursor as soon as they finish.
+// Where a sample's incoming energy / Philox key come from and where its trial count goes: the SM pass indexes the
+// wave's stack records directly, the dark pass goes through its candidate list.
+struct SampleIO {
+  const double* E4;        // incoming energy of entry i at E4[4*i]
+  const uint2* key;        // particle keys
+  const int* key_index;    // entry i uses key[key_index[i]] (nullptr: key[i])
+  int* ntr;                // trials used by entry i at ntr[i * ntr_stride]; -1 if the sampler gave up
+  int ntr_stride;
+};
+
 template <int G>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
-k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, long long begin) {
+k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, SampleIO io, Work W) {
   __shared__ __align__(128) double s_grid[GRID_SMEM_DOUBLES];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_tile, s_cursor;
@@ -515,8 +542,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
     phase ^= 1;
     const long long max_trials = M.max_trials;
     // group state
-    int cur = -1;          // wave-local particle index, -1 = need a new one, -2 = tile exhausted
-    long long slot = 0;
+    int cur = -1;          // entry index, -1 = need a new one, -2 = tile exhausted
     double E = 0.0; uint2 key = make_uint2(0, 0);
     uint32_t round = 0;
     for (;;) {
@@ -526,9 +552,8 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
         j = __shfl_sync(gmask, j, gbase);
         if (j < tcount) {
           cur = W.sorted[tstart + j];
-          slot = begin + cur;
-          E = S.pf[4 * slot];
-          key = S.key[slot];
+          E = io.E4[4 * (size_t)cur];
+          key = io.key[io.key_index ? io.key_index[cur] : cur];
           round = 0;
         } else cur = -2;
       }
@@ -552,7 +577,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
             double2* xo = reinterpret_cast<double2*>(W.xs + 4 * (size_t)cur);
             xo[0] = make_double2(x[0], x[1]); xo[1] = make_double2(x[2], x[3]);
             int ntr = (int)(round * G + sub + 1);
-            S.aux[slot].x = ntr;
+            io.ntr[(size_t)cur * io.ntr_stride] = ntr;
             c_trials += ntr; c_samples += 1;
           }
           cur = -1;
@@ -560,7 +585,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
           ++round;
           if ((long long)round * G >= max_trials) {      // "No Sample Found" (shower.py:460-461)
             if (sub == 0) {
-              S.meta[slot].z |= (PB_FLAG_NO_SAMPLE << 8);
+              io.ntr[(size_t)cur * io.ntr_stride] = -1;
               W.bucket[cur] = P_NONE * LU_MAX;
               c_trials += (unsigned long long)max_trials; c_fail += 1;
             }
@@ -606,6 +631,7 @@ k_emit(const __grid_constant__ Material M, Stack S, Work W, long long begin, int
     int i = W.sorted[j];
     int bucket = W.bucket[i];
     proc = bucket / LU_MAX;
+    if (proc == P_NONE && S.aux[begin + i].x < 0) S.meta[begin + i].z |= (PB_FLAG_NO_SAMPLE << 8);   // sampler gave up
     if (proc != P_NONE) {
       slot = begin + i;
       const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * slot);
@@ -698,6 +724,221 @@ __global__ void k_init_primaries(Stack S, Work W, const double* __restrict__ p, 
   const bool ch = is_charged(pid[i]) && !(flags[i] & PB_FLAG_SHORT_LIVED);
   unsigned long long old = atomicAdd(&W.tail[1], ch ? 1ull : (1ull << 32));
   if (ch) W.next_c[(int)(old & 0xffffffffu)] = (int)i; else W.next_n[(int)(old >> 32)] = (int)i;
+}
+
+
+// ------------------------------------------------------------------------------------------ dark pass
+// log-log table of dark_shower.py:31-46 (interpolate1d): 10 ** lin(log10 E), 1e-20 outside the grid
+__device__ __forceinline__ double loglog_eval(const NSigmaTable& T, double E) {
+  double lx = log10(E);
+  if (T.n < 2 || !(lx >= T.xmin && lx <= T.xmax)) return pow(10.0, -20.0);
+  return pow(10.0, nsigma_at(T, nsigma_locate(T, lx), lx));
+}
+
+// np.sum over 10 doubles (pairwise summation kernel: 8 accumulators, then the remainder)
+__device__ __forceinline__ double np_sum10(const double* a) {
+  double r = __dadd_rn(__dadd_rn(__dadd_rn(a[0], a[1]), __dadd_rn(a[2], a[3])), __dadd_rn(__dadd_rn(a[4], a[5]), __dadd_rn(a[6], a[7])));
+  r = __dadd_rn(r, a[8]);
+  return __dadd_rn(r, a[9]);
+}
+
+// GetBSMWeights (dark_shower.py:595-647) + the pre-sampling half of produce_bsm_particle (:721-768): interaction-energy
+// bin, MCS + energy loss down to it, threshold short-cuts -> candidate (SM slot, process, weight, four-momentum, bucket).
+__global__ void __launch_bounds__(128)
+k_dark_prepare(const __grid_constant__ Material M, const __grid_constant__ Tables T, const __grid_constant__ DarkTables D,
+               Stack S, Work W, DarkCand C, long long n, unsigned active) {
+  long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int nc = 0;
+  int c_proc[2]; double c_wg[2]; V4 c_pf[2]; int c_bucket[2];
+  if (s < n) {
+    int4 meta = S.meta[s];
+    int pid = meta.x;
+    const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
+    double2 a0 = p0p[0], a1 = p0p[1];
+    V4 p0{a0.x, a0.y, a1.x, a1.y};
+    double E0 = p0.E;
+    double mass = S.rf[4 * s + 3];
+    uint2 key = S.key[s];
+    const double pre = M.g_e * M.g_e / (4 * kPi * kAlpha);
+    int procs[2] = {-1, -1};
+    if (pid == 11) procs[0] = P_DARKBREM;
+    else if (pid == -11) { procs[0] = P_DARKBREM; procs[1] = P_DARKANN; }
+    else if (pid == 22) procs[0] = P_DARKCOMP;
+    else if (pid == 13 || pid == -13) procs[0] = P_DARKMUONBREM;
+    else if (pid == 111) procs[0] = P_BSMDECAY;
+    // the reference visits active_processes in list order; host code restores that order, here DarkBrem < DarkAnn
+    for (int k = 0; k < 2; ++k) {
+      int proc = procs[k];
+      if (proc < 0 || !((active >> proc) & 1u)) continue;
+      double wg = 0.0;
+      int wt = -1;                                                      // weight / drate table
+      if (proc == P_BSMDECAY) {
+        double r = M.mV / mass;
+        if (!(r >= 1.0)) { double q = 1.0 - r * r; wg = 2 * M.eps * M.eps * (q * q * q) * 0.98823; }
+      } else {
+        double thr = D.min_E[proc - P_DARKBREM];
+        if (E0 < thr) continue;
+        if (proc == P_DARKCOMP) {
+          if (E0 < M.min_calc[2]) continue;
+          double lE = log(E0);
+          wg = pre * loglog_eval(D.nsdark_comp, E0) / (nsigma_log(T.ns[P_PAIRPROD], lE, E0) + nsigma_log(T.ns[P_COMP], lE, E0));
+        } else {
+          wt = (proc == P_DARKBREM) ? (pid == 11 ? 0 : 1) : (proc == P_DARKANN ? 2 : 3);
+          wg = pre * nsigma_eval(D.w[wt], E0);
+        }
+      }
+      if (!(wg > 0.0)) continue;
+      const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * s);
+      double2 f0 = pfp[0], f1 = pfp[1];
+      V4 pf{f0.x, f0.y, f1.x, f1.y};
+      int bucket;
+      if (proc == P_BSMDECAY) {
+        bucket = P_BSMDECAY * LU_MAX;
+      } else {
+        if (wt >= 0) {                                                  // dark_shower.py:738-759
+          const double* Es = D.dE[wt];
+          int nE = D.dn[wt];
+          int ie;
+          if (E0 < __ldg(Es)) ie = 0;
+          else if (E0 > __ldg(Es + nE - 1)) ie = nE - 1;
+          else { int lo = 0, hi = nE; while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(Es + mid) <= E0) lo = mid + 1; else hi = mid; } ie = lo - 1; }
+          double Ei = __ldg(Es + ie);
+          const double* tab = D.dT[wt] + (size_t)ie * 20;
+          double rate[10];
+          for (int b = 0; b < 10; ++b) rate[b] = __ldg(tab + 2 * b + 1);
+          double tot = np_sum10(rate);
+          if (tot == 0.0) continue;                                     // "return None"
+          for (int b = 0; b < 10; ++b) rate[b] = rate[b] / tot;
+          double norm = np_sum10(rate);
+          double cdf[10], acc = 0.0;
+          for (int b = 0; b < 10; ++b) { acc = __dadd_rn(acc, rate[b] / norm); cdf[b] = acc; }
+          double u = draw2(key, 0, ST_DBIN, 0, proc).a;
+          int pick = 9;
+          for (int b = 9; b >= 0; --b) if (u < cdf[b] / acc) pick = b;
+          double E_int = __ldg(tab + 2 * pick) + (E0 - Ei);
+          double dist = (E0 - E_int) / M.dEdx;
+          pf = p0;
+          double pn = norm3_nofma(pf.x, pf.y, pf.z);
+          if (pn > 0) {                                                 // SURVEY Q-12: default (electron) m_lepton
+            McsDraw d = mcs_draw(key, MCS_FINAL_INDEX, proc);
+            pf = mcs_scatter(M, pf, pn, M.rho * (dist / kCmToM), kMe, mass, d);
+          }
+          pf = lose_energy(pf, mass, E0 - E_int);
+        }
+        double E = pf.E;
+        if ((proc == P_DARKANN && E <= M.E_res_ann) || (proc == P_DARKCOMP && E <= M.E_thr_comp)) bucket = P_BSMDECAY * LU_MAX + 1;
+        else bucket = proc * LU_MAX + lookup_row(T.map[proc], log(E), E);
+      }
+      c_proc[nc] = proc; c_wg[nc] = wg; c_pf[nc] = pf; c_bucket[nc] = bucket;
+      ++nc;
+    }
+  }
+  int incl = nc;
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  int total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = 0;
+  if (lane == 31 && total > 0) base = atomicAdd(C.count, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  for (int k = 0; k < nc; ++k) {
+    int i = base + (incl - nc) + k;
+    C.slot[i] = (int)s; C.proc[i] = c_proc[k]; C.wg[i] = c_wg[k]; C.ntr[i] = 0;
+    double2* o = reinterpret_cast<double2*>(C.pf + 4 * (size_t)i);
+    o[0] = make_double2(c_pf[k].E, c_pf[k].x); o[1] = make_double2(c_pf[k].y, c_pf[k].z);
+    W.bucket[i] = c_bucket[k];
+    atomicAdd(&W.hist[c_bucket[k]], 1);
+  }
+}
+
+// Second half of produce_bsm_particle (dark_shower.py:761-804) and the TwoBody_BSMDecay branch (:836-844): dark-vector
+// four-momentum in the parent frame, rotation to the lab, record appended to the dark stack.
+__global__ void __launch_bounds__(128)
+k_dark_emit(const __grid_constant__ Material M, Stack S, Stack O, Work W, DarkCand C, int n_cand) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool keep = false;
+  V4 v{0, 0, 0, 0};
+  double wgt = 0.0, rx = 0, ry = 0, rz = 0;
+  int slot = 0, proc = P_NONE, ntr = 0;
+  int4 meta = make_int4(0, 0, 0, 0);
+  uint2 key = make_uint2(0, 0);
+  if (j < n_cand) {
+    int i = W.sorted[j];
+    int bucket = W.bucket[i];
+    if (bucket / LU_MAX != P_NONE) {
+      slot = C.slot[i]; proc = C.proc[i]; ntr = C.ntr[i];
+      double wg = C.wg[i];
+      const double2* pfp = reinterpret_cast<const double2*>(C.pf + 4 * (size_t)i);
+      double2 f0 = pfp[0], f1 = pfp[1];
+      V4 pf{f0.x, f0.y, f1.x, f1.y};
+      const double2* rfp = reinterpret_cast<const double2*>(S.rf + 4 * (size_t)slot);
+      double2 b0 = rfp[0], b1 = rfp[1];
+      rx = b0.x; ry = b0.y; rz = b1.x;
+      double mass = b1.y;
+      meta = S.meta[slot];
+      key = S.key[slot];
+      double w0 = S.r0w[4 * (size_t)slot + 3];
+      const double mV = M.mV, me = kMe;
+      double E = pf.E;
+      if (proc == P_BSMDECAY) {
+        D2 u = draw2(key, 0, ST_DECAY, 0, P_BSMDECAY);
+        V4 g;
+        two_body_decay(pf, mass, 0.0, mV, u.a, u.b, &g, &v);
+      } else {
+        if (bucket == P_BSMDECAY * LU_MAX + 1) {
+          if (proc == P_DARKANN) v = V4{sqrt(E * E - me * me + mV * mV), 0.0, 0.0, sqrt(E * E - me * me)};
+          else v = V4{sqrt(E * E + mV * mV), 0.0, 0.0, E};
+        } else {
+          const double2* xp = reinterpret_cast<const double2*>(W.xs + 4 * (size_t)i);
+          double2 x01 = xp[0], x23 = xp[1];
+          double x[4] = {x01.x, x01.y, x23.x, x23.y};
+          if (proc == P_DARKCOMP) {                                      // bound electron (dark_shower.py:774-784)
+            double c = electron_wave_function(M.Zeff, kAlpha * M.Zeff * me / sqrt(3.0));
+            double pe = 0.0;
+            for (uint32_t it = 0;; ++it) {                               // draw_pe_sample (dark_shower.py:710-719)
+              D2 u = draw2(key, it, ST_PE, 0, proc);
+              pe = 1e-3 * u.a;
+              if (u.b < electron_wave_function(M.Zeff, pe) / c) break;
+            }
+            double c0 = -1.0 + 2.0 * draw2(key, 0, ST_C0, 0, proc).a;
+            double ss = me * me + 2 * E * (sqrt(me * me + pe * pe) - c0 * pe);
+            double Ee = (ss - mV * mV + me * me) / (2 * sqrt(ss));
+            if (Ee < me) { v = V4{mV, 0.0, 0.0, 0.0}; wg = 0.0; }
+            else { D2 u = draw2(key, 0, ST_KIN, 0, proc); v = kin_compton_bound_V(E, mV, x[0], pe, c0, u.a, u.b); }
+          } else if (proc == P_DARKANN) {
+            v = kin_darkann_V(E, mV, x[0]);
+          } else {
+            v = kin_darkbrem_V(E, mV, x, draw2(key, 0, ST_KIN, 0, proc).a);
+          }
+        }
+        Rot R = rotation_to(pf);
+        v = rotate(R, v);
+      }
+      wgt = wg * w0;
+      keep = true;
+    }
+  }
+  unsigned ball = __ballot_sync(0xffffffffu, keep);
+  int total = __popc(ball);
+  unsigned long long base = 0;
+  if (lane == 0 && total > 0) base = atomicAdd(&W.tail[0], (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (keep) {
+    long long dst = (long long)base + __popc(ball & ((1u << lane) - 1u));
+    if (dst >= O.capacity) { atomicAdd(&W.counters[CNT_OVERFLOW], 1ull); return; }
+    double2* p0p = reinterpret_cast<double2*>(O.p0 + 4 * dst);
+    double2* r0p = reinterpret_cast<double2*>(O.r0w + 4 * dst);
+    double2* pfp = reinterpret_cast<double2*>(O.pf + 4 * dst);
+    double2* rfp = reinterpret_cast<double2*>(O.rf + 4 * dst);
+    p0p[0] = make_double2(v.E, v.x); p0p[1] = make_double2(v.y, v.z);
+    pfp[0] = make_double2(v.E, v.x); pfp[1] = make_double2(v.y, v.z);
+    r0p[0] = make_double2(rx, ry);   r0p[1] = make_double2(rz, wgt);
+    rfp[0] = make_double2(rx, ry);   rfp[1] = make_double2(rz, M.mV);
+    O.key[dst] = child_key(key, 16u + (uint32_t)proc);
+    int gen = ((meta.z >> 16) & 0xffff) + 1;
+    O.meta[dst] = make_int4(4900022, slot, pack_info(gen, proc == P_BSMDECAY ? 1 : 0, 0, proc), meta.w);
+    O.aux[dst] = make_int2(ntr, 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ tallies
@@ -810,6 +1051,8 @@ struct pb_engine_s {
   void* work_blob = nullptr;
   void* fixed_blob = nullptr;    // hist/offsets/cursor/ctrl/tail/counters
   int* order_blob = nullptr; long long order_cap = 0;
+  DarkTables dark{}; bool dark_ready = false;
+  void* cand_blob = nullptr; long long cand_cap = 0; DarkCand cand{};
   double* prim_mass = nullptr; long long prim_cap = 0;
   void* prim_stage = nullptr; size_t prim_stage_bytes = 0;
   int n_sm = 148;
@@ -899,6 +1142,7 @@ extern "C" void pb_destroy(pb_engine e) {
   if (e->work_blob) cudaFree(e->work_blob);
   if (e->fixed_blob) cudaFree(e->fixed_blob);
   if (e->order_blob) cudaFree(e->order_blob);
+  if (e->cand_blob) cudaFree(e->cand_blob);
   if (e->prim_mass) cudaFree(e->prim_mass);
   if (e->prim_stage) cudaFree(e->prim_stage);
   for (int i = 0; i < 2 * 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -947,6 +1191,17 @@ extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int 
   mi.inv_dlog = (nE > 1 && E_inc[0] > 0 && E_inc[nE - 1] > E_inc[0]) ? (double)(nE - 1) / log(E_inc[nE - 1] / E_inc[0]) : 0.0;
   e->tab.map[process] = mi;
   return PB_OK;
+}
+
+static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream) {
+  switch (e->sample_group) {
+    case 1: k_sample<1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    case 2: k_sample<2><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    case 4: k_sample<4><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    case 16: k_sample<16><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    case 32: k_sample<32><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    default: k_sample<8><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+  }
 }
 
 // order lists (current + next wave) live apart from the other scratch: growing them must keep the current lists
@@ -1089,14 +1344,8 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, (int)n);
     tock(PB_K_FILL); tick(PB_K_SAMPLE);
     int sg = (int)std::min<long long>(sample_grid, (n + 31) / 32 + 1);
-    switch (e->sample_group) {
-      case 1: k_sample<1><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
-      case 2: k_sample<2><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
-      case 4: k_sample<4><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
-      case 16: k_sample<16><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
-      case 32: k_sample<32><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
-      default: k_sample<8><<<sg, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, S, e->work, begin); break;
-    }
+    SampleIO io{S.pf + 4 * begin, S.key + begin, nullptr, reinterpret_cast<int*>(S.aux + begin), 2};
+    launch_sample(e, sg, io, stream);
     tock(PB_K_SAMPLE); tick(PB_K_EMIT);
     k_emit<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, S, e->work, begin, (int)n);
     tock(PB_K_EMIT);
@@ -1123,6 +1372,128 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
   for (int p = 0; p < 16; ++p) { e->prof.trials[p] = (int64_t)cnt[CNT_PROC_TRIALS + p]; e->prof.samples[p] = (int64_t)cnt[CNT_PROC_SAMPLES + p]; }
   if (cnt[CNT_OVERFLOW]) { e->err = "particle stack overflow"; return PB_ERR_CAPACITY; }
   if (cnt[CNT_NOSAMPLE]) { e->err = "No Sample Found for " + std::to_string(cnt[CNT_NOSAMPLE]) + " particle(s)"; return PB_ERR_NO_SAMPLE; }
+  return PB_OK;
+}
+
+static int upload_table(pb_engine e, const double* x, const double* y, int n, NSigmaTable* out) {
+  std::vector<double> node(4 * (size_t)std::max(n, 1), 0.0);
+  for (int i = 0; i < n; ++i) {
+    node[4 * i] = x[i]; node[4 * i + 1] = y[i];
+    node[4 * i + 2] = (i + 1 < n) ? (y[i + 1] - y[i]) / (x[i + 1] - x[i]) : 0.0;
+  }
+  double* d = nullptr;
+  PB_CUDA(e, cudaMalloc(&d, sizeof(double) * node.size()));
+  e->owned.push_back(d);
+  PB_CUDA(e, cudaMemcpy(d, node.data(), sizeof(double) * node.size(), cudaMemcpyHostToDevice));
+  *out = NSigmaTable{(const double4*)d, n ? x[0] : 0.0, n ? x[n - 1] : 0.0, 0.0, 0.0, n, 0};
+  return PB_OK;
+}
+
+extern "C" int pb_upload_dark(pb_engine e, const pb_dark_tables* t) {
+  if (!e || !t) return PB_ERR_ARG;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  for (int k = 0; k < 4; ++k) {
+    int rc = upload_table(e, t->w_E[k], t->w_y[k], t->w_n[k], &e->dark.w[k]);
+    if (rc != PB_OK) return rc;
+    int n = t->d_n[k];
+    double* d = nullptr;
+    PB_CUDA(e, cudaMalloc(&d, sizeof(double) * (size_t)std::max(n, 1) * 21));
+    e->owned.push_back(d);
+    PB_CUDA(e, cudaMemcpy(d, t->d_E[k], sizeof(double) * n, cudaMemcpyHostToDevice));
+    PB_CUDA(e, cudaMemcpy(d + n, t->d_table[k], sizeof(double) * (size_t)n * 20, cudaMemcpyHostToDevice));
+    e->dark.dE[k] = d; e->dark.dT[k] = d + n; e->dark.dn[k] = n;
+    e->dark.min_E[k] = t->min_E[k];
+  }
+  int rc = upload_table(e, t->nsdark_comp_lx, t->nsdark_comp_ly, t->nsdark_comp_n, &e->dark.nsdark_comp);
+  if (rc != PB_OK) return rc;
+  e->dark_ready = true;
+  return PB_OK;
+}
+
+extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32_t active, pb_stack* dk, pb_counters* out,
+                           void* stream_) {
+  if (!e || !sm || !dk || n_sm < 0 || n_sm > sm->capacity) return PB_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  if (!e->dark_ready) { e->err = "dark tables not uploaded"; return PB_ERR_STATE; }
+  for (int p = P_DARKBREM; p <= P_DARKMUONBREM; ++p)
+    if (((active >> p) & 1u) && e->tab.map[p].grid == nullptr) { e->err = "dark maps not uploaded for an active process"; return PB_ERR_STATE; }
+  if (2 * n_sm > 0x7fffffffLL) { e->err = "too many SM records for one dark pass"; return PB_ERR_CAPACITY; }
+  int B = 300;
+  for (int p = P_DARKBREM; p <= P_DARKMUONBREM; ++p) if (e->tab.map[p].grid) { B = e->tab.map[p].B; break; }
+  e->mat.max_trials = (long long)std::min<double>((double)e->cfg.max_sweeps * (double)B, 4.0e9);
+  Stack S{sm->p0, sm->r0w, sm->pf, sm->rf, (uint2*)sm->key, (int4*)sm->meta, (int2*)sm->aux, sm->capacity};
+  Stack O{dk->p0, dk->r0w, dk->pf, dk->rf, (uint2*)dk->key, (int4*)dk->meta, (int2*)dk->aux, dk->capacity};
+  long long ncap = std::max<long long>(2 * n_sm, 1);
+  int rc = ensure_work(e, ncap);
+  if (rc != PB_OK) return rc;
+  if (ncap > e->cand_cap) {
+    if (e->cand_blob) cudaFree(e->cand_blob);
+    long long cap = ncap * 5 / 4 + 1024;
+    PB_CUDA(e, cudaMalloc(&e->cand_blob, (size_t)cap * (4 + 4 + 8 + 32 + 4) + 64));
+    char* p = (char*)e->cand_blob;
+    e->cand.pf = (double*)p; p += (size_t)cap * 32;
+    e->cand.wg = (double*)p; p += (size_t)cap * 8;
+    e->cand.slot = (int*)p; p += (size_t)cap * 4;
+    e->cand.proc = (int*)p; p += (size_t)cap * 4;
+    e->cand.ntr = (int*)p; p += (size_t)cap * 4;
+    e->cand.count = (int*)p;
+    e->cand_cap = cap;
+  }
+  const bool prof = e->profiling;
+  memset(&e->prof, 0, sizeof(e->prof));
+  bool recorded[8] = {false, false, false, false, false, false, false, false};
+  auto tick = [&](int k) { if (prof) { cudaEventRecord(e->ev[2 * k], stream); recorded[k] = true; } };
+  auto tock = [&](int k) { if (prof) cudaEventRecord(e->ev[2 * k + 1], stream); ++e->prof.launches[k]; };
+  unsigned long long tail0[2] = {0ull, 0ull};
+  PB_CUDA(e, cudaMemcpyAsync(e->work.tail, tail0, sizeof(tail0), cudaMemcpyHostToDevice, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.counters, 0, sizeof(unsigned long long) * CNT_N, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.hist, 0, sizeof(int) * NBUCKET, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.ctrl, 0, sizeof(int) * 8, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->cand.count, 0, sizeof(int), stream));
+  long long launches = 0;
+  int n_cand = 0;
+  if (n_sm > 0) {
+    tick(PB_K_FINALIZE);
+    k_dark_prepare<<<(unsigned)((n_sm + 127) / 128), 128, 0, stream>>>(e->mat, e->tab, e->dark, S, e->work, e->cand, n_sm, active);
+    tock(PB_K_FINALIZE);
+    PB_CUDA(e, cudaMemcpyAsync(&n_cand, e->cand.count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(e, cudaStreamSynchronize(stream));
+    ++launches;
+  }
+  if (n_cand > 0) {
+    if (n_cand > dk->capacity) { e->err = "dark stack capacity exhausted"; return PB_ERR_CAPACITY; }
+    tick(PB_K_SCAN);
+    k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
+    tock(PB_K_SCAN); tick(PB_K_FILL);
+    k_bucket_fill<<<(unsigned)((n_cand + 255) / 256), 256, 0, stream>>>(e->work, n_cand);
+    tock(PB_K_FILL); tick(PB_K_SAMPLE);
+    int sg = (int)std::min<long long>((long long)e->n_sm * 4, (n_cand + 31) / 32 + 1);
+    SampleIO io{e->cand.pf, S.key, e->cand.slot, e->cand.ntr, 1};
+    launch_sample(e, sg, io, stream);
+    tock(PB_K_SAMPLE); tick(PB_K_EMIT);
+    k_dark_emit<<<(unsigned)((n_cand + 127) / 128), 128, 0, stream>>>(e->mat, S, O, e->work, e->cand, n_cand);
+    tock(PB_K_EMIT);
+    launches += 4;
+  }
+  unsigned long long tl[2] = {0, 0};
+  unsigned long long cnt[CNT_N];
+  PB_CUDA(e, cudaMemcpyAsync(tl, e->work.tail, sizeof(tl), cudaMemcpyDeviceToHost, stream));
+  PB_CUDA(e, cudaMemcpyAsync(cnt, e->work.counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+  PB_CUDA(e, cudaStreamSynchronize(stream));
+  for (int k = 0; k < PB_K_N; ++k) {
+    if (!recorded[k]) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]) == cudaSuccess) e->prof.ms[k] += ms;
+  }
+  for (int p = 0; p < 16; ++p) { e->prof.trials[p] = (int64_t)cnt[CNT_PROC_TRIALS + p]; e->prof.samples[p] = (int64_t)cnt[CNT_PROC_SAMPLES + p]; }
+  if (out) {
+    memset(out, 0, sizeof(*out));
+    out->n_particles = (int64_t)std::min<unsigned long long>(tl[0], (unsigned long long)dk->capacity);
+    out->n_steps = n_cand; out->n_samples = (int64_t)cnt[CNT_SAMPLES]; out->n_trials = (int64_t)cnt[CNT_TRIALS];
+    out->n_no_sample = (int64_t)cnt[CNT_NOSAMPLE]; out->n_launches = launches; out->max_wave = n_cand; out->n_waves = 1;
+  }
+  if (cnt[CNT_OVERFLOW]) { e->err = "dark stack overflow"; return PB_ERR_CAPACITY; }
   return PB_OK;
 }
 

@@ -546,6 +546,65 @@ __device__ __forceinline__ void kin_mue(double Einc, double ct, double u_az, V4*
   *b = V4{g0 * Ee0 - b0 * g0 * pe * ct, -pe * st * sp, -pe * st * cp, b0 * g0 * Ee0 - g0 * pe * ct};
 }
 
+// kinematics.py:43-68 (l_to_lV_fourvecs): only the dark vector is used downstream
+__device__ __forceinline__ V4 kin_darkbrem_V(double ep, double mV, const double* x, double u_az) {
+  double w = x[0] * ep;
+  double ct = 1 - pow(10.0, x[1]);
+  double k = sqrt(w * w - mV * mV);
+  double sal, cal;
+  sincos(u_az * kTwoPi, &sal, &cal);
+  double st = sqrt(1.0 - ct * ct);
+  return V4{w, k * cal * st, k * sal * st, k * ct};
+}
+
+// kinematics.py:267-299 (radiative_return_fourvecs) with radiative_return.py:18-24 (boost): collinear ISR, no azimuth
+__device__ __forceinline__ V4 kin_darkann_V(double Ee, double mV, double u0) {
+  const double me = kMe;
+  double s = 2.0 * me * (me + Ee);
+  double beta = kf_beta(s);
+  double umax = pow(1.0 - mV * mV / s, beta / 2.0);
+  double x1 = 1.0 - pow(u0 * umax, 2.0 / beta);
+  double x2 = mV * mV / (x1 * s);
+  double rs = sqrt(s);
+  double E1 = x1 * rs / 2.0, E2 = x2 * rs / 2.0;
+  double v0 = E1 + E2, v3 = E1 - E2;                       // pV = p1 + p2 in the CM frame
+  double p0 = rs / 2.0, p3 = -sqrt(s / 4.0 - me * me);     // CM four-momentum of the target electron
+  double rsq = sqrt(p0 * p0 - p3 * p3);
+  double b0 = (p0 * v0 - p3 * v3) / rsq;
+  double c1 = (v0 + b0) / (rsq + p0);
+  return V4{b0, 0.0, 0.0, v3 - c1 * p3};
+}
+
+// dark_shower.py:706-708 (electron_wave_function): hydrogenic |psi(p)|^2 p^2
+__device__ __forceinline__ double electron_wave_function(double Zeff, double pe) {
+  double lam = kAlpha * Zeff * kMe;
+  double lam2 = lam * lam, d = pe * pe + lam2, d2 = d * d;
+  return 32 / kPi * (lam2 * lam2 * lam) * pe * pe / (d2 * d2);
+}
+
+// kinematics.py:134-183 (compton_fourvecs_boundelectron): only the dark vector is returned
+__device__ __forceinline__ V4 kin_compton_bound_V(double Eg, double mV, double ct, double Pe, double cte, double u1, double u2) {
+  const double me = kMe;
+  double s = me * me + 2 * Eg * (sqrt(me * me + Pe * Pe) - cte * Pe);
+  double rs = sqrt(s);
+  double Ee = (s - mV * mV + me * me) / (2 * rs);
+  double EV = (s + mV * mV - me * me) / (2 * rs);
+  double pF = sqrt(Ee * Ee - me * me);
+  double bnum = sqrt(Eg * Eg + 2 * cte * Eg * Pe + Pe * Pe);
+  double bden = Eg + sqrt(me * me + Pe * Pe);
+  double b0 = bnum / bden;
+  double g0 = 1.0 / sqrt(1.0 - b0 * b0);
+  double sp, cp, se, ce;
+  sincos(u1 * kTwoPi, &sp, &cp);
+  double st = sqrt(1 - ct * ct);
+  double EVLab = g0 * EV - b0 * g0 * pF * ct;
+  double vx = pF * st * sp, vy = pF * st * cp, vz = b0 * g0 * EV - g0 * pF * ct;
+  double ctz = (Eg + cte * Pe) / bnum;
+  double stz = sqrt(1.0 - ctz * ctz);
+  sincos(u2 * kTwoPi, &se, &ce);
+  return V4{EVLab, ctz * ce * vx - se * vy + stz * ce * vz, ctz * se * vx + ce * vy + stz * se * vz, -stz * vx + ctz * vz};
+}
+
 // particle.py:187-256 (boost_matrix, two_body_decay, isotropic)
 __device__ __forceinline__ void two_body_decay(V4 pf, double mX, double m1, double m2, double u_cos, double u_phi, V4* a, V4* b) {
   double E1 = (mX * mX - m2 * m2 + m1 * m1) / (2 * mX);
