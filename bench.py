@@ -178,6 +178,7 @@ def ours(args):
     from petite_b200.shower import Shower
     from petite_b200 import roofline as rl
     from petite_b200 import _capi as capi
+    from petite_b200.distributed import shard
 
     dev = torch.device("cuda", local_rank)
     sh = Shower(DATA, MATERIAL, EMIN, seed=SEED, device=local_rank)
@@ -205,7 +206,7 @@ def ours(args):
     capacity = int(n * per * 1.06 + 2.3 * cal.counters["max_wave"] / ncal * n) + (1 << 16)
     sh._ensure_stack(capacity)
     tally = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=dev)
-    base_id = rank * n
+    base_id, _ = shard(world * n, rank, world)          # weak scaling: rank r steps global showers [r*n, (r+1)*n)
 
     def step(first_id, arrays):
         b = sh.run_arrays(*arrays, capacity=capacity, first_shower_id=first_id)
