@@ -179,11 +179,25 @@ __device__ __forceinline__ int lookup_row(const MapInfo& m, double logE, double 
 // One dE/dx + multiple-scattering sub-step state of a charged track (shower.py:559-581)
 struct Track {
   V4 p; double rx, ry, rz;
-  double mass, ml, pmin, delta_z;
+  double mass, Kp, pmin, delta_z, pn;
   uint2 key;
   int tb[3], hint[3];
   int it;          // loop iterations done == accepted sub-steps while the loop is alive
 };
+
+// Track set-up computed where the particle is created (k_emit / k_init_primaries, all lanes busy) instead of at refill
+// time inside k_loop (3 of 32 lanes busy): |p| and the three table hints, parked in the record's not-yet-used rf slot.
+__device__ __forceinline__ void store_track_setup(const Tables& T, Stack& S, long long slot, int pid, double E, double px,
+                                                  double py, double pz) {
+  int tb[3];
+  species_tables(pid, tb);
+  double logE = log(E);
+  int h[3];
+  for (int k = 0; k < 3; ++k) h[k] = (tb[k] >= 0) ? nsigma_locate_log(T.ns[tb[k]], logE, E) : 1;
+  double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * slot);
+  rfp[0] = make_double2(norm3_nofma(px, py, pz), __hiloint2double(h[1], h[0]));
+  rfp[1] = make_double2(__hiloint2double(0, h[2]), 0.0);
+}
 
 // Sub-step loop of propagate_particle, charged species only.  Persistent warps pull chunks of the wave's charged
 // list; a lane that finishes its track (hard scatter drawn, or energy below threshold) stores it and immediately
@@ -225,11 +239,13 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
         t.key = S.key[s];
         int pid = meta.x;
         t.mass = (meta.y < 0) ? prim_mass[s] : pid_mass(pid);
-        t.ml = pid_mass(pid);
+        t.Kp = 1e3 * pid_mass(pid) / t.mass;
         t.pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), t.mass);   // shower.py:532-533
         species_tables(pid, t.tb);
-        double logE = log(t.p.E);
-        for (int k = 0; k < 3; ++k) t.hint[k] = (t.tb[k] >= 0) ? nsigma_locate_log(T.ns[t.tb[k]], logE, t.p.E) : 1;
+        const double2* sup = reinterpret_cast<const double2*>(S.rf + 4 * s);     // store_track_setup
+        double2 s0 = sup[0], s1 = sup[1];
+        t.pn = s0.x;
+        t.hint[0] = __double2loint(s0.y); t.hint[1] = __double2hiint(s0.y); t.hint[2] = __double2loint(s1.x);
         t.delta_z = 0.0; t.it = 0;
       }
       next += min(__popc(need), avail);
@@ -248,15 +264,24 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
         t.delta_z = mfp / (6.0 + 14.0 * u.b);
         if (u.a > exp(-t.delta_z / mfp)) done = true;                    // hard scatter (shower.py:564)
         else {
-          t.p = lose_energy(t.p, t.mass, M.dEdx * t.delta_z);
-          double pn = norm3_nofma(t.p.x, t.p.y, t.p.z);
-          if (pn > 0.0) {
-            double s = t.delta_z / pn;
+          // lose_energy (particle.py:143-153) with |p| carried along the track instead of recomputed
+          double Eu = t.p.E - M.dEdx * t.delta_z;
+          if (Eu <= t.mass) Eu = t.mass;
+          double p3f = sqrt(__dsub_rn(__dmul_rn(Eu, Eu), __dmul_rn(t.mass, t.mass)));
+          if (p3f > 0.0) {
+            double r = p3f / t.pn;
+            t.p = V4{Eu, t.p.x * r, t.p.y * r, t.p.z * r};
+            t.pn = p3f;
+            double inv = 1.0 / p3f;
+            double s = t.delta_z * inv;
             t.rx += t.p.x * s; t.ry += t.p.y * s; t.rz += t.p.z * s;
             if (ms_e) {
               McsDraw d = mcs_draw(t.key, (uint32_t)t.it, 0);
-              t.p = mcs_scatter(M, t.p, pn, M.rho * (t.delta_z / kCmToM), t.ml, t.mass, d);
+              t.p = mcs_fast(M, t.p, p3f, inv, M.rho * (t.delta_z * (1.0 / kCmToM)), t.Kp, d.sign, d.radial, d.uphi);
             }
+          } else {
+            t.p = V4{t.mass, 0.0, 0.0, 0.0};
+            t.pn = 0.0;
           }
           ++t.it; ++c_sub;
         }
@@ -472,7 +497,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // max_F * u < (jac / B) * f(x)  (shower.py:453-459).
 template <int DIM>
 __device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, const double* __restrict__ g, int proc,
-                                      double E, double maxF, uint2 key, uint32_t t, double* x) {
+                                      double E, const SampleConst& sc, double maxF, uint2 key, uint32_t t, double* x) {
   double D[DIM + 2];
 #pragma unroll
   for (int j = 0; j < (DIM + 2) / 2; ++j) {
@@ -491,7 +516,13 @@ __device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, cons
     x[d] = __dadd_rn(g0, __dmul_rn(inc, yn - iy));
     jac *= inc * ninc;
   }
-  double f = dsigma(M, proc, E, x);
+  double f;
+  if (DIM == 4) {
+    if (proc == P_PAIRPROD) f = ds_pairprod_fast(sc, E, x);
+    else f = ds_brem_fast(M, sc, E, proc == P_BREM ? kMe : kMmu, x);
+  } else {
+    f = dsigma(M, proc, E, x);
+  }
   return maxF * D[DIM] < (jac / mi.B) * f;
 }
 
@@ -544,6 +575,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
     // group state
     int cur = -1;          // entry index, -1 = need a new one, -2 = tile exhausted
     double E = 0.0; uint2 key = make_uint2(0, 0);
+    SampleConst sc{0, 0, 0, 0, 0};
     uint32_t round = 0;
     for (;;) {
       if (cur == -1) {
@@ -555,6 +587,9 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
           E = io.E4[4 * (size_t)cur];
           key = io.key[io.key_index ? io.key_index[cur] : cur];
           round = 0;
+          if (proc == P_PAIRPROD) sc = pairprod_const(M, E);
+          else if (proc == P_BREM) sc = brem_const(M, E, kMe);
+          else if (proc == P_MUONBREM) sc = brem_const(M, E, kMmu);
         } else cur = -2;
       }
       if (__all_sync(0xffffffffu, cur == -2)) break;
@@ -563,9 +598,9 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
       uint32_t t = round * G + sub;
       if (cur >= 0 && (long long)t < max_trials) {
         switch (mi.dim) {
-          case 4: acc = trial<4>(M, mi, s_grid, proc, E, maxF, key, t, x); break;
-          case 3: acc = trial<3>(M, mi, s_grid, proc, E, maxF, key, t, x); break;
-          default: acc = trial<1>(M, mi, s_grid, proc, E, maxF, key, t, x); break;
+          case 4: acc = trial<4>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
+          case 3: acc = trial<3>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
+          default: acc = trial<1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
         }
       }
       unsigned ball = __ballot_sync(0xffffffffu, acc);
@@ -617,7 +652,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
 
 // Kinematics + rotation + daughter append, in bucket order (warps are process-coherent).
 __global__ void __launch_bounds__(128)
-k_emit(const __grid_constant__ Material M, Stack S, Work W, long long begin, int n) {
+k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, long long begin, int n) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   V4 da{0, 0, 0, 0}, db{0, 0, 0, 0};
@@ -704,14 +739,16 @@ k_emit(const __grid_constant__ Material M, Stack S, Work W, long long begin, int
       r0p[0] = make_double2(rx, ry);   r0p[1] = make_double2(rz, wgt);
       S.key[dst] = child_key(key, bit);
       S.meta[dst] = make_int4(bit ? pid_b : pid_a, (int)slot, pack_info(gen, bit, 0, proc), meta.w);
-      if (bit ? ch_b : ch_a) W.next_c[ci++] = (int)(dst - next_begin);
-      else W.next_n[ni++] = (int)(dst - next_begin);
+      if (bit ? ch_b : ch_a) {
+        W.next_c[ci++] = (int)(dst - next_begin);
+        store_track_setup(T, S, dst, bit ? pid_b : pid_a, d.E, d.x, d.y, d.z);
+      } else W.next_n[ni++] = (int)(dst - next_begin);
       ++dst;
     }
   }
 }
 
-__global__ void k_init_primaries(Stack S, Work W, const double* __restrict__ p, const double* __restrict__ r,
+__global__ void k_init_primaries(const __grid_constant__ Tables T, Stack S, Work W, const double* __restrict__ p, const double* __restrict__ r,
                                  const double* __restrict__ w, const int* __restrict__ pid, const int* __restrict__ flags,
                                  long long n, unsigned long long seed, unsigned long long first_id) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -723,7 +760,10 @@ __global__ void k_init_primaries(Stack S, Work W, const double* __restrict__ p, 
   S.meta[i] = make_int4(pid[i], -1, pack_info(0, 0, flags[i], P_INPUT), (int)i);
   const bool ch = is_charged(pid[i]) && !(flags[i] & PB_FLAG_SHORT_LIVED);
   unsigned long long old = atomicAdd(&W.tail[1], ch ? 1ull : (1ull << 32));
-  if (ch) W.next_c[(int)(old & 0xffffffffu)] = (int)i; else W.next_n[(int)(old >> 32)] = (int)i;
+  if (ch) {
+    W.next_c[(int)(old & 0xffffffffu)] = (int)i;
+    store_track_setup(T, S, i, pid[i], p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+  } else W.next_n[(int)(old >> 32)] = (int)i;
 }
 
 
@@ -992,7 +1032,13 @@ __global__ void k_probe(const __grid_constant__ Material M, const __grid_constan
   const double* a = in + i * is;
   double* o = out + i * os;
   switch (what) {
-    case PB_PROBE_DSIGMA: o[0] = dsigma(M, process, a[0], a + 1); break;
+    case PB_PROBE_DSIGMA:
+      if (process >= 32) {      // the folded forms used inside k_sample
+        int p = process - 32;
+        if (p == P_PAIRPROD) { SampleConst sc = pairprod_const(M, a[0]); o[0] = ds_pairprod_fast(sc, a[0], a + 1); }
+        else { double ml = (p == P_BREM) ? kMe : kMmu; SampleConst sc = brem_const(M, a[0], ml); o[0] = ds_brem_fast(M, sc, a[0], ml, a + 1); }
+      } else o[0] = dsigma(M, process, a[0], a + 1);
+      break;
     case PB_PROBE_NSIGMA: o[0] = nsigma_eval(T.ns[process], a[0]); break;
     case PB_PROBE_MAP: {
       const MapInfo& mi = T.map[process];
@@ -1092,6 +1138,9 @@ static void derive_material(pb_engine e) {
   m.dff_inel_pref = c.Z_T / (c1 * c1 * (c.Z_T * c.Z_T));
   m.dff_pref = (c.Z_T * c.Z_T) * (c1 * c1);
   m.Z23 = pow(c.Z_T, 2.0 / 3.0);
+  m.mcs_C4 = 0.157 * c.Z_T * (c.Z_T + 1) / c.A_T;
+  m.mcs_Cw = m.mcs_C4 / (2.007e-5 * m.Z23);
+  m.mcs_c3 = 3.34 * (c.Z_T * kAlpha) * (c.Z_T * kAlpha);
   m.me4 = pow(kMe, 4);
   m.mV4 = pow(c.mV, 4);
   m.mV = c.mV; m.g_e = c.g_e; m.eps = c.kinetic_mixing; m.Zeff = c.Zeff;
@@ -1300,7 +1349,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
   PB_CUDA(e, cudaMemcpyAsync(e->work.tail, tail0, sizeof(tail0), cudaMemcpyHostToDevice, stream));
   PB_CUDA(e, cudaMemsetAsync(e->work.ctrl, 0, sizeof(int) * 8, stream));
   tick(PB_K_INIT);
-  k_init_primaries<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(S, e->work, d_p, d_r, d_w, d_pid, d_fl, n0, seed, first_id);
+  k_init_primaries<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(e->tab, S, e->work, d_p, d_r, d_w, d_pid, d_fl, n0, seed, first_id);
   tock(PB_K_INIT);
   ++launches;
   unsigned long long lists0[2] = {0, 0};
@@ -1347,7 +1396,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     SampleIO io{S.pf + 4 * begin, S.key + begin, nullptr, reinterpret_cast<int*>(S.aux + begin), 2};
     launch_sample(e, sg, io, stream);
     tock(PB_K_SAMPLE); tick(PB_K_EMIT);
-    k_emit<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, S, e->work, begin, (int)n);
+    k_emit<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, e->tab, S, e->work, begin, (int)n);
     tock(PB_K_EMIT);
     launches += 5;
     unsigned long long tl[2] = {0, 0};

@@ -43,6 +43,7 @@ struct Material {
   double dff_pref;                // Z^2 c1^2
   double Z23;                     // Z^(2/3)   moliere.py:218
   double me4, mV4;                // m_e**4, mV**4 as CPython computes them (libm pow)
+  double mcs_C4, mcs_Cw, mcs_c3;  // Lynch-Dahl constants folded for mcs_fast
   long long max_trials;           // max_n_integrators * B
   // dark sector
   double mV, g_e, eps, Zeff, E_res_ann, E_thr_comp;
@@ -152,6 +153,79 @@ __device__ __forceinline__ double m_(double a, double b) { return __dmul_rn(a, b
 __device__ __forceinline__ double a_(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double s_(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double d_(double a, double b) { return __ddiv_rn(a, b); }
+
+// ---- folded forms of the two 4-D integrands for the sampling loop.  Same functions as ds_brem / ds_pairprod: the
+// energy-only factors are computed once per sample (SampleConst), q^4 is cancelled analytically between the
+// prefactor and the elastic form factor, and the ten divisions collapse to three.  Differences are re-association
+// only (~1e-15 relative); points outside the kinematic mask return 0 (the reference returns 0 or NaN there - both
+// are rejected by max_F*u < wgt*f).
+struct SampleConst { double a, b, c, d, e; };
+
+__device__ __forceinline__ SampleConst brem_const(const Material& M, double ep, double ml) {
+  SampleConst s;
+  s.a = ep - ml - M.Eg_min;                       // span
+  s.b = ep / (2 * ml);                            // k
+  s.c = 1.0 / ep;
+  double aem = kAlpha / ml;
+  double ml2 = ml * ml;
+  s.d = (8.0 / kPi * kAlpha * (aem * aem)) * (ml2 * ml2) * s.c * (kPi * ep * ep * s.a / ml2) * M.ff_Z2a04;
+  s.e = ml2;
+  return s;
+}
+__device__ __forceinline__ double ds_brem_fast(const Material& M, const SampleConst& s, double ep, double ml, const double* x) {
+  const double Egmin = M.Eg_min;
+  double w = Egmin + x[0] * s.a;
+  double d = s.b * (x[1] + x[2]);
+  double dp = s.b * (x[1] - x[2]);
+  double epp = ep - w;
+  bool ok = (Egmin < w) && (w < ep - ml) && (ml < epp) && (epp < ep) && (d > 0.0) && (dp > 0.0);
+  if (!ok) return 0.0;
+  double cph = cospi(2.0 * x[3] - 1.0);           // cos((x4 - 1/2) 2 pi)
+  double d2 = d * d, dp2 = dp * dp;
+  double od = 1 + d2, odp = 1 + dp2;
+  double iepp = 1.0 / epp;
+  double u = od * (0.5 * s.c) - odp * (0.5 * iepp);
+  double ddc = d * dp * cph;
+  double qsq = s.e * ((d2 + dp2 - 2 * ddc) + s.e * u * u);
+  double den = 1.0 + M.ff_a0sq * qsq;
+  double io = 1.0 / (od * odp);
+  double i1 = odp * io, i2 = od * io;             // 1/od, 1/odp
+  double T = d2 * (i1 * i1) + dp2 * (i2 * i2) + (w * w) * (0.5 * s.c * iepp) * (d2 + dp2) * io - (epp * s.c + ep * iepp) * ddc * io;
+  return s.d * (epp * d * dp) / (w * den * den) * T;
+}
+
+__device__ __forceinline__ SampleConst pairprod_const(const Material& M, double w) {
+  const double me = kMe, me2 = kMe * kMe;
+  SampleConst s;
+  s.a = w - 2 * me;
+  s.b = w / (2 * me);
+  double aem = kAlpha / me;
+  s.d = (8.0 / kPi * kAlpha * (aem * aem)) / (w * w * w) * (kPi * w * w * s.a / me2) * (M.ff_Z2a04 * (me2 * me2));
+  s.c = M.ff_a0sq * me2;
+  s.e = 0.0;
+  return s;
+}
+__device__ __forceinline__ double ds_pairprod_fast(const SampleConst& s, double w, const double* x) {
+  const double me = kMe, me2 = kMe * kMe;
+  double epp = me + x[0] * s.a;
+  double dp = s.b * (x[1] + x[2]);
+  double dm = s.b * (x[1] - x[2]);
+  double epm = w - epp;
+  bool ok = (me < epm) && (epm < w) && (me < epp) && (epp < w) && (dm > 0.0) && (dp > 0.0);
+  if (!ok) return 0.0;
+  double cph = cospi(2.0 * x[3]);
+  double dp2 = dp * dp, dm2 = dm * dm;
+  double op = 1.0 + dp2, om = 1.0 + dm2;
+  double ie = 1.0 / (epp * epm);
+  double u = op * (0.5 * epm * ie) + om * (0.5 * epp * ie);
+  double ddc = dp * dm * cph;
+  double q2r = (dp2 + dm2 + 2.0 * ddc) + me2 * u * u;
+  double den = 1.0 + s.c * q2r;
+  double io = 1.0 / (op * om);
+  double i1 = om * io, i2 = op * io;
+  double T = -dp2 * (i1 * i1) - dm2 * (i2 * i2) + (w * w) * (0.5 * ie) * (dp2 + dm2) * io + (epp * epp + epm * epm) * ie * ddc * io;
+  return s.d * (epp * epm * dp * dm) / (den * den) * T;
+}
 
 // all_processes.py:625-742 (dsigma_compton_dCT); mV > 0 is DarkComp.
 __device__ __forceinline__ double ds_compton(const Material& M, double Eg, double mV, double ct) {
@@ -402,6 +476,45 @@ __device__ __forceinline__ V4 mcs_apply(const Material& M, V4 p4, double pn, dou
   // R = Rb Ra = [[cb ca, -cb sa, sb], [sa, ca, 0], [-sb ca, sb sa, cb]] ; lab = R^T q
   V4 o;
   o.E = p4.E;
+  o.x = (cb * ca) * q0 + sa * q1 + (-sb * ca) * q2;
+  o.y = (-cb * sa) * q0 + ca * q1 + (sb * sa) * q2;
+  o.z = sb * q0 + cb * q2;
+  return o;
+}
+
+// Same physics as mcs_apply for the sub-step loop, with the algebra folded (2 divisions instead of 8):
+//   beta^2 = pn^2/E^2,  p_MeV = Kp pn (Kp = 1e3 m_lepton / mass),  1/(p_MeV beta) = E / (Kp pn^2)
+//   chic2 = C4 t / (p_MeV beta)^2,  omega = chic2/chia2 = Cw t / (beta^2 + c3),  v = omega / (2 (1-F))
+// inv_pn = 1/pn is supplied by the caller (it also advances the position with it).  Results differ from mcs_apply
+// by re-association only (~1e-15 relative).
+__device__ __forceinline__ V4 mcs_fast(const Material& M, V4 p4, double pn, double inv_pn, double t, double Kp,
+                                       double sign, double radial, double u_phi) {
+  const double F = 0.98;
+  double E = p4.E;
+  double e_ip = E * inv_pn * inv_pn;                    // E / pn^2
+  double ipb = e_ip / Kp;                               // 1 / (p_MeV beta)
+  double chic2 = M.mcs_C4 * t * (ipb * ipb);
+  double E2 = E * E;
+  double omega = M.mcs_Cw * t * E2 / (pn * pn + M.mcs_c3 * E2);
+  double v = omega * (0.5 / (1.0 - F));
+  double th0 = sqrt(chic2 * ((1.0 + v) * log(1.0 + v) / v - 1) * (1.0 / (1.0 + F * F)));
+  double theta = sign * (radial * th0) * M.rescale_mcs;
+  double vx = p4.x, vy = p4.y, vz = p4.z;
+  double ca, sa, vxp;
+  if (vx != 0.0 && vy != 0.0) { double pt2 = vx * vx + vy * vy; double r = rsqrt(pt2); ca = vx * r; sa = -vy * r; vxp = pt2 * r; }
+  else if (vy != 0.0) { ca = 0.0; sa = 1.0; vxp = -vy; }
+  else { ca = 1.0; sa = 0.0; vxp = vx; }
+  double cb, sb;
+  if (vz != 0.0 && vxp != 0.0) { cb = vz * inv_pn; sb = -vxp * inv_pn; }
+  else if (vxp > 0.0) { cb = 0.0; sb = -1.0; }
+  else if (vxp < 0.0) { cb = 0.0; sb = 1.0; }
+  else { cb = 1.0; sb = 0.0; }
+  double cth, sth, cph, sph;
+  sincos(theta, &sth, &cth);
+  sincospi(2.0 * u_phi, &sph, &cph);
+  double q0 = pn * (sph * sth), q1 = pn * (-cph * sth), q2 = pn * cth;
+  V4 o;
+  o.E = E;
   o.x = (cb * ca) * q0 + sa * q1 + (-sb * ca) * q2;
   o.y = (-cb * sa) * q0 + ca * q1 + (sb * sa) * q2;
   o.z = sb * q0 + cb * q2;
