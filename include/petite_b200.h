@@ -178,10 +178,22 @@ int pb_upload_dark(pb_engine e, const pb_dark_tables* t);
 int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32_t active_mask, pb_stack* dark,
                 pb_counters* counters /*[host] out*/, void* stream);
 
+/* draw_sample / draw_dark_sample (shower.py:401-465, dark_shower.py:649-704) for n independent incoming energies:
+ * sample i uses the Philox key (seed, first_id + i).  lu_key < 0 selects the map row as the reference does (Q-1).
+ * x_out [host] n x 4 (map variables, unused slots 0), ntrials_out [host] n (the VB counter; -1 = "No Sample Found"). */
+int pb_draw_samples(pb_engine e, int process, const double* E /*[host]*/, int64_t n, int lu_key, uint64_t seed,
+                    uint64_t first_id, double* x_out, int32_t* ntrials_out, void* stream);
+
+/* do_find_max_work (utilities/find_maxes.py:55-119) for every trained map row of one process with the engine's target
+ * (Z_T, A_T): n_trials sweeps of `neval` points, max_F = max over sweeps of max(wgt*f) (a sweep containing a NaN never
+ * raises it), sigma = sum(wgt*f)/n_trials.  mT > 0 overrides event_info['mT'] (the table builder uses the true
+ * nuclear mass, the sampler A_T: SURVEY Q-19).  max_F_out, sigma_out: [host] n_energy each. */
+int pb_find_max(pb_engine e, int process, int n_trials, uint64_t seed, double mT, double* max_F_out, double* sigma_out);
+
 /* Histogram / yield tallies over records [first, first+n) of a stack, ACCUMULATED into tally[PB_TALLY_SIZE] [dev]. */
 int pb_tally(pb_engine e, const pb_stack* stack, int64_t first, int64_t n, double* tally /*[dev]*/, void* stream);
 
-int pb_set_profiling(pb_engine e, int on);
+int pb_set_profiling(pb_engine e, int level);   /* 0 off; 1 = time k_loop and k_sample only; 2 = time every kernel */
 int pb_get_profile(pb_engine e, pb_profile* out /*[host]*/);
 
 /* FP64 FMA-chain microbenchmark on the engine's device: the measured FP64 roofline denominator (TFLOP/s). */

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpetite_b200.so")
+LIB_PATH = os.environ.get("PETITE_B200_LIB") or os.path.join(_HERE, "libpetite_b200.so")   # override: tuning builds only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -79,6 +79,9 @@ SIGNATURES = {
     "pb_upload_dark": (C.c_int, [pb_engine, C.POINTER(pb_dark_tables)]),
     "pb_run_dark": (C.c_int, [pb_engine, C.POINTER(pb_stack), C.c_int64, C.c_uint32, C.POINTER(pb_stack),
                               C.POINTER(pb_counters), C.c_void_p]),
+    "pb_draw_samples": (C.c_int, [pb_engine, C.c_int, c_double_p, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, c_double_p,
+                                  c_int32_p, C.c_void_p]),
+    "pb_find_max": (C.c_int, [pb_engine, C.c_int, C.c_int, C.c_uint64, C.c_double, c_double_p, c_double_p]),
     "pb_tally": (C.c_int, [pb_engine, C.POINTER(pb_stack), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "pb_set_profiling": (C.c_int, [pb_engine, C.c_int]),
     "pb_get_profile": (C.c_int, [pb_engine, C.POINTER(pb_profile)]),

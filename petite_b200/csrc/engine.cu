@@ -28,8 +28,20 @@ namespace pb {
 
 constexpr int LU_MAX = 256;                 // energy rows per process (100 in data/, 150 in data_400GeV/)
 constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
-constexpr int TILE = 256;                   // samples per tile
-constexpr int SAMPLE_THREADS = 128;
+#ifndef PB_TILE
+#define PB_TILE 256
+#endif
+#ifndef PB_SAMPLE_THREADS
+#define PB_SAMPLE_THREADS 128
+#endif
+#ifndef PB_SAMPLE_MINB
+#define PB_SAMPLE_MINB 4
+#endif
+#ifndef PB_LOOP_MINB
+#define PB_LOOP_MINB 6
+#endif
+constexpr int TILE = PB_TILE;               // samples per tile
+constexpr int SAMPLE_THREADS = PB_SAMPLE_THREADS;
 constexpr int GRID_SMEM_DOUBLES = 4096;     // >= padded stride of a 4-D map row (3964 -> 3968)
 
 struct NSigmaTable { const double4* node; double xmin, xmax; double log_x0, inv_dlog; int n; int pad; };   // node = (x, y, slope to next, 0)
@@ -204,7 +216,7 @@ __device__ __forceinline__ void store_track_setup(const Tables& T, Stack& S, lon
 // takes the next entry of the chunk, so the warp stays converged on the loop body whatever the per-track sub-step
 // count (geometric, mean ~7, tail > 50).  The final partial step and the process choice are done by k_finalize.
 constexpr int LOOP_CHUNK = 64;
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PB_LOOP_MINB)
 k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, long long begin,
        int n_charged, const double* __restrict__ prim_mass, int ms_e) {
   const int lane = threadIdx.x & 31;
@@ -541,7 +553,7 @@ struct SampleIO {
 };
 
 template <int G>
-__global__ void __launch_bounds__(SAMPLE_THREADS)
+__global__ void __launch_bounds__(SAMPLE_THREADS, PB_SAMPLE_MINB)
 k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, SampleIO io, Work W) {
   __shared__ __align__(128) double s_grid[GRID_SMEM_DOUBLES];
   __shared__ __align__(8) uint64_t s_bar;
@@ -981,6 +993,73 @@ k_dark_emit(const __grid_constant__ Material M, Stack S, Stack O, Work W, DarkCa
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ stand-alone sampling
+__global__ void __launch_bounds__(256)
+k_prepare_draws(const __grid_constant__ Tables T, Work W, DarkCand C, uint2* keys, const double* __restrict__ E, int n,
+                int process, int lu_key, unsigned long long seed, unsigned long long first_id) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double Ei = E[i];
+  C.pf[4 * (size_t)i] = Ei;
+  C.ntr[i] = 0;
+  keys[i] = root_key(seed, first_id + (unsigned long long)i);
+  const MapInfo& mi = T.map[process];
+  int lu = (lu_key < 0 || lu_key > mi.nE) ? lookup_row(mi, log(Ei), Ei) : min(lu_key, mi.nE - 1);
+  int bucket = process * LU_MAX + lu;
+  W.bucket[i] = bucket;
+  atomicAdd(&W.hist[bucket], 1);
+}
+
+// find_maxes: one CTA per map row, thread t owns sweep t (B points) - utilities/find_maxes.py:105-110
+__global__ void __launch_bounds__(128)
+k_find_max(const __grid_constant__ Material M, const __grid_constant__ Tables T, int process, int n_trials,
+           unsigned long long seed, double* __restrict__ out_max, double* __restrict__ out_sum) {
+  __shared__ __align__(128) double s_grid[GRID_SMEM_DOUBLES];
+  __shared__ double s_max[128], s_sum[128];
+  const MapInfo& mi = T.map[process];
+  int row = blockIdx.x;
+  const double* g = mi.grid + (size_t)row * mi.stride;
+  for (int k = threadIdx.x; k < mi.stride; k += blockDim.x) s_grid[k] = g[k];
+  __syncthreads();
+  double E = mi.E[row];
+  uint2 key = root_key(seed, ((unsigned long long)process << 32) | (unsigned long long)row);
+  double bmax_all = 0.0, sum_all = 0.0;
+  for (int sweep = threadIdx.x; sweep < n_trials; sweep += blockDim.x) {
+    double bmax = -1.0 / 0.0, bsum = 0.0;
+    bool has_nan = false;
+    for (int j = 0; j < mi.B; ++j) {
+      uint32_t t = (uint32_t)(sweep * mi.B + j);
+      double D[6];
+      for (int c = 0; c < (mi.dim + 2) / 2; ++c) { D2 d = draw2(key, t, ST_VEGAS, c, process); D[2 * c] = d.a; D[2 * c + 1] = d.b; }
+      double x[4] = {0, 0, 0, 0}, jac = 1.0;
+      for (int d = 0; d < mi.dim; ++d) {
+        int ninc = mi.ninc[d];
+        double yn = D[d] * ninc;
+        int iy = min((int)yn, ninc - 1);
+        double g0 = s_grid[mi.off[d] + iy], g1 = s_grid[mi.off[d] + iy + 1];
+        double inc = g1 - g0;
+        x[d] = __dadd_rn(g0, __dmul_rn(inc, yn - iy));
+        jac *= inc * ninc;
+      }
+      double mm = (jac / mi.B) * dsigma(M, process, E, x);
+      if (mm != mm) has_nan = true;
+      bmax = fmax(bmax, mm);
+      bsum += mm;
+    }
+    if (!has_nan && bmax > bmax_all) bmax_all = bmax;      // np.max of a sweep with a NaN is NaN and never wins
+    sum_all += bsum;
+  }
+  s_max[threadIdx.x] = bmax_all; s_sum[threadIdx.x] = sum_all;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0, s = 0.0;
+    for (int k = 0; k < blockDim.x; ++k) { m = fmax(m, s_max[k]); s += s_sum[k]; }
+    out_max[row] = m;
+    out_sum[row] = s / n_trials;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ tallies
 __device__ __forceinline__ int species_of(int pid) {
   switch (pid) { case 11: return 0; case -11: return 1; case 22: return 2; case 13: return 3; case -13: return 4; case 4900022: return 5; }
@@ -1102,7 +1181,7 @@ struct pb_engine_s {
   double* prim_mass = nullptr; long long prim_cap = 0;
   void* prim_stage = nullptr; size_t prim_stage_bytes = 0;
   int n_sm = 148;
-  bool profiling = false;
+  int profiling = 0;             // 0 off, 1 = the two dominant kernels only (k_loop, k_sample), 2 = every kernel
   int sample_group = 8;          // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
   cudaEvent_t ev[2 * 8] = {};
   pb_profile prof{};
@@ -1242,6 +1321,7 @@ extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int 
   return PB_OK;
 }
 
+static int ensure_cand(pb_engine e, long long ncap);
 static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream) {
   switch (e->sample_group) {
     case 1: k_sample<1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
@@ -1331,11 +1411,12 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     PB_CUDA(e, cudaMemcpyAsync((void*)d_pid, prim->pid, sizeof(int) * n0, kind, stream));
     PB_CUDA(e, cudaMemcpyAsync((void*)d_fl, prim->flags, sizeof(int) * n0, kind, stream));
   }
-  const bool prof = e->profiling;
+  const int plevel = e->profiling;
   memset(&e->prof, 0, sizeof(e->prof));
   bool recorded[8] = {false, false, false, false, false, false, false, false};
-  auto tick = [&](int k) { if (prof) { cudaEventRecord(e->ev[2 * k], stream); recorded[k] = true; } };
-  auto tock = [&](int k) { if (prof) cudaEventRecord(e->ev[2 * k + 1], stream); ++e->prof.launches[k]; };
+  auto timed = [&](int k) { return plevel >= 2 || (plevel == 1 && (k == PB_K_PROPAGATE || k == PB_K_SAMPLE)); };
+  auto tick = [&](int k) { if (timed(k)) { cudaEventRecord(e->ev[2 * k], stream); recorded[k] = true; } };
+  auto tock = [&](int k) { if (timed(k)) cudaEventRecord(e->ev[2 * k + 1], stream); ++e->prof.launches[k]; };
   auto collect = [&]() {     // after a stream synchronize: add up every kernel timed since the last collect
     for (int k = 0; k < PB_K_N; ++k) {
       if (!recorded[k]) continue;
@@ -1476,20 +1557,9 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
   long long ncap = std::max<long long>(2 * n_sm, 1);
   int rc = ensure_work(e, ncap);
   if (rc != PB_OK) return rc;
-  if (ncap > e->cand_cap) {
-    if (e->cand_blob) cudaFree(e->cand_blob);
-    long long cap = ncap * 5 / 4 + 1024;
-    PB_CUDA(e, cudaMalloc(&e->cand_blob, (size_t)cap * (4 + 4 + 8 + 32 + 4) + 64));
-    char* p = (char*)e->cand_blob;
-    e->cand.pf = (double*)p; p += (size_t)cap * 32;
-    e->cand.wg = (double*)p; p += (size_t)cap * 8;
-    e->cand.slot = (int*)p; p += (size_t)cap * 4;
-    e->cand.proc = (int*)p; p += (size_t)cap * 4;
-    e->cand.ntr = (int*)p; p += (size_t)cap * 4;
-    e->cand.count = (int*)p;
-    e->cand_cap = cap;
-  }
-  const bool prof = e->profiling;
+  rc = ensure_cand(e, ncap);
+  if (rc != PB_OK) return rc;
+  const bool prof = e->profiling != 0;
   memset(&e->prof, 0, sizeof(e->prof));
   bool recorded[8] = {false, false, false, false, false, false, false, false};
   auto tick = [&](int k) { if (prof) { cudaEventRecord(e->ev[2 * k], stream); recorded[k] = true; } };
@@ -1546,9 +1616,75 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
   return PB_OK;
 }
 
+static int ensure_cand(pb_engine e, long long ncap) {
+  if (ncap <= e->cand_cap) return PB_OK;
+  if (e->cand_blob) cudaFree(e->cand_blob);
+  long long cap = ncap * 5 / 4 + 1024;
+  PB_CUDA(e, cudaMalloc(&e->cand_blob, (size_t)cap * (4 + 4 + 8 + 32 + 4) + 64));
+  char* p = (char*)e->cand_blob;
+  e->cand.pf = (double*)p; p += (size_t)cap * 32;
+  e->cand.wg = (double*)p; p += (size_t)cap * 8;
+  e->cand.slot = (int*)p; p += (size_t)cap * 4;
+  e->cand.proc = (int*)p; p += (size_t)cap * 4;
+  e->cand.ntr = (int*)p; p += (size_t)cap * 4;
+  e->cand.count = (int*)p;
+  e->cand_cap = cap;
+  return PB_OK;
+}
+
+extern "C" int pb_draw_samples(pb_engine e, int process, const double* E, int64_t n, int lu_key, uint64_t seed,
+                               uint64_t first_id, double* x_out, int32_t* ntr_out, void* stream_) {
+  if (!e || !E || !x_out || n <= 0 || n > 0x3fffffff || process < 0 || process >= N_SAMPLED) return PB_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  if (e->tab.map[process].grid == nullptr) { e->err = "maps not uploaded for this process"; return PB_ERR_STATE; }
+  e->mat.max_trials = (long long)std::min<double>((double)e->cfg.max_sweeps * (double)e->tab.map[process].B, 4.0e9);
+  int rc = ensure_work(e, n);
+  if (rc != PB_OK) return rc;
+  rc = ensure_cand(e, n);
+  if (rc != PB_OK) return rc;
+  double* dE = nullptr;
+  PB_CUDA(e, cudaMalloc(&dE, sizeof(double) * n + sizeof(uint2) * n));
+  uint2* dkeys = (uint2*)(dE + n);
+  PB_CUDA(e, cudaMemcpyAsync(dE, E, sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.counters, 0, sizeof(unsigned long long) * CNT_N, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.hist, 0, sizeof(int) * NBUCKET, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.ctrl, 0, sizeof(int) * 8, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.xs, 0, sizeof(double) * 4 * n, stream));
+  k_prepare_draws<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->tab, e->work, e->cand, dkeys, dE, (int)n, process, lu_key, seed, first_id);
+  k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
+  k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, (int)n);
+  SampleIO io{e->cand.pf, dkeys, nullptr, e->cand.ntr, 1};
+  launch_sample(e, (int)std::min<long long>((long long)e->n_sm * 4, (n + 31) / 32 + 1), io, stream);
+  cudaError_t c = cudaMemcpyAsync(x_out, e->work.xs, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, stream);
+  if (c == cudaSuccess && ntr_out) c = cudaMemcpyAsync(ntr_out, e->cand.ntr, sizeof(int) * n, cudaMemcpyDeviceToHost, stream);
+  if (c == cudaSuccess) c = cudaStreamSynchronize(stream);
+  cudaFree(dE);
+  if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
+  return PB_OK;
+}
+
+extern "C" int pb_find_max(pb_engine e, int process, int n_trials, uint64_t seed, double mT, double* max_out, double* sum_out) {
+  if (!e || !max_out || !sum_out || process < 0 || process >= N_SAMPLED || n_trials < 1) return PB_ERR_ARG;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  const MapInfo& mi = e->tab.map[process];
+  if (mi.grid == nullptr) { e->err = "maps not uploaded for this process"; return PB_ERR_STATE; }
+  Material m = e->mat;
+  if (mT > 0) m.mT = mT;
+  double* d = nullptr;
+  PB_CUDA(e, cudaMalloc(&d, sizeof(double) * 2 * mi.nE));
+  k_find_max<<<mi.nE, 128>>>(m, e->tab, process, n_trials, seed, d, d + mi.nE);
+  cudaError_t c = cudaDeviceSynchronize();
+  if (c == cudaSuccess) c = cudaMemcpy(max_out, d, sizeof(double) * mi.nE, cudaMemcpyDeviceToHost);
+  if (c == cudaSuccess) c = cudaMemcpy(sum_out, d + mi.nE, sizeof(double) * mi.nE, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
+  return PB_OK;
+}
+
 extern "C" int pb_set_profiling(pb_engine e, int on) {
   if (!e) return PB_ERR_ARG;
-  e->profiling = on != 0;
+  e->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
   return PB_OK;
 }
 extern "C" int pb_get_profile(pb_engine e, pb_profile* out) {

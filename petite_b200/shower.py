@@ -466,8 +466,9 @@ class Shower:
                                                    C.c_void_p(stream)))
         return out
 
-    def set_profiling(self, on=True):
-        capi.check(self._engine, capi.lib.pb_set_profiling(self._engine, 1 if on else 0))
+    def set_profiling(self, level=2):
+        """0 off; 1 = CUDA-event timing of the two dominant kernels only; 2 = every kernel (adds ~6 % to a step)."""
+        capi.check(self._engine, capi.lib.pb_set_profiling(self._engine, int(level)))
 
     def get_profile(self):
         """Per-kernel device milliseconds / launches and per-process trial counts of the last run."""
@@ -482,6 +483,79 @@ class Shower:
         v = (C.c_double * 1)(0.0)
         capi.check(self._engine, capi.lib.pb_measure_fp64_peak(self._engine, v))
         return float(v[0])
+
+    # ------------------------------------------------------------------ single-process sampling (tutorial API)
+    _ALL_CODES = dict(process_code, DarkBrem=8, DarkAnn=9, DarkComp=10, DarkMuonBrem=11)
+
+    def draw_samples(self, Einc, process, LU_Key=-1, first_id=None):
+        """Batched ``draw_sample``: energies (n,) -> (x (n, dim), trials (n,)).  Sample i uses the Philox key
+        (seed, first_id + i); ``trials`` is the reference's ``VB`` counter."""
+        E = np.ascontiguousarray(np.atleast_1d(Einc), dtype=np.float64)
+        n = len(E)
+        if first_id is None:
+            first_id = self._next_shower_id
+            self._next_shower_id += n
+        x = np.zeros((n, 4))
+        ntr = np.zeros(n, dtype=np.int32)
+        stream = self._torch.cuda.current_stream(self._device).cuda_stream
+        rc = capi.lib.pb_draw_samples(self._engine, self._ALL_CODES[process], capi.dptr(E), n, int(LU_Key), self._seed,
+                                      int(first_id), capi.dptr(x), capi.iptr(ntr), C.c_void_p(stream))
+        capi.check(self._engine, rc)
+        return x[:, :tb.PROC_DIM[process]], ntr
+
+    def draw_sample(self, Einc, LU_Key=-1, process='PairProd', VB=False):
+        """One VEGAS accept/reject sample for ``process`` at ``Einc`` (shower.py:401-465)."""
+        if process not in process_code:
+            raise Exception("Your process is not in the list")
+        x, ntr = self.draw_samples([Einc], process, LU_Key)
+        if ntr[0] < 0:
+            raise Exception("No Sample Found", process, Einc, LU_Key)
+        return np.concatenate([x[0], [ntr[0]]]) if VB else x[0]
+
+    def sample_scattering(self, p0, process, VB=False):
+        """Hard scatter of ``p0`` through ``process`` -> [Particle, Particle] or None below threshold (shower.py:467-507)."""
+        ids = p0.get_ids()
+        E0 = p0.get_pf()[0]
+        if E0 <= np.max([self._minimum_calculable_energy[ids["PID"]], self.min_energy, ids["mass"]]):
+            return None
+        RM = np.array(p0.rotation_matrix(), dtype=float)
+        x = self.draw_sample(E0, process=process, VB=VB)
+        fid = self._next_shower_id
+        self._next_shower_id += 1
+        key = self._probe(capi.PROBE_PHILOX, 0, [[self._seed & 0xFFFFFFFF, self._seed >> 32, fid & 0xFFFFFFFF, fid >> 32, 0, 0xA0]], 2)
+        inp = np.zeros((1, 8))
+        inp[0, 0], inp[0, 1], inp[0, 6] = E0, ids["mass"], key[0, 0]
+        inp[0, 2:2 + dimensionalities[process]] = x[:dimensionalities[process]]
+        v = self._probe(capi.PROBE_KIN, process_code[process], inp, 8)[0]
+        out = []
+        for bit, pid in enumerate(process_PIDS[process]):
+            pid = ids["PID"] if pid == 0 else pid
+            four = v[4 * bit:4 * bit + 4]
+            lab = np.concatenate([[four[0]], RM @ four[1:]])
+            d = {"PID": pid, "parent_PID": ids["PID"], "ID": 2 * ids["ID"] + bit, "parent_ID": ids["ID"],
+                 "generation_number": ids["generation_number"] + 1, "generation_process": process, "weight": ids["weight"],
+                 "mass": mass_dict[pid]}
+            out.append(Particle(lab, p0.get_rf(), d))
+        return out
+
+    def _probe(self, what, process, inp, out_cols):
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        out = np.zeros((len(inp), out_cols))
+        capi.check(self._engine, capi.lib.pb_probe(self._engine, what, process, capi.dptr(inp), len(inp), inp.shape[1],
+                                                   capi.dptr(out), out_cols))
+        return out
+
+    def find_max(self, process, n_trials=100, seed=20261017, mT=None):
+        """GPU ``do_find_max_work`` (utilities/find_maxes.py:55-119) for this target: -> (max_F (nE,), sigma (nE,))."""
+        code = self._ALL_CODES[process]
+        ms = (self._maps.get(process) if process in self._maps else getattr(self, "_dark_maps", {}).get(process))
+        if ms is None:
+            raise Exception("Process String does not match library")
+        mf = np.zeros(len(ms.E)); sg = np.zeros(len(ms.E))
+        if mT is None:
+            mT = K.target_information[self._target_material]["mT"]
+        capi.check(self._engine, capi.lib.pb_find_max(self._engine, code, int(n_trials), int(seed), float(mT), capi.dptr(mf), capi.dptr(sg)))
+        return mf, sg
 
     # ------------------------------------------------------------------ public stepping API
     def generate_showers(self, primaries, GlobalMS=True, capacity=None, first_shower_id=None):
