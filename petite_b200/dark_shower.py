@@ -167,9 +167,19 @@ class DarkShower(Shower):
     def _load_setup(self):
         path = self._setup_path()
         if not os.path.exists(path):
-            from . import dark_setup
-            print("Weights not previously calculated, calculating now...")
-            path = dark_setup.build(self, path)
+            # the reference writes its caches into dict_dir and fails on a read-only one (SURVEY Q-3); fall back to a
+            # per-user cache directory instead
+            alt = os.path.join(os.path.expanduser(os.environ.get("PETITE_B200_CACHE", "~/.cache/petite_b200")), os.path.basename(path))
+            if os.path.exists(alt):
+                path = alt
+            else:
+                from . import dark_setup
+                print("Weights not previously calculated, calculating now...")
+                try:
+                    path = dark_setup.build(self, path)
+                except OSError:
+                    os.makedirs(os.path.dirname(alt), exist_ok=True)
+                    path = dark_setup.build(self, alt)
         z = np.load(path)
         self._weights = {k: LinearTable(z[f"weights/{k}"][:, 0], z[f"weights/{k}"][:, 1]) for k in _WEIGHT_ORDER}
         self._brem_elec_numerical_weight, self._brem_positron_numerical_weight = self._weights["brem_elec"], self._weights["brem_positron"]
