@@ -297,6 +297,19 @@ class DarkShower(Shower):
         b._mV = self._mV
         return b
 
+    def tally_dark(self, dark_batch, out=None):
+        """``pb_tally`` over a :class:`DarkBatch` (weighted yield, energy and angle spectra of the dark vectors)."""
+        torch = self._torch
+        if out is None:
+            out = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=torch.device("cuda", self._device))
+        t = self._dark_stack
+        st = capi.pb_stack(t["p0"].data_ptr(), t["r0w"].data_ptr(), t["pf"].data_ptr(), t["rf"].data_ptr(),
+                           t["key"].data_ptr(), t["meta"].data_ptr(), t["aux"].data_ptr(), self._dark_capacity)
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        capi.check(self._engine, capi.lib.pb_tally(self._engine, C.byref(st), 0, dark_batch.n, C.c_void_p(out.data_ptr()),
+                                                   C.c_void_p(stream)))
+        return out
+
     def generate_dark_shower(self, ExDir=None, SParams=None):
         """dark_shower.py:806-849: (SM shower, list of dark vectors) for one existing or new SM shower."""
         if ExDir is None and SParams is None:

@@ -390,10 +390,26 @@ class Shower:
         self._stack_capacity = capacity
 
     def estimate_records(self, energies, pids):
-        """Rough upper estimate of stack records for a batch (used to size HBM; the run fails loudly if exceeded)."""
+        """Stack records needed for a batch.  Small batches use a generous closed-form bound; large ones are sized from
+        a pilot run of 512 of their own primaries (records per GeV and widest wave), so that HBM is not over-allocated.
+        The engine fails loudly (PB_ERR_CAPACITY) if the estimate is exceeded and ``run_arrays`` retries once, doubled."""
         E = np.asarray(energies, dtype=np.float64)
-        per = 64 + 4.0 * E / max(self.min_energy, 1e-4)
-        return int(np.sum(per) * 1.5) + 1024
+        bound = int(np.sum(64 + 4.0 * E / max(self.min_energy, 1e-4)) * 1.5) + 1024
+        if len(E) <= 2048 or bound < (1 << 22):
+            return bound
+        key = (len(E), float(E.sum()))
+        if getattr(self, "_pilot_key", None) != key:
+            self._pilot_key, self._pilot = key, None
+        return bound if self._pilot is None else min(bound, self._pilot)
+
+    def _pilot_capacity(self, p, r, w, m, pid, flags, GlobalMS):
+        n = len(pid)
+        idx = np.linspace(0, n - 1, 512).astype(np.int64)
+        b = self.run_arrays(p[idx], r[idx], w[idx], m[idx], pid[idx], flags[idx], GlobalMS=GlobalMS,
+                            capacity=int(np.sum(64 + 4.0 * p[idx, 0] / max(self.min_energy, 1e-4)) * 1.5) + 1024,
+                            first_shower_id=(1 << 62))
+        scale = float(np.sum(p[:, 0]) / max(np.sum(p[idx, 0]), 1e-300))
+        return int(b.n * scale * 1.10 + 2.5 * b.counters["max_wave"] * scale) + (1 << 16)
 
     @staticmethod
     def _pack_primaries(plist):
@@ -439,8 +455,12 @@ class Shower:
             p = np.ascontiguousarray(p, dtype=np.float64); r = np.ascontiguousarray(r, dtype=np.float64)
             w = np.ascontiguousarray(w, dtype=np.float64); m = np.ascontiguousarray(m, dtype=np.float64)
             pid = np.ascontiguousarray(pid, dtype=np.int32); flags = np.ascontiguousarray(flags, dtype=np.int32)
-            if capacity is None:
+            auto = capacity is None
+            if auto:
                 capacity = self.estimate_records(p[:, 0], pid)
+                if n > 2048 and capacity >= (1 << 22) and getattr(self, "_pilot", None) is None:
+                    self._pilot = self._pilot_capacity(p, r, w, m, pid, flags, GlobalMS)
+                    capacity = min(capacity, self._pilot)
             prim = capi.pb_primaries(capi.dptr(p), capi.dptr(r), capi.dptr(w), capi.dptr(m), capi.iptr(pid), capi.iptr(flags), n, 0)
         self._ensure_stack(int(capacity))
         if first_shower_id is None:
@@ -452,8 +472,36 @@ class Shower:
         stream = self._torch.cuda.current_stream(self._device).cuda_stream
         rc = capi.lib.pb_run_showers(self._engine, C.byref(prim), self._seed, int(first_shower_id), 1 if GlobalMS else 0,
                                      C.byref(st), C.byref(cnt), C.c_void_p(stream))
+        if rc == capi.PB_ERR_CAPACITY and not on_device and auto:
+            # pilot estimate too small (heavy-tailed batch): one retry with twice the room; showers depend only on
+            # (seed, shower id), so the rerun reproduces the same particles
+            self._pilot = None
+            return self.run_arrays(p, r, w, m, pid, flags, GlobalMS=GlobalMS, capacity=2 * self._stack_capacity,
+                                   first_shower_id=first_shower_id)
         capi.check(self._engine, rc)
         return ShowerBatch(self, t, cnt.n_particles, cnt.as_dict(), n, first_shower_id)
+
+    def run_tallies(self, p, r, w, m, pid, flags, batch=32768, GlobalMS=True, first_shower_id=0, dark=None):
+        """Memory-bounded run: step the primaries ``batch`` at a time, keep only the tallies (``pb_tally``), discard the
+        particle history.  ``dark`` (a DarkShower sharing this object) adds the dark-vector tallies of each batch.
+        Returns (sm_tally, dark_tally or None, summed counters)."""
+        torch = self._torch
+        dev = torch.device("cuda", self._device)
+        sm_t = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=dev)
+        dk_t = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=dev) if dark is not None else None
+        tot = {}
+        n = len(pid)
+        for a in range(0, n, batch):
+            sl = slice(a, min(a + batch, n))
+            b = self.run_arrays(p[sl], r[sl], w[sl], m[sl], pid[sl], flags[sl], GlobalMS=GlobalMS, first_shower_id=first_shower_id + a)
+            self.tally(b, sm_t)
+            for k, v in b.counters.items():
+                tot[k] = max(tot.get(k, 0), v) if k == "max_wave" else tot.get(k, 0) + v
+            if dark is not None:
+                d = dark.generate_dark_showers(b)
+                dark.tally_dark(d, dk_t)
+                tot["n_dark"] = tot.get("n_dark", 0) + d.n
+        return sm_t, dk_t, tot
 
     def tally(self, batch, out=None):
         """Histogram / yield tallies of a batch (``pb_tally``), accumulated into ``out`` (torch float64[1024], CUDA)."""
