@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+from tests.conftest import DATA as DATA_DIR
 from tests.gpu_util import shower, primaries
 from tests.parity import compare_with_oracle, oracle_showers
 
@@ -117,3 +118,57 @@ def test_ensemble_statistics_vs_oracle():
     el_gpu = th(h["p0"][(np.abs(h["pid"]) == 11) & (h["parent"] >= 0)])
     el_orc = th(np.array([q.p0 for r in ref for q in r[1:] if abs(q.PID) == 11]))
     assert ks_2samp(el_gpu, el_orc).pvalue > 0.01
+
+
+def test_edge_cases_empty_ragged_and_invalid():
+    """Boundary behaviour: mixed species and energies in one batch (incl. below-threshold primaries that must come back
+    untouched), neutrinos, and inputs the reference would hang or crash on."""
+    from petite_b200 import Particle
+    from petite_b200.constants import m_electron, m_muon
+    from petite_b200 import _capi as capi
+    sh = shower("graphite", 0.010, seed=8)
+    mk = lambda pid, E, m, **kw: Particle([E, 0, 0, np.sqrt(max(E * E - m * m, 0.0))], [0, 0, 0], dict({"PID": pid, "ID": 1, "mass": m}, **kw))
+    prims = [mk(11, 0.004, m_electron), mk(22, 0.0012, 0.0), mk(-11, 0.5, m_electron), mk(14, 3.0, 0.0), mk(13, 0.1, m_muon),
+             mk(22, 3.0, 0.0), mk(11, 0.0101, m_electron)]
+    batch = sh.generate_showers(prims, first_shower_id=40)
+    rep = compare_with_oracle(batch, prims, "graphite", 0.010, seed=8)
+    assert rep["structure_mismatch"] == 0, rep
+    out = batch.to_particles(prims)
+    assert len(out[0]) == 1 and np.array_equal(out[0][0].get_pf(), out[0][0].get_p0())      # below min_energy: untouched
+    assert len(out[3]) == 1                                                                   # neutrino just ends
+    assert len(out[4]) == 1                                                                   # muon below 0.2 GeV threshold
+    assert len(out[2]) > 1 and len(out[5]) > 1
+    with pytest.raises(ValueError):                                                           # Q-20: would loop forever
+        sh.generate_showers([mk(2212, 5.0, 0.938)])
+    with pytest.raises(ValueError):
+        sh.generate_showers([mk(211, 5.0, 0.1396, stability="long-lived")])
+    with pytest.raises(capi.EngineError) as ei:                                               # too small a stack fails loudly
+        sh.generate_showers(primaries(11, 5.0, 64), capacity=200)
+    assert ei.value.code == capi.PB_ERR_CAPACITY
+    assert sh.generate_showers(primaries(11, 1.0, 4)).n > 4                                   # engine usable afterwards
+
+
+def test_no_sample_found_is_reported():
+    """max_n_integrators exhausted -> the reference raises "No Sample Found" (shower.py:460-461)."""
+    from petite_b200.shower import Shower
+    from petite_b200 import _capi as capi
+    s = Shower(DATA_DIR, "lead", 0.010, max_n_integrators=1, maxF_fudge_global=1e6, seed=1)
+    with pytest.raises(capi.EngineError) as ei:
+        s.generate_showers(primaries(22, 5.0, 32))
+    assert ei.value.code == capi.PB_ERR_NO_SAMPLE and "No Sample Found" in str(ei.value)
+
+
+def test_tally_matches_host_histograms():
+    from petite_b200 import _capi as capi
+    sh = shower("lead", 0.010, seed=12)
+    b = sh.generate_showers(primaries(22, 4.0, 300))
+    t = sh.tally(b).cpu().numpy()
+    h = b.to_host()
+    sp = {11: 0, -11: 1, 22: 2}
+    for pid, k in sp.items():
+        sel = h["pid"] == pid
+        assert t[capi.TALLY_COUNT + k] == sel.sum()
+        assert abs(t[capi.TALLY_WESUM + k] - np.sum(h["weight"][sel] * h["p0"][sel][:, 0])) < 1e-6 * t[capi.TALLY_WESUM + k]
+        eb = np.clip(np.floor((np.log10(h["p0"][sel][:, 0]) + 3) * (64 / 6)).astype(int), 0, 63)
+        assert np.array_equal(t[capi.TALLY_EHIST + k * 64: capi.TALLY_EHIST + (k + 1) * 64], np.bincount(eb, minlength=64))
+    assert t[capi.TALLY_COUNT:capi.TALLY_COUNT + 7].sum() == b.n
