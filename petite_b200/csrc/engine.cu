@@ -82,6 +82,18 @@ struct Stack {
   long long capacity;
 };
 
+// Wave bookkeeping kept on the device so that waves can be enqueued back to back without a host round trip.
+struct WaveState {
+  long long begin, end;      // stack slots of the current wave
+  long long capacity;        // of the particle stack
+  long long tot_charged;
+  int n, n_charged;          // size of the current wave, of its charged list
+  int parity;                // which pair of index lists the current wave reads
+  int status;                // 0 running, 1 finished (empty wave), 2 stack capacity exhausted, 3 scratch too small (host grows it)
+  int waves, max_wave;
+  int work_cap, order_cap;   // capacities of the per-wave scratch / of each index list
+};
+
 struct Work {            // per-wave scratch, sized to the widest wave seen so far
   int* bucket;           // [n] bucket of particle (begin + i)
   int* sorted;           // [n] wave-local indices in bucket order
@@ -93,10 +105,9 @@ struct Work {            // per-wave scratch, sized to the widest wave seen so f
   int* tile_start;
   int* tile_count;
   int* ctrl;             // [0] n_tiles, [1] tile cursor, [2] k_loop chunk cursor
-  int* order_c;          // [n] wave-local indices of the wave's charged (dE/dx-stepping) particles
-  int* order_n;          // [n] ... of everything else (photons, decaying mesons, neutrinos)
-  int* next_c;           // same two lists being built for the next wave by k_emit
-  int* next_n;
+  int* list[4];          // wave-local index lists, two parities x {charged (dE/dx-stepping), everything else}: the wave
+                         // reads list[2*parity + k], k_emit builds list[2*(parity^1) + k] for the next wave
+  struct WaveState* ws;  // device-resident wave bookkeeping (lets the host enqueue several waves per synchronisation)
   unsigned long long* tail;      // [0] stack tail (next free record); [1] = (n_neutral_next << 32) | n_charged_next
   unsigned long long* counters;  // [CNT_N]: steps, substeps, samples, trials, no_sample, overflow, per-process trials/samples
 };
@@ -211,15 +222,45 @@ __device__ __forceinline__ void store_track_setup(const Tables& T, Stack& S, lon
   rfp[1] = make_double2(__hiloint2double(0, h[2]), 0.0);
 }
 
+// First kernel of every wave: turn what the previous wave appended (stack tail, list sizes) into this wave's extent.
+// Idempotent when it has to pause (status 3), so the host can grow the scratch and re-enqueue the same wave.
+__global__ void k_wave_begin(Work W) {
+  WaveState& ws = *W.ws;
+  if (ws.status != 0 && ws.status != 3) { ws.n = 0; ws.n_charged = 0; return; }
+  unsigned long long tail = W.tail[0], lists = W.tail[1];
+  long long begin = ws.status == 3 ? ws.begin : ws.end;
+  long long end = (long long)min(tail, (unsigned long long)ws.capacity);
+  long long n = end - begin;
+  ws.status = 0;
+  if (n <= 0) { ws.status = 1; ws.n = 0; ws.n_charged = 0; return; }
+  if (end + 2 * n > ws.capacity) { ws.status = 2; ws.n = 0; ws.n_charged = 0; return; }
+  if (n > ws.work_cap || 2 * n > ws.order_cap) { ws.status = 3; ws.begin = begin; ws.n = 0; ws.n_charged = 0; return; }
+  ws.begin = begin; ws.end = end;
+  ws.n = (int)n;
+  ws.n_charged = (int)(lists & 0xffffffffull);
+  ws.parity ^= 1;
+  ws.tot_charged += ws.n_charged;
+  ws.waves += 1;
+  ws.max_wave = max(ws.max_wave, (int)n);
+  W.tail[1] = 0;
+  W.ctrl[1] = 0; W.ctrl[2] = 0;
+}
+
 // Sub-step loop of propagate_particle, charged species only.  Persistent warps pull chunks of the wave's charged
 // list; a lane that finishes its track (hard scatter drawn, or energy below threshold) stores it and immediately
 // takes the next entry of the chunk, so the warp stays converged on the loop body whatever the per-track sub-step
 // count (geometric, mean ~7, tail > 50).  The final partial step and the process choice are done by k_finalize.
 constexpr int LOOP_CHUNK = 64;
 __global__ void __launch_bounds__(128, PB_LOOP_MINB)
-k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, long long begin,
-       int n_charged, const double* __restrict__ prim_mass, int ms_e) {
+k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
+       const double* __restrict__ prim_mass, int ms_e) {
+  const long long begin = W.ws->begin;
+  const int n_charged = W.ws->n_charged;
+  if (n_charged <= 0) return;
+  const int* __restrict__ order_c = W.list[2 * W.ws->parity];
   const int lane = threadIdx.x & 31;
+  // small waves: smaller chunks so that the tracks spread over all resident warps (latency, not throughput, bound)
+  const int chunk = min(LOOP_CHUNK, max(8, n_charged / (int)(gridDim.x * (blockDim.x / 32))));
   const unsigned lt_mask = (1u << lane) - 1u;
   int next = 0, chunk_end = 0;       // warp-uniform cursor into the charged list
   int cur = -1;                       // -1: needs a track, -2: no more work
@@ -231,16 +272,16 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     while (need) {
       if (next >= chunk_end) {
         int c = 0;
-        if (lane == 0) c = atomicAdd(&W.ctrl[2], LOOP_CHUNK);
+        if (lane == 0) c = atomicAdd(&W.ctrl[2], chunk);
         c = __shfl_sync(0xffffffffu, c, 0);
-        next = c; chunk_end = min(c + LOOP_CHUNK, n_charged);
+        next = c; chunk_end = min(c + chunk, n_charged);
         if (next >= chunk_end) { if (cur == -1) cur = -2; break; }
       }
       int avail = chunk_end - next;
       int rank = __popc(need & lt_mask);
       bool take = (cur == -1) && rank < avail;
       if (take) {
-        cur = W.order_c[next + rank];
+        cur = order_c[next + rank];
         long long s = begin + cur;
         const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
         const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
@@ -317,12 +358,15 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
 // photon's free path, process choice, sample_scattering threshold and map look-up key -> bucket + histogram.
 __global__ void __launch_bounds__(128)
 k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
-           long long begin, int n_charged, int n, const double* __restrict__ prim_mass, int ms_e) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
+           const double* __restrict__ prim_mass, int ms_e) {
+  const long long begin = W.ws->begin;
+  const int n = W.ws->n, n_charged = W.ws->n_charged;
+  const int* __restrict__ order_c = W.list[2 * W.ws->parity];
+  const int* __restrict__ order_n = W.list[2 * W.ws->parity + 1];
   unsigned long long c_steps = 0;
-  if (j < n) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const bool charged = j < n_charged;
-    int i = charged ? W.order_c[j] : W.order_n[j - n_charged];
+    int i = charged ? order_c[j] : order_n[j - n_charged];
     long long s = begin + i;
     int4 meta = S.meta[s];
     uint2 key = S.key[s];
@@ -345,7 +389,7 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
       double E_start = p0p[0].x;
       double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
       if (!(E_start < pmin)) {                                            // shower.py:534-536: otherwise untouched
-        c_steps = 1;
+        c_steps += 1;
         int tb[3];
         species_tables(pid, tb);
         double distC = draw2(key, 0, ST_FINAL).a;                         // shower.py:583-598
@@ -380,7 +424,7 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
       } else if (pid == 22) {
         double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
         if (!(p.E < pmin)) {                                              // shower.py:538-553 (MS_g is always False)
-          c_steps = 1;
+          c_steps += 1;
           double lE = log(p.E);
           double mfp = mfp_from(nsigma_log(T.ns[P_PAIRPROD], lE, p.E) + nsigma_log(T.ns[P_COMP], lE, p.E));
           double distC = draw2(key, 0, ST_FINAL).a;
@@ -466,17 +510,19 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
   if (t == 0) W.ctrl[2] = 0;
 }
 
-__global__ void __launch_bounds__(256) k_bucket_fill(Work W, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int b = W.bucket[i];
+// n_explicit < 0: the wave size comes from the device-side wave state
+__global__ void __launch_bounds__(256) k_bucket_fill(Work W, int n_explicit) {
+  const int n = n_explicit < 0 ? W.ws->n : n_explicit;
   const int lane = threadIdx.x & 31;
-  unsigned peers = __match_any_sync(__activemask(), b);        // lanes of this warp that share the bucket
-  int leader = __ffs(peers) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(&W.cursor[b], __popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  W.sorted[W.offsets[b] + base + __popc(peers & ((1u << lane) - 1u))] = i;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int b = W.bucket[i];
+    unsigned peers = __match_any_sync(__activemask(), b);        // lanes of this warp that share the bucket
+    int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&W.cursor[b], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    W.sorted[W.offsets[b] + base + __popc(peers & ((1u << lane) - 1u))] = i;
+  }
 }
 
 // ---- TMA (bulk async copy) helpers: global -> shared, completion on an mbarrier
@@ -550,6 +596,7 @@ struct SampleIO {
   const int* key_index;    // entry i uses key[key_index[i]] (nullptr: key[i])
   int* ntr;                // trials used by entry i at ntr[i * ntr_stride]; -1 if the sampler gave up
   int ntr_stride;
+  const WaveState* ws;     // SM pass: entry i is stack slot ws->begin + i (E4/key/ntr then point at slot 0)
 };
 
 template <int G>
@@ -566,6 +613,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
   unsigned long long c_trials = 0, c_samples = 0, c_fail = 0;
   __shared__ unsigned long long s_ptrials, s_psamples;
   if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_ptrials = 0; s_psamples = 0; }
+  const size_t off = io.ws ? (size_t)io.ws->begin : 0;
   __syncthreads();
   for (;;) {
     if (threadIdx.x == 0) { s_tile = atomicAdd(&W.ctrl[1], 1); s_cursor = 0; }
@@ -596,8 +644,8 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
         j = __shfl_sync(gmask, j, gbase);
         if (j < tcount) {
           cur = W.sorted[tstart + j];
-          E = io.E4[4 * (size_t)cur];
-          key = io.key[io.key_index ? io.key_index[cur] : cur];
+          E = io.E4[4 * (off + (size_t)cur)];
+          key = io.key[io.key_index ? (size_t)io.key_index[cur] : off + (size_t)cur];
           round = 0;
           if (proc == P_PAIRPROD) sc = pairprod_const(M, E);
           else if (proc == P_BREM) sc = brem_const(M, E, kMe);
@@ -624,7 +672,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
             double2* xo = reinterpret_cast<double2*>(W.xs + 4 * (size_t)cur);
             xo[0] = make_double2(x[0], x[1]); xo[1] = make_double2(x[2], x[3]);
             int ntr = (int)(round * G + sub + 1);
-            io.ntr[(size_t)cur * io.ntr_stride] = ntr;
+            io.ntr[(off + (size_t)cur) * io.ntr_stride] = ntr;
             c_trials += ntr; c_samples += 1;
           }
           cur = -1;
@@ -632,7 +680,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
           ++round;
           if ((long long)round * G >= max_trials) {      // "No Sample Found" (shower.py:460-461)
             if (sub == 0) {
-              io.ntr[(size_t)cur * io.ntr_stride] = -1;
+              io.ntr[(off + (size_t)cur) * io.ntr_stride] = -1;
               W.bucket[cur] = P_NONE * LU_MAX;
               c_trials += (unsigned long long)max_trials; c_fail += 1;
             }
@@ -664,9 +712,15 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
 
 // Kinematics + rotation + daughter append, in bucket order (warps are process-coherent).
 __global__ void __launch_bounds__(128)
-k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, long long begin, int n) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
+k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W) {
+  const long long begin = W.ws->begin;
+  const int n = W.ws->n;
+  int* __restrict__ next_c = W.list[2 * (W.ws->parity ^ 1)];
+  int* __restrict__ next_n = W.list[2 * (W.ws->parity ^ 1) + 1];
   const int lane = threadIdx.x & 31;
+  // warp-uniform grid-stride loop (the append below uses full-warp shuffles)
+  for (int jbase = (blockIdx.x * blockDim.x + threadIdx.x) - lane; jbase < n; jbase += gridDim.x * blockDim.x) {
+  const int j = jbase + lane;
   V4 da{0, 0, 0, 0}, db{0, 0, 0, 0};
   int pid_a = 0, pid_b = 0, proc = P_NONE;
   bool keep_a = false, keep_b = false;
@@ -752,12 +806,13 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       S.key[dst] = child_key(key, bit);
       S.meta[dst] = make_int4(bit ? pid_b : pid_a, (int)slot, pack_info(gen, bit, 0, proc), meta.w);
       if (bit ? ch_b : ch_a) {
-        W.next_c[ci++] = (int)(dst - next_begin);
+        next_c[ci++] = (int)(dst - next_begin);
         store_track_setup(T, S, dst, bit ? pid_b : pid_a, d.E, d.x, d.y, d.z);
-      } else W.next_n[ni++] = (int)(dst - next_begin);
+      } else next_n[ni++] = (int)(dst - next_begin);
       ++dst;
     }
   }
+  }   // grid-stride loop
 }
 
 __global__ void k_init_primaries(const __grid_constant__ Tables T, Stack S, Work W, const double* __restrict__ p, const double* __restrict__ r,
@@ -773,9 +828,9 @@ __global__ void k_init_primaries(const __grid_constant__ Tables T, Stack S, Work
   const bool ch = is_charged(pid[i]) && !(flags[i] & PB_FLAG_SHORT_LIVED);
   unsigned long long old = atomicAdd(&W.tail[1], ch ? 1ull : (1ull << 32));
   if (ch) {
-    W.next_c[(int)(old & 0xffffffffu)] = (int)i;
+    W.list[2][(int)(old & 0xffffffffu)] = (int)i;          // parity 1: the first k_wave_begin flips 0 -> 1
     store_track_setup(T, S, i, pid[i], p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
-  } else W.next_n[(int)(old >> 32)] = (int)i;
+  } else W.list[3][(int)(old >> 32)] = (int)i;
 }
 
 
@@ -1183,7 +1238,10 @@ struct pb_engine_s {
   int n_sm = 148;
   int profiling = 0;             // 0 off, 1 = the two dominant kernels only (k_loop, k_sample), 2 = every kernel
   int sample_group = 8;          // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
+  static constexpr int LOOKAHEAD = 8;   // waves enqueued per host synchronisation while the shower tail shrinks
   cudaEvent_t ev[2 * 8] = {};
+  cudaEvent_t evp[LOOKAHEAD][2][2] = {};   // lookahead slot x {k_loop, k_sample} x {start, stop}
+  WaveState* h_ws = nullptr;             // pinned read-back of the device wave state (+ tail)
   pb_profile prof{};
   std::string err;
 };
@@ -1241,17 +1299,21 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   e->cfg = *cfg;
   derive_material(e);
   if (const char* g = getenv("PB_SAMPLE_G")) e->sample_group = atoi(g);
-  size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * (8 + CNT_N);
+  size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * (8 + CNT_N) + sizeof(WaveState) + 64;
   if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
   cudaMemset(e->fixed_blob, 0, fixed);
   for (int i = 0; i < 2 * 8; ++i) cudaEventCreate(&e->ev[i]);
+  for (int a = 0; a < pb_engine_s::LOOKAHEAD; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) cudaEventCreate(&e->evp[a][b][c]);
   char* p = (char*)e->fixed_blob;
   e->work.tail = (unsigned long long*)p; p += 8 * sizeof(unsigned long long);
   e->work.counters = (unsigned long long*)p; p += CNT_N * sizeof(unsigned long long);
   e->work.hist = (int*)p; p += NBUCKET * sizeof(int);
   e->work.offsets = (int*)p; p += (NBUCKET + 1) * sizeof(int);
   e->work.cursor = (int*)p; p += NBUCKET * sizeof(int);
-  e->work.ctrl = (int*)p;
+  e->work.ctrl = (int*)p; p += 16 * sizeof(int);
+  p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+  e->work.ws = (WaveState*)p;
+  cudaMallocHost(&e->h_ws, sizeof(WaveState) + 16);
   *out = e;
   return PB_OK;
 }
@@ -1274,6 +1336,8 @@ extern "C" void pb_destroy(pb_engine e) {
   if (e->prim_mass) cudaFree(e->prim_mass);
   if (e->prim_stage) cudaFree(e->prim_stage);
   for (int i = 0; i < 2 * 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  for (int a = 0; a < pb_engine_s::LOOKAHEAD; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) if (e->evp[a][b][c]) cudaEventDestroy(e->evp[a][b][c]);
+  if (e->h_ws) cudaFreeHost(e->h_ws);
   delete e;
 }
 
@@ -1333,20 +1397,20 @@ static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_
   }
 }
 
-// order lists (current + next wave) live apart from the other scratch: growing them must keep the current lists
-static int ensure_order(pb_engine e, long long n_cur, long long n_next_max, cudaStream_t stream) {
-  if (n_next_max <= e->order_cap) return PB_OK;
-  long long cap = std::max<long long>(n_next_max * 5 / 4, 1 << 16);
+// index lists live apart from the other scratch: growing them must keep their contents (a paused wave still needs them)
+static int ensure_order(pb_engine e, long long n_list, cudaStream_t stream) {
+  if (n_list <= e->order_cap) return PB_OK;
+  long long cap = std::max<long long>(n_list * 5 / 4, 1 << 16);
   int* blob = nullptr;
   PB_CUDA(e, cudaMalloc(&blob, sizeof(int) * 4 * (size_t)cap));
-  if (e->order_blob && n_cur > 0) {
-    PB_CUDA(e, cudaMemcpyAsync(blob, e->work.order_c, sizeof(int) * n_cur, cudaMemcpyDeviceToDevice, stream));
-    PB_CUDA(e, cudaMemcpyAsync(blob + cap, e->work.order_n, sizeof(int) * n_cur, cudaMemcpyDeviceToDevice, stream));
+  if (e->order_blob) {
+    for (int k = 0; k < 4; ++k)
+      PB_CUDA(e, cudaMemcpyAsync(blob + k * cap, e->work.list[k], sizeof(int) * e->order_cap, cudaMemcpyDeviceToDevice, stream));
     PB_CUDA(e, cudaStreamSynchronize(stream));
+    cudaFree(e->order_blob);
   }
-  if (e->order_blob) cudaFree(e->order_blob);
   e->order_blob = blob;
-  e->work.order_c = blob; e->work.order_n = blob + cap; e->work.next_c = blob + 2 * cap; e->work.next_n = blob + 3 * cap;
+  for (int k = 0; k < 4; ++k) e->work.list[k] = blob + k * cap;
   e->order_cap = cap;
   return PB_OK;
 }
@@ -1411,84 +1475,108 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     PB_CUDA(e, cudaMemcpyAsync((void*)d_pid, prim->pid, sizeof(int) * n0, kind, stream));
     PB_CUDA(e, cudaMemcpyAsync((void*)d_fl, prim->flags, sizeof(int) * n0, kind, stream));
   }
+  { int rc0 = ensure_order(e, std::max<long long>(2 * n0, 1 << 16), stream); if (rc0 != PB_OK) return rc0; }
+  { int rc0 = ensure_work(e, std::max<long long>(2 * n0, 1 << 16)); if (rc0 != PB_OK) return rc0; }
+  unsigned long long tail0[2] = {(unsigned long long)n0, 0ull};
+  PB_CUDA(e, cudaMemcpyAsync(e->work.tail, tail0, sizeof(tail0), cudaMemcpyHostToDevice, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.ctrl, 0, sizeof(int) * 8, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.counters, 0, sizeof(unsigned long long) * CNT_N, stream));
+  PB_CUDA(e, cudaMemsetAsync(e->work.hist, 0, sizeof(int) * NBUCKET, stream));
+  WaveState ws0{};
+  ws0.capacity = st->capacity; ws0.work_cap = (int)std::min<long long>(e->work_n, 0x7fffffff);
+  ws0.order_cap = (int)std::min<long long>(e->order_cap, 0x7fffffff);
+  PB_CUDA(e, cudaMemcpyAsync(e->work.ws, &ws0, sizeof(ws0), cudaMemcpyHostToDevice, stream));
   const int plevel = e->profiling;
   memset(&e->prof, 0, sizeof(e->prof));
+  // every-kernel timing (level 2) needs one event pair per launch: it runs one wave per synchronisation; level 1 times
+  // k_loop and k_sample only, from a small pool, and keeps the lookahead
   bool recorded[8] = {false, false, false, false, false, false, false, false};
-  auto timed = [&](int k) { return plevel >= 2 || (plevel == 1 && (k == PB_K_PROPAGATE || k == PB_K_SAMPLE)); };
-  auto tick = [&](int k) { if (timed(k)) { cudaEventRecord(e->ev[2 * k], stream); recorded[k] = true; } };
-  auto tock = [&](int k) { if (timed(k)) cudaEventRecord(e->ev[2 * k + 1], stream); ++e->prof.launches[k]; };
-  auto collect = [&]() {     // after a stream synchronize: add up every kernel timed since the last collect
+  bool rec_pool[pb_engine_s::LOOKAHEAD][2] = {};
+  auto tick = [&](int k, int slot) {
+    if (plevel >= 2) { cudaEventRecord(e->ev[2 * k], stream); recorded[k] = true; }
+    else if (plevel == 1 && (k == PB_K_PROPAGATE || k == PB_K_SAMPLE)) { cudaEventRecord(e->evp[slot][k == PB_K_SAMPLE][0], stream); rec_pool[slot][k == PB_K_SAMPLE] = true; }
+  };
+  auto tock = [&](int k, int slot) {
+    if (plevel >= 2) cudaEventRecord(e->ev[2 * k + 1], stream);
+    else if (plevel == 1 && (k == PB_K_PROPAGATE || k == PB_K_SAMPLE)) cudaEventRecord(e->evp[slot][k == PB_K_SAMPLE][1], stream);
+  };
+  auto collect = [&]() {     // after a stream synchronise
     for (int k = 0; k < PB_K_N; ++k) {
       if (!recorded[k]) continue;
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]) == cudaSuccess) e->prof.ms[k] += ms;
       recorded[k] = false;
     }
+    for (int a = 0; a < pb_engine_s::LOOKAHEAD; ++a) for (int b = 0; b < 2; ++b) {
+      if (!rec_pool[a][b]) continue;
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e->evp[a][b][0], e->evp[a][b][1]) == cudaSuccess) e->prof.ms[b ? PB_K_SAMPLE : PB_K_PROPAGATE] += ms;
+      rec_pool[a][b] = false;
+    }
   };
-  { int rc0 = ensure_order(e, 0, std::max<long long>(2 * n0, 1 << 16), stream); if (rc0 != PB_OK) return rc0; }
-  unsigned long long tail0[2] = {(unsigned long long)n0, 0ull};
-  PB_CUDA(e, cudaMemcpyAsync(e->work.tail, tail0, sizeof(tail0), cudaMemcpyHostToDevice, stream));
-  PB_CUDA(e, cudaMemsetAsync(e->work.ctrl, 0, sizeof(int) * 8, stream));
-  tick(PB_K_INIT);
+  tick(PB_K_INIT, 0);
   k_init_primaries<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(e->tab, S, e->work, d_p, d_r, d_w, d_pid, d_fl, n0, seed, first_id);
-  tock(PB_K_INIT);
+  tock(PB_K_INIT, 0);
+  ++e->prof.launches[PB_K_INIT];
   ++launches;
-  unsigned long long lists0[2] = {0, 0};
-  PB_CUDA(e, cudaMemcpyAsync(lists0, e->work.tail, sizeof(lists0), cudaMemcpyDeviceToHost, stream));
-  PB_CUDA(e, cudaStreamSynchronize(stream));
-  long long n_charged = (long long)(lists0[1] & 0xffffffffull);
-  PB_CUDA(e, cudaMemsetAsync(e->work.counters, 0, sizeof(unsigned long long) * CNT_N, stream));
-  PB_CUDA(e, cudaMemsetAsync(e->work.hist, 0, sizeof(int) * NBUCKET, stream));
 
-  long long begin = 0, end = n0, waves = 0, max_wave = 0, tot_charged = 0;
-  const int sample_grid = e->n_sm * 4;
-  while (begin < end) {
-    long long n = end - begin;
-    if (n > 0x7fffffffLL) { e->err = "wave wider than 2^31"; return PB_ERR_CAPACITY; }
-    if (end + 2 * n > st->capacity) {
-      e->err = "particle stack capacity exhausted (wave " + std::to_string(waves) + ")";
-      return PB_ERR_CAPACITY;
+  WaveState* hws = e->h_ws;
+  unsigned long long* htail = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(hws) + sizeof(WaveState));
+  long long n_known = n0, n_prev = 0;
+  const int ms_flag = global_ms ? 1 : 0;
+  for (;;) {
+    // grow phase (or full profiling): one wave per synchronisation; shrinking tail: LOOKAHEAD waves per synchronisation
+    const int K = (plevel >= 2 || n_known > n_prev) ? 1 : pb_engine_s::LOOKAHEAD;
+    const long long bound = std::max<long long>(K == 1 ? (n_known * 9) / 8 : 2 * n_known, 4096);
+    // one thread per entry of the (upper-bounded) wave; the kernels are grid-stride, so a wave that outgrows the bound
+    // inside a lookahead batch is still processed completely
+    const unsigned g128 = (unsigned)((bound + 127) / 128);
+    const unsigned g256 = (unsigned)((bound + 255) / 256);
+    const int lg = (int)std::min<long long>((long long)e->n_sm * 8, (bound + 4 * 8 - 1) / (4 * 8));
+    const int sg = (int)std::min<long long>((long long)e->n_sm * 4, (bound + 31) / 32 + 1);
+    for (int j = 0; j < K; ++j) {
+      k_wave_begin<<<1, 1, 0, stream>>>(e->work);
+      tick(PB_K_PROPAGATE, j);
+      k_loop<<<lg, 128, 0, stream>>>(e->mat, e->tab, S, e->work, e->prim_mass, ms_flag);
+      tock(PB_K_PROPAGATE, j); tick(PB_K_FINALIZE, j);
+      k_finalize<<<g128, 128, 0, stream>>>(e->mat, e->tab, S, e->work, e->prim_mass, ms_flag);
+      tock(PB_K_FINALIZE, j); tick(PB_K_SCAN, j);
+      k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
+      tock(PB_K_SCAN, j); tick(PB_K_FILL, j);
+      k_bucket_fill<<<g256, 256, 0, stream>>>(e->work, -1);
+      tock(PB_K_FILL, j); tick(PB_K_SAMPLE, j);
+      SampleIO io{S.pf, S.key, nullptr, reinterpret_cast<int*>(S.aux), 2, e->work.ws};
+      launch_sample(e, sg, io, stream);
+      tock(PB_K_SAMPLE, j); tick(PB_K_EMIT, j);
+      k_emit<<<g128, 128, 0, stream>>>(e->mat, e->tab, S, e->work);
+      tock(PB_K_EMIT, j);
+      launches += 7;
     }
-    int rc = ensure_work(e, n);
-    if (rc != PB_OK) return rc;
-    std::swap(e->work.order_c, e->work.next_c);          // lists built by the previous wave become current
-    std::swap(e->work.order_n, e->work.next_n);
-    rc = ensure_order(e, n, 2 * n, stream);
-    if (rc != PB_OK) return rc;
-    max_wave = std::max(max_wave, n);
-    PB_CUDA(e, cudaMemsetAsync(e->work.tail + 1, 0, sizeof(unsigned long long), stream));
-    tot_charged += n_charged;
-    if (n_charged > 0) {
-      tick(PB_K_PROPAGATE);
-      int lg = (int)std::min<long long>((long long)e->n_sm * 8, (n_charged + 4 * LOOP_CHUNK - 1) / (4 * LOOP_CHUNK));
-      k_loop<<<lg, 128, 0, stream>>>(e->mat, e->tab, S, e->work, begin, (int)n_charged, e->prim_mass, global_ms ? 1 : 0);
-      tock(PB_K_PROPAGATE);
-      ++launches;
-    }
-    tick(PB_K_FINALIZE);
-    k_finalize<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, e->tab, S, e->work, begin, (int)n_charged, (int)n,
-                                                                 e->prim_mass, global_ms ? 1 : 0);
-    tock(PB_K_FINALIZE); tick(PB_K_SCAN);
-    k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
-    tock(PB_K_SCAN); tick(PB_K_FILL);
-    k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, (int)n);
-    tock(PB_K_FILL); tick(PB_K_SAMPLE);
-    int sg = (int)std::min<long long>(sample_grid, (n + 31) / 32 + 1);
-    SampleIO io{S.pf + 4 * begin, S.key + begin, nullptr, reinterpret_cast<int*>(S.aux + begin), 2};
-    launch_sample(e, sg, io, stream);
-    tock(PB_K_SAMPLE); tick(PB_K_EMIT);
-    k_emit<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(e->mat, e->tab, S, e->work, begin, (int)n);
-    tock(PB_K_EMIT);
-    launches += 5;
-    unsigned long long tl[2] = {0, 0};
-    PB_CUDA(e, cudaMemcpyAsync(tl, e->work.tail, sizeof(tl), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(e, cudaMemcpyAsync(hws, e->work.ws, sizeof(WaveState), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(e, cudaMemcpyAsync(htail, e->work.tail, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     PB_CUDA(e, cudaStreamSynchronize(stream));
-    unsigned long long tail = tl[0];
     collect();
-    n_charged = (long long)(tl[1] & 0xffffffffull);
-    begin = end;
-    end = (long long)std::min<unsigned long long>(tail, (unsigned long long)st->capacity);
-    ++waves;
+    if (hws->status == 3) {             // scratch too small for the next wave: grow (contents preserved) and resume it
+      long long need = (long long)std::min<unsigned long long>(htail[0], (unsigned long long)st->capacity) - hws->begin;
+      if (need > 0x3fffffffLL) { e->err = "wave wider than 2^30"; return PB_ERR_CAPACITY; }
+      int rc = ensure_work(e, 2 * need);
+      if (rc != PB_OK) return rc;
+      rc = ensure_order(e, 4 * need, stream);
+      if (rc != PB_OK) return rc;
+      int caps[2] = {(int)std::min<long long>(e->work_n, 0x7fffffff), (int)std::min<long long>(e->order_cap, 0x7fffffff)};
+      PB_CUDA(e, cudaMemcpyAsync(&e->work.ws->work_cap, caps, sizeof(caps), cudaMemcpyHostToDevice, stream));
+      n_prev = 0; n_known = need;
+      continue;
+    }
+    if (hws->status != 0) break;
+    n_prev = n_known;
+    n_known = hws->n;
+  }
+  for (int k = 1; k < PB_K_N; ++k) e->prof.launches[k] = hws->waves;
+  long long end = hws->end, waves = hws->waves, max_wave = hws->max_wave, tot_charged = hws->tot_charged;
+  if (hws->status == 2) {
+    e->err = "particle stack capacity exhausted (wave " + std::to_string(waves) + ")";
+    return PB_ERR_CAPACITY;
   }
   unsigned long long cnt[CNT_N];
   PB_CUDA(e, cudaMemcpyAsync(cnt, e->work.counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
@@ -1588,7 +1676,7 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
     k_bucket_fill<<<(unsigned)((n_cand + 255) / 256), 256, 0, stream>>>(e->work, n_cand);
     tock(PB_K_FILL); tick(PB_K_SAMPLE);
     int sg = (int)std::min<long long>((long long)e->n_sm * 4, (n_cand + 31) / 32 + 1);
-    SampleIO io{e->cand.pf, S.key, e->cand.slot, e->cand.ntr, 1};
+    SampleIO io{e->cand.pf, S.key, e->cand.slot, e->cand.ntr, 1, nullptr};
     launch_sample(e, sg, io, stream);
     tock(PB_K_SAMPLE); tick(PB_K_EMIT);
     k_dark_emit<<<(unsigned)((n_cand + 127) / 128), 128, 0, stream>>>(e->mat, S, O, e->work, e->cand, n_cand);
@@ -1654,7 +1742,7 @@ extern "C" int pb_draw_samples(pb_engine e, int process, const double* E, int64_
   k_prepare_draws<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->tab, e->work, e->cand, dkeys, dE, (int)n, process, lu_key, seed, first_id);
   k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
   k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, (int)n);
-  SampleIO io{e->cand.pf, dkeys, nullptr, e->cand.ntr, 1};
+  SampleIO io{e->cand.pf, dkeys, nullptr, e->cand.ntr, 1, nullptr};
   launch_sample(e, (int)std::min<long long>((long long)e->n_sm * 4, (n + 31) / 32 + 1), io, stream);
   cudaError_t c = cudaMemcpyAsync(x_out, e->work.xs, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, stream);
   if (c == cudaSuccess && ntr_out) c = cudaMemcpyAsync(ntr_out, e->cand.ntr, sizeof(int) * n, cudaMemcpyDeviceToHost, stream);
