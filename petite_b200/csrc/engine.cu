@@ -37,6 +37,9 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #ifndef PB_SAMPLE_MINB
 #define PB_SAMPLE_MINB 4
 #endif
+#ifndef PB_SAMPLE_MINB_SM
+#define PB_SAMPLE_MINB_SM 5
+#endif
 #ifndef PB_LOOP_MINB
 #define PB_LOOP_MINB 6
 #endif
@@ -243,7 +246,7 @@ __global__ void k_wave_begin(Work W) {
   ws.waves += 1;
   ws.max_wave = max(ws.max_wave, (int)n);
   W.tail[1] = 0;
-  W.ctrl[1] = 0; W.ctrl[2] = 0;
+  W.ctrl[1] = 0; W.ctrl[2] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0;
 }
 
 // Sub-step loop of propagate_particle, charged species only.  Persistent warps pull chunks of the wave's charged
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
     }
     cbase += cnt[k]; tbase += til[k];
   }
-  if (t == 1023) { W.offsets[NBUCKET] = cbase; W.ctrl[0] = tbase; W.ctrl[1] = 0; }
+  if (t == 1023) { W.offsets[NBUCKET] = cbase; W.ctrl[0] = tbase; W.ctrl[1] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0; }
   if (t == 0) W.ctrl[2] = 0;
 }
 
@@ -553,7 +556,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // One accept/reject trial: Philox doubles D[0..dim] = y_0..y_{dim-1}, u_accept; map y -> x through the staged
 // grid (vegas AdaptiveMap: x = g[i] + (g[i+1]-g[i]) * (y*ninc - i), jac = prod ninc*(g[i+1]-g[i])); accept iff
 // max_F * u < (jac / B) * f(x)  (shower.py:453-459).
-template <int DIM>
+template <int DIM, int FAM>
 __device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, const double* __restrict__ g, int proc,
                                       double E, const SampleConst& sc, double maxF, uint2 key, uint32_t t, double* x) {
   double D[DIM + 2];
@@ -578,6 +581,14 @@ __device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, cons
   if (DIM == 4) {
     if (proc == P_PAIRPROD) f = ds_pairprod_fast(sc, E, x);
     else f = ds_brem_fast(M, sc, E, proc == P_BREM ? kMe : kMmu, x);
+  } else if (FAM == 1) {
+    switch (proc) {            // the five 1-D SM processes only
+      case P_COMP: f = ds_compton(M, E, 0.0, x[0]); break;
+      case P_ANN: f = ds_annihilation(E, 0.0, M.Eg_min, x[0]); break;
+      case P_MOLLER: f = ds_moller(E, M.Ee_min, x[0]); break;
+      case P_BHABHA: f = ds_bhabha(E, M.Ee_min, x[0]); break;
+      default: f = ds_muone(E, M.Ee_min, x[0]); break;
+    }
   } else {
     f = dsigma(M, proc, E, x);
   }
@@ -599,8 +610,12 @@ struct SampleIO {
   const WaveState* ws;     // SM pass: entry i is stack slot ws->begin + i (E4/key/ntr then point at slot 0)
 };
 
-template <int G>
-__global__ void __launch_bounds__(SAMPLE_THREADS, PB_SAMPLE_MINB)
+__host__ __device__ constexpr int proc_family(int p) {
+  return (p == P_BREM || p == P_PAIRPROD || p == P_MUONBREM) ? 0 : (p < P_DARKBREM ? 1 : 2);
+}
+
+template <int G, int FAM>
+__global__ void __launch_bounds__(SAMPLE_THREADS, (FAM == 0 || FAM == 1) ? PB_SAMPLE_MINB_SM : PB_SAMPLE_MINB)
 k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, SampleIO io, Work W) {
   __shared__ __align__(128) double s_grid[GRID_SMEM_DOUBLES];
   __shared__ __align__(8) uint64_t s_bar;
@@ -616,12 +631,13 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
   const size_t off = io.ws ? (size_t)io.ws->begin : 0;
   __syncthreads();
   for (;;) {
-    if (threadIdx.x == 0) { s_tile = atomicAdd(&W.ctrl[1], 1); s_cursor = 0; }
+    if (threadIdx.x == 0) { s_tile = atomicAdd(&W.ctrl[FAM < 0 ? 1 : 4 + FAM], 1); s_cursor = 0; }
     __syncthreads();
     int tile = s_tile;
     if (tile >= W.ctrl[0]) break;
     int bucket = W.tile_bucket[tile], tstart = W.tile_start[tile], tcount = W.tile_count[tile];
     int proc = bucket / LU_MAX, lu = bucket % LU_MAX;
+    if (FAM >= 0 && proc_family(proc) != FAM) { __syncthreads(); continue; }     // another family's kernel takes this tile
     const MapInfo& mi = T.map[proc];
     if (threadIdx.x == 0) {
       uint32_t bytes = (uint32_t)mi.stride * 8u;
@@ -657,10 +673,12 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
       bool acc = false;
       uint32_t t = round * G + sub;
       if (cur >= 0 && (long long)t < max_trials) {
-        switch (mi.dim) {
-          case 4: acc = trial<4>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
-          case 3: acc = trial<3>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
-          default: acc = trial<1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
+        if (FAM == 0) acc = trial<4, 0>(M, mi, s_grid, proc, E, sc, maxF, key, t, x);
+        else if (FAM == 1) acc = trial<1, 1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x);
+        else switch (mi.dim) {
+          case 4: acc = trial<4, -1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
+          case 3: acc = trial<3, -1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
+          default: acc = trial<1, -1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
         }
       }
       unsigned ball = __ballot_sync(0xffffffffu, acc);
@@ -1386,14 +1404,21 @@ extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int 
 }
 
 static int ensure_cand(pb_engine e, long long ncap);
-static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream) {
+// SM pass: one launch per integrand family (4-D small-angle processes; 1-D two-body processes), so that the hot 4-D
+// kernel is not register-allocated for the dark-brem integrand.  Dark pass / stand-alone sampling: one generic launch.
+static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream, bool sm_families = false) {
+  if (sm_families && e->sample_group == 8) {
+    k_sample<8, 0><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work);
+    k_sample<8, 1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work);
+    return;
+  }
   switch (e->sample_group) {
-    case 1: k_sample<1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    case 2: k_sample<2><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    case 4: k_sample<4><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    case 16: k_sample<16><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    case 32: k_sample<32><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    default: k_sample<8><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    case 1: k_sample<1, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    case 2: k_sample<2, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    case 4: k_sample<4, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    case 16: k_sample<16, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    case 32: k_sample<32, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    default: k_sample<8, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
   }
 }
 
@@ -1546,7 +1571,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
       k_bucket_fill<<<g256, 256, 0, stream>>>(e->work, -1);
       tock(PB_K_FILL, j); tick(PB_K_SAMPLE, j);
       SampleIO io{S.pf, S.key, nullptr, reinterpret_cast<int*>(S.aux), 2, e->work.ws};
-      launch_sample(e, sg, io, stream);
+      launch_sample(e, sg, io, stream);   // one generic launch: splitting by integrand family (k_sample<8,0>/<8,1>) was measured slower
       tock(PB_K_SAMPLE, j); tick(PB_K_EMIT, j);
       k_emit<<<g128, 128, 0, stream>>>(e->mat, e->tab, S, e->work);
       tock(PB_K_EMIT, j);
