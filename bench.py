@@ -301,6 +301,13 @@ def ours(args):
                       "alg_GBps": (rl.kernel_bytes(k, tot) / (prof_ms[k] * 1e-3) / 1e9) if prof_ms[k] > 0 else 0.0,
                       "model_fp64_tflops": (rl.kernel_flops(k, tot, trials) / (prof_ms[k] * 1e-3) / 1e12) if prof_ms[k] > 0 else 0.0}
                   for k in prof_ms}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
     line = {
         "metric": "showers/sec", "value": world * n * K / (ms * 1e-3), "unit": "showers/s", "n_gpus": world, "steps": K,
         "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -316,7 +323,8 @@ def ours(args):
                        "substeps": tot["n_substeps"] / (K * n), "trials": tot["n_trials"] / (K * n),
                        "waves": tot["n_waves"] / K},
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": ach / hbm_peak, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                     "traffic_capture": traffic, "peak_source": peak_src,
                      "launches": prof_launch[dom], "avg_launch_ms": dom_ms / max(prof_launch[dom], 1),
                      "algorithmic_bytes_per_launch": dom_bytes / max(prof_launch[dom], 1),
                      "share_of_step": dom_ms / step_ms_total if step_ms_total else None,

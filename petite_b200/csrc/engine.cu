@@ -1139,30 +1139,49 @@ __device__ __forceinline__ int species_of(int pid) {
   return 6;
 }
 __global__ void __launch_bounds__(256) k_tally(Stack S, long long first, long long n, double* __restrict__ tally) {
-  __shared__ double s_t[PB_TALLY_SIZE];
-  for (int k = threadIdx.x; k < PB_TALLY_SIZE; k += blockDim.x) s_t[k] = 0.0;
+  // per-warp private histograms (8 x 1024 doubles of dynamic shared memory) and register accumulators for the three
+  // per-species sums: almost every record of a shower batch falls into the same handful of bins, and one shared copy
+  // serialises on them
+  extern __shared__ double s_t[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* mine = s_t + warp * PB_TALLY_SIZE;
+  for (int k = threadIdx.x; k < 8 * PB_TALLY_SIZE; k += blockDim.x) s_t[k] = 0.0;
   __syncthreads();
+  double cnt[PB_TALLY_NSPECIES], ws[PB_TALLY_NSPECIES], wes[PB_TALLY_NSPECIES];
+#pragma unroll
+  for (int k = 0; k < PB_TALLY_NSPECIES; ++k) { cnt[k] = 0.0; ws[k] = 0.0; wes[k] = 0.0; }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     long long s = first + i;
     const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
     double2 a0 = p0p[0], a1 = p0p[1];
     double w = S.r0w[4 * s + 3];
     int sp = species_of(S.meta[s].x);
-    atomicAdd(&s_t[PB_TALLY_COUNT + sp], 1.0);
-    atomicAdd(&s_t[PB_TALLY_WSUM + sp], w);
-    atomicAdd(&s_t[PB_TALLY_WESUM + sp], w * a0.x);
+#pragma unroll
+    for (int k = 0; k < PB_TALLY_NSPECIES; ++k)
+      if (sp == k) { cnt[k] += 1.0; ws[k] += w; wes[k] += w * a0.x; }
     int eb = (int)floor((log10(a0.x) + 3.0) * (PB_TALLY_EBINS / 6.0));
     eb = min(max(eb, 0), PB_TALLY_EBINS - 1);
-    atomicAdd(&s_t[PB_TALLY_EHIST + sp * PB_TALLY_EBINS + eb], w);
+    atomicAdd(&mine[PB_TALLY_EHIST + sp * PB_TALLY_EBINS + eb], w);
     double pt = sqrt(a0.y * a0.y + a1.x * a1.x);
     double th = atan2(pt, a1.y);
     int tb = (th > 0) ? (int)floor((log10(th) + 7.0) * (PB_TALLY_TBINS / 8.0)) : 0;
     tb = min(max(tb, 0), PB_TALLY_TBINS - 1);
-    atomicAdd(&s_t[PB_TALLY_THIST + sp * PB_TALLY_TBINS + tb], w);
+    atomicAdd(&mine[PB_TALLY_THIST + sp * PB_TALLY_TBINS + tb], w);
+  }
+#pragma unroll
+  for (int k = 0; k < PB_TALLY_NSPECIES; ++k) {
+    double c = cnt[k], a = ws[k], b = wes[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      c += __shfl_down_sync(0xffffffffu, c, o); a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { mine[PB_TALLY_COUNT + k] = c; mine[PB_TALLY_WSUM + k] = a; mine[PB_TALLY_WESUM + k] = b; }
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < PB_TALLY_SIZE; k += blockDim.x)
-    if (s_t[k] != 0.0) atomicAdd(&tally[k], s_t[k]);
+  for (int k = threadIdx.x; k < PB_TALLY_SIZE; k += blockDim.x) {
+    double v = 0.0;
+    for (int wv = 0; wv < 8; ++wv) v += s_t[wv * PB_TALLY_SIZE + k];
+    if (v != 0.0) atomicAdd(&tally[k], v);
+  }
 }
 
 // FP64 roofline denominator: 8 independent DFMA chains per thread
@@ -1594,6 +1613,9 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
       continue;
     }
     if (hws->status != 0) break;
+    if (const char* lw = getenv("PB_LOG_WAVES")) {        // measurement aid: sizes of the waves the host sees
+      if (FILE* f = fopen(lw, "a")) { fprintf(f, "wave %d n %d n_charged %d\n", hws->waves, hws->n, hws->n_charged); fclose(f); }
+    }
     n_prev = n_known;
     n_known = hws->n;
   }
@@ -1811,8 +1833,9 @@ extern "C" int pb_tally(pb_engine e, const pb_stack* st, int64_t first, int64_t 
   if (n == 0) return PB_OK;
   PB_CUDA(e, cudaSetDevice(e->device));
   Stack S{st->p0, st->r0w, st->pf, st->rf, (uint2*)st->key, (int4*)st->meta, (int2*)st->aux, st->capacity};
-  int grid = (int)std::min<long long>((n + 255) / 256, (long long)e->n_sm * 8);
-  k_tally<<<grid, 256, 0, (cudaStream_t)stream_>>>(S, first, n, tally);
+  int grid = (int)std::min<long long>((n + 255) / 256, (long long)e->n_sm * 3);
+  cudaFuncSetAttribute(k_tally, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * PB_TALLY_SIZE * (int)sizeof(double));
+  k_tally<<<grid, 256, 8 * PB_TALLY_SIZE * sizeof(double), (cudaStream_t)stream_>>>(S, first, n, tally);
   PB_CUDA(e, cudaGetLastError());
   return PB_OK;
 }
