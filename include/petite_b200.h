@@ -193,6 +193,15 @@ int pb_find_max(pb_engine e, int process, int n_trials, uint64_t seed, double mT
 /* Histogram / yield tallies over records [first, first+n) of a stack, ACCUMULATED into tally[PB_TALLY_SIZE] [dev]. */
 int pb_tally(pb_engine e, const pb_stack* stack, int64_t first, int64_t n, double* tally /*[dev]*/, void* stream);
 
+/* detector_cut / transverse_position (shower.py:815-864): straight-line extrapolation of records [first, first+n) from
+ * their creation point to the planes z = z_det[k] and test r_T in (inner_radius, radius); records are first filtered by
+ * E_lo < E < E_hi (pass -inf/+inf for no cut).  weight_pass [host] n_det = summed weights inside the ring ("TotalWeight"),
+ * weight_all [host] 1 = summed weight after the energy cut ("Efficiency" = ratio); mask [dev] n x n_det bytes or NULL
+ * ("SampleW"). */
+int pb_detector_cut(pb_engine e, const pb_stack* stack, int64_t first, int64_t n, const double* z_det /*[host]*/, int n_det,
+                    double radius, double inner_radius, double E_lo, double E_hi, double* weight_pass, double* weight_all,
+                    uint8_t* mask /*[dev]*/, void* stream);
+
 int pb_set_profiling(pb_engine e, int level);   /* 0 off; 1 = time k_loop and k_sample only; 2 = time every kernel */
 int pb_get_profile(pb_engine e, pb_profile* out /*[host]*/);
 

@@ -83,6 +83,8 @@ SIGNATURES = {
                                   c_int32_p, C.c_void_p]),
     "pb_find_max": (C.c_int, [pb_engine, C.c_int, C.c_int, C.c_uint64, C.c_double, c_double_p, c_double_p]),
     "pb_tally": (C.c_int, [pb_engine, C.POINTER(pb_stack), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pb_detector_cut": (C.c_int, [pb_engine, C.POINTER(pb_stack), C.c_int64, C.c_int64, c_double_p, C.c_int, C.c_double, C.c_double,
+                                  C.c_double, C.c_double, c_double_p, c_double_p, C.c_void_p, C.c_void_p]),
     "pb_set_profiling": (C.c_int, [pb_engine, C.c_int]),
     "pb_get_profile": (C.c_int, [pb_engine, C.POINTER(pb_profile)]),
     "pb_measure_fp64_peak": (C.c_int, [pb_engine, c_double_p]),

@@ -1184,6 +1184,41 @@ __global__ void __launch_bounds__(256) k_tally(Stack S, long long first, long lo
   }
 }
 
+// detector_cut (shower.py:815-864): one thread per record, loop over detector planes
+constexpr int MAX_DET = 16;
+struct DetPlanes { double z[MAX_DET]; int n; };
+__global__ void __launch_bounds__(256)
+k_detector_cut(Stack S, long long first, long long n, const __grid_constant__ DetPlanes D, double radius, double inner,
+               double E_lo, double E_hi, double* __restrict__ sums /*[MAX_DET + 1]*/, unsigned char* __restrict__ mask) {
+  double acc[MAX_DET + 1];
+#pragma unroll
+  for (int k = 0; k <= MAX_DET; ++k) acc[k] = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long s = first + i;
+    const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
+    const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
+    double2 a0 = p0p[0], a1 = p0p[1], b0 = r0p[0], b1 = r0p[1];
+    bool in_E = (a0.x < E_hi) && (a0.x > E_lo);
+    if (in_E) acc[MAX_DET] += b1.y;
+#pragma unroll
+    for (int k = 0; k < MAX_DET; ++k) {
+      if (k >= D.n) break;
+      double T = (D.z[k] - b1.x) / a1.y;                 // (z - z0) / pz
+      double xf = b0.x + T * a0.y, yf = b0.y + T * a1.x;
+      double rT = sqrt(xf * xf + yf * yf);
+      bool pass = in_E && (rT > inner) && (rT < radius);
+      if (pass) acc[k] += b1.y;
+      if (mask) mask[i * D.n + k] = pass ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k <= MAX_DET; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&sums[k], v);
+  }
+}
+
 // FP64 roofline denominator: 8 independent DFMA chains per thread
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -1814,6 +1849,33 @@ extern "C" int pb_find_max(pb_engine e, int process, int n_trials, uint64_t seed
   if (c == cudaSuccess) c = cudaMemcpy(sum_out, d + mi.nE, sizeof(double) * mi.nE, cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
+  return PB_OK;
+}
+
+extern "C" int pb_detector_cut(pb_engine e, const pb_stack* st, int64_t first, int64_t n, const double* z_det, int n_det,
+                               double radius, double inner, double E_lo, double E_hi, double* wpass, double* wall,
+                               uint8_t* mask, void* stream_) {
+  if (!e || !st || !z_det || n_det < 1 || n_det > MAX_DET || n < 0 || first < 0 || first + n > st->capacity) return PB_ERR_ARG;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Stack S{st->p0, st->r0w, st->pf, st->rf, (uint2*)st->key, (int4*)st->meta, (int2*)st->aux, st->capacity};
+  DetPlanes D{};
+  D.n = n_det;
+  for (int k = 0; k < n_det; ++k) D.z[k] = z_det[k];
+  double* d = nullptr;
+  PB_CUDA(e, cudaMalloc(&d, sizeof(double) * (MAX_DET + 1)));
+  PB_CUDA(e, cudaMemsetAsync(d, 0, sizeof(double) * (MAX_DET + 1), stream));
+  if (n > 0) {
+    int grid = (int)std::min<long long>((n + 255) / 256, (long long)e->n_sm * 8);
+    k_detector_cut<<<grid, 256, 0, stream>>>(S, first, n, D, radius, inner, E_lo, E_hi, d, mask);
+  }
+  double h[MAX_DET + 1];
+  cudaError_t c = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream);
+  if (c == cudaSuccess) c = cudaStreamSynchronize(stream);
+  cudaFree(d);
+  if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
+  for (int k = 0; k < n_det; ++k) if (wpass) wpass[k] = h[k];
+  if (wall) *wall = h[MAX_DET];
   return PB_OK;
 }
 

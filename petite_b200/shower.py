@@ -605,6 +605,30 @@ class Shower:
         capi.check(self._engine, capi.lib.pb_find_max(self._engine, code, int(n_trials), int(seed), float(mT), capi.dptr(mf), capi.dptr(sg)))
         return mf, sg
 
+    def batch_from_particles(self, plist):
+        """Upload an existing list of SM ``Particle`` objects as stack records (one pseudo-shower; fresh Philox keys)."""
+        torch = self._torch
+        n = len(plist)
+        self._ensure_stack(max(n, 1024))
+        p0 = np.array([np.asarray(p.get_p0(), dtype=float) for p in plist]).reshape(n, 4)
+        pf = np.array([np.asarray(p.get_pf(), dtype=float) for p in plist]).reshape(n, 4)
+        r0w = np.column_stack([np.array([np.asarray(p.get_r0(), dtype=float) for p in plist]).reshape(n, 3),
+                               [p.get_ids()["weight"] for p in plist]])
+        rf = np.column_stack([np.array([np.asarray(p.get_rf(), dtype=float) for p in plist]).reshape(n, 3),
+                              [p.get_ids()["mass"] for p in plist]])
+        gen = np.array([p.get_ids()["generation_number"] for p in plist], dtype=np.int64) & 0xFFFF
+        meta = np.column_stack([[p.get_ids()["PID"] for p in plist], np.full(n, -1), (gen << 16) | 15, np.zeros(n)]).astype(np.int32)
+        rng = np.random.default_rng((self._seed, self._next_shower_id))
+        self._next_shower_id += 1
+        key = rng.integers(0, 2 ** 32, size=(n, 2), dtype=np.uint64).astype(np.uint32).view(np.int32)
+        t = self._stack_tensors
+        for name, arr in (("p0", p0), ("pf", pf), ("r0w", r0w), ("rf", rf), ("meta", meta), ("key", key)):
+            t[name][:n].copy_(torch.from_numpy(np.ascontiguousarray(arr)))
+        t["aux"][:n].zero_()
+        b = ShowerBatch(self, t, n, {}, 1, 0)
+        b.reference_order = lambda: (np.arange(n), np.array([0, n]))      # the list IS the reference order
+        return b
+
     # ------------------------------------------------------------------ public stepping API
     def generate_showers(self, primaries, GlobalMS=True, capacity=None, first_shower_id=None):
         """Step many independent primaries (list of :class:`Particle`) at once -> :class:`ShowerBatch`."""

@@ -349,9 +349,34 @@ def golden_dark(rng):
     np.savez_compressed(os.path.join(HERE, "dark.npz"), **out)
 
 
+def golden_detector(rng):
+    """shower.detector_cut (shower.py:825-864) on a random particle list."""
+    from PETITE.shower import detector_cut
+    n = 400
+    p3 = rng.normal(size=(n, 3)) * np.array([0.05, 0.05, 1.0]) + np.array([0, 0, 2.0])
+    E = np.sqrt(np.sum(p3 ** 2, axis=1) + m_electron ** 2)
+    r0 = rng.normal(size=(n, 3)) * 0.05
+    w = rng.random(n) * 2
+    plist = [Particle([E[i], *p3[i]], list(r0[i]), {"PID": 11, "mass": m_electron, "weight": float(w[i])}) for i in range(n)]
+    z = [1.0, 10.0, 50.0]
+    out = {"p0": np.column_stack([E, p3]), "r0": r0, "w": w, "z": np.array(z)}
+    for tag, kw in (("a", dict(detector_radius=0.5)), ("b", dict(detector_radius=2.0, energy_cut=(1.0, 3.0), detector_inner_radius=0.2))):
+        out[f"{tag}/total"] = np.array(detector_cut(plist, z, method="TotalWeight", **kw), dtype=float)
+        out[f"{tag}/eff"] = np.array(detector_cut(plist, z, method="Efficiency", **kw), dtype=float)
+        m = np.array(detector_cut(plist, z, method="SampleW", **kw))
+        out[f"{tag}/mask"] = m
+        if "energy_cut" in kw:
+            sel = (E < kw["energy_cut"][1]) & (E > kw["energy_cut"][0])
+            out[f"{tag}/kept"] = np.nonzero(sel)[0]
+    np.savez_compressed(os.path.join(HERE, "detector.npz"), **out)
+
+
 if __name__ == "__main__":
     rng = np.random.default_rng(20261017)
     build_reference_dict_dir()
+    if "--detector-only" in sys.argv:
+        golden_detector(rng)
+        sys.exit(0)
     if "--dark-only" in sys.argv:
         golden_dark(rng)
         sys.exit(0)
@@ -362,6 +387,7 @@ if __name__ == "__main__":
     golden_nsigma()
     golden_showers()
     golden_dark(rng)
+    golden_detector(rng)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -65,3 +65,25 @@ def test_gpu_find_max_reproduces_shipped_cross_sections(material):
         pos = want > 0
         r = mf[pos] / want[pos]
         assert np.median(r) > 0.6 and np.median(r) < 1.6, (P, np.median(r))
+
+
+def test_detector_cut_vs_reference_golden(golden):
+    """pb_detector_cut against the reference's detector_cut (shower.py:825-864) on the same particle list."""
+    from petite_b200 import Particle
+    from petite_b200.analysis import detector_cut
+    g = golden("detector")
+    sh = shower("graphite", 0.010, seed=4)
+    plist = [Particle(list(g["p0"][i]), list(g["r0"][i]), {"PID": 11, "mass": 0.00051099895, "weight": float(g["w"][i])})
+             for i in range(len(g["w"]))]
+    batch = sh.batch_from_particles(plist)
+    z = list(g["z"])
+    for tag, kw in (("a", dict(detector_radius=0.5)), ("b", dict(detector_radius=2.0, energy_cut=(1.0, 3.0), detector_inner_radius=0.2))):
+        tot = detector_cut(batch, sh, z, method="TotalWeight", **kw)
+        eff = detector_cut(batch, sh, z, method="Efficiency", **kw)
+        assert np.allclose(tot, g[f"{tag}/total"], rtol=1e-12)
+        assert np.allclose(eff, g[f"{tag}/eff"], rtol=1e-12)
+        m = detector_cut(batch, sh, z, method="SampleW", **kw)
+        want = g[f"{tag}/mask"]
+        if tag == "b":                                   # the reference drops energy-cut particles before masking
+            m = m[:, g["b/kept"]]
+        assert np.array_equal(m, want)
