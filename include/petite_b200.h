@@ -190,6 +190,17 @@ int pb_draw_samples(pb_engine e, int process, const double* E /*[host]*/, int64_
  * nuclear mass, the sampler A_T: SURVEY Q-19).  max_F_out, sigma_out: [host] n_energy each. */
 int pb_find_max(pb_engine e, int process, int n_trials, uint64_t seed, double mT, double* max_F_out, double* sigma_out);
 
+/* One VEGAS training sweep for n_energy maps of one process (utilities/generate_integrators.py:49-110 ->
+ * all_processes.py:1160-1226 -> vegas' AdaptiveMap training data): n_points uniform y per map are pushed through the
+ * CURRENT node grids `grid` ([host] n_energy rows, same layout as pb_upload_maps) and the integrand of `process` at
+ * E_inc[k]; per axis and increment the sums of (jac*f)^2 and the hit counts are returned in d_out / n_out ([host]
+ * n_energy x sum(ninc+1), slot i of an axis = increment i, last slot unused), the plain MC integral in integral_out.
+ * The grid refinement itself (smoothing, alpha damping, rebinning) is done by the caller (petite_b200/train.py).
+ * Z_T/A_T/mT/mV of the integrand come from the engine's configuration. */
+int pb_train_accumulate(pb_engine e, int process, const double* grid, int n_energy, int dim, const int32_t* ninc,
+                        const double* E_inc, int64_t n_points, uint64_t seed, double mT, double* d_out, double* n_out,
+                        double* integral_out);
+
 /* Histogram / yield tallies over records [first, first+n) of a stack, ACCUMULATED into tally[PB_TALLY_SIZE] [dev]. */
 int pb_tally(pb_engine e, const pb_stack* stack, int64_t first, int64_t n, double* tally /*[dev]*/, void* stream);
 

@@ -1133,6 +1133,53 @@ k_find_max(const __grid_constant__ Material M, const __grid_constant__ Tables T,
   }
 }
 
+// VEGAS training data (sum of (jac f)^2 and counts per axis increment): blockIdx.y = map (energy), dynamic shared memory =
+// node grid + fp64 accumulators + counters of that map
+__global__ void __launch_bounds__(256)
+k_train(const __grid_constant__ Material M, int process, int dim, int stride, int4 ninc4, const double* __restrict__ grids,
+        const double* __restrict__ E_inc, long long n_points, unsigned long long seed, double* __restrict__ d_out,
+        double* __restrict__ n_out, double* __restrict__ integral_out) {
+  extern __shared__ double s_mem[];
+  double* s_grid = s_mem;
+  double* s_d = s_mem + stride;
+  int* s_n = reinterpret_cast<int*>(s_mem + 2 * stride);
+  const int row = blockIdx.y;
+  const int ninc[4] = {ninc4.x, ninc4.y, ninc4.z, ninc4.w};
+  int off[4]; { int o = 0; for (int d = 0; d < 4; ++d) { off[d] = o; o += (d < dim) ? ninc[d] + 1 : 0; } }
+  for (int k = threadIdx.x; k < stride; k += blockDim.x) { s_grid[k] = grids[(size_t)row * stride + k]; s_d[k] = 0.0; s_n[k] = 0; }
+  __syncthreads();
+  const double E = E_inc[row];
+  uint2 key = root_key(seed, ((unsigned long long)process << 32) | (unsigned long long)row);
+  double acc = 0.0;
+  const long long per_block = (n_points + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per_block, p1 = min(n_points, p0 + per_block);
+  for (long long pt = p0 + threadIdx.x; pt < p1; pt += blockDim.x) {
+    double D[6];
+    for (int c = 0; c < (dim + 1) / 2; ++c) { D2 d = draw2(key, (uint32_t)pt, ST_VEGAS, c, (uint32_t)(pt >> 32)); D[2 * c] = d.a; D[2 * c + 1] = d.b; }
+    double x[4] = {0, 0, 0, 0}, jac = 1.0;
+    int iy[4];
+    for (int d = 0; d < dim; ++d) {
+      double yn = D[d] * ninc[d];
+      iy[d] = min((int)yn, ninc[d] - 1);
+      double g0 = s_grid[off[d] + iy[d]], g1 = s_grid[off[d] + iy[d] + 1];
+      double inc = g1 - g0;
+      x[d] = g0 + inc * (yn - iy[d]);
+      jac *= inc * ninc[d];
+    }
+    double f = jac * dsigma(M, process, E, x);
+    if (f == f && fabs(f) < 1e300) {
+      acc += f;
+      double f2 = f * f;
+      for (int d = 0; d < dim; ++d) { atomicAdd(&s_d[off[d] + iy[d]], f2); atomicAdd(&s_n[off[d] + iy[d]], 1); }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc != 0.0) atomicAdd(&integral_out[row], acc / (double)n_points);
+  __syncthreads();
+  for (int k = threadIdx.x; k < stride; k += blockDim.x)
+    if (s_n[k]) { atomicAdd(&d_out[(size_t)row * stride + k], s_d[k]); atomicAdd(&n_out[(size_t)row * stride + k], (double)s_n[k]); }
+}
+
 // ------------------------------------------------------------------------------------------ tallies
 __device__ __forceinline__ int species_of(int pid) {
   switch (pid) { case 11: return 0; case -11: return 1; case 22: return 2; case 13: return 3; case -13: return 4; case 4900022: return 5; }
@@ -1876,6 +1923,39 @@ extern "C" int pb_detector_cut(pb_engine e, const pb_stack* st, int64_t first, i
   if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
   for (int k = 0; k < n_det; ++k) if (wpass) wpass[k] = h[k];
   if (wall) *wall = h[MAX_DET];
+  return PB_OK;
+}
+
+extern "C" int pb_train_accumulate(pb_engine e, int process, const double* grid, int nE, int dim, const int32_t* ninc,
+                                   const double* E_inc, int64_t n_points, uint64_t seed, double mT, double* d_out,
+                                   double* n_out, double* integral_out) {
+  if (!e || !grid || !ninc || !E_inc || !d_out || !n_out || !integral_out || nE < 1 || dim < 1 || dim > 4 || n_points < 1 ||
+      process < 0 || process >= N_SAMPLED) return PB_ERR_ARG;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  int stride = 0;
+  int nn[4] = {0, 0, 0, 0};
+  for (int d = 0; d < dim; ++d) { nn[d] = ninc[d]; stride += ninc[d] + 1; }
+  size_t smem = (size_t)stride * (8 + 8 + 4);
+  if (smem > 200 * 1024) { e->err = "map too large for the training kernel"; return PB_ERR_ARG; }
+  Material m = e->mat;
+  if (mT > 0) m.mT = mT;
+  size_t rows = (size_t)nE * stride;
+  double* d = nullptr;
+  PB_CUDA(e, cudaMalloc(&d, sizeof(double) * (3 * rows + 2 * (size_t)nE)));
+  double *d_grid = d, *d_d = d + rows, *d_n = d + 2 * rows, *d_E = d + 3 * rows, *d_I = d_E + nE;
+  PB_CUDA(e, cudaMemcpy(d_grid, grid, sizeof(double) * rows, cudaMemcpyHostToDevice));
+  PB_CUDA(e, cudaMemcpy(d_E, E_inc, sizeof(double) * nE, cudaMemcpyHostToDevice));
+  PB_CUDA(e, cudaMemset(d_d, 0, sizeof(double) * (2 * rows)));
+  PB_CUDA(e, cudaMemset(d_I, 0, sizeof(double) * nE));
+  PB_CUDA(e, cudaFuncSetAttribute(k_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int bx = (int)std::max<long long>(1, std::min<long long>(64, n_points / 4096));
+  k_train<<<dim3(bx, nE), 256, smem>>>(m, process, dim, stride, make_int4(nn[0], nn[1], nn[2], nn[3]), d_grid, d_E, n_points, seed, d_d, d_n, d_I);
+  cudaError_t c = cudaDeviceSynchronize();
+  if (c == cudaSuccess) c = cudaMemcpy(d_out, d_d, sizeof(double) * rows, cudaMemcpyDeviceToHost);
+  if (c == cudaSuccess) c = cudaMemcpy(n_out, d_n, sizeof(double) * rows, cudaMemcpyDeviceToHost);
+  if (c == cudaSuccess) c = cudaMemcpy(integral_out, d_I, sizeof(double) * nE, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
   return PB_OK;
 }
 

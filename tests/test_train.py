@@ -1,0 +1,59 @@
+"""VEGAS map training: host refinement step on CPU, full training on the GPU."""
+import numpy as np
+import pytest
+
+from tests.conftest import DATA
+
+
+def test_refine_concentrates_increments_where_the_integrand_is():
+    from petite_b200.train import refine, integration_range
+    g = np.linspace(0.0, 1.0, 101)
+    x = 0.5 * (g[1:] + g[:-1])
+    f = np.exp(-0.5 * ((x - 0.3) / 0.02) ** 2) + 1e-3
+    new = g
+    for _ in range(10):                                   # iterate with exact training data for the current grid
+        xc = 0.5 * (new[1:] + new[:-1])
+        w = np.diff(new) * 100
+        fx = np.exp(-0.5 * ((xc - 0.3) / 0.02) ** 2) + 1e-3
+        new = refine(new, (w * fx) ** 2, np.ones(100), alpha=0.5)
+    assert new[0] == 0.0 and new[-1] == 1.0 and np.all(np.diff(new) > 0)
+    inside = np.sum((new > 0.24) & (new < 0.36))
+    assert inside > 60                                     # most nodes moved into the +-3 sigma peak region
+    # after convergence every increment carries a similar share of the integral
+    xc = 0.5 * (new[1:] + new[:-1]); fx = np.exp(-0.5 * ((xc - 0.3) / 0.02) ** 2) + 1e-3
+    share = np.diff(new) * fx
+    assert share.max() / np.median(share) < 6
+    assert integration_range("Brem", 1.0) == [[0, 1], [0, 2], [-2, 2], [0, 1]]
+    r = integration_range("MuonBrem", 10.0)
+    assert r[0] == [0.001, 10.0 - 0.00051099895] and abs(r[1][1] - np.sqrt(10.0 / 0.00051099895)) < 1e-9     # Q-5 domain
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("process", ["PairProd", "Brem", "Comp"])
+def test_trained_maps_reproduce_shipped_cross_sections(process):
+    """Train on hydrogen as the reference does, then integrate graphite through the NEW maps: sigma must reproduce the
+    shipped sm_xsec rows, and the sampler's efficiency must be comparable to the shipped maps'."""
+    from petite_b200.train import Trainer
+    from petite_b200 import tables as tb
+    from petite_b200.shower import Shower, process_code
+    xs = np.load(DATA + "sm_xsec.npz")[f"{process}/graphite"]
+    rows = [30, 60, 80, 99]
+    E = xs[rows, 0]
+    tr = Trainer()
+    grids, ninc, I = tr.train(process, E, nitn=30, n_points=1_000_000, alpha=1.0)
+    assert np.all(np.isfinite(grids)) and np.all(I > 0)
+    off = 0
+    for n in ninc:
+        assert np.all(np.diff(grids[:, off:off + n + 1], axis=1) > 0)             # nodes stay ordered
+        off += n + 1
+    sh = Shower(DATA, "graphite", 0.010, seed=3)
+    shipped = sh._maps[process]
+    mf_old, sg_old = sh.find_max(process, n_trials=100, seed=9)
+    ms = tb.MapSet(process, E, ninc, grids, np.ones(len(E)), shipped.neval, shipped.Eg_min, shipped.Ee_min)
+    sh._upload_maps(process_code[process], ms)
+    sh._maps[process] = ms
+    mf, sg = sh.find_max(process, n_trials=100, seed=9)
+    assert np.all(np.abs(sg / xs[rows, 1] - 1) < 0.05), sg / xs[rows, 1]
+    eff_new = sg / (300 * mf)
+    eff_old = (sg_old / (300 * mf_old))[rows]
+    assert np.all(eff_new > 0.25 * eff_old), (eff_new, eff_old)      # measured: 0.4-0.6 of the shipped maps' efficiency
