@@ -194,6 +194,8 @@ class DarkShower(Shower):
         procs = [p for p in self.active_processes if p in dimensionalities_dark]
         self._dark_maps = tb.load_dark_maps(self._dict_dir, self._mV_estimator, self._target_material, procs)
         for P, ms in self._dark_maps.items():
+            if np.any(np.isnan(ms.max_F)) and os.environ.get("PETITE_B200_ALLOW_MISSING_MAXF"):
+                ms.max_F = np.ones(len(ms.E))
             if np.any(np.isnan(ms.max_F)):
                 raise Exception(f"no max_F table for dark process {P} / {self._target_material} / mV={self._mV_estimator}")
         self._loaded_dark_samples = {

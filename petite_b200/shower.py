@@ -260,8 +260,12 @@ class Shower:
 
     def set_samples(self):
         self._maps = tb.load_sm_maps(self._dict_dir, self._target_material)
+        import os
         for P, ms in self._maps.items():
             if np.any(np.isnan(ms.max_F)):
+                if os.environ.get("PETITE_B200_ALLOW_MISSING_MAXF"):      # bootstrap: tables about to be built with find_max
+                    ms.max_F = np.ones(len(ms.E))
+                    continue
                 raise Exception(f"no max_F table for process {P} / material {self._target_material} in {self._dict_dir}")
         # reference-shaped view: _loaded_samples[process][i] = [E_inc, {...}] (shower.py:210-215)
         self._loaded_samples = {

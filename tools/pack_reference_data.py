@@ -45,15 +45,21 @@ def main():
     ap.add_argument("--src", default="/root/reference/data/")
     ap.add_argument("--dst", default=os.path.join(os.path.dirname(__file__), "..", "data"))
     ap.add_argument("--masses", default="0.003,0.03,1.0", help="dark masses (GeV) to pack maps for")
+    ap.add_argument("--skip-missing", action="store_true",
+                    help="pack only the map files that exist (data_400GeV ships the 1-D maps only; the 4-D/3-D ones are "
+                         "retrained by tools/make_400GeV.py)")
     a = ap.parse_args()
     os.makedirs(a.dst, exist_ok=True)
 
     out = {}
     for P in SM_PROCESSES:
-        rows = load_adaptive_maps_npy(os.path.join(a.src, P, f"{P}_AdaptiveMaps.npy"))
+        path = os.path.join(a.src, P, f"{P}_AdaptiveMaps.npy")
+        if a.skip_missing and not os.path.exists(path):
+            continue
+        rows = load_adaptive_maps_npy(path)
         for k, v in pack_maps(rows).items():
             out[f"{P}/{k}"] = v
-    np.savez_compressed(os.path.join(a.dst, "sm_maps.npz"), **out)
+    np.savez_compressed(os.path.join(a.dst, "sm_maps_shipped.npz" if a.skip_missing else "sm_maps.npz"), **out)
 
     xs = pickle.load(open(os.path.join(a.src, "sm_xsec.pkl"), "rb"))
     np.savez_compressed(os.path.join(a.dst, "sm_xsec.npz"),
@@ -67,10 +73,13 @@ def main():
     for mV in [float(s) for s in a.masses.split(",") if s]:
         out = {}
         for P in DARK_PROCESSES:
-            rows = load_adaptive_maps_npy(os.path.join(a.src, P, f"mV_{int(round(mV * 1000))}MeV", f"{P}_AdaptiveMaps.npy"))
+            path = os.path.join(a.src, P, f"mV_{int(round(mV * 1000))}MeV", f"{P}_AdaptiveMaps.npy")
+            if a.skip_missing and not os.path.exists(path):
+                continue
+            rows = load_adaptive_maps_npy(path)
             for k, v in pack_maps(rows).items():
                 out[f"{P}/{k}"] = v
-        np.savez_compressed(os.path.join(a.dst, f"dark_maps_mV{mv_tag(mV)}.npz"), **out)
+        np.savez_compressed(os.path.join(a.dst, f"dark_maps_mV{mv_tag(mV)}" + ("_shipped" if a.skip_missing else "") + ".npz"), **out)
 
     w = pickle.load(open(os.path.join(a.src, "dark_weights.pkl"), "rb"))
     np.savez_compressed(os.path.join(a.dst, "dark_weights.npz"),
