@@ -57,3 +57,23 @@ def test_trained_maps_reproduce_shipped_cross_sections(process):
     eff_new = sg / (300 * mf)
     eff_old = (sg_old / (300 * mf_old))[rows]
     assert np.all(eff_new > 0.25 * eff_old), (eff_new, eff_old)      # measured: 0.4-0.6 of the shipped maps' efficiency
+
+
+@pytest.mark.gpu
+def test_trained_dark_brem_maps_reproduce_shipped_dark_xsec():
+    from petite_b200.train import Trainer
+    from petite_b200 import tables as tb
+    from petite_b200.dark_shower import DarkShower
+    xs = np.load(DATA + "dark_xsec.npz")["0.03/DarkBrem/graphite"]
+    rows = [20, 50, 80, 99]
+    E = xs[rows, 0]
+    tr = Trainer(mT=200.0, mV=0.03)                      # the reference trains on hydrogen with mT = 200 GeV (map readme)
+    grids, ninc, _ = tr.train("DarkBrem", E, nitn=30, n_points=1_000_000)
+    ds = DarkShower(DATA, "graphite", 0.010, 0.03, active_processes=["DarkBrem", "DarkComp", "DarkAnn"], seed=2)
+    old = ds._dark_maps["DarkBrem"]
+    ms = tb.MapSet("DarkBrem", E, ninc, grids, np.ones(len(E)), old.neval, old.Eg_min, old.Ee_min)
+    ds._upload_maps(8, ms)
+    ds._dark_maps["DarkBrem"] = ms
+    mf, sg = ds.find_max("DarkBrem", n_trials=100, seed=4)
+    assert np.all(np.abs(sg / xs[rows, 1] - 1) < 0.05), sg / xs[rows, 1]
+    assert np.all(sg / (300 * mf) > 0.01)
