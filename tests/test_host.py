@@ -113,3 +113,49 @@ def test_reference_order_reconstruction():
     assert list(offs) == [0, 5, 9]
     assert list(order[:5]) == [0, 4, 3, 8, 6]      # shower 0: primary; daughters bit0, bit1; then slot 3's daughters
     assert list(order[5:]) == [1, 5, 2, 7]
+
+
+def test_reference_format_dict_dir_is_accepted(tmp_path):
+    """Drop-in: a PETITE-style dict_dir (sm_xsec.pkl, sm_maps.pkl with pickled vegas AdaptiveMap objects, dark_*.pkl) must
+    load without vegas and give the same tables as the repacked .npz files."""
+    import pickle
+    import sys
+    import types
+    from petite_b200 import tables as tb
+
+    class AdaptiveMap:                       # stands in for vegas._vegas.AdaptiveMap when WRITING the fixture
+        def __init__(self, grid):
+            self.grid = grid
+
+        def __reduce__(self):
+            return (AdaptiveMap, ([list(map(float, g)) for g in self.grid],))
+    AdaptiveMap.__module__, AdaptiveMap.__qualname__ = "vegas._vegas", "AdaptiveMap"
+    mod = types.ModuleType("vegas._vegas"); mod.AdaptiveMap = AdaptiveMap
+    pkg = types.ModuleType("vegas"); pkg._vegas = mod
+    saved = {k: sys.modules.get(k) for k in ("vegas", "vegas._vegas")}
+    sys.modules["vegas"], sys.modules["vegas._vegas"] = pkg, mod
+    try:
+        npz = tb.load_sm_maps(DATA, "lead")
+        xs = tb.load_sm_xsec(DATA, "lead")
+        d = str(tmp_path) + "/"
+        maps = {P: [[float(ms.E[i]), {"neval": ms.neval, "max_F": {"lead": float(ms.max_F[i])}, "Eg_min": ms.Eg_min, "Ee_min": ms.Ee_min,
+                                      "adaptive_map": AdaptiveMap([ms.axis_nodes(i, k) for k in range(ms.dim)])}] for i in range(0, 100, 33)]
+                for P, ms in npz.items()}
+        pickle.dump(maps, open(d + "sm_maps.pkl", "wb"))
+        pickle.dump({P: {"lead": [list(r) for r in xs[P]]} for P in xs}, open(d + "sm_xsec.pkl", "wb"))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    assert "vegas" not in sys.modules                       # reading must not need it
+    got = tb.load_sm_maps(d, "lead")
+    for P, ms in got.items():
+        assert ms.dim == npz[P].dim and list(ms.ninc) == list(npz[P].ninc)
+        assert np.array_equal(ms.grid, npz[P].grid[::33]) and np.array_equal(ms.max_F, npz[P].max_F[::33])
+        assert ms.neval == 300
+    gx = tb.load_sm_xsec(d, "lead")
+    assert all(np.array_equal(gx[P], xs[P]) for P in xs)
+    with pytest.raises(Exception, match="Target Material is not in library"):
+        tb.load_sm_xsec(d, "graphite")
