@@ -87,16 +87,21 @@ class CounterDraws:
         return self._d(0, ph.ST_FINAL)[0]
 
     def mcs(self, i, pc=0):
-        us, up = self._d(i, ph.ST_MCS, 0, pc)
-        ua, ur = self._d(i, ph.ST_MCS, 1, pc)
-        z1, z2 = normals_from_uniforms(ua, ur)
-        return (-1 if us < 0.5 else 1), z1, z2, up
+        # one call: (u_phi, u_radius) + the sign from a spare bit; only |z| = sqrt(z1^2 + z2^2) enters the reference's
+        # angle (moliere.py:265-284), so the Box-Muller angle is fixed to 0 (z1 = |z|, z2 = 0)
+        up, ur, spare = ph.draw2s(self.key, i, ph.ST_MCS, 0, pc)
+        z1, z2 = normals_from_uniforms(0.0, float(ur))
+        return (1 if int(spare) & 1 else -1), z1, z2, float(up)
 
     def choice(self, pc=0):
         return self._d(0, ph.ST_CHOICE, 0, pc)[0]
 
     def _trial_doubles(self, sweep, B, dim, pc):
         t = np.arange(sweep * B, (sweep + 1) * B, dtype=np.uint64)
+        if dim == 4:        # two calls: y_0..y_3, and u_accept from the calls' spare bits
+            a0, b0, s0 = ph.draw2s(self.key, t, ph.ST_VEGAS, 0, pc)
+            a1, b1, s1 = ph.draw2s(self.key, t, ph.ST_VEGAS, 1, pc)
+            return np.stack([a0, b0, a1, b1, ph.u48(s0, s1)], axis=1)
         ncall = (dim + 2) // 2
         cols = []
         for j in range(ncall):

@@ -53,6 +53,7 @@ struct MapInfo {
   const double* E;
   const double* maxF;
   int nE, dim, stride, B;
+  double invB;               // 1 / B (points per sweep): wgt = jac / B
   double log_E0, inv_dlog;   // geometric-grid guess for the row look-up
   int ninc[4];
   int off[4];
@@ -101,6 +102,8 @@ struct Work {            // per-wave scratch, sized to the widest wave seen so f
   int* bucket;           // [n] bucket of particle (begin + i)
   int* sorted;           // [n] wave-local indices in bucket order
   double* xs;            // [n x 4] accepted sample (map variables)
+  double* sE;            // [n] incoming energy, gathered into bucket order by k_bucket_fill (contiguous per tile)
+  uint2* skey;           // [n] particle key, likewise
   int* hist;             // [NBUCKET]
   int* offsets;          // [NBUCKET + 1]
   int* cursor;           // [NBUCKET]
@@ -205,7 +208,7 @@ __device__ __forceinline__ int lookup_row(const MapInfo& m, double logE, double 
 // One dE/dx + multiple-scattering sub-step state of a charged track (shower.py:559-581)
 struct Track {
   V4 p; double rx, ry, rz;
-  double mass, Kp, pmin, delta_z, pn;
+  double mass, iKp, pmin, delta_z, pn, ipn;     // iKp = mass / (1e3 m_species): 1 / (momentum scale of the MCS width)
   uint2 key;
   int tb[3], hint[3];
   int it;          // loop iterations done == accepted sub-steps while the loop is alive
@@ -249,23 +252,82 @@ __global__ void k_wave_begin(Work W) {
   W.ctrl[1] = 0; W.ctrl[2] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0;
 }
 
-// Sub-step loop of propagate_particle, charged species only.  Persistent warps pull chunks of the wave's charged
+// Sub-step loop of propagate_particle, charged species only.  Persistent warps pull 32-entry chunks of the wave's charged
 // list; a lane that finishes its track (hard scatter drawn, or energy below threshold) stores it and immediately
 // takes the next entry of the chunk, so the warp stays converged on the loop body whatever the per-track sub-step
 // count (geometric, mean ~7, tail > 50).  The final partial step and the process choice are done by k_finalize.
-constexpr int LOOP_CHUNK = 64;
+//
+// Refill runs with ~3 of 32 lanes, so it must not wait on HBM: each warp keeps a three-deep software pipeline --
+// chunk cursor (atomic, consumed one chunk later) -> the chunk's list indices (register, consumed one chunk later) ->
+// the chunk's records copied asynchronously (cp.async / LDGSTS, no registers) into the idle half of a per-warp
+// double buffer in shared memory -> consumed with shared-memory reads.
+constexpr int LOOP_CHUNK = 32;
+struct LoopBuf {                 // one chunk of track records: p0, r0w, track set-up (rf), ids
+  double2 v[6][LOOP_CHUNK];
+  int4 meta[LOOP_CHUNK];
+  uint2 key[LOOP_CHUNK];
+  int idx[LOOP_CHUNK];
+};
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __global__ void __launch_bounds__(128, PB_LOOP_MINB)
 k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
        const double* __restrict__ prim_mass, int ms_e) {
+  __shared__ __align__(16) LoopBuf s_buf[4][2];
   const long long begin = W.ws->begin;
   const int n_charged = W.ws->n_charged;
   if (n_charged <= 0) return;
   const int* __restrict__ order_c = W.list[2 * W.ws->parity];
   const int lane = threadIdx.x & 31;
-  // small waves: smaller chunks so that the tracks spread over all resident warps (latency, not throughput, bound)
-  const int chunk = min(LOOP_CHUNK, max(8, n_charged / (int)(gridDim.x * (blockDim.x / 32))));
+  LoopBuf* buf = s_buf[threadIdx.x >> 5];
   const unsigned lt_mask = (1u << lane) - 1u;
-  int next = 0, chunk_end = 0;       // warp-uniform cursor into the charged list
+  // small waves: smaller chunks, so that the three chunks every warp holds in its pipeline do not starve the other warps
+  const int chunk = min(LOOP_CHUNK, max(1, n_charged / (3 * (int)(gridDim.x * (blockDim.x / 32)))));
+  // ---- pipeline state (warp-uniform unless noted)
+  int which = 0;                 // half of the double buffer being consumed
+  int pos = 0, cnt = 0;          // consumed / valid entries of that half
+  int cnt_fly = 0;               // valid entries of the chunk being copied into the other half
+  int pre_idx = -1, pre_cnt = 0; // (per lane) list index of the chunk after that, and its size
+  int c_raw = 0;                 // (lane 0) cursor of the chunk after that; read one chunk later
+  bool dry = false;              // the list is exhausted
+  auto fetch_cursor = [&]() { if (lane == 0) c_raw = atomicAdd(&W.ctrl[2], chunk); };
+  auto fetch_index = [&]() {     // consumes c_raw, issues the index load
+    int c = __shfl_sync(0xffffffffu, c_raw, 0);
+    pre_cnt = min(max(n_charged - c, 0), chunk);
+    pre_idx = (lane < pre_cnt) ? order_c[c + lane] : -1;
+  };
+  auto issue_copy = [&](int half) {   // consumes pre_idx, starts the record copies into buf[half]
+    LoopBuf& B = buf[half];
+    if (lane < pre_cnt) {
+      long long s = begin + pre_idx;
+      const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
+      const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
+      const double2* sup = reinterpret_cast<const double2*>(S.rf + 4 * s);     // store_track_setup
+      cp_async16(&B.v[0][lane], p0p); cp_async16(&B.v[1][lane], p0p + 1);
+      cp_async16(&B.v[2][lane], r0p); cp_async16(&B.v[3][lane], r0p + 1);
+      cp_async16(&B.v[4][lane], sup); cp_async16(&B.v[5][lane], sup + 1);
+      cp_async16(&B.meta[lane], S.meta + s);
+      cp_async8(&B.key[lane], S.key + s);
+      B.idx[lane] = pre_idx;
+    }
+    cnt_fly = pre_cnt;
+  };
+  auto advance = [&]() {          // the consumed half is empty: switch to the one in flight, refill the pipeline behind it
+    cp_async_wait_all();
+    __syncwarp();
+    which ^= 1; pos = 0; cnt = cnt_fly;
+    issue_copy(which ^ 1);
+    fetch_index();
+    fetch_cursor();
+  };
+  fetch_cursor(); fetch_index(); fetch_cursor();
+  issue_copy(1); fetch_index(); fetch_cursor();
   int cur = -1;                       // -1: needs a track, -2: no more work
   Track t;
   unsigned long long c_sub = 0;
@@ -273,38 +335,32 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     // ---- refill
     unsigned need = __ballot_sync(0xffffffffu, cur == -1);
     while (need) {
-      if (next >= chunk_end) {
-        int c = 0;
-        if (lane == 0) c = atomicAdd(&W.ctrl[2], chunk);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        next = c; chunk_end = min(c + chunk, n_charged);
-        if (next >= chunk_end) { if (cur == -1) cur = -2; break; }
+      if (pos >= cnt) {
+        if (!dry) { advance(); dry = (cnt == 0); }
+        if (dry) { if (cur == -1) cur = -2; break; }
       }
-      int avail = chunk_end - next;
+      int avail = cnt - pos;
       int rank = __popc(need & lt_mask);
       bool take = (cur == -1) && rank < avail;
       if (take) {
-        cur = order_c[next + rank];
-        long long s = begin + cur;
-        const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
-        const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
-        double2 a0 = p0p[0], a1 = p0p[1], b0 = r0p[0], b1 = r0p[1];
+        const LoopBuf& B = buf[which];
+        const int e = pos + rank;
+        cur = B.idx[e];
+        double2 a0 = B.v[0][e], a1 = B.v[1][e], b0 = B.v[2][e], b1 = B.v[3][e], s0 = B.v[4][e], s1 = B.v[5][e];
         t.p = V4{a0.x, a0.y, a1.x, a1.y};
         t.rx = b0.x; t.ry = b0.y; t.rz = b1.x;
-        int4 meta = S.meta[s];
-        t.key = S.key[s];
+        int4 meta = B.meta[e];
+        t.key = B.key[e];
         int pid = meta.x;
-        t.mass = (meta.y < 0) ? prim_mass[s] : pid_mass(pid);
-        t.Kp = 1e3 * pid_mass(pid) / t.mass;
+        t.mass = pid_mass(pid); t.iKp = 1e-3;
+        if (meta.y < 0) { t.mass = prim_mass[begin + cur]; t.iKp = t.mass / (1e3 * pid_mass(pid)); }
         t.pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), t.mass);   // shower.py:532-533
         species_tables(pid, t.tb);
-        const double2* sup = reinterpret_cast<const double2*>(S.rf + 4 * s);     // store_track_setup
-        double2 s0 = sup[0], s1 = sup[1];
-        t.pn = s0.x;
+        t.pn = s0.x; t.ipn = 1.0 / s0.x;
         t.hint[0] = __double2loint(s0.y); t.hint[1] = __double2hiint(s0.y); t.hint[2] = __double2loint(s1.x);
         t.delta_z = 0.0; t.it = 0;
       }
-      next += min(__popc(need), avail);
+      pos += min(__popc(need), avail);
       need = __ballot_sync(0xffffffffu, cur == -1);
     }
     if (__all_sync(0xffffffffu, cur == -2)) break;
@@ -315,29 +371,31 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       else {
         double ns = nsigma_hinted(T.ns[t.tb[0]], t.hint[0], t.p.E) + nsigma_hinted(T.ns[t.tb[1]], t.hint[1], t.p.E);
         if (t.tb[2] >= 0) ns += nsigma_hinted(T.ns[t.tb[2]], t.hint[2], t.p.E);
-        double mfp = mfp_from(ns);
+        double mfp = (ns <= 0.0) ? 1.0e12 : kCmToM * fast_rcp(ns);        // shower.py:386-389
         D2 u = draw2(t.key, (uint32_t)t.it, ST_SUBSTEP);
-        t.delta_z = mfp / (6.0 + 14.0 * u.b);
-        if (u.a > exp(-t.delta_z / mfp)) done = true;                    // hard scatter (shower.py:564)
+        double iv = fast_rcp(6.0 + 14.0 * u.b);                           // delta_z = mfp / U(6, 20); delta_z / mfp = 1 / U
+        t.delta_z = mfp * iv;
+        if (u.a > exp(-iv)) done = true;                                  // hard scatter (shower.py:564)
         else {
           // lose_energy (particle.py:143-153) with |p| carried along the track instead of recomputed
           double Eu = t.p.E - M.dEdx * t.delta_z;
           if (Eu <= t.mass) Eu = t.mass;
           double p3f = sqrt(__dsub_rn(__dmul_rn(Eu, Eu), __dmul_rn(t.mass, t.mass)));
           if (p3f > 0.0) {
-            double r = p3f / t.pn;
+            double r = p3f * t.ipn;
             t.p = V4{Eu, t.p.x * r, t.p.y * r, t.p.z * r};
             t.pn = p3f;
-            double inv = 1.0 / p3f;
+            double inv = fast_rcp(p3f);
+            t.ipn = inv;
             double s = t.delta_z * inv;
             t.rx += t.p.x * s; t.ry += t.p.y * s; t.rz += t.p.z * s;
             if (ms_e) {
               McsDraw d = mcs_draw(t.key, (uint32_t)t.it, 0);
-              t.p = mcs_fast(M, t.p, p3f, inv, M.rho * (t.delta_z * (1.0 / kCmToM)), t.Kp, d.sign, d.radial, d.uphi);
+              t.p = mcs_fast(M, t.p, p3f, inv, M.rho * (t.delta_z * (1.0 / kCmToM)), t.iKp, d.sign, d.radial, d.uphi);
             }
           } else {
             t.p = V4{t.mass, 0.0, 0.0, 0.0};
-            t.pn = 0.0;
+            t.pn = 0.0; t.ipn = 0.0;
           }
           ++t.it; ++c_sub;
         }
@@ -513,18 +571,40 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
   if (t == 0) W.ctrl[2] = 0;
 }
 
-// n_explicit < 0: the wave size comes from the device-side wave state
-__global__ void __launch_bounds__(256) k_bucket_fill(Work W, int n_explicit) {
+// Where a sample's incoming energy / Philox key come from and where its trial count goes: the SM pass indexes the
+// wave's stack records directly, the dark pass goes through its candidate list.
+struct SampleIO {
+  const double* E4;        // incoming energy of entry i at E4[4*i]
+  const uint2* key;        // particle keys
+  const int* key_index;    // entry i uses key[key_index[i]] (nullptr: key[i])
+  int* ntr;                // trials used by entry i at ntr[i * ntr_stride]; -1 if the sampler gave up
+  int ntr_stride;
+  const WaveState* ws;     // SM pass: entry i is stack slot ws->begin + i (E4/key/ntr then point at slot 0)
+};
+
+// n_explicit < 0: the wave size comes from the device-side wave state.  Besides the counting-sort scatter of the indices, the
+// sampler's two per-entry inputs (incoming energy, Philox key) are gathered into bucket order here, where the reads are
+// coalesced, so that k_sample stages a tile with contiguous loads instead of two dependent scattered ones per sample.
+__global__ void __launch_bounds__(256) k_bucket_fill(Work W, SampleIO io, int n_explicit) {
   const int n = n_explicit < 0 ? W.ws->n : n_explicit;
   const int lane = threadIdx.x & 31;
+  const size_t off = io.ws ? (size_t)io.ws->begin : 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int b = W.bucket[i];
+    const bool sampled = b < N_SAMPLED * LU_MAX;
+    double E = 0.0; uint2 key = make_uint2(0, 0);
+    if (sampled) {
+      E = io.E4[4 * (off + (size_t)i)];
+      key = io.key[io.key_index ? (size_t)io.key_index[i] : off + (size_t)i];
+    }
     unsigned peers = __match_any_sync(__activemask(), b);        // lanes of this warp that share the bucket
     int leader = __ffs(peers) - 1;
     int base = 0;
     if (lane == leader) base = atomicAdd(&W.cursor[b], __popc(peers));
     base = __shfl_sync(peers, base, leader);
-    W.sorted[W.offsets[b] + base + __popc(peers & ((1u << lane) - 1u))] = i;
+    int pos = W.offsets[b] + base + __popc(peers & ((1u << lane) - 1u));
+    W.sorted[pos] = i;
+    if (sampled) { W.sE[pos] = E; W.skey[pos] = key; }
   }
 }
 
@@ -560,10 +640,17 @@ template <int DIM, int FAM>
 __device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, const double* __restrict__ g, int proc,
                                       double E, const SampleConst& sc, double maxF, uint2 key, uint32_t t, double* x) {
   double D[DIM + 2];
+  if (DIM == 4) {          // two calls: four map coordinates, and the accept uniform from the calls' 2 x 24 spare bits
+    uint32_t s0, s1;
+    D2 d0 = draw2s(key, t, ST_VEGAS, 0, proc, s0), d1 = draw2s(key, t, ST_VEGAS, 1, proc, s1);
+    D[0] = d0.a; D[1] = d0.b; D[2] = d1.a; D[3] = d1.b;
+    D[4] = u48(s0, s1);
+  } else {
 #pragma unroll
-  for (int j = 0; j < (DIM + 2) / 2; ++j) {
-    D2 d = draw2(key, t, ST_VEGAS, j, proc);
-    D[2 * j] = d.a; D[2 * j + 1] = d.b;
+    for (int j = 0; j < (DIM + 2) / 2; ++j) {
+      D2 d = draw2(key, t, ST_VEGAS, j, proc);
+      D[2 * j] = d.a; D[2 * j + 1] = d.b;
+    }
   }
   double jac = 1.0;
 #pragma unroll
@@ -592,24 +679,13 @@ __device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, cons
   } else {
     f = dsigma(M, proc, E, x);
   }
-  return maxF * D[DIM] < (jac / mi.B) * f;
+  return maxF * D[DIM] < (jac * mi.invB) * f;
 }
 
 // Persistent sampling kernel.  G lanes cooperate on one sample: lane l of the group evaluates trial r*G + l in
 // round r and the lowest accepted trial wins - identical to the reference's sequential first-accept rule because
 // every trial's uniforms are a pure function of (particle key, trial index).  Groups pull the next sample of the
 // tile from a shared cursor as soon as they finish.
-// Where a sample's incoming energy / Philox key come from and where its trial count goes: the SM pass indexes the
-// wave's stack records directly, the dark pass goes through its candidate list.
-struct SampleIO {
-  const double* E4;        // incoming energy of entry i at E4[4*i]
-  const uint2* key;        // particle keys
-  const int* key_index;    // entry i uses key[key_index[i]] (nullptr: key[i])
-  int* ntr;                // trials used by entry i at ntr[i * ntr_stride]; -1 if the sampler gave up
-  int ntr_stride;
-  const WaveState* ws;     // SM pass: entry i is stack slot ws->begin + i (E4/key/ntr then point at slot 0)
-};
-
 __host__ __device__ constexpr int proc_family(int p) {
   return (p == P_BREM || p == P_PAIRPROD || p == P_MUONBREM) ? 0 : (p < P_DARKBREM ? 1 : 2);
 }
@@ -618,6 +694,9 @@ template <int G, int FAM>
 __global__ void __launch_bounds__(SAMPLE_THREADS, (FAM == 0 || FAM == 1) ? PB_SAMPLE_MINB_SM : PB_SAMPLE_MINB)
 k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, SampleIO io, Work W) {
   __shared__ __align__(128) double s_grid[GRID_SMEM_DOUBLES];
+  __shared__ __align__(16) double s_E[TILE], s_cb[TILE], s_cc[TILE], s_cd[TILE];   // per-entry energy and sampler constants
+  __shared__ __align__(16) uint2 s_key[TILE];
+  __shared__ int s_idx[TILE];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_tile, s_cursor;
   const int lane = threadIdx.x & 31;
@@ -644,9 +723,22 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
       mbar_expect_tx(&s_bar, bytes);
       tma_bulk_g2s(s_grid, mi.grid + (size_t)lu * mi.stride, bytes, &s_bar);
     }
+    // stage the tile's entries (contiguous in bucket order, see k_bucket_fill) while the node grid is in flight, and
+    // compute the per-sample constants of the 4-D integrands here with every lane busy
+    for (int k = threadIdx.x; k < tcount; k += SAMPLE_THREADS) {
+      double Ek = W.sE[tstart + k];
+      s_E[k] = Ek;
+      s_key[k] = W.skey[tstart + k];
+      s_idx[k] = W.sorted[tstart + k];
+      if (proc == P_PAIRPROD || proc == P_BREM || proc == P_MUONBREM) {
+        SampleConst c = (proc == P_PAIRPROD) ? pairprod_const(M, Ek) : brem_const(M, Ek, proc == P_BREM ? kMe : kMmu);
+        s_cb[k] = c.b; s_cc[k] = c.c; s_cd[k] = c.d;
+      }
+    }
     double maxF = __ldg(mi.maxF + lu) * M.fudge;
     mbar_wait(&s_bar, phase);
     phase ^= 1;
+    __syncthreads();
     const long long max_trials = M.max_trials;
     // group state
     int cur = -1;          // entry index, -1 = need a new one, -2 = tile exhausted
@@ -659,13 +751,13 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
         if (sub == 0) j = atomicAdd(&s_cursor, 1);
         j = __shfl_sync(gmask, j, gbase);
         if (j < tcount) {
-          cur = W.sorted[tstart + j];
-          E = io.E4[4 * (off + (size_t)cur)];
-          key = io.key[io.key_index ? (size_t)io.key_index[cur] : off + (size_t)cur];
+          cur = s_idx[j];
+          E = s_E[j];
+          key = s_key[j];
           round = 0;
-          if (proc == P_PAIRPROD) sc = pairprod_const(M, E);
-          else if (proc == P_BREM) sc = brem_const(M, E, kMe);
-          else if (proc == P_MUONBREM) sc = brem_const(M, E, kMmu);
+          if (proc == P_PAIRPROD) sc = SampleConst{E - 2 * kMe, s_cb[j], s_cc[j], s_cd[j], 0.0};
+          else if (proc == P_BREM) sc = SampleConst{E - kMe - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMe * kMe};
+          else if (proc == P_MUONBREM) sc = SampleConst{E - kMmu - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMmu * kMmu};
         } else cur = -2;
       }
       if (__all_sync(0xffffffffu, cur == -2)) break;
@@ -1104,7 +1196,7 @@ k_find_max(const __grid_constant__ Material M, const __grid_constant__ Tables T,
     for (int j = 0; j < mi.B; ++j) {
       uint32_t t = (uint32_t)(sweep * mi.B + j);
       double D[6];
-      for (int c = 0; c < (mi.dim + 2) / 2; ++c) { D2 d = draw2(key, t, ST_VEGAS, c, process); D[2 * c] = d.a; D[2 * c + 1] = d.b; }
+      for (int c = 0; c < (mi.dim + 1) / 2; ++c) { D2 d = draw2(key, t, ST_VEGAS, c, process); D[2 * c] = d.a; D[2 * c + 1] = d.b; }
       double x[4] = {0, 0, 0, 0}, jac = 1.0;
       for (int d = 0; d < mi.dim; ++d) {
         int ninc = mi.ninc[d];
@@ -1357,6 +1449,9 @@ struct pb_engine_s {
   int n_sm = 148;
   int profiling = 0;             // 0 off, 1 = the two dominant kernels only (k_loop, k_sample), 2 = every kernel
   int sample_group = 8;          // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
+  int sample_split = 1;          // SM pass: 4-D and 1-D integrand families as two concurrent kernels (PB_SAMPLE_SPLIT=0: one generic launch)
+  cudaStream_t side = nullptr;   // second stream for the concurrent family kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   static constexpr int LOOKAHEAD = 8;   // waves enqueued per host synchronisation while the shower tail shrinks
   cudaEvent_t ev[2 * 8] = {};
   cudaEvent_t evp[LOOKAHEAD][2][2] = {};   // lookahead slot x {k_loop, k_sample} x {start, stop}
@@ -1418,6 +1513,10 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   e->cfg = *cfg;
   derive_material(e);
   if (const char* g = getenv("PB_SAMPLE_G")) e->sample_group = atoi(g);
+  if (const char* g = getenv("PB_SAMPLE_SPLIT")) e->sample_split = atoi(g);
+  cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
   size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * (8 + CNT_N) + sizeof(WaveState) + 64;
   if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
   cudaMemset(e->fixed_blob, 0, fixed);
@@ -1457,6 +1556,9 @@ extern "C" void pb_destroy(pb_engine e) {
   for (int i = 0; i < 2 * 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   for (int a = 0; a < pb_engine_s::LOOKAHEAD; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) if (e->evp[a][b][c]) cudaEventDestroy(e->evp[a][b][c]);
   if (e->h_ws) cudaFreeHost(e->h_ws);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->side) cudaStreamDestroy(e->side);
   delete e;
 }
 
@@ -1497,7 +1599,7 @@ extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int 
   double* dE = d + (size_t)padded * nE;
   PB_CUDA(e, cudaMemcpy(dE, E_inc, sizeof(double) * nE, cudaMemcpyHostToDevice));
   PB_CUDA(e, cudaMemcpy(dE + nE, max_F, sizeof(double) * nE, cudaMemcpyHostToDevice));
-  mi.grid = d; mi.E = dE; mi.maxF = dE + nE; mi.nE = nE; mi.dim = dim; mi.stride = padded; mi.B = neval;
+  mi.grid = d; mi.E = dE; mi.maxF = dE + nE; mi.nE = nE; mi.dim = dim; mi.stride = padded; mi.B = neval; mi.invB = 1.0 / (double)neval;
   mi.log_E0 = (E_inc[0] > 0) ? log(E_inc[0]) : 0.0;
   mi.inv_dlog = (nE > 1 && E_inc[0] > 0 && E_inc[nE - 1] > E_inc[0]) ? (double)(nE - 1) / log(E_inc[nE - 1] / E_inc[0]) : 0.0;
   e->tab.map[process] = mi;
@@ -1505,12 +1607,20 @@ extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int 
 }
 
 static int ensure_cand(pb_engine e, long long ncap);
-// SM pass: one launch per integrand family (4-D small-angle processes; 1-D two-body processes), so that the hot 4-D
-// kernel is not register-allocated for the dark-brem integrand.  Dark pass / stand-alone sampling: one generic launch.
+// SM pass: one kernel per integrand family (4-D small-angle processes; 1-D two-body processes), so that the hot 4-D
+// kernel is not register-allocated for the dark-brem integrand and keeps 5 CTAs per SM.  The two kernels run
+// CONCURRENTLY (the 1-D one on a side stream): launched back to back on one stream the second drain cost more than
+// the registers gained; side by side the cheap 1-D tiles fill the SMs the 4-D kernel's tail leaves idle.
+// Dark pass / stand-alone sampling: one generic launch.
 static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream, bool sm_families = false) {
-  if (sm_families && e->sample_group == 8) {
-    k_sample<8, 0><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work);
-    k_sample<8, 1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work);
+  if (sm_families && e->sample_group == 8 && e->sample_split && e->side) {
+    const int g5 = std::max(1, std::min(e->n_sm * PB_SAMPLE_MINB_SM, grid * 2));
+    cudaEventRecord(e->ev_fork, stream);
+    cudaStreamWaitEvent(e->side, e->ev_fork, 0);
+    k_sample<8, 0><<<g5, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work);
+    k_sample<8, 1><<<g5, SAMPLE_THREADS, 0, e->side>>>(e->mat, e->tab, io, e->work);
+    cudaEventRecord(e->ev_join, e->side);
+    cudaStreamWaitEvent(stream, e->ev_join, 0);
     return;
   }
   switch (e->sample_group) {
@@ -1546,10 +1656,12 @@ static int ensure_work(pb_engine e, long long n) {
   long long cap = std::max<long long>(n * 5 / 4, 1 << 16);
   if (e->work_blob) { cudaFree(e->work_blob); e->work_blob = nullptr; }
   long long max_tiles = cap / TILE + N_SAMPLED * LU_MAX + 1;
-  size_t bytes = (size_t)cap * (4 + 4 + 32) + (size_t)max_tiles * 12 + 256;
+  size_t bytes = (size_t)cap * (4 + 4 + 32 + 8 + 8) + (size_t)max_tiles * 12 + 256;
   PB_CUDA(e, cudaMalloc(&e->work_blob, bytes));
   char* p = (char*)e->work_blob;
   e->work.xs = (double*)p; p += (size_t)cap * 32;
+  e->work.sE = (double*)p; p += (size_t)cap * 8;
+  e->work.skey = (uint2*)p; p += (size_t)cap * 8;
   e->work.bucket = (int*)p; p += (size_t)cap * 4;
   e->work.sorted = (int*)p; p += (size_t)cap * 4;
   e->work.tile_bucket = (int*)p; p += (size_t)max_tiles * 4;
@@ -1669,10 +1781,11 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
       tock(PB_K_FINALIZE, j); tick(PB_K_SCAN, j);
       k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
       tock(PB_K_SCAN, j); tick(PB_K_FILL, j);
-      k_bucket_fill<<<g256, 256, 0, stream>>>(e->work, -1);
-      tock(PB_K_FILL, j); tick(PB_K_SAMPLE, j);
       SampleIO io{S.pf, S.key, nullptr, reinterpret_cast<int*>(S.aux), 2, e->work.ws};
-      launch_sample(e, sg, io, stream);   // one generic launch: splitting by integrand family (k_sample<8,0>/<8,1>) was measured slower
+      k_bucket_fill<<<g256, 256, 0, stream>>>(e->work, io, -1);
+      tock(PB_K_FILL, j); tick(PB_K_SAMPLE, j);
+      launch_sample(e, sg, io, stream, true);
+      if (e->sample_split) ++launches;
       tock(PB_K_SAMPLE, j); tick(PB_K_EMIT, j);
       k_emit<<<g128, 128, 0, stream>>>(e->mat, e->tab, S, e->work);
       tock(PB_K_EMIT, j);
@@ -1802,10 +1915,10 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
     tick(PB_K_SCAN);
     k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
     tock(PB_K_SCAN); tick(PB_K_FILL);
-    k_bucket_fill<<<(unsigned)((n_cand + 255) / 256), 256, 0, stream>>>(e->work, n_cand);
+    SampleIO io{e->cand.pf, S.key, e->cand.slot, e->cand.ntr, 1, nullptr};
+    k_bucket_fill<<<(unsigned)((n_cand + 255) / 256), 256, 0, stream>>>(e->work, io, n_cand);
     tock(PB_K_FILL); tick(PB_K_SAMPLE);
     int sg = (int)std::min<long long>((long long)e->n_sm * 4, (n_cand + 31) / 32 + 1);
-    SampleIO io{e->cand.pf, S.key, e->cand.slot, e->cand.ntr, 1, nullptr};
     launch_sample(e, sg, io, stream);
     tock(PB_K_SAMPLE); tick(PB_K_EMIT);
     k_dark_emit<<<(unsigned)((n_cand + 127) / 128), 128, 0, stream>>>(e->mat, S, O, e->work, e->cand, n_cand);
@@ -1870,8 +1983,8 @@ extern "C" int pb_draw_samples(pb_engine e, int process, const double* E, int64_
   PB_CUDA(e, cudaMemsetAsync(e->work.xs, 0, sizeof(double) * 4 * n, stream));
   k_prepare_draws<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->tab, e->work, e->cand, dkeys, dE, (int)n, process, lu_key, seed, first_id);
   k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
-  k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, (int)n);
   SampleIO io{e->cand.pf, dkeys, nullptr, e->cand.ntr, 1, nullptr};
+  k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, io, (int)n);
   launch_sample(e, (int)std::min<long long>((long long)e->n_sm * 4, (n + 31) / 32 + 1), io, stream);
   cudaError_t c = cudaMemcpyAsync(x_out, e->work.xs, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, stream);
   if (c == cudaSuccess && ntr_out) c = cudaMemcpyAsync(ntr_out, e->cand.ntr, sizeof(int) * n, cudaMemcpyDeviceToHost, stream);

@@ -69,6 +69,18 @@ __device__ __forceinline__ double norm3_nofma(double x, double y, double z) {
   return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
 }
 
+// Reciprocal without the IEEE division's special-case branch and slow-path call: MUFU.RCP64H seed (rel. error 2^-23) and two
+// Newton steps (-> rounding level, <= 1 ulp).  Only for the re-associated hot-loop forms (ds_*_fast, mcs_fast, the sub-step),
+// whose arguments are finite, normal and non-zero by construction and whose results are compared at 1e-12, not bit for bit.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 // ---------------------------------------------------------------- form factors
 __device__ __forceinline__ double ff_elastic(const Material& M, double t) {  // all_processes.py:99-103
   double den = 1.0 + M.ff_a0sq * t;
@@ -183,15 +195,15 @@ __device__ __forceinline__ double ds_brem_fast(const Material& M, const SampleCo
   double cph = cospi(2.0 * x[3] - 1.0);           // cos((x4 - 1/2) 2 pi)
   double d2 = d * d, dp2 = dp * dp;
   double od = 1 + d2, odp = 1 + dp2;
-  double iepp = 1.0 / epp;
+  double iepp = fast_rcp(epp);
   double u = od * (0.5 * s.c) - odp * (0.5 * iepp);
   double ddc = d * dp * cph;
   double qsq = s.e * ((d2 + dp2 - 2 * ddc) + s.e * u * u);
   double den = 1.0 + M.ff_a0sq * qsq;
-  double io = 1.0 / (od * odp);
+  double io = fast_rcp(od * odp);
   double i1 = odp * io, i2 = od * io;             // 1/od, 1/odp
   double T = d2 * (i1 * i1) + dp2 * (i2 * i2) + (w * w) * (0.5 * s.c * iepp) * (d2 + dp2) * io - (epp * s.c + ep * iepp) * ddc * io;
-  return s.d * (epp * d * dp) / (w * den * den) * T;
+  return s.d * (epp * d * dp) * fast_rcp(w * den * den) * T;
 }
 
 __device__ __forceinline__ SampleConst pairprod_const(const Material& M, double w) {
@@ -216,15 +228,15 @@ __device__ __forceinline__ double ds_pairprod_fast(const SampleConst& s, double 
   double cph = cospi(2.0 * x[3]);
   double dp2 = dp * dp, dm2 = dm * dm;
   double op = 1.0 + dp2, om = 1.0 + dm2;
-  double ie = 1.0 / (epp * epm);
+  double ie = fast_rcp(epp * epm);
   double u = op * (0.5 * epm * ie) + om * (0.5 * epp * ie);
   double ddc = dp * dm * cph;
   double q2r = (dp2 + dm2 + 2.0 * ddc) + me2 * u * u;
   double den = 1.0 + s.c * q2r;
-  double io = 1.0 / (op * om);
+  double io = fast_rcp(op * om);
   double i1 = om * io, i2 = op * io;
   double T = -dp2 * (i1 * i1) - dm2 * (i2 * i2) + (w * w) * (0.5 * ie) * (dp2 + dm2) * io + (epp * epp + epm * epm) * ie * ddc * io;
-  return s.d * (epp * epm * dp * dm) / (den * den) * T;
+  return s.d * (epp * epm * dp * dm) * fast_rcp(den * den) * T;
 }
 
 // all_processes.py:625-742 (dsigma_compton_dCT); mV > 0 is DarkComp.
@@ -487,17 +499,17 @@ __device__ __forceinline__ V4 mcs_apply(const Material& M, V4 p4, double pn, dou
 //   chic2 = C4 t / (p_MeV beta)^2,  omega = chic2/chia2 = Cw t / (beta^2 + c3),  v = omega / (2 (1-F))
 // inv_pn = 1/pn is supplied by the caller (it also advances the position with it).  Results differ from mcs_apply
 // by re-association only (~1e-15 relative).
-__device__ __forceinline__ V4 mcs_fast(const Material& M, V4 p4, double pn, double inv_pn, double t, double Kp,
+__device__ __forceinline__ V4 mcs_fast(const Material& M, V4 p4, double pn, double inv_pn, double t, double iKp,
                                        double sign, double radial, double u_phi) {
   const double F = 0.98;
   double E = p4.E;
   double e_ip = E * inv_pn * inv_pn;                    // E / pn^2
-  double ipb = e_ip / Kp;                               // 1 / (p_MeV beta)
+  double ipb = e_ip * iKp;                              // 1 / (p_MeV beta)
   double chic2 = M.mcs_C4 * t * (ipb * ipb);
   double E2 = E * E;
-  double omega = M.mcs_Cw * t * E2 / (pn * pn + M.mcs_c3 * E2);
+  double omega = M.mcs_Cw * t * E2 * fast_rcp(pn * pn + M.mcs_c3 * E2);
   double v = omega * (0.5 / (1.0 - F));
-  double th0 = sqrt(chic2 * ((1.0 + v) * log(1.0 + v) / v - 1) * (1.0 / (1.0 + F * F)));
+  double th0 = sqrt(chic2 * ((1.0 + v) * log(1.0 + v) * fast_rcp(v) - 1) * (1.0 / (1.0 + F * F)));
   double theta = sign * (radial * th0) * M.rescale_mcs;
   double vx = p4.x, vy = p4.y, vz = p4.z;
   double ca, sa, vxp;
@@ -522,15 +534,16 @@ __device__ __forceinline__ V4 mcs_fast(const Material& M, V4 p4, double pn, doub
 }
 
 // The MCS block's four draws: sign, two normals, azimuth.  CPython's gauss pair is
-// (cos, sin)(2 pi u_a) * sqrt(-2 ln(1 - u_r)), so sqrt(z1^2 + z2^2) = sqrt(-2 ln(1 - u_r)) and u_a drops out.
+// (cos, sin)(2 pi u_a) * sqrt(-2 ln(1 - u_r)), so sqrt(z1^2 + z2^2) = sqrt(-2 ln(1 - u_r)) and u_a drops out: one Philox
+// call gives (u_phi, u_r) and the sign comes from a spare bit (oracle/draws.py CounterDraws.mcs).
 struct McsDraw { double sign, radial, uphi; };
 __device__ __forceinline__ McsDraw mcs_draw(uint2 key, uint32_t index, uint32_t pc) {
-  D2 a = draw2(key, index, ST_MCS, 0, pc);
-  D2 b = draw2(key, index, ST_MCS, 1, pc);
+  uint32_t sp;
+  D2 a = draw2s(key, index, ST_MCS, 0, pc, sp);
   McsDraw d;
-  d.sign = a.a < 0.5 ? -1.0 : 1.0;
-  d.uphi = a.b;
-  d.radial = sqrt(-2.0 * log(1.0 - b.b));
+  d.sign = (sp & 1u) ? 1.0 : -1.0;
+  d.uphi = a.a;
+  d.radial = sqrt(-2.0 * log(1.0 - a.b));
   return d;
 }
 __device__ __forceinline__ V4 mcs_scatter(const Material& M, V4 p4, double pn, double t, double m_lepton, double mass,

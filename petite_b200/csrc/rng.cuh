@@ -3,6 +3,7 @@
 // CPU oracle (oracle/philox.py) so that both consume identical uniforms.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 namespace pb {
 
@@ -37,17 +38,42 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t
   return c;
 }
 
-// 53-bit uniform in [0,1): ((hi>>5)*2^26 + (lo>>6)) * 2^-53
-__host__ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
-  uint64_t m = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
-  return (double)m * (1.0 / 9007199254740992.0);
+// 52-bit uniform in [0,1) from two words, built in the mantissa of a double in [1,2) (three integer instructions and one
+// DADD; no 64-bit integer -> double conversion): mantissa = hi (32 bits) : lo >> 12 (20 bits).  The low 12 bits of `lo`
+// are left over ("spare" bits): a call's two spare fields feed the draws that need only a few bits.
+__host__ __device__ __forceinline__ double u52(uint32_t hi, uint32_t lo) {
+#ifdef __CUDA_ARCH__
+  return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12))) - 1.0;
+#else
+  uint64_t bits = ((uint64_t)(0x3FF00000u | (hi >> 12)) << 32) | (uint64_t)((hi << 20) | (lo >> 12));
+  double d;
+  memcpy(&d, &bits, sizeof(d));
+  return d - 1.0;
+#endif
 }
 
 struct D2 { double a, b; };
 
 __host__ __device__ __forceinline__ D2 draw2(uint2 key, uint32_t c0, uint32_t stream, uint32_t c2 = 0, uint32_t c3 = 0) {
   U4 o = philox4x32_10(U4{c0, stream, c2, c3}, key.x, key.y);
-  return D2{u53(o.x, o.y), u53(o.z, o.w)};
+  return D2{u52(o.x, o.y), u52(o.z, o.w)};
+}
+// same two doubles plus the call's 24 spare bits ((o1 & 0xFFF) << 12 | (o3 & 0xFFF))
+__host__ __device__ __forceinline__ D2 draw2s(uint2 key, uint32_t c0, uint32_t stream, uint32_t c2, uint32_t c3, uint32_t& spare) {
+  U4 o = philox4x32_10(U4{c0, stream, c2, c3}, key.x, key.y);
+  spare = ((o.y & 0xFFFu) << 12) | (o.w & 0xFFFu);
+  return D2{u52(o.x, o.y), u52(o.z, o.w)};
+}
+// 48-bit uniform in [0,1) from the spare bits of two calls (the accept/reject uniform of a 4-D trial)
+__host__ __device__ __forceinline__ double u48(uint32_t s0, uint32_t s1) {
+#ifdef __CUDA_ARCH__
+  return __hiloint2double((int)(0x3FF00000u | (s0 >> 4)), (int)(((s0 & 0xFu) << 28) | (s1 << 4))) - 1.0;
+#else
+  uint64_t bits = ((uint64_t)(0x3FF00000u | (s0 >> 4)) << 32) | (uint64_t)(((s0 & 0xFu) << 28) | (s1 << 4));
+  double d;
+  memcpy(&d, &bits, sizeof(d));
+  return d - 1.0;
+#endif
 }
 
 __host__ __device__ __forceinline__ uint2 root_key(uint64_t seed, uint64_t shower) {
