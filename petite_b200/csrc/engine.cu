@@ -1449,7 +1449,7 @@ struct pb_engine_s {
   int n_sm = 148;
   int profiling = 0;             // 0 off, 1 = the two dominant kernels only (k_loop, k_sample), 2 = every kernel
   int sample_group = 8;          // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
-  int sample_split = 1;          // SM pass: 4-D and 1-D integrand families as two concurrent kernels (PB_SAMPLE_SPLIT=0: one generic launch)
+  int sample_split = 0;          // PB_SAMPLE_SPLIT=1: SM pass with the 4-D and 1-D integrand families as two concurrent kernels (measured: no gain)
   cudaStream_t side = nullptr;   // second stream for the concurrent family kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   static constexpr int LOOKAHEAD = 8;   // waves enqueued per host synchronisation while the shower tail shrinks
@@ -1794,6 +1794,8 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     PB_CUDA(e, cudaMemcpyAsync(hws, e->work.ws, sizeof(WaveState), cudaMemcpyDeviceToHost, stream));
     PB_CUDA(e, cudaMemcpyAsync(htail, e->work.tail, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     PB_CUDA(e, cudaStreamSynchronize(stream));
+    double ms_before[PB_K_N];
+    for (int k = 0; k < PB_K_N; ++k) ms_before[k] = e->prof.ms[k];
     collect();
     if (hws->status == 3) {             // scratch too small for the next wave: grow (contents preserved) and resume it
       long long need = (long long)std::min<unsigned long long>(htail[0], (unsigned long long)st->capacity) - hws->begin;
@@ -1809,7 +1811,12 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     }
     if (hws->status != 0) break;
     if (const char* lw = getenv("PB_LOG_WAVES")) {        // measurement aid: sizes of the waves the host sees
-      if (FILE* f = fopen(lw, "a")) { fprintf(f, "wave %d n %d n_charged %d\n", hws->waves, hws->n, hws->n_charged); fclose(f); }
+      if (FILE* f = fopen(lw, "a")) {
+        fprintf(f, "wave %d n %d n_charged %d", hws->waves, hws->n, hws->n_charged);
+        if (plevel >= 2) { fprintf(f, " ms"); for (int k = 1; k < PB_K_N; ++k) fprintf(f, " %.4f", e->prof.ms[k] - ms_before[k]); }   // this wave's kernels
+        fprintf(f, "\n");
+        fclose(f);
+      }
     }
     n_prev = n_known;
     n_known = hws->n;
