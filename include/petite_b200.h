@@ -226,7 +226,9 @@ enum pb_probe {
   PB_PROBE_MAP = 2,      /* in: n x (1 + dim): energy row index, y[dim]; out: n x (dim+1): x[dim], jac */
   PB_PROBE_MCS = 3,      /* in: n x 9: p4[4], dist_m, m_lepton, u_sign, z1, z2 ... see tests; out: n x 4 */
   PB_PROBE_KIN = 4,      /* in: n x 8: E, mass, x[4], u_az, pad;          out: n x 8 two four-vectors (parent along z) */
-  PB_PROBE_PHILOX = 5    /* in: n x 6 (as doubles): key0,key1,c0,stream,c2,c3; out: n x 2 doubles */
+  PB_PROBE_PHILOX = 5,   /* in: n x 6 (as doubles): key0,key1,c0,stream,c2,c3; out: n x 2 doubles */
+  PB_PROBE_HOTMATH = 6   /* in: n x 4: x_log (> 0), x_exp in [1/20, 1/6], theta, u in [0,1);
+                            out: n x 7: hot_log, hot_exp_neg_step, sin, cos (theta), sin, cos (2 pi u), fast_rcp(x_log) */
 };
 int pb_probe(pb_engine e, int what, int process, const double* in, int64_t n, int in_stride, double* out, int out_stride);
 

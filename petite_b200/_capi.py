@@ -99,7 +99,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 PB_OK, PB_ERR_CUDA, PB_ERR_ARG, PB_ERR_CAPACITY, PB_ERR_STATE, PB_ERR_NO_SAMPLE = 0, -1, -2, -3, -4, -5
 PB_FLAG_SHORT_LIVED, PB_FLAG_NO_SAMPLE = 1, 2
-PROBE_DSIGMA, PROBE_NSIGMA, PROBE_MAP, PROBE_MCS, PROBE_KIN, PROBE_PHILOX = range(6)
+PROBE_DSIGMA, PROBE_NSIGMA, PROBE_MAP, PROBE_MCS, PROBE_KIN, PROBE_PHILOX, PROBE_HOTMATH = range(7)
 
 
 class EngineError(RuntimeError):

@@ -375,7 +375,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
         D2 u = draw2(t.key, (uint32_t)t.it, ST_SUBSTEP);
         double iv = fast_rcp(6.0 + 14.0 * u.b);                           // delta_z = mfp / U(6, 20); delta_z / mfp = 1 / U
         t.delta_z = mfp * iv;
-        if (u.a > exp(-iv)) done = true;                                  // hard scatter (shower.py:564)
+        if (u.a > hot_exp_neg_step(iv)) done = true;                      // hard scatter (shower.py:564)
         else {
           // lose_energy (particle.py:143-153) with |p| carried along the track instead of recomputed
           double Eu = t.p.E - M.dEdx * t.delta_z;
@@ -1418,6 +1418,13 @@ __global__ void k_probe(const __grid_constant__ Material M, const __grid_constan
         case P_SMDECAY: two_body_decay(V4{a[0], a[2], a[3], a[4]}, a[1], 0.0, 0.0, a[6], a[7], &va, &vb); break;
       }
       o[0] = va.E; o[1] = va.x; o[2] = va.y; o[3] = va.z; o[4] = vb.E; o[5] = vb.x; o[6] = vb.y; o[7] = vb.z;
+    } break;
+    case PB_PROBE_HOTMATH: {
+      o[0] = hot_log(a[0]);
+      o[1] = hot_exp_neg_step(a[1]);
+      hot_sincos(a[2], &o[2], &o[3]);
+      hot_sincos_2pi(a[3], &o[4], &o[5]);
+      o[6] = fast_rcp(a[0]);
     } break;
     case PB_PROBE_PHILOX: {
       D2 d = draw2(make_uint2((uint32_t)a[0], (uint32_t)a[1]), (uint32_t)a[2], (uint32_t)a[3], (uint32_t)a[4], (uint32_t)a[5]);

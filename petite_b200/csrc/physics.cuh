@@ -81,6 +81,86 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(r, e, r);
 }
 
+// ---------------------------------------------------------------- hot-loop elementary functions
+// The sub-step loop calls exp, log (twice), sincos and sincospi once per iteration.  libdevice's versions are accurate but
+// ptxas materialises each of their ~60 fp64 polynomial coefficients as a pair of 32-bit immediate moves (24 % of k_loop's
+// executed instructions, profiles/r01_summary.md).  The versions below keep the coefficients in constant memory, where a
+// DFMA reads them as a c[bank][offset] operand, and drop the argument ranges the loop cannot produce.  Algorithms and
+// coefficients are the classic fdlibm kernels (e_log.c, k_sin.c, k_cos.c; <= 1 ulp on the reduced range, checked against
+// libm by tests/test_gpu_probes.py::test_hot_math).
+__constant__ double kHotMath[] = {
+  /* 0  Lg1..Lg7 */ 6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+                    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
+  /* 7  ln2_hi, ln2_lo */ 6.93147180369123816490e-01, 1.90821492927058770002e-10,
+  /* 9  S1..S6 */ -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                  2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+  /* 15 C1..C6 */ 4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                  -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,
+  /* 21 exp(-0.1) * (-1)^k / k!, k = 0..10 */
+  0.9048374180359596, -0.9048374180359596, 0.4524187090179798, -0.1508062363393266,
+  0.03770155908483165, -0.00754031181696633, 0.001256718636161055, -0.00017953123373729357,
+  2.2441404217161696e-05, -2.4934893574624107e-06, 2.4934893574624105e-07,
+  /* 32 pi_hi, pi_lo */ 3.141592653589793116e+00, 1.2246467991473532e-16
+};
+
+// log(x) for finite normal x > 0 (e_log.c without the subnormal / special-value branches)
+__device__ __forceinline__ double hot_log(double x) {
+  const double* K = kHotMath;
+  int hx = __double2hiint(x), lx = __double2loint(x);
+  int k = (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  int i = (hx + 0x95f64) & 0x100000;
+  double m = __hiloint2double(hx | (i ^ 0x3ff00000), lx);     // mantissa in [sqrt(1/2), sqrt(2))
+  k += i >> 20;
+  double f = m - 1.0;
+  double s = f * fast_rcp(2.0 + f);
+  double z = s * s, w = z * z;
+  double t1 = w * fma(w, fma(w, K[5], K[3]), K[1]);
+  double t2 = z * fma(w, fma(w, fma(w, K[6], K[4]), K[2]), K[0]);
+  double R = t1 + t2;
+  double hfsq = 0.5 * f * f;
+  double dk = (double)k;
+  return dk * K[7] - ((hfsq - fma(s, hfsq + R, dk * K[8])) - f);
+}
+// exp(-x) for x in [1/20, 1/6] (the hard-scatter test of a sub-step: x = 1 / U(6, 20)): degree-10 Taylor series about 0.1
+__device__ __forceinline__ double hot_exp_neg_step(double x) {
+  const double* K = kHotMath + 21;
+  double d = x - 0.1;
+  double r = K[10];
+#pragma unroll
+  for (int k = 9; k >= 0; --k) r = fma(r, d, K[k]);
+  return r;
+}
+// sin and cos of x, |x| <= pi/4 (k_sin.c / k_cos.c)
+__device__ __forceinline__ void hot_sincos_kernel(double x, double* sn, double* cs) {
+  const double* K = kHotMath;
+  double z = x * x;
+  double rs = fma(z, fma(z, fma(z, fma(z, K[14], K[13]), K[12]), K[11]), K[10]);
+  *sn = fma(z * x, fma(z, rs, K[9]), x);
+  double rc = z * fma(z, fma(z, fma(z, fma(z, fma(z, K[20], K[19]), K[18]), K[17]), K[16]), K[15]);
+  *cs = 1.0 - fma(0.5, z, -(z * rc));
+}
+__device__ __forceinline__ void hot_sincos(double x, double* sn, double* cs) {
+  if (fabs(x) <= 0.78539816339744828) hot_sincos_kernel(x, sn, cs);
+  else sincos(x, sn, cs);                                     // rare: multiple-scattering angles are small
+}
+// sin and cos of 2 pi u, u in [0, 1)
+__device__ __forceinline__ void hot_sincos_2pi(double u, double* sn, double* cs) {
+  double t = 2.0 * u;
+  double q = rint(2.0 * t);                                   // quadrant 0..4
+  double r = fma(q, -0.5, t);                                 // exact, |r| <= 1/4
+  double x = r * kHotMath[32];
+  double xl = fma(r, kHotMath[32], -x) + r * kHotMath[33];    // low part of r * pi
+  double s, c;
+  hot_sincos_kernel(x, &s, &c);
+  s = fma(xl, c, s);
+  c = fma(-xl, s, c);
+  int iq = (int)q & 3;
+  double so = (iq & 1) ? c : s, co = (iq & 1) ? s : c;
+  *sn = (iq & 2) ? -so : so;
+  *cs = ((iq + 1) & 2) ? -co : co;
+}
+
 // ---------------------------------------------------------------- form factors
 __device__ __forceinline__ double ff_elastic(const Material& M, double t) {  // all_processes.py:99-103
   double den = 1.0 + M.ff_a0sq * t;
@@ -509,7 +589,7 @@ __device__ __forceinline__ V4 mcs_fast(const Material& M, V4 p4, double pn, doub
   double E2 = E * E;
   double omega = M.mcs_Cw * t * E2 * fast_rcp(pn * pn + M.mcs_c3 * E2);
   double v = omega * (0.5 / (1.0 - F));
-  double th0 = sqrt(chic2 * ((1.0 + v) * log(1.0 + v) * fast_rcp(v) - 1) * (1.0 / (1.0 + F * F)));
+  double th0 = sqrt(chic2 * ((1.0 + v) * hot_log(1.0 + v) * fast_rcp(v) - 1) * (1.0 / (1.0 + F * F)));
   double theta = sign * (radial * th0) * M.rescale_mcs;
   double vx = p4.x, vy = p4.y, vz = p4.z;
   double ca, sa, vxp;
@@ -522,8 +602,8 @@ __device__ __forceinline__ V4 mcs_fast(const Material& M, V4 p4, double pn, doub
   else if (vxp < 0.0) { cb = 0.0; sb = 1.0; }
   else { cb = 1.0; sb = 0.0; }
   double cth, sth, cph, sph;
-  sincos(theta, &sth, &cth);
-  sincospi(2.0 * u_phi, &sph, &cph);
+  hot_sincos(theta, &sth, &cth);
+  hot_sincos_2pi(u_phi, &sph, &cph);
   double q0 = pn * (sph * sth), q1 = pn * (-cph * sth), q2 = pn * cth;
   V4 o;
   o.E = E;
@@ -543,7 +623,7 @@ __device__ __forceinline__ McsDraw mcs_draw(uint2 key, uint32_t index, uint32_t 
   McsDraw d;
   d.sign = (sp & 1u) ? 1.0 : -1.0;
   d.uphi = a.a;
-  d.radial = sqrt(-2.0 * log(1.0 - a.b));
+  d.radial = sqrt(-2.0 * hot_log(1.0 - a.b));
   return d;
 }
 __device__ __forceinline__ V4 mcs_scatter(const Material& M, V4 p4, double pn, double t, double m_lepton, double mass,

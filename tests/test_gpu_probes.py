@@ -24,6 +24,35 @@ def test_philox_matches_oracle():
     assert np.array_equal(got[:, 0], w0) and np.array_equal(got[:, 1], w1)     # bit-exact
 
 
+def test_hot_math():
+    """The constant-memory elementary functions of the sub-step loop (physics.cuh hot_*) against libm: <= 2 ulp on the
+    ranges the loop produces (log of (0, 1] and of [1, inf); exp(-x) on [1/20, 1/6]; sincos on [-pi/4, pi/4] and the libdevice
+    fall-back beyond; sincos(2 pi u)); the branch-free reciprocal <= 1 ulp."""
+    from petite_b200 import _capi as capi
+    sh = shower()
+    rng = np.random.default_rng(11)
+    n = 40000
+    xlog = np.concatenate([1.0 - rng.random(n // 4), 2.0 ** -rng.uniform(0, 52, n // 4), 1.0 + 10.0 ** rng.uniform(-9, 9, n // 4),
+                           10.0 ** rng.uniform(-300, 300, n // 4)])
+    xlog[:3] = [1.0, 2.0 ** -52, 0.5]
+    xexp = rng.uniform(1 / 20, 1 / 6, n); xexp[:2] = [1 / 20, 1 / 6]
+    th = np.concatenate([rng.uniform(-np.pi / 4, np.pi / 4, n // 2), rng.normal(0, 1e-4, n // 4), rng.uniform(-50, 50, n // 4)])
+    u = rng.random(n); u[:5] = [0.0, 0.25, 0.5, 0.75, 1 - 2.0 ** -52]
+    got = probe(sh, capi.PROBE_HOTMATH, 0, np.column_stack([xlog, xexp, th, u]), 7)
+    ulps = lambda a, b: np.abs(a - b) / np.spacing(np.maximum(np.abs(b), 1e-300))
+    assert got[0, 0] == 0.0                                                   # log(1) is exactly 0
+    lg = np.log(xlog)
+    assert np.max(ulps(got[:, 0], lg)[lg != 0]) <= 2
+    assert np.max(ulps(got[:, 1], np.exp(-xexp))) <= 2
+    assert np.max(ulps(got[:, 2], np.sin(th))) <= 2 and np.max(ulps(got[:, 3], np.cos(th))) <= 2
+    # sin / cos (2 pi u): compared in absolute terms (numpy rounds the argument 2 pi u, the kernel reduces exactly)
+    L = np.longdouble
+    a = 2 * L(np.pi) * u.astype(L) + 2 * L(1.2246467991473532e-16) * u.astype(L)
+    assert np.max(np.abs(got[:, 4] - np.sin(a).astype(np.float64))) < 4e-16
+    assert np.max(np.abs(got[:, 5] - np.cos(a).astype(np.float64))) < 4e-16
+    assert np.max(ulps(got[:, 6], 1.0 / xlog)) <= 1
+
+
 def _four_dim_condition(process, E, x):
     """Condition numbers of the cancellations inside the Brem / PairProd integrands (all_processes.py:140-206, 532-622)."""
     L = np.longdouble
