@@ -676,6 +676,8 @@ __device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, cons
       case P_BHABHA: f = ds_bhabha(E, M.Ee_min, x[0]); break;
       default: f = ds_muone(E, M.Ee_min, x[0]); break;
     }
+  } else if (DIM == 3) {
+    f = ds_darkbrem_fast(M, sc, E, proc == P_DARKBREM ? kMe : kMmu, x);      // the two 3-D processes
   } else {
     f = dsigma(M, proc, E, x);
   }
@@ -733,6 +735,9 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
       if (proc == P_PAIRPROD || proc == P_BREM || proc == P_MUONBREM) {
         SampleConst c = (proc == P_PAIRPROD) ? pairprod_const(M, Ek) : brem_const(M, Ek, proc == P_BREM ? kMe : kMmu);
         s_cb[k] = c.b; s_cc[k] = c.c; s_cd[k] = c.d;
+      } else if (FAM != 1 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) {
+        SampleConst c = darkbrem_const(M, Ek, proc == P_DARKBREM ? kMe : kMmu);
+        s_cb[k] = c.b; s_cc[k] = c.c; s_cd[k] = c.e;          // |p|, tconv, 1/|p|
       }
     }
     double maxF = __ldg(mi.maxF + lu) * M.fudge;
@@ -758,6 +763,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
           if (proc == P_PAIRPROD) sc = SampleConst{E - 2 * kMe, s_cb[j], s_cc[j], s_cd[j], 0.0};
           else if (proc == P_BREM) sc = SampleConst{E - kMe - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMe * kMe};
           else if (proc == P_MUONBREM) sc = SampleConst{E - kMmu - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMmu * kMmu};
+          else if (FAM != 1 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) sc = SampleConst{0.0, s_cb[j], s_cc[j], M.i2mT, s_cd[j]};
         } else cur = -2;
       }
       if (__all_sync(0xffffffffu, cur == -2)) break;
@@ -822,7 +828,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
 
 // Kinematics + rotation + daughter append, in bucket order (warps are process-coherent).
 __global__ void __launch_bounds__(128)
-k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W) {
+k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, int wave_order) {
   const long long begin = W.ws->begin;
   const int n = W.ws->n;
   int* __restrict__ next_c = W.list[2 * (W.ws->parity ^ 1)];
@@ -839,7 +845,7 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   uint2 key = make_uint2(0, 0);
   double wgt = 0.0, rx = 0, ry = 0, rz = 0;
   if (j < n) {
-    int i = W.sorted[j];
+    int i = wave_order ? j : W.sorted[j];
     int bucket = W.bucket[i];
     proc = bucket / LU_MAX;
     if (proc == P_NONE && S.aux[begin + i].x < 0) S.meta[begin + i].z |= (PB_FLAG_NO_SAMPLE << 8);   // sampler gave up
@@ -1381,6 +1387,12 @@ __global__ void k_probe(const __grid_constant__ Material M, const __grid_constan
       if (process >= 32) {      // the folded forms used inside k_sample
         int p = process - 32;
         if (p == P_PAIRPROD) { SampleConst sc = pairprod_const(M, a[0]); o[0] = ds_pairprod_fast(sc, a[0], a + 1); }
+        else if (p == P_DARKBREM || p == P_DARKMUONBREM) {
+          double ml = (p == P_DARKBREM) ? kMe : kMmu;
+          SampleConst sc = darkbrem_const(M, a[0], ml);
+          sc.d = M.i2mT;
+          o[0] = ds_darkbrem_fast(M, sc, a[0], ml, a + 1);
+        }
         else { double ml = (p == P_BREM) ? kMe : kMmu; SampleConst sc = brem_const(M, a[0], ml); o[0] = ds_brem_fast(M, sc, a[0], ml, a + 1); }
       } else o[0] = dsigma(M, process, a[0], a + 1);
       break;
@@ -1456,6 +1468,7 @@ struct pb_engine_s {
   int n_sm = 148;
   int profiling = 0;             // 0 off, 1 = the two dominant kernels only (k_loop, k_sample), 2 = every kernel
   int sample_group = 8;          // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
+  int emit_wave_order = 0;       // PB_EMIT_ORDER=1: k_emit walks the wave in record order (coalesced) instead of bucket order
   int sample_split = 0;          // PB_SAMPLE_SPLIT=1: SM pass with the 4-D and 1-D integrand families as two concurrent kernels (measured: no gain)
   cudaStream_t side = nullptr;   // second stream for the concurrent family kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1492,10 +1505,12 @@ static void derive_material(pb_engine e) {
   double c1 = pow(111 * pow(c.Z_T, -1.0 / 3) / kMe, 2);
   m.dff_c1 = c1;
   m.dff_c2 = 0.164 * pow(c.A_T, -2.0 / 3);
+  m.dff_ic2 = 1.0 / m.dff_c2;
   m.dff_ap2 = pow(773.0 * pow(c.Z_T, -2.0 / 3) / kMe, 2);
   m.dff_inel_pref = c.Z_T / (c1 * c1 * (c.Z_T * c.Z_T));
   m.dff_pref = (c.Z_T * c.Z_T) * (c1 * c1);
   m.Z23 = pow(c.Z_T, 2.0 / 3.0);
+  m.i2mT = 1.0 / (2.0 * c.mT_sampler);
   m.mcs_C4 = 0.157 * c.Z_T * (c.Z_T + 1) / c.A_T;
   m.mcs_Cw = m.mcs_C4 / (2.007e-5 * m.Z23);
   m.mcs_c3 = 3.34 * (c.Z_T * kAlpha) * (c.Z_T * kAlpha);
@@ -1521,6 +1536,7 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   derive_material(e);
   if (const char* g = getenv("PB_SAMPLE_G")) e->sample_group = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_SPLIT")) e->sample_split = atoi(g);
+  if (const char* g = getenv("PB_EMIT_ORDER")) e->emit_wave_order = atoi(g);
   cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
@@ -1794,7 +1810,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
       launch_sample(e, sg, io, stream, true);
       if (e->sample_split) ++launches;
       tock(PB_K_SAMPLE, j); tick(PB_K_EMIT, j);
-      k_emit<<<g128, 128, 0, stream>>>(e->mat, e->tab, S, e->work);
+      k_emit<<<g128, 128, 0, stream>>>(e->mat, e->tab, S, e->work, e->emit_wave_order);
       tock(PB_K_EMIT, j);
       launches += 7;
     }

@@ -39,9 +39,11 @@ struct Material {
   double ff_a0sq;                 // (184.15 * 2.718^-0.5 * Z^(-1/3) / m_e)^2        all_processes.py:92-103
   double ff_Z2a04;                // Z^2 * a0^4
   double dff_c1, dff_c2, dff_ap2; // all_processes.py:123-126
+  double dff_ic2;                 // 1 / dff_c2
   double dff_inel_pref;           // Z / (c1^2 Z^2)
   double dff_pref;                // Z^2 c1^2
   double Z23;                     // Z^(2/3)   moliere.py:218
+  double i2mT;                    // 1 / (2 mT)
   double me4, mV4;                // m_e**4, mV**4 as CPython computes them (libm pow)
   double mcs_C4, mcs_Cw, mcs_c3;  // Lynch-Dahl constants folded for mcs_fast
   long long max_trials;           // max_n_integrators * B
@@ -100,7 +102,11 @@ __constant__ double kHotMath[] = {
   0.9048374180359596, -0.9048374180359596, 0.4524187090179798, -0.1508062363393266,
   0.03770155908483165, -0.00754031181696633, 0.001256718636161055, -0.00017953123373729357,
   2.2441404217161696e-05, -2.4934893574624107e-06, 2.4934893574624105e-07,
-  /* 32 pi_hi, pi_lo */ 3.141592653589793116e+00, 1.2246467991473532e-16
+  /* 32 pi_hi, pi_lo */ 3.141592653589793116e+00, 1.2246467991473532e-16,
+  /* 34 log2(10), log10(2) hi (42 bits), lo, ln(10) */ 3.321928094887362, 0.30102999566395283, 2.8363394551044964e-14, 2.302585092994046,
+  /* 38 1/k!, k = 2..13 */ 0.5, 0.16666666666666666, 0.041666666666666664, 0.008333333333333333, 0.001388888888888889,
+  0.0001984126984126984, 2.48015873015873e-05, 2.7557319223985893e-06, 2.755731922398589e-07, 2.505210838544172e-08,
+  2.08767569878681e-09, 1.6059043836821613e-10
 };
 
 // log(x) for finite normal x > 0 (e_log.c without the subnormal / special-value branches)
@@ -130,6 +136,20 @@ __device__ __forceinline__ double hot_exp_neg_step(double x) {
 #pragma unroll
   for (int k = 9; k >= 0; --k) r = fma(r, d, K[k]);
   return r;
+}
+// 10^y for |y| < 300 (no overflow / subnormal handling): y = n log10(2) + r, 10^r = exp(r ln 10) by a degree-13 Taylor series
+// (|r ln 10| <= ln(2)/2), scaled by 2^n through the exponent field.  <= 1 ulp against libm's pow(10, y).
+__device__ __forceinline__ double hot_exp10(double y) {
+  const double* K = kHotMath + 34;
+  double n = rint(y * K[0]);
+  double r = fma(-n, K[2], fma(-n, K[1], y));
+  double z = r * K[3];
+  double s = K[15];
+#pragma unroll
+  for (int k = 14; k >= 4; --k) s = fma(s, z, K[k]);
+  s = fma(s, z, 1.0);
+  s = fma(s, z, 1.0);
+  return __hiloint2double(__double2hiint(s) + ((int)n << 20), __double2loint(s));
 }
 // sin and cos of x, |x| <= pi/4 (k_sin.c / k_cos.c)
 __device__ __forceinline__ void hot_sincos_kernel(double x, double* sn, double* cs) {
@@ -465,6 +485,88 @@ __device__ __forceinline__ double ds_darkbrem(const Material& M, double Eb, doub
   double FF = ff_el_inel_over_t2(M, t);
   double ans = FF * (kAlpha * kAlpha * kAlpha) * k * Eb * phi_int / (p * sqrt(k * k + p * p - 2 * p * k * cth));
   return ans * tconv * Jac;
+}
+
+// ---- the dark-brem integrand as the sampler evaluates it: same formula and operation order in the cancellation-prone
+// parts (utilde, discr, Y, W), but 10^x through hot_exp10, the energy-only factors hoisted per sample (SampleConst:
+// b = |p|, c = tconv, d = 1 / (2 mT), e = 1 / |p|), divisions by shared denominators as branch-free reciprocals, and the
+// kinematic cuts tested as soon as their inputs exist.  Agrees with ds_darkbrem to ~1e-13 relative away from W -> 0.
+__device__ __forceinline__ SampleConst darkbrem_const(const Material& M, double Eb, double ml) {
+  const double MT = M.mT, ml2 = ml * ml;
+  SampleConst s;
+  s.a = 0.0;
+  s.b = sqrt(Eb * Eb - ml2);
+  double tc = 2 * MT * (MT + Eb) * sqrt(Eb * Eb + ml2) / (MT * (MT + 2 * Eb) + ml2);
+  s.c = tc * tc;
+  s.d = 1.0 / (2 * MT);
+  s.e = 1.0 / s.b;
+  return s;
+}
+__device__ __forceinline__ double ff_el_inel_over_t2_fast(const Material& M, double t) {
+  const double mu_p = 2.79;
+  double ia = 1.0 + M.dff_c1 * t, b = 1.0 + t * M.dff_ic2;
+  double g = fast_rcp(ia * b);
+  double Gel = g * g;
+  double r = M.dff_ap2 * fast_rcp(1.0 + M.dff_ap2 * t);
+  double d = 1.0 + t * (1.0 / 0.71);
+  double d2 = d * d;
+  double Ginel = M.dff_inel_pref * (r * r) * ((1.0 + t * ((mu_p * mu_p - 1.0) / (4.0 * kMp * kMp))) * fast_rcp(d2 * d2));
+  return M.dff_pref * (Gel + Ginel);
+}
+__device__ __forceinline__ double ds_darkbrem_fast(const Material& M, const SampleConst& sc, double Eb, double ml, const double* xx) {
+  const double mV = M.mV, MT = M.mT;
+  const double LN10 = 2.302585092994046;
+  double x = xx[0];
+  double xE = x * Eb;
+  if (!(xE >= mV)) return 0.0;
+  double omc = hot_exp10(xx[1]);
+  double cth = 1.0 - omc;
+  double ttilde = hot_exp10(xx[2]);
+  double mV2 = mV * mV, ml2 = ml * ml;
+  double k = sqrt(fabs(xE * xE - mV2));
+  const double p = sc.b;
+  double V2 = p * p + k * k - 2 * p * k * cth;
+  double V = sqrt(V2);
+  double VV = V * V;
+  double utilde = -2 * (x * Eb * Eb - k * p * cth) + mV2;
+  double Er = (1 - x) * Eb + MT;
+  double discr = utilde * utilde + 4 * MT * utilde * Er + 4 * MT * MT * VV;
+  if (!(discr >= 0)) return 0.0;
+  double sq = sqrt(discr);
+  double iden = fast_rcp(2 * Er * Er - 2 * VV);
+  double cmn = V * (utilde + 2 * MT * Er);
+  double Qp = fabs((cmn + Er * sq) * iden);
+  double Qm = fabs((cmn - Er * sq) * iden);
+  double tplus = 2 * MT * (sqrt(MT * MT + Qp * Qp) - MT);
+  double tminus = 2 * MT * (sqrt(MT * MT + Qm * Qm) - MT);
+  const double tconv = sc.c, i2MT = sc.d;
+  double t = ttilde * tconv;
+  if (!((tplus > tminus) && (t > tminus) && (t < tplus))) return 0.0;
+  double q0 = -t * i2MT;
+  double q = sqrt(t * t * (i2MT * i2MT) + t);
+  double e3 = Eb + q0 - xE;
+  double iV = fast_rcp(V), iq = fast_rcp(q);
+  double cthq = -(VV + q * q + ml2 - e3 * e3) * (0.5 * iV * iq);
+  double mm = mV2 + 2 * ml2;
+  double Y = -t + 2 * q0 * Eb - 2 * q * p * (p - k * cth) * cthq * iV;
+  double W = fabs(Y * Y - 4 * q * q * p * p * k * k * (1 - cth * cth) * (1 - cthq * cthq) * (iV * iV));
+  if (!((fabs(cthq) <= 1.0) && (W > 0))) return 0.0;
+  double iu = fast_rcp(utilde);
+  double Am2 = -8 * MT * (4 * Eb * Eb * MT - t * (2 * Eb + MT)) * mm;
+  double A1 = 8 * MT * MT * iu;
+  double Am1 = (8 * iu) * (MT * MT * (2 * t * utilde + utilde * utilde
+                                      + 4 * Eb * Eb * (2 * (x - 1) * mm - t * ((x - 2) * x + 2))
+                                      + 2 * t * (-mV2 + 2 * ml2 + t))
+                           - 2 * Eb * MT * t * ((1 - x) * utilde + (x - 2) * (mm + t))
+                           + t * t * (utilde - mV2));
+  double A0 = (8 * iu * iu) * (MT * MT * (2 * t * utilde + (t - 4 * Eb * Eb * (x - 1) * (x - 1)) * mm)
+                               + 2 * Eb * MT * t * (utilde - (x - 1) * mm));
+  double sW = sqrt(W);
+  double isW = fast_rcp(sW);
+  double phi_int = (A0 + Y * A1 + Am1 * isW + Y * Am2 * (isW * isW * isW)) * (0.5 * i2MT * i2MT);
+  double FF = ff_el_inel_over_t2_fast(M, t);
+  double Jac = omc * ttilde * (LN10 * LN10);
+  return FF * (kAlpha * kAlpha * kAlpha) * k * Eb * phi_int * (sc.e * iV) * tconv * Jac;
 }
 
 // radiative_return.py:26-79 + all_processes.py:400-466 (dsigma_radiative_return_du)

@@ -117,6 +117,39 @@ def test_dsigma_vs_reference_golden(golden, material, process):
 
 
 @pytest.mark.parametrize("material", ["graphite", "lead"])
+@pytest.mark.parametrize("process,code", [("DarkBrem", 8), ("DarkAnn", 9), ("DarkComp", 10), ("DarkMuonBrem", 11)])
+def test_dark_dsigma_vs_reference_golden(golden, material, process, code):
+    """Dark integrands (all_processes.py:208-372, 401-466, 625-742 with mV > 0) against values of the unmodified reference
+    functions; for the two dark-brem processes also the folded form the sampler evaluates (ds_darkbrem_fast, probe code + 32)."""
+    from petite_b200 import _capi as capi
+    from tests.test_gpu_dark import dark_shower
+    g = golden("integrands")
+    E, x, f = g[f"{material}/{process}/E"], g[f"{material}/{process}/x"], g[f"{material}/{process}/f"]
+    ds = dark_shower(material, 0.03)
+    forms = [probe(ds, capi.PROBE_DSIGMA, code, np.column_stack([E, x]), 1)[:, 0]]
+    brem = "Brem" in process
+    if brem:
+        forms.append(probe(ds, capi.PROBE_DSIGMA, code + 32, np.column_stack([E, x]), 1)[:, 0])
+    # The dark-brem formula subtracts p^2 + k^2 - 2 p k cos(theta) with 1 - cos(theta) down to 1e-12 (map variable
+    # log10(1 - cos)), so even the reference's own float64 value carries a rounding error of about eps / (1 - cos); the
+    # GPU forms contract multiply-adds and land within that band (measured: median 5e-12, 7e-6 at 1 - cos = 5e-12, always
+    below 1.1 eps / (1 - cos); bound: 9 eps / (1 - cos)).
+    cond = 2e-15 / 10.0 ** x[:, 1] if brem else 0.0
+    for got in forms:
+        assert np.array_equal(got == 0, f == 0)
+        for Einc in np.unique(E):
+            sel = E == Einc
+            scale = np.max(np.abs(f[sel])) if np.any(f[sel] != 0) else 1.0
+            tol = (1e-12 + (1e-11 + cond[sel] if brem else 0.0)) * np.abs(f[sel]) + (1e-9 * scale if brem else 0.0)
+            assert np.all(np.abs(got[sel] - f[sel]) <= tol + 1e-300), (process, Einc)
+    if brem:       # the folded form follows the plain one far more closely than either follows the reference
+        a, b = forms
+        nz = a != 0
+        assert np.all(np.abs(a[nz] - b[nz]) <= (1e-10 + cond[nz]) * np.abs(a[nz]))
+        assert np.median(np.abs(a[nz] - b[nz]) / np.abs(a[nz])) < 1e-12
+
+
+@pytest.mark.parametrize("material", ["graphite", "lead"])
 def test_nsigma_vs_reference_golden(golden, material):
     from petite_b200 import _capi as capi
     g = golden("nsigma")
