@@ -133,7 +133,7 @@ def test_dark_dsigma_vs_reference_golden(golden, material, process, code):
     # The dark-brem formula subtracts p^2 + k^2 - 2 p k cos(theta) with 1 - cos(theta) down to 1e-12 (map variable
     # log10(1 - cos)), so even the reference's own float64 value carries a rounding error of about eps / (1 - cos); the
     # GPU forms contract multiply-adds and land within that band (measured: median 5e-12, 7e-6 at 1 - cos = 5e-12, always
-    below 1.1 eps / (1 - cos); bound: 9 eps / (1 - cos)).
+    # below 1.1 eps / (1 - cos); bound: 9 eps / (1 - cos)).
     cond = 2e-15 / 10.0 ** x[:, 1] if brem else 0.0
     for got in forms:
         assert np.array_equal(got == 0, f == 0)
