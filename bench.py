@@ -74,7 +74,7 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
     pool.map(_cpu_one, range(cores))
-    n = args.cpu_showers or max(2 * cores, 32)
+    n = args.cpu_showers or max(8 * cores, 64)
     for w in range(args.warmup):
         cpu_run(n, cores, first_id=10_000 + w * n, pool=pool)
     tot_t, tot_p, tot_s = 0.0, 0, 0
@@ -164,7 +164,7 @@ def ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # before CUDA is initialised in this process (fork-safe)
         cores = os.cpu_count() or 1
-        n_cpu = args.cpu_showers or max(2 * cores, 32)
+        n_cpu = args.cpu_showers or max(8 * cores, 64)
         dt, npart, nsteps = cpu_run(n_cpu, cores)
         cpu = {"value": n_cpu / dt, "unit": "showers/s", "cores": cores, "kind": "port",
                "sample": f"{n_cpu} showers of the same workload through the CPU oracle (multiprocessing, {cores} procs), {dt:.1f} s",
@@ -357,7 +357,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--primaries", type=int, default=100_000, help="primaries per GPU per step")
-    ap.add_argument("--cpu-showers", type=int, default=0, help="size of the CPU-baseline sample (0 = 2 x cores)")
+    ap.add_argument("--cpu-showers", type=int, default=0, help="size of the CPU-baseline sample (0 = 8 x cores: about 15-20 s of CPU work on all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

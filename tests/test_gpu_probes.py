@@ -140,8 +140,12 @@ def test_dark_dsigma_vs_reference_golden(golden, material, process, code):
         for Einc in np.unique(E):
             sel = E == Einc
             scale = np.max(np.abs(f[sel])) if np.any(f[sel] != 0) else 1.0
-            tol = (1e-12 + (1e-11 + cond[sel] if brem else 0.0)) * np.abs(f[sel]) + (1e-9 * scale if brem else 0.0)
-            assert np.all(np.abs(got[sel] - f[sel]) <= tol + 1e-300), (process, Einc)
+            # DarkAnn: u ** (2 / beta) with 2 / beta ~ 40 followed by the 1 - x subtraction next to the resonance amplifies the
+            # last-bit differences between libdevice's and libm's pow (measured 1.9e-10) -> 1e-9 there
+            rtol = 1e-9 if process == "DarkAnn" else 1e-12
+            tol = (rtol + (1e-11 + cond[sel] if brem else 0.0)) * np.abs(f[sel]) + (1e-9 * scale if brem else 0.0)
+            worst = float(np.max(np.abs(got[sel] - f[sel]) / (tol + 1e-300)))
+            assert worst <= 1.0, (process, Einc, worst)
     if brem:       # the folded form follows the plain one far more closely than either follows the reference
         a, b = forms
         nz = a != 0

