@@ -60,6 +60,8 @@ struct MapInfo {
 };
 struct Tables {
   NSigmaTable ns[16];
+  NSigmaTable sp[3];         // total n*sigma of a charged species (e-, e+, mu+-) on the union grid of its processes: the sub-step
+                             // loop only needs the sum, one node load and one hint instead of two or three (build_species_tables)
   MapInfo map[N_SAMPLED];
 };
 
@@ -180,6 +182,7 @@ __device__ __forceinline__ void species_tables(int pid, int* t) {
   else if (pid == -11) { t[0] = P_BREM; t[1] = P_BHABHA; t[2] = P_ANN; }
   else { t[0] = P_MUONBREM; t[1] = P_MUONE; t[2] = -1; }
 }
+__device__ __forceinline__ int species_index(int pid) { return pid == 11 ? 0 : (pid == -11 ? 1 : 2); }
 __device__ __forceinline__ double mfp_from(double ns) { return (ns <= 0.0) ? 1.0e12 : kCmToM / ns; }   // shower.py:386-389
 
 __device__ __forceinline__ double nsigma_log(const NSigmaTable& T, double logE, double E) {
@@ -210,22 +213,18 @@ struct Track {
   V4 p; double rx, ry, rz;
   double mass, iKp, pmin, delta_z, pn, ipn;     // iKp = mass / (1e3 m_species): 1 / (momentum scale of the MCS width)
   uint2 key;
-  int tb[3], hint[3];
+  int sp, hint;    // species table (Tables::sp) and the look-up hint into it
   int it;          // loop iterations done == accepted sub-steps while the loop is alive
 };
 
 // Track set-up computed where the particle is created (k_emit / k_init_primaries, all lanes busy) instead of at refill
-// time inside k_loop (3 of 32 lanes busy): |p| and the three table hints, parked in the record's not-yet-used rf slot.
+// time inside k_loop (3 of 32 lanes busy): |p| and the species-table hint, parked in the record's not-yet-used rf slot.
 __device__ __forceinline__ void store_track_setup(const Tables& T, Stack& S, long long slot, int pid, double E, double px,
                                                   double py, double pz) {
-  int tb[3];
-  species_tables(pid, tb);
-  double logE = log(E);
-  int h[3];
-  for (int k = 0; k < 3; ++k) h[k] = (tb[k] >= 0) ? nsigma_locate_log(T.ns[tb[k]], logE, E) : 1;
+  int h = nsigma_locate(T.sp[species_index(pid)], E);
   double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * slot);
-  rfp[0] = make_double2(norm3_nofma(px, py, pz), __hiloint2double(h[1], h[0]));
-  rfp[1] = make_double2(__hiloint2double(0, h[2]), 0.0);
+  rfp[0] = make_double2(norm3_nofma(px, py, pz), __hiloint2double(0, h));
+  rfp[1] = make_double2(0.0, 0.0);
 }
 
 // First kernel of every wave: turn what the previous wave appended (stack tail, list sizes) into this wave's extent.
@@ -263,7 +262,7 @@ __global__ void k_wave_begin(Work W) {
 // double buffer in shared memory -> consumed with shared-memory reads.
 constexpr int LOOP_CHUNK = 32;
 struct LoopBuf {                 // one chunk of track records: p0, r0w, track set-up (rf), ids
-  double2 v[6][LOOP_CHUNK];
+  double2 v[5][LOOP_CHUNK];
   int4 meta[LOOP_CHUNK];
   uint2 key[LOOP_CHUNK];
   int idx[LOOP_CHUNK];
@@ -311,7 +310,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       const double2* sup = reinterpret_cast<const double2*>(S.rf + 4 * s);     // store_track_setup
       cp_async16(&B.v[0][lane], p0p); cp_async16(&B.v[1][lane], p0p + 1);
       cp_async16(&B.v[2][lane], r0p); cp_async16(&B.v[3][lane], r0p + 1);
-      cp_async16(&B.v[4][lane], sup); cp_async16(&B.v[5][lane], sup + 1);
+      cp_async16(&B.v[4][lane], sup);
       cp_async16(&B.meta[lane], S.meta + s);
       cp_async8(&B.key[lane], S.key + s);
       B.idx[lane] = pre_idx;
@@ -346,7 +345,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
         const LoopBuf& B = buf[which];
         const int e = pos + rank;
         cur = B.idx[e];
-        double2 a0 = B.v[0][e], a1 = B.v[1][e], b0 = B.v[2][e], b1 = B.v[3][e], s0 = B.v[4][e], s1 = B.v[5][e];
+        double2 a0 = B.v[0][e], a1 = B.v[1][e], b0 = B.v[2][e], b1 = B.v[3][e], s0 = B.v[4][e];
         t.p = V4{a0.x, a0.y, a1.x, a1.y};
         t.rx = b0.x; t.ry = b0.y; t.rz = b1.x;
         int4 meta = B.meta[e];
@@ -355,9 +354,9 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
         t.mass = pid_mass(pid); t.iKp = 1e-3;
         if (meta.y < 0) { t.mass = prim_mass[begin + cur]; t.iKp = t.mass / (1e3 * pid_mass(pid)); }
         t.pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), t.mass);   // shower.py:532-533
-        species_tables(pid, t.tb);
+        t.sp = species_index(pid);
         t.pn = s0.x; t.ipn = 1.0 / s0.x;
-        t.hint[0] = __double2loint(s0.y); t.hint[1] = __double2hiint(s0.y); t.hint[2] = __double2loint(s1.x);
+        t.hint = __double2loint(s0.y);
         t.delta_z = 0.0; t.it = 0;
       }
       pos += min(__popc(need), avail);
@@ -369,8 +368,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     if (cur >= 0) {
       if (!(t.p.E >= t.pmin)) done = true;                               // loop condition (shower.py:559)
       else {
-        double ns = nsigma_hinted(T.ns[t.tb[0]], t.hint[0], t.p.E) + nsigma_hinted(T.ns[t.tb[1]], t.hint[1], t.p.E);
-        if (t.tb[2] >= 0) ns += nsigma_hinted(T.ns[t.tb[2]], t.hint[2], t.p.E);
+        double ns = nsigma_hinted(T.sp[t.sp], t.hint, t.p.E);              // sum over the species' processes (shower.py:357-368)
         double mfp = (ns <= 0.0) ? 1.0e12 : kCmToM * fast_rcp(ns);        // shower.py:386-389
         D2 u = draw2(t.key, (uint32_t)t.it, ST_SUBSTEP);
         double iv = fast_rcp(6.0 + 14.0 * u.b);                           // delta_z = mfp / U(6, 20); delta_z / mfp = 1 / U
@@ -1456,6 +1454,8 @@ struct pb_engine_s {
   Material mat{};
   Tables tab{};
   std::vector<void*> owned;      // device allocations for tables
+  std::vector<double> ns_x[16], ns_y[16];   // host copies of the n*sigma tables (for the per-species sums)
+  bool species_dirty = true;
   Work work{};
   long long work_n = 0;          // capacity of per-wave scratch
   void* work_blob = nullptr;
@@ -1600,6 +1600,55 @@ extern "C" int pb_upload_nsigma(pb_engine e, int id, const double* E, const doub
   double lx0 = (n > 1 && E[0] > 0) ? log(E[0]) : 0.0;
   double idl = (n > 1 && E[0] > 0 && E[n - 1] > E[0]) ? (double)(n - 1) / log(E[n - 1] / E[0]) : 0.0;
   e->tab.ns[id] = NSigmaTable{(const double4*)d, n ? E[0] : 0.0, n ? E[n - 1] : 0.0, lx0, idl, n, 0};
+  e->ns_x[id].assign(E, E + n);
+  e->ns_y[id].assign(y, y + n);
+  e->species_dirty = true;
+  return PB_OK;
+}
+
+// Total n*sigma(E) of each charged species as ONE piecewise-linear table on the union of its processes' grids.  A member
+// table contributes to a union segment iff the segment lies inside its range (scipy's fill_value = 0 outside), with the
+// value and slope of its own segment there; nodes store the right-hand limit, so the jump at a member's upper end is exact.
+// (At a member's lower end the single point E == x_0 gets 0 instead of y_0.)  Sums differ from the reference's
+// term-by-term sum by rounding only.
+static int build_species_tables(pb_engine e) {
+  static const int members[3][3] = {{P_BREM, P_MOLLER, -1}, {P_BREM, P_BHABHA, P_ANN}, {P_MUONBREM, P_MUONE, -1}};
+  for (int sp = 0; sp < 3; ++sp) {
+    std::vector<double> u;
+    for (int k = 0; k < 3; ++k) {
+      int id = members[sp][k];
+      if (id >= 0 && e->ns_x[id].size() >= 2) u.insert(u.end(), e->ns_x[id].begin(), e->ns_x[id].end());
+    }
+    std::sort(u.begin(), u.end());
+    u.erase(std::unique(u.begin(), u.end()), u.end());
+    const int m = (int)u.size();
+    std::vector<double> node(4 * (size_t)std::max(m, 1), 0.0);
+    for (int j = 0; j < m; ++j) {
+      double Y = 0.0, S = 0.0;
+      if (j + 1 < m) {
+        for (int k = 0; k < 3; ++k) {
+          int id = members[sp][k];
+          if (id < 0 || e->ns_x[id].size() < 2) continue;
+          const std::vector<double>& x = e->ns_x[id];
+          const std::vector<double>& y = e->ns_y[id];
+          const int n = (int)x.size();
+          if (!(x[0] <= u[j] && u[j + 1] <= x[n - 1])) continue;
+          int i = (int)(std::upper_bound(x.begin(), x.end(), u[j]) - x.begin()) - 1;
+          i = std::min(std::max(i, 0), n - 2);
+          double slope = (y[i + 1] - y[i]) / (x[i + 1] - x[i]);
+          Y += slope * (u[j] - x[i]) + y[i];
+          S += slope;
+        }
+      }
+      node[4 * j] = u[j]; node[4 * j + 1] = Y; node[4 * j + 2] = S;
+    }
+    double* d = nullptr;
+    PB_CUDA(e, cudaMalloc(&d, sizeof(double) * node.size()));
+    e->owned.push_back(d);
+    PB_CUDA(e, cudaMemcpy(d, node.data(), sizeof(double) * node.size(), cudaMemcpyHostToDevice));
+    e->tab.sp[sp] = NSigmaTable{(const double4*)d, m ? u[0] : 0.0, m ? u[m - 1] : 0.0, 0.0, 0.0, m, 0};
+  }
+  e->species_dirty = false;
   return PB_OK;
 }
 
@@ -1703,6 +1752,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
   if (n0 <= 0 || n0 > st->capacity) { e->err = "primaries exceed stack capacity"; return PB_ERR_CAPACITY; }
   for (int p = 0; p < 8; ++p)
     if (e->tab.map[p].grid == nullptr || e->tab.ns[p].n == 0) { e->err = "tables not uploaded"; return PB_ERR_STATE; }
+  if (e->species_dirty) { int rcs = build_species_tables(e); if (rcs != PB_OK) return rcs; }
   int B = e->tab.map[P_BREM].B;
   e->mat.max_trials = (long long)std::min<double>((double)e->cfg.max_sweeps * (double)B, 4.0e9);
   Stack S{st->p0, st->r0w, st->pf, st->rf, (uint2*)st->key, (int4*)st->meta, (int2*)st->aux, st->capacity};
