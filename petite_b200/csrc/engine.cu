@@ -29,7 +29,7 @@ namespace pb {
 constexpr int LU_MAX = 256;                 // energy rows per process (100 in data/, 150 in data_400GeV/)
 constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #ifndef PB_TILE
-#define PB_TILE 256
+#define PB_TILE 192
 #endif
 #ifndef PB_SAMPLE_THREADS
 #define PB_SAMPLE_THREADS 128
@@ -1843,8 +1843,8 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     // inside a lookahead batch is still processed completely
     const unsigned g128 = (unsigned)((bound + 127) / 128);
     const unsigned g256 = (unsigned)((bound + 255) / 256);
-    const int lg = (int)std::min<long long>((long long)e->n_sm * 8, (bound + 4 * 8 - 1) / (4 * 8));
-    const int sg = (int)std::min<long long>((long long)e->n_sm * 4, (bound + 31) / 32 + 1);
+    const int lg = (int)std::min<long long>((long long)e->n_sm * PB_LOOP_MINB, (bound + 4 * 8 - 1) / (4 * 8));
+    const int sg = (int)std::min<long long>((long long)e->n_sm * PB_SAMPLE_MINB, (bound + 31) / 32 + 1);
     for (int j = 0; j < K; ++j) {
       k_wave_begin<<<1, 1, 0, stream>>>(e->work);
       tick(PB_K_PROPAGATE, j);
@@ -1998,7 +1998,7 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
     SampleIO io{e->cand.pf, S.key, e->cand.slot, e->cand.ntr, 1, nullptr};
     k_bucket_fill<<<(unsigned)((n_cand + 255) / 256), 256, 0, stream>>>(e->work, io, n_cand);
     tock(PB_K_FILL); tick(PB_K_SAMPLE);
-    int sg = (int)std::min<long long>((long long)e->n_sm * 4, (n_cand + 31) / 32 + 1);
+    int sg = (int)std::min<long long>((long long)e->n_sm * PB_SAMPLE_MINB, (n_cand + 31) / 32 + 1);
     launch_sample(e, sg, io, stream);
     tock(PB_K_SAMPLE); tick(PB_K_EMIT);
     k_dark_emit<<<(unsigned)((n_cand + 127) / 128), 128, 0, stream>>>(e->mat, S, O, e->work, e->cand, n_cand);
@@ -2065,7 +2065,7 @@ extern "C" int pb_draw_samples(pb_engine e, int process, const double* E, int64_
   k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
   SampleIO io{e->cand.pf, dkeys, nullptr, e->cand.ntr, 1, nullptr};
   k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, io, (int)n);
-  launch_sample(e, (int)std::min<long long>((long long)e->n_sm * 4, (n + 31) / 32 + 1), io, stream);
+  launch_sample(e, (int)std::min<long long>((long long)e->n_sm * PB_SAMPLE_MINB, (n + 31) / 32 + 1), io, stream);
   cudaError_t c = cudaMemcpyAsync(x_out, e->work.xs, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, stream);
   if (c == cudaSuccess && ntr_out) c = cudaMemcpyAsync(ntr_out, e->cand.ntr, sizeof(int) * n, cudaMemcpyDeviceToHost, stream);
   if (c == cudaSuccess) c = cudaStreamSynchronize(stream);

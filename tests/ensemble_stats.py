@@ -19,6 +19,9 @@ CONFIGS = {
     "c1_e_graphite": dict(material="graphite", pid=11, E0=10.0, mass=m_e, E_min=0.010, seed=20261017, n_oracle=600, mV=None),
     # BASELINE config 3 (dark shower, 10 GeV e- -> graphite) at the physically intended lightest trained mass
     "c3_dark_graphite": dict(material="graphite", pid=11, E0=10.0, mass=m_e, E_min=0.010, seed=20261017, n_oracle=240, mV=0.003),
+    # BASELINE config 5, SM part (100 GeV mu- -> lead: MuonBrem / MuonE + multiple scattering); the oracle's dark-muon-brem pass
+    # (~300 trials per emission, 6.6e3 emissions per shower) is too slow for a fixture and is covered by the replay tests instead
+    "c5_mu_lead": dict(material="lead", pid=13, E0=100.0, mass=0.1056583755, E_min=0.010, seed=20261017, n_oracle=160, mV=None),
 }
 SPEC_EDGES = np.logspace(-2, 1, 9)       # 8 bins, 10 MeV .. 10 GeV
 

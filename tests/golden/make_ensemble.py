@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Oracle-side ensembles for the >= 1e5-shower statistical tests (tests/test_gpu_ensemble.py).
 
-    python tests/golden/make_ensemble.py            # -> tests/golden/ensemble.npz  (a few minutes on 8 cores)
+    python tests/golden/make_ensemble.py [config ...]   # -> tests/golden/ensemble.npz  (about 20 minutes on 8 cores)
 
 For each configuration the CPU oracle (counter-mode draws, shower ids well away from the ones the GPU test uses) steps
 N independent showers and keeps PER-SHOWER summaries only - showers are the independent units a KS / chi-square test may
@@ -42,14 +42,18 @@ def _one(args):
 
 
 def main():
-    out = {}
+    path = os.path.join(ROOT, "tests", "golden", "ensemble.npz")
+    only = [a for a in sys.argv[1:] if a in CONFIGS]            # e.g. `make_ensemble.py c5_mu_lead`: redo these, keep the rest
+    out = dict(np.load(path)) if only and os.path.exists(path) else {}
     with Pool(os.cpu_count()) as pool:
         for name, cfg in CONFIGS.items():
+            if only and name not in only:
+                continue
             rows = pool.map(_one, [(name, i) for i in range(cfg["n_oracle"])], chunksize=4)
             for k in rows[0]:
                 out[f"{name}/{k}"] = np.array([r[k] for r in rows])
             print(name, len(rows), {k: float(np.mean(out[f"{name}/{k}"])) for k in rows[0] if np.ndim(rows[0][k]) == 0})
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ensemble.npz"), **out)
+    np.savez_compressed(path, **out)
 
 
 if __name__ == "__main__":
