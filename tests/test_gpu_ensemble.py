@@ -89,3 +89,20 @@ def test_dark_observables_1e5_showers(golden):
     print(name, {k: round(float(v), 4) for k, v in pvals.items()}, "dark vectors", dk.n)
     assert all(v > 0.01 for v in pvals.values()), pvals
     assert dk.n > 50 * N_GPU
+
+
+def test_reference_recorded_single_shower_numbers():
+    """The only numbers the reference records for whole showers (stored notebook outputs, single seeds):
+    10 GeV e- into graphite, E_min = 10 MeV -> 655 particles (multiple_coulomb_scattering.ipynb:[11]); the profiled shower of
+    tutorial.ipynb:[37] made 700 propagate_particle calls and 4 998 get_scattered_momentum_fast calls.  They must be
+    ordinary members of the GPU ensemble: inside its central 99 %, and the multiple-scattering calls per step within 15 %."""
+    name = "c1_e_graphite"
+    sh = _engine(name)
+    n = 20_000
+    batch = _run(sh, name, n)
+    mult = es.summarise_gpu_sm(batch, n)["mult"]
+    lo, hi = np.quantile(mult, [0.005, 0.995])
+    assert lo <= 655 <= hi and lo <= 700 <= hi, (lo, hi)
+    c = batch.counters
+    mcs_calls_per_step = (c["n_substeps"] + c["n_charged"]) / c["n_steps"]      # one call per sub-step + one for the final step
+    assert abs(mcs_calls_per_step / (4998 / 700) - 1) < 0.15, mcs_calls_per_step
