@@ -278,6 +278,30 @@ def ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
 
+    # ---- extra (N = 1 only): the same step as `parts` concurrent sub-batches (Shower.run_arrays_split: one engine handle,
+    # stream and host thread per part).  Kept out of `value`: per-launch kernel times overlap there, and the roofline
+    # above is defined on launches that own the GPU.
+    conc = None
+    if world == 1 and args.parts > 1:
+        def split_step():
+            bs = sh.run_arrays_split(*devp, parts=args.parts, capacity=capacity, first_shower_id=base_id)
+            tally.zero_()
+            sh.tally_batches(bs, tally)
+            return bs
+        split_step()                                            # warm-up: peer engine tables, stacks, scratch growth
+        split_step()
+        barrier()
+        e0.record()
+        for k in range(e2e_steps):
+            bs = split_step()
+        e1.record()
+        barrier()
+        ms_c = e0.elapsed_time(e1)
+        conc = {"parts": args.parts, "value": n * e2e_steps / (ms_c * 1e-3), "unit": "showers/s", "ms_per_step": ms_c / e2e_steps,
+                "steps": e2e_steps, "records_per_step": sum(b.n for b in bs),
+                "tally_records": float(tally.cpu().numpy()[capi.TALLY_COUNT:capi.TALLY_COUNT + 7].sum()),
+                "api": "Shower.run_arrays_split(device primaries) + Shower.tally_batches"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -343,6 +367,7 @@ def ours(args):
         "clocks": clk,
         "tally_check": {"records": float(tally_host[capi.TALLY_COUNT:capi.TALLY_COUNT + 7].sum()),
                         "expected": world * tot["n_particles"] / K},
+        "concurrent": conc,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -359,6 +384,7 @@ def main():
     ap.add_argument("--primaries", type=int, default=100_000, help="primaries per GPU per step")
     ap.add_argument("--cpu-showers", type=int, default=0, help="size of the CPU-baseline sample (0 = 8 x cores: about 15-20 s of CPU work on all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parts", type=int, default=2, help="extra measurement: the step as this many concurrent sub-batches (0/1 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

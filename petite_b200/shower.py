@@ -485,6 +485,77 @@ class Shower:
         capi.check(self._engine, rc)
         return ShowerBatch(self, t, cnt.n_particles, cnt.as_dict(), n, first_shower_id)
 
+    # ------------------------------------------------------------------ concurrent sub-batches
+    def _clone_engine(self):
+        """A second engine handle on the same GPU with the same tables (own scratch, own stack).  The host-side tables
+        are shared by reference; only the device copies (13.5 MB) are duplicated."""
+        import copy
+        peer = copy.copy(self)
+        peer._peers, peer._pool, peer._peer_streams = [], None, []
+        peer._engine = capi.pb_engine()
+        peer._stack_tensors, peer._stack_capacity = None, 0
+        peer._create_engine()
+        return peer
+
+    def _ensure_peers(self, parts):
+        from concurrent.futures import ThreadPoolExecutor
+        torch = self._torch
+        peers = self.__dict__.setdefault("_peers", [])
+        streams = self.__dict__.setdefault("_peer_streams", [])
+        with torch.cuda.device(self._device):
+            while len(peers) < parts - 1:
+                peers.append(self._clone_engine())
+            while len(streams) < parts:
+                streams.append(torch.cuda.Stream(device=self._device))
+        if self.__dict__.get("_pool") is None or self._pool._max_workers < parts:
+            self._pool = ThreadPoolExecutor(max_workers=parts)
+        return [self] + peers[: parts - 1], streams[:parts]
+
+    def run_arrays_split(self, p, r, w, m, pid, flags, parts=2, GlobalMS=True, capacity=None, first_shower_id=None):
+        """``run_arrays`` over ``parts`` contiguous sub-batches stepped CONCURRENTLY: one engine handle, one stack, one
+        CUDA stream and one host thread per part (handles are independent, include/petite_b200.h).  Every wave kernel
+        is a persistent grid whose last CTAs finish late (the longest track / tile of the wave) and the shrinking tail
+        of a batch is latency-bound; a second batch in flight fills both.  Showers are keyed by (seed, shower id) and
+        part k starts at ``first_shower_id + offset_k``, so the particles are those of the single-batch call.
+
+        Stream semantics are those of a synchronous call on the caller's current stream: the parts start after the
+        work already queued there and the current stream waits for all of them.  -> list of :class:`ShowerBatch`."""
+        torch = self._torch
+        n = len(pid)
+        parts = max(1, min(int(parts), n))
+        if first_shower_id is None:
+            first_shower_id = self._next_shower_id
+            self._next_shower_id += n
+        if parts == 1:
+            return [self.run_arrays(p, r, w, m, pid, flags, GlobalMS=GlobalMS, capacity=capacity, first_shower_id=first_shower_id)]
+        engines, streams = self._ensure_peers(parts)
+        bounds = [n * k // parts for k in range(parts + 1)]
+        cap = None if capacity is None else int(capacity) // parts + (1 << 16)
+        cur = torch.cuda.current_stream(self._device)
+        start = torch.cuda.Event()
+        start.record(cur)
+
+        def work(k):
+            sl = slice(bounds[k], bounds[k + 1])
+            with torch.cuda.device(self._device), torch.cuda.stream(streams[k]):
+                streams[k].wait_event(start)
+                b = engines[k].run_arrays(p[sl], r[sl], w[sl], m[sl], pid[sl], flags[sl], GlobalMS=GlobalMS, capacity=cap,
+                                          first_shower_id=first_shower_id + bounds[k])
+                done = torch.cuda.Event()
+                done.record(streams[k])
+            return b, done
+
+        out = [f.result() for f in [self._pool.submit(work, k) for k in range(parts)]]
+        for _, done in out:
+            cur.wait_event(done)
+        return [b for b, _ in out]
+
+    def tally_batches(self, batches, out=None):
+        """``tally`` over the batches of a split run, accumulated into one buffer."""
+        for b in batches:
+            out = b._owner.tally(b, out)
+        return out
+
     def run_tallies(self, p, r, w, m, pid, flags, batch=32768, GlobalMS=True, first_shower_id=0, dark=None):
         """Memory-bounded run: step the primaries ``batch`` at a time, keep only the tallies (``pb_tally``), discard the
         particle history.  ``dark`` (a DarkShower sharing this object) adds the dark-vector tallies of each batch.

@@ -80,6 +80,34 @@ def test_batch_split_and_determinism():
         assert np.array_equal(x, y)
 
 
+def test_concurrent_sub_batches_match_single_batch():
+    """run_arrays_split: two engine handles, two streams, two host threads - same showers as one call, and the same tallies."""
+    sh = shower("lead", 0.010, seed=9)
+    prims = primaries(22, 2.0, 65)
+    arrays = sh._pack_primaries(prims)
+
+    def signature(batch):
+        h = batch.to_host()
+        order, offs = batch.reference_order()
+        return [np.concatenate([h["p0"][order[offs[i]:offs[i + 1]]].ravel(), h["rf"][order[offs[i]:offs[i + 1]]].ravel()]) for i in range(batch.n_primaries)]
+    one = sh.run_arrays(*arrays, first_shower_id=500)
+    a = signature(one)
+    t_one = sh.tally(one).cpu().numpy()
+    parts = sh.run_arrays_split(*arrays, parts=2, first_shower_id=500)
+    assert [b.n_primaries for b in parts] == [32, 33] and parts[0]._owner is not parts[1]._owner
+    b = signature(parts[0]) + signature(parts[1])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    t_two = sh.tally_batches(parts).cpu().numpy()
+    assert np.allclose(t_one, t_two, rtol=1e-12, atol=0)
+    assert sum(p.n for p in parts) == one.n
+    # device-resident primaries, three parts
+    import torch
+    dev = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in arrays]
+    parts3 = sh.run_arrays_split(*dev, parts=3, capacity=one.n * 2 + 4096, first_shower_id=500)
+    assert sum(p.n for p in parts3) == one.n
+
+
 def test_energy_accounting_full_size_property():
     """Size-independent property at a BASELINE-like size: daughters never carry more energy than the parent had at
     the vertex (up to the rest mass of the struck atomic electron), and weights are inherited."""

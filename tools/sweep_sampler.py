@@ -1,0 +1,64 @@
+"""Tuning + safety sweep of the accept/reject sampler variants (one process, one engine per configuration; the knobs are
+read from the environment by pb_create): for every (PB_SAMPLE_STREAM, PB_SAMPLE_G, PB_SAMPLE_TOKENS)
+
+  1. correctness: 2 000 showers of config 2 must give the SAME records and trial counts as the reference configuration
+     (tile kernel, G = 8) - the draws are counter-based, so any schedule has to reproduce them bit for bit;
+  2. timing: config 2 at 1e5 primaries, CUDA events, per-step and per-kernel (profiling level 1).
+
+    python tools/sweep_sampler.py [n_timing] > gpurun_out/sweep_sampler.log
+"""
+import os, sys, json
+import numpy as np, torch
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from petite_b200.shower import Shower
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "data", "")
+N_T = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
+CONFIGS = [(0, 8, 4)] + [(1, g, 4) for g in (8, 4, 2)] + [(1, 4, t) for t in (2, 8, 16)] + [(1, 8, 8), (1, 2, 8), (0, 4, 4)]
+if len(sys.argv) > 2:
+    CONFIGS = [tuple(int(v) for v in c.split(",")) for c in sys.argv[2:]]
+
+
+def prim(k, dev=None):
+    p = np.tile(np.array([10.0, 0, 0, 10.0]), (k, 1)); r = np.zeros((k, 3)); w = np.ones(k); m = np.zeros(k)
+    a = [p, r, w, m, np.full(k, 22, np.int32), np.zeros(k, np.int32)]
+    if dev is not None:
+        a = [torch.from_numpy(x).to(dev) for x in a]
+    return a
+
+
+def digest(sh):
+    b = sh.run_arrays(*prim(2000), first_shower_id=777_000)
+    h = b.to_host()
+    o = np.lexsort((h["p0"][:, 3], h["p0"][:, 0], h["generation"], h["shower"]))
+    return dict(b.counters), h["p0"][o].copy(), h["pf"][o].copy(), h["ntrials"][o].copy(), h["pid"][o].copy()
+
+
+dev = torch.device("cuda", 0)
+ref = None
+for stream, G, tok in CONFIGS:
+    os.environ["PB_SAMPLE_STREAM"], os.environ["PB_SAMPLE_G"], os.environ["PB_SAMPLE_TOKENS"] = str(stream), str(G), str(tok)
+    sh = Shower(DATA, "lead", 0.010, seed=20261017)
+    d = digest(sh)
+    if ref is None:
+        ref = d
+    same = all(d[0][k] == ref[0][k] for k in ("n_particles", "n_steps", "n_substeps", "n_samples", "n_trials", "n_no_sample")) and \
+        all(np.array_equal(a, b) for a, b in zip(d[1:], ref[1:]))
+    devp = prim(N_T, dev)
+    cal = sh.run_arrays(*prim(2000), first_shower_id=10 ** 9)
+    cap = int(N_T * cal.n / 2000 * 1.06 + 2.3 * cal.counters["max_wave"] / 2000 * N_T) + (1 << 16)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sh.run_arrays(*devp, capacity=cap, first_shower_id=0)          # warm-up (scratch growth)
+    sh.set_profiling(1)
+    ms, ks, kl = [], [], []
+    for rep in range(3):
+        torch.cuda.synchronize(); e0.record()
+        b = sh.run_arrays(*devp, capacity=cap, first_shower_id=0)
+        e1.record(); torch.cuda.synchronize()
+        pr = sh.get_profile()
+        ms.append(e0.elapsed_time(e1)); ks.append(pr["ms"]["k_sample"]); kl.append(pr["ms"]["k_loop"])
+    print(json.dumps({"stream": stream, "G": G, "tokens": tok, "same_as_reference": bool(same), "records": d[0]["n_particles"],
+                      "trials": d[0]["n_trials"], "step_ms": round(min(ms), 2), "k_sample_ms": round(min(ks), 2),
+                      "k_loop_ms": round(min(kl), 2), "showers_per_s": round(N_T / min(ms) * 1e3)}), flush=True)
+    del sh, b, cal, devp
+    torch.cuda.empty_cache()
