@@ -40,6 +40,19 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #ifndef PB_SAMPLE_MINB_SM
 #define PB_SAMPLE_MINB_SM 5
 #endif
+#ifndef PB_FIN_MINB
+#define PB_FIN_MINB 8                    // 64 registers, 8 CTAs per SM: measured 17.8 -> 15.3 ms per step (10: 15.7, 12: 16.2, uncapped 94 registers: 17.8) although it spills 92 B
+#endif
+#ifdef PB_FIN_MINB
+#define PB_FIN_BOUNDS __launch_bounds__(128, PB_FIN_MINB)
+#else
+#define PB_FIN_BOUNDS __launch_bounds__(128)
+#endif
+#ifdef PB_EMIT_MINB
+#define PB_EMIT_BOUNDS __launch_bounds__(128, PB_EMIT_MINB)
+#else
+#define PB_EMIT_BOUNDS __launch_bounds__(128)
+#endif
 #ifndef PB_LOOP_MINB
 #define PB_LOOP_MINB 6
 #endif
@@ -109,7 +122,6 @@ struct Work {            // per-wave scratch, sized to the widest wave seen so f
   int* hist;             // [NBUCKET]
   int* offsets;          // [NBUCKET + 1]
   int* cursor;           // [NBUCKET]
-  int* take;             // [NBUCKET] samples of the bucket already claimed by k_sample_stream warps
   int* tile_bucket;      // [max_tiles]
   int* tile_start;
   int* tile_count;
@@ -274,9 +286,6 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __global__ void __launch_bounds__(128, PB_LOOP_MINB)
@@ -419,7 +428,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
 
 // Per particle of the wave (charged list first, then the rest): final partial step of a charged track or the
 // photon's free path, process choice, sample_scattering threshold and map look-up key -> bucket + histogram.
-__global__ void __launch_bounds__(128)
+__global__ void PB_FIN_BOUNDS
 k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
            const double* __restrict__ prim_mass, int ms_e) {
   const long long begin = W.ws->begin;
@@ -535,39 +544,20 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
 }
 
 // Exclusive scan over NBUCKET bins + tile table; one CTA of 1024 threads, NBUCKET/1024 bins per thread.
-// Tile size: TILE samples for the tile-drained k_sample.  For k_sample_stream a tile is only a token that sends one CTA to
-// a bucket (see there), and W.ctrl[8] > 0 holds the number of tokens the sampler grid wants per wave: the token size is
-// then samples / ctrl[8], a multiple of TILE in [TILE, TOKEN_MAX], so that in a wide wave a CTA stays on a bucket for
-// thousands of samples while a narrow wave still yields one token per TILE samples.  The size used is left in ctrl[9].
-constexpr int TOKEN_MAX = 16 * TILE;
 __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
   constexpr int PER = NBUCKET / 1024;
   __shared__ int s_cnt[1024], s_til[1024];
-  __shared__ int s_total;
   int t = threadIdx.x;
   int cnt[PER], til[PER];
-  int csum = 0, tsum = 0, ssum = 0;
-  if (t == 0) s_total = 0;
-  __syncthreads();
+  int csum = 0, tsum = 0;
   for (int k = 0; k < PER; ++k) {
     int b = t * PER + k;
     int c = W.hist[b];
     cnt[k] = c;
-    csum += c;
-    if (b < N_SAMPLED * LU_MAX) ssum += c;
+    til[k] = (b < N_SAMPLED * LU_MAX) ? (c + TILE - 1) / TILE : 0;
+    csum += c; tsum += til[k];
     W.hist[b] = 0;
     W.cursor[b] = 0;
-    W.take[b] = 0;
-  }
-  if (ssum) atomicAdd(&s_total, ssum);
-  __syncthreads();
-  int tok = TILE;
-  const int want = W.ctrl[8];
-  if (want > 0) tok = min(max(((s_total / want + TILE - 1) / TILE) * TILE, TILE), TOKEN_MAX);
-  for (int k = 0; k < PER; ++k) {
-    int b = t * PER + k;
-    til[k] = (b < N_SAMPLED * LU_MAX) ? (cnt[k] + tok - 1) / tok : 0;
-    tsum += til[k];
   }
   s_cnt[t] = csum; s_til[t] = tsum;
   __syncthreads();
@@ -583,12 +573,12 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
     W.offsets[b] = cbase;
     for (int j = 0; j < til[k]; ++j) {
       W.tile_bucket[tbase + j] = b;
-      W.tile_start[tbase + j] = cbase + j * tok;
-      W.tile_count[tbase + j] = min(tok, cnt[k] - j * tok);
+      W.tile_start[tbase + j] = cbase + j * TILE;
+      W.tile_count[tbase + j] = min(TILE, cnt[k] - j * TILE);
     }
     cbase += cnt[k]; tbase += til[k];
   }
-  if (t == 1023) { W.offsets[NBUCKET] = cbase; W.ctrl[0] = tbase; W.ctrl[1] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0; W.ctrl[9] = tok; }
+  if (t == 1023) { W.offsets[NBUCKET] = cbase; W.ctrl[0] = tbase; W.ctrl[1] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0; }
   if (t == 0) W.ctrl[2] = 0;
 }
 
@@ -770,7 +760,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
     int cur = -1;          // entry index, -1 = need a new one, -2 = tile exhausted
     double E = 0.0; uint2 key = make_uint2(0, 0);
     SampleConst sc{0, 0, 0, 0, 0};
-    uint32_t round = 0;
+    uint32_t next_t = 0;   // first trial index this sample has not evaluated yet
     for (;;) {
       if (cur == -1) {
         int j = 0;
@@ -780,17 +770,47 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
           cur = s_idx[j];
           E = s_E[j];
           key = s_key[j];
-          round = 0;
+          next_t = 0;
           if (proc == P_PAIRPROD) sc = SampleConst{E - 2 * kMe, s_cb[j], s_cc[j], s_cd[j], 0.0};
           else if (proc == P_BREM) sc = SampleConst{E - kMe - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMe * kMe};
           else if (proc == P_MUONBREM) sc = SampleConst{E - kMmu - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMmu * kMmu};
           else if (FAM != 1 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) sc = SampleConst{0.0, s_cb[j], s_cc[j], M.i2mT, s_cd[j]};
         } else cur = -2;
       }
-      if (__all_sync(0xffffffffu, cur == -2)) break;
+      // ---- drain help.  Once the tile's cursor is exhausted a group that finishes has nothing left to fetch; instead of
+      // idling until the slowest sample of the warp is accepted (the geometric tail: 1 sample in 200 needs > 100 trials) it
+      // joins a sample that is still open in its warp.  The open samples ("owners", k of them) share the idle groups evenly:
+      // idle group i helps owner i mod k as that sample's (1 + i / k)-th group, with the owner's state fetched by shuffles
+      // (the helper's own registers are dead), and the m groups on a sample cover trials next_t .. next_t + m G - 1 of the
+      // round.  Trial indices, not lanes, define the draws, so the first accepted INDEX wins whoever evaluated it.
+      const unsigned own = __ballot_sync(0xffffffffu, sub == 0 && cur >= 0);
+      const unsigned idl = __ballot_sync(0xffffffffu, sub == 0 && cur == -2);
+      if (own == 0) break;                                // every group is out of work: the tile is done
+      const bool help = (G < 32) && idl != 0;             // warp-uniform
+      bool helper = false;
+      uint32_t r = 0, m = 1;                              // my group's rank among the groups on my sample, and their number
+      unsigned peers = gmask;
+      if (help) {
+        const unsigned below = (1u << gbase) - 1u;
+        const int k = __popc(own), n_idle = __popc(idl);
+        int j;                                            // which owner (in lane order) my group works for
+        if (cur == -2) { const int ir = __popc(idl & below); j = ir % k; r = 1 + ir / k; helper = true; }
+        else j = __popc(own & below);
+        m = 1 + (n_idle - j + k - 1) / k;
+        const int src = __fns(own, 0, j + 1);             // leader lane of that owner
+        const double Eh = __shfl_sync(0xffffffffu, E, src);
+        const unsigned kx = __shfl_sync(0xffffffffu, key.x, src), ky = __shfl_sync(0xffffffffu, key.y, src);
+        const double sa = __shfl_sync(0xffffffffu, sc.a, src), sb = __shfl_sync(0xffffffffu, sc.b, src), sc_ = __shfl_sync(0xffffffffu, sc.c, src),
+                     sd = __shfl_sync(0xffffffffu, sc.d, src), se = __shfl_sync(0xffffffffu, sc.e, src);
+        const int ch = __shfl_sync(0xffffffffu, cur, src);
+        const uint32_t nh = __shfl_sync(0xffffffffu, next_t, src);
+        if (helper) { E = Eh; key = make_uint2(kx, ky); sc = SampleConst{sa, sb, sc_, sd, se}; cur = ch; next_t = nh; }
+        peers = __match_any_sync(0xffffffffu, cur);
+      }
       double x[4] = {0.0, 0.0, 0.0, 0.0};
       bool acc = false;
-      uint32_t t = round * G + sub;
+      const uint32_t code = r * G + sub;                  // my trial of this round, relative to next_t
+      const uint32_t t = next_t + code;
       if (cur >= 0 && (long long)t < max_trials) {
         if (FAM == 0) acc = trial<4, 0>(M, mi, s_grid, proc, E, sc, maxF, key, t, x);
         else if (FAM == 1) acc = trial<1, 1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x);
@@ -800,23 +820,26 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
           default: acc = trial<1, -1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
         }
       }
-      unsigned ball = __ballot_sync(0xffffffffu, acc);
-      unsigned gb = ball & gmask;
+      uint32_t best;                                      // lowest accepted trial of my sample in this round
+      if (help) best = __reduce_min_sync(peers, acc ? code : 0xffffffffu);
+      else {
+        const unsigned gb = __ballot_sync(0xffffffffu, acc) & gmask;
+        best = gb ? (uint32_t)(__ffs(gb) - 1 - gbase) : 0xffffffffu;
+      }
       if (cur >= 0) {
-        if (gb) {
-          int win = __ffs(gb) - 1;                       // absolute lane of the first accepted trial
-          if (lane == win) {
+        if (best != 0xffffffffu) {
+          if (acc && code == best) {
             double2* xo = reinterpret_cast<double2*>(W.xs + 4 * (size_t)cur);
             xo[0] = make_double2(x[0], x[1]); xo[1] = make_double2(x[2], x[3]);
-            int ntr = (int)(round * G + sub + 1);
+            int ntr = (int)(t + 1);
             io.ntr[(off + (size_t)cur) * io.ntr_stride] = ntr;
             c_trials += ntr; c_samples += 1;
           }
           cur = -1;
         } else {
-          ++round;
-          if ((long long)round * G >= max_trials) {      // "No Sample Found" (shower.py:460-461)
-            if (sub == 0) {
+          next_t += m * G;
+          if ((long long)next_t >= max_trials) {           // "No Sample Found" (shower.py:460-461)
+            if (sub == 0 && !helper) {
               io.ntr[(off + (size_t)cur) * io.ntr_stride] = -1;
               W.bucket[cur] = P_NONE * LU_MAX;
               c_trials += (unsigned long long)max_trials; c_fail += 1;
@@ -825,6 +848,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
           }
         }
       }
+      if (helper) cur = -2;
     }
     // per-tile counter flush (a tile is one process): warp reduce -> shared -> one global atomic per CTA
     for (int o = 16; o > 0; o >>= 1) {
@@ -847,211 +871,8 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
   }
 }
 
-// ---- streaming variant of the sampler (default; PB_SAMPLE_STREAM=0 selects the tile kernel above).
-// The tile kernel drains the whole CTA at the end of every 192-sample tile: the group that drew the longest
-// accept/reject sequence holds the other groups idle, and the cost of that drain is what forbids small G (measured
-// G sweep, profiles/r01_summary.md: the drain model explains 1.0 / 1.28 / 1.8 relative cost per trial at G = 8 / 4 / 2)
-// although small G wastes fewer speculative trials (trials evaluated per accepted sample at 1/14 acceptance: 17.9 / 15.6 /
-// 14.5).  Here a tile of the table is only a TOKEN that sends one CTA to a bucket: the CTA stages the bucket's node grid once
-// (TMA) and its warps then stream the bucket's samples from a global per-bucket cursor (W.take) in chunks of at most 32 with
-// guided self-scheduling (chunks shrink towards the end of the bucket), until the bucket is exhausted - by this CTA and
-// by every other CTA that holds a token of the same bucket.  Each warp keeps the k_loop-style pipeline: claim (atomic, read
-// one chunk later) -> cp.async of the chunk's (energy, key, index) into the idle half of a per-warp double buffer ->
-// per-sample constants computed by all 32 lanes at the buffer swap -> groups take entries with warp ballots, no shared
-// atomics.  A CTA synchronises only when it changes bucket.
-struct SampBuf { double E[32], cb[32], cc[32], cd[32]; uint2 key[32]; int idx[32]; };
-
-template <int G>
-__global__ void __launch_bounds__(SAMPLE_THREADS, PB_SAMPLE_MINB)
-k_sample_stream(const __grid_constant__ Material M, const __grid_constant__ Tables T, SampleIO io, Work W) {
-  constexpr int NG = 32 / G;                      // groups per warp
-  __shared__ __align__(128) double s_grid[GRID_SMEM_DOUBLES];
-  __shared__ __align__(16) SampBuf s_buf[SAMPLE_THREADS / 32][2];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_tile, s_live;
-  __shared__ unsigned long long s_ptrials, s_psamples;
-  const int lane = threadIdx.x & 31;
-  const int sub = lane % G;
-  const int gbase = lane - sub;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
-  const unsigned below = (1u << gbase) - 1u;      // lanes of the groups before mine
-  SampBuf* buf = s_buf[threadIdx.x >> 5];
-  uint32_t phase = 0;
-  unsigned long long c_trials = 0, c_samples = 0, c_fail = 0;
-  if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_ptrials = 0; s_psamples = 0; }
-  const size_t off = io.ws ? (size_t)io.ws->begin : 0;
-  const long long max_trials = M.max_trials;
-  __syncthreads();
-  for (;;) {
-    if (threadIdx.x == 0) {
-      // first pass: tokens in table order.  Second pass (the queue is empty, this CTA would idle until the kernel ends): walk
-      // the table once more, backwards, and join whatever bucket is still being worked on.
-      const int n_tiles = W.ctrl[0];
-      int t = atomicAdd(&W.ctrl[1], 1);
-      if (t >= n_tiles) t = (t < 2 * n_tiles) ? 2 * n_tiles - 1 - t : -1;
-      int live = 0;
-      if (t >= 0) {
-        int b = W.tile_bucket[t];
-        live = *(volatile int*)&W.take[b] < W.offsets[b + 1] - W.offsets[b];     // someone may have finished it already
-      }
-      s_tile = t; s_live = live;
-    }
-    __syncthreads();
-    const int tile = s_tile;
-    if (tile < 0) break;
-    if (!s_live) { __syncthreads(); continue; }
-    const int bucket = W.tile_bucket[tile];
-    const int bstart = W.offsets[bucket], bcount = W.offsets[bucket + 1] - bstart;
-    const int proc = bucket / LU_MAX, lu = bucket % LU_MAX;
-    const MapInfo& mi = T.map[proc];
-    if (threadIdx.x == 0) {
-      uint32_t bytes = (uint32_t)mi.stride * 8u;
-      mbar_expect_tx(&s_bar, bytes);
-      tma_bulk_g2s(s_grid, mi.grid + (size_t)lu * mi.stride, bytes, &s_bar);
-    }
-    const bool four_d = (proc == P_PAIRPROD || proc == P_BREM || proc == P_MUONBREM);
-    const bool dark3 = (proc == P_DARKBREM || proc == P_DARKMUONBREM);
-    // ---- per-warp sample pipeline (warp-uniform unless noted)
-    const int token = max(W.ctrl[9], 1);
-    const int sched = 2 * (SAMPLE_THREADS / 32) * ((bcount + token - 1) / token);   // 2 x the warps expected on this bucket
-    auto chunk_for = [&](int remaining) { return min(32, max(NG, (max(remaining, 0) + sched - 1) / sched)); };
-    int which = 0, pos = 0, cnt = 0, cnt_fly = 0;
-    int c_raw = 0, c_len = 0;       // (lane 0 / uniform) start and length of the chunk claimed last, not yet copied
-    bool dry = false;
-    auto claim = [&](int remaining) {
-      c_len = chunk_for(remaining);
-      if (lane == 0) c_raw = atomicAdd(&W.take[bucket], c_len);
-    };
-    auto issue_copy = [&](int half) -> int {        // consumes the pending claim; returns its start
-      int c = __shfl_sync(0xffffffffu, c_raw, 0);
-      int n = min(max(bcount - c, 0), c_len);
-      if (lane < n) {
-        SampBuf& B = buf[half];
-        const size_t g = (size_t)bstart + (size_t)c + (size_t)lane;
-        cp_async8(&B.E[lane], W.sE + g);
-        cp_async8(&B.key[lane], W.skey + g);
-        cp_async4(&B.idx[lane], W.sorted + g);
-      }
-      cnt_fly = n;
-      return c;
-    };
-    auto advance = [&]() {          // the consumed half is empty: switch to the one in flight, refill the pipeline behind it
-      cp_async_wait_all();
-      __syncwarp();
-      which ^= 1; pos = 0; cnt = cnt_fly;
-      if (lane < cnt) {             // per-sample constants of the 4-D / dark-brem integrands, every lane busy
-        SampBuf& B = buf[which];
-        double Ek = B.E[lane];
-        if (four_d) {
-          SampleConst c = (proc == P_PAIRPROD) ? pairprod_const(M, Ek) : brem_const(M, Ek, proc == P_BREM ? kMe : kMmu);
-          B.cb[lane] = c.b; B.cc[lane] = c.c; B.cd[lane] = c.d;
-        } else if (dark3) {
-          SampleConst c = darkbrem_const(M, Ek, proc == P_DARKBREM ? kMe : kMmu);
-          B.cb[lane] = c.b; B.cc[lane] = c.c; B.cd[lane] = c.e;          // |p|, tconv, 1/|p|
-        }
-      }
-      __syncwarp();
-      if (cnt > 0) {
-        int c = issue_copy(which ^ 1);
-        claim(bcount - c - c_len);
-      } else {
-        cnt_fly = 0;
-      }
-    };
-    claim(bcount);
-    { int c = issue_copy(1); claim(bcount - c - c_len); }
-    const double maxF = __ldg(mi.maxF + lu) * M.fudge;
-    mbar_wait(&s_bar, phase);
-    phase ^= 1;
-    // ---- group state (identical in the G lanes of a group)
-    int cur = -1;          // wave-local index of the sample, -1 = need a new one, -2 = bucket exhausted
-    double E = 0.0; uint2 key = make_uint2(0, 0);
-    SampleConst sc{0, 0, 0, 0, 0};
-    uint32_t round = 0;
-    for (;;) {
-      unsigned need = __ballot_sync(0xffffffffu, cur == -1 && sub == 0);      // one bit per group that wants a sample
-      while (need) {
-        if (pos >= cnt) {
-          if (!dry) { advance(); dry = (cnt == 0); }
-          if (dry) { if (cur == -1) cur = -2; break; }
-        }
-        const int avail = cnt - pos;
-        const int rank = __popc(need & below);
-        if (cur == -1 && rank < avail) {
-          const SampBuf& B = buf[which];
-          const int j = pos + rank;
-          cur = B.idx[j];
-          E = B.E[j];
-          key = B.key[j];
-          round = 0;
-          if (proc == P_PAIRPROD) sc = SampleConst{E - 2 * kMe, B.cb[j], B.cc[j], B.cd[j], 0.0};
-          else if (proc == P_BREM) sc = SampleConst{E - kMe - M.Eg_min, B.cb[j], B.cc[j], B.cd[j], kMe * kMe};
-          else if (proc == P_MUONBREM) sc = SampleConst{E - kMmu - M.Eg_min, B.cb[j], B.cc[j], B.cd[j], kMmu * kMmu};
-          else if (dark3) sc = SampleConst{0.0, B.cb[j], B.cc[j], M.i2mT, B.cd[j]};
-        }
-        pos += min(__popc(need), avail);
-        need = __ballot_sync(0xffffffffu, cur == -1 && sub == 0);
-      }
-      if (__all_sync(0xffffffffu, cur == -2)) break;
-      double x[4] = {0.0, 0.0, 0.0, 0.0};
-      bool acc = false;
-      const uint32_t t = round * G + sub;
-      if (cur >= 0 && (long long)t < max_trials) {
-        switch (mi.dim) {
-          case 4: acc = trial<4, -1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
-          case 3: acc = trial<3, -1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
-          default: acc = trial<1, -1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
-        }
-      }
-      const unsigned gb = __ballot_sync(0xffffffffu, acc) & gmask;
-      if (cur >= 0) {
-        if (gb) {
-          const int win = __ffs(gb) - 1;                   // absolute lane of the first accepted trial
-          if (lane == win) {
-            double2* xo = reinterpret_cast<double2*>(W.xs + 4 * (size_t)cur);
-            xo[0] = make_double2(x[0], x[1]); xo[1] = make_double2(x[2], x[3]);
-            const int ntr = (int)(round * G + sub + 1);
-            io.ntr[(off + (size_t)cur) * io.ntr_stride] = ntr;
-            c_trials += ntr; c_samples += 1;
-          }
-          cur = -1;
-        } else {
-          ++round;
-          if ((long long)round * G >= max_trials) {        // "No Sample Found" (shower.py:460-461)
-            if (sub == 0) {
-              io.ntr[(off + (size_t)cur) * io.ntr_stride] = -1;
-              W.bucket[cur] = P_NONE * LU_MAX;
-              c_trials += (unsigned long long)max_trials; c_fail += 1;
-            }
-            cur = -1;
-          }
-        }
-      }
-    }
-    cp_async_wait_all();     // nothing is in flight here (the last claims were empty); keeps the buffers safe for the next bucket
-    // per-bucket counter flush (a bucket is one process): warp reduce -> shared -> one global atomic per CTA
-    for (int o = 16; o > 0; o >>= 1) {
-      c_trials += __shfl_down_sync(0xffffffffu, c_trials, o);
-      c_samples += __shfl_down_sync(0xffffffffu, c_samples, o);
-      c_fail += __shfl_down_sync(0xffffffffu, c_fail, o);
-    }
-    if (lane == 0) {
-      if (c_trials) atomicAdd(&s_ptrials, c_trials);
-      if (c_samples) atomicAdd(&s_psamples, c_samples);
-      if (c_fail) atomicAdd(&W.counters[CNT_NOSAMPLE], c_fail);
-    }
-    c_trials = 0; c_samples = 0; c_fail = 0;
-    __syncthreads();   // everyone is done with s_grid (and the counters) before the next bucket overwrites it
-    if (threadIdx.x == 0) {
-      if (s_ptrials) { atomicAdd(&W.counters[CNT_TRIALS], s_ptrials); atomicAdd(&W.counters[CNT_PROC_TRIALS + proc], s_ptrials); }
-      if (s_psamples) { atomicAdd(&W.counters[CNT_SAMPLES], s_psamples); atomicAdd(&W.counters[CNT_PROC_SAMPLES + proc], s_psamples); }
-      s_ptrials = 0; s_psamples = 0;
-    }
-  }
-}
-
 // Kinematics + rotation + daughter append, in bucket order (warps are process-coherent).
-__global__ void __launch_bounds__(128)
+__global__ void PB_EMIT_BOUNDS
 k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, int wave_order) {
   const long long begin = W.ws->begin;
   const int n = W.ws->n;
@@ -1530,7 +1351,7 @@ __global__ void __launch_bounds__(256) k_tally(Stack S, long long first, long lo
       if (sp == k) { cnt[k] += 1.0; ws[k] += w; wes[k] += w * a0.x; }
     int eb = (int)floor((log10(a0.x) + 3.0) * (PB_TALLY_EBINS / 6.0));
     eb = min(max(eb, 0), PB_TALLY_EBINS - 1);
-    atomicAdd(&mine[PB_TALLY_EHIST + sp * PB_TALLY_EBINS + eb], w);
+    atomicAdd(&mine[PB_TALLY_EHIST + sp * PB_TALLY_EBINS + eb], w);    // (a warp-wide pre-sum per bin by shuffles was measured slower: 4.3 vs 3.0 ms per 7.5e7 records)
     double pt = sqrt(a0.y * a0.y + a1.x * a1.x);
     double th = atan2(pt, a1.y);
     int tb = (th > 0) ? (int)floor((log10(th) + 7.0) * (PB_TALLY_TBINS / 8.0)) : 0;
@@ -1693,10 +1514,8 @@ struct pb_engine_s {
   void* prim_stage = nullptr; size_t prim_stage_bytes = 0;
   int n_sm = 148;
   int profiling = 0;             // 0 off, 1 = the two dominant kernels only (k_loop, k_sample), 2 = every kernel
-  int sample_group = 8;          // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
+  int sample_group = 4;          // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G; 4 is fastest with drain help)
   int emit_wave_order = 0;       // PB_EMIT_ORDER=1: k_emit walks the wave in record order (coalesced) instead of bucket order
-  int sample_stream = 1;         // PB_SAMPLE_STREAM=0: tile-drained k_sample instead of the bucket-streaming k_sample_stream
-  int sample_tokens = 4;         // PB_SAMPLE_TOKENS: tokens per sampler CTA and wave that k_bucket_scan aims for (streaming sampler)
   int sample_split = 0;          // PB_SAMPLE_SPLIT=1: SM pass with the 4-D and 1-D integrand families as two concurrent kernels (measured: no gain)
   cudaStream_t side = nullptr;   // second stream for the concurrent family kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1764,13 +1583,11 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   derive_material(e);
   if (const char* g = getenv("PB_SAMPLE_G")) e->sample_group = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_SPLIT")) e->sample_split = atoi(g);
-  if (const char* g = getenv("PB_SAMPLE_STREAM")) e->sample_stream = atoi(g);
-  if (const char* g = getenv("PB_SAMPLE_TOKENS")) e->sample_tokens = std::max(1, atoi(g));
   if (const char* g = getenv("PB_EMIT_ORDER")) e->emit_wave_order = atoi(g);
   cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
-  size_t fixed = sizeof(int) * (NBUCKET * 4 + 1 + 16) + sizeof(unsigned long long) * (8 + CNT_N) + sizeof(WaveState) + 64;
+  size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * (8 + CNT_N) + sizeof(WaveState) + 64;
   if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
   cudaMemset(e->fixed_blob, 0, fixed);
   for (int i = 0; i < 2 * 8; ++i) cudaEventCreate(&e->ev[i]);
@@ -1781,15 +1598,10 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   e->work.hist = (int*)p; p += NBUCKET * sizeof(int);
   e->work.offsets = (int*)p; p += (NBUCKET + 1) * sizeof(int);
   e->work.cursor = (int*)p; p += NBUCKET * sizeof(int);
-  e->work.take = (int*)p; p += NBUCKET * sizeof(int);
   e->work.ctrl = (int*)p; p += 16 * sizeof(int);
   p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
   e->work.ws = (WaveState*)p;
   cudaMallocHost(&e->h_ws, sizeof(WaveState) + 16);
-  if (e->sample_stream) {      // token budget per wave for k_bucket_scan (ctrl[8] == 0: fixed TILE-sized tiles)
-    int want = e->n_sm * PB_SAMPLE_MINB * e->sample_tokens;
-    cudaMemcpy(e->work.ctrl + 8, &want, sizeof(int), cudaMemcpyHostToDevice);
-  }
   *out = e;
   return PB_OK;
 }
@@ -1920,17 +1732,6 @@ static int ensure_cand(pb_engine e, long long ncap);
 // the registers gained; side by side the cheap 1-D tiles fill the SMs the 4-D kernel's tail leaves idle.
 // Dark pass / stand-alone sampling: one generic launch.
 static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream, bool sm_families = false) {
-  if (e->sample_stream) {
-    switch (e->sample_group) {
-      case 1: k_sample_stream<1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-      case 2: k_sample_stream<2><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-      case 4: k_sample_stream<4><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-      case 16: k_sample_stream<16><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-      case 32: k_sample_stream<32><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-      default: k_sample_stream<8><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    }
-    return;
-  }
   if (sm_families && e->sample_group == 8 && e->sample_split && e->side) {
     const int g5 = std::max(1, std::min(e->n_sm * PB_SAMPLE_MINB_SM, grid * 2));
     cudaEventRecord(e->ev_fork, stream);
@@ -1944,10 +1745,10 @@ static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_
   switch (e->sample_group) {
     case 1: k_sample<1, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
     case 2: k_sample<2, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    case 4: k_sample<4, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
     case 16: k_sample<16, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
     case 32: k_sample<32, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    default: k_sample<8, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    case 8: k_sample<8, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
+    default: k_sample<4, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
   }
 }
 

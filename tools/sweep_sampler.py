@@ -1,5 +1,5 @@
 """Tuning + safety sweep of the accept/reject sampler variants (one process, one engine per configuration; the knobs are
-read from the environment by pb_create): for every (PB_SAMPLE_STREAM, PB_SAMPLE_G, PB_SAMPLE_TOKENS)
+read from the environment by pb_create): for every (PB_SAMPLE_STREAM, PB_SAMPLE_G, PB_SAMPLE_TOKENS, PB_SAMPLE_CHUNK)
 
   1. correctness: 2 000 showers of config 2 must give the SAME records and trial counts as the reference configuration
      (tile kernel, G = 8) - the draws are counter-based, so any schedule has to reproduce them bit for bit;
@@ -14,7 +14,7 @@ from petite_b200.shower import Shower
 
 DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "data", "")
 N_T = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
-CONFIGS = [(0, 8, 4)] + [(1, g, 4) for g in (8, 4, 2)] + [(1, 4, t) for t in (2, 8, 16)] + [(1, 8, 8), (1, 2, 8), (0, 4, 4)]
+CONFIGS = [(0, g, 0, 0) for g in (8, 4, 2, 16)]
 if len(sys.argv) > 2:
     CONFIGS = [tuple(int(v) for v in c.split(",")) for c in sys.argv[2:]]
 
@@ -36,8 +36,9 @@ def digest(sh):
 
 dev = torch.device("cuda", 0)
 ref = None
-for stream, G, tok in CONFIGS:
+for stream, G, tok, chunk in CONFIGS:
     os.environ["PB_SAMPLE_STREAM"], os.environ["PB_SAMPLE_G"], os.environ["PB_SAMPLE_TOKENS"] = str(stream), str(G), str(tok)
+    os.environ["PB_SAMPLE_CHUNK"] = str(chunk)
     sh = Shower(DATA, "lead", 0.010, seed=20261017)
     d = digest(sh)
     if ref is None:
@@ -49,7 +50,7 @@ for stream, G, tok in CONFIGS:
     cap = int(N_T * cal.n / 2000 * 1.06 + 2.3 * cal.counters["max_wave"] / 2000 * N_T) + (1 << 16)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sh.run_arrays(*devp, capacity=cap, first_shower_id=0)          # warm-up (scratch growth)
-    sh.set_profiling(1)
+    sh.set_profiling(int(os.environ.get("SWEEP_PROFILING", "1")))
     ms, ks, kl = [], [], []
     for rep in range(3):
         torch.cuda.synchronize(); e0.record()
@@ -57,8 +58,8 @@ for stream, G, tok in CONFIGS:
         e1.record(); torch.cuda.synchronize()
         pr = sh.get_profile()
         ms.append(e0.elapsed_time(e1)); ks.append(pr["ms"]["k_sample"]); kl.append(pr["ms"]["k_loop"])
-    print(json.dumps({"stream": stream, "G": G, "tokens": tok, "same_as_reference": bool(same), "records": d[0]["n_particles"],
+    print(json.dumps({"stream": stream, "G": G, "tokens": tok, "chunk": chunk, "same_as_reference": bool(same), "records": d[0]["n_particles"],
                       "trials": d[0]["n_trials"], "step_ms": round(min(ms), 2), "k_sample_ms": round(min(ks), 2),
-                      "k_loop_ms": round(min(kl), 2), "showers_per_s": round(N_T / min(ms) * 1e3)}), flush=True)
+                      "k_loop_ms": round(min(kl), 2), "other": {k: round(v, 2) for k, v in pr["ms"].items() if v and k not in ("k_sample", "k_loop")}, "showers_per_s": round(N_T / min(ms) * 1e3)}), flush=True)
     del sh, b, cal, devp
     torch.cuda.empty_cache()
