@@ -208,20 +208,26 @@ def ours(args):
     tally = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=dev)
     base_id, _ = shard(world * n, rank, world)          # weak scaling: rank r steps global showers [r*n, (r+1)*n)
 
-    def step(first_id, arrays):
-        b = sh.run_arrays(*arrays, capacity=capacity, first_shower_id=first_id)
+    P = max(1, args.parts)
+
+    def step(first_id, arrays, parts=1):
+        if parts > 1:                     # concurrent sub-batches: one engine handle, stream and host thread per part
+            bs = sh.run_arrays_split(*arrays, parts=parts, capacity=capacity, first_shower_id=first_id)
+        else:
+            bs = [sh.run_arrays(*arrays, capacity=capacity, first_shower_id=first_id)]
         tally.zero_()
-        sh.tally(b, tally)
+        sh.tally_batches(bs, tally)
         if world > 1:
             dist.all_reduce(tally)        # the only collective: 8 KB of tallies over NVLink
-        return b
+        return bs
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up; the last warm-up step times EVERY kernel (profiling level 2, ~6 % overhead) for the per-kernel table
+    # warm-up (single stream; in split mode also the peer engines: tables, stacks, scratch growth); the last single-stream
+    # warm-up step times EVERY kernel (profiling level 2, ~6 % overhead) for the per-kernel table
     full_ms, full_launch = {}, {}
     for w in range(args.warmup):
         if w == args.warmup - 1:
@@ -230,45 +236,68 @@ def ours(args):
     if args.warmup:
         pr = sh.get_profile()
         full_ms, full_launch = dict(pr["ms"]), dict(pr["launches"])
-    # ---- timed region: K steps, device-resident primaries; only the two dominant kernels carry CUDA events (level 1)
-    sh.set_profiling(1)
-    prof_ms = {k: 0.0 for k in capi.KERNEL_NAMES}
-    prof_launch = {k: 0 for k in capi.KERNEL_NAMES}
-    trials = {}
-    tot = dict(n_particles=0, n_steps=0, n_substeps=0, n_samples=0, n_trials=0, n_launches=0, n_waves=0, n_charged=0)
+    sh.set_profiling(0)
+    if P > 1:
+        for w in range(max(args.warmup, 1)):
+            step(base_id, devp, P)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    COUNT_KEYS = ("n_particles", "n_steps", "n_substeps", "n_samples", "n_trials", "n_launches", "n_waves", "n_charged")
+
+    def timed_region(parts, level):
+        """K steps bracketed by barrier + synchronize; -> (ms max over ranks, summed counters, per-kernel ms / launches, trials)."""
+        sh.set_profiling(level)
+        pm = {k: 0.0 for k in capi.KERNEL_NAMES}
+        pl = {k: 0 for k in capi.KERNEL_NAMES}
+        tr = {}
+        tt = {k: 0 for k in COUNT_KEYS}
+        barrier()
+        e0.record()
+        for k in range(args.steps):
+            bs = step(base_id, devp, parts)
+            if level:
+                pr = sh.get_profile()
+                for name in pm:
+                    pm[name] += pr["ms"][name]; pl[name] += pr["launches"][name]
+                for p_, v in pr["trials"].items():
+                    tr[p_] = tr.get(p_, 0) + v
+            for b in bs:
+                for key in tt:
+                    tt[key] += b.counters[key]
+            tt["n_launches"] += len(bs) + (1 if world > 1 else 0)     # k_tally per part (+ NCCL kernel)
+        e1.record()
+        barrier()
+        t_ms = e0.elapsed_time(e1)
+        sh.set_profiling(0)
+        if world > 1:
+            t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms, tt, pm, pl, tr
+
+    # ---- timed region: K steps, device-resident primaries.  With --parts P > 1 (default 2) a step runs as P concurrent
+    # sub-batches and carries no per-kernel events; the single-stream pass after it (same K steps, same inputs) times the two
+    # dominant kernels with CUDA events (level 1) while each launch owns the GPU: that is what the roofline is defined on.
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for k in range(args.steps):
-        b = step(base_id, devp)
-        pr = sh.get_profile()
-        for name in prof_ms:
-            prof_ms[name] += pr["ms"][name]; prof_launch[name] += pr["launches"][name]
-        for p_, v in pr["trials"].items():
-            trials[p_] = trials.get(p_, 0) + v
-        for key in tot:
-            tot[key] += b.counters[key]
-        tot["n_launches"] += 1 + (1 if world > 1 else 0)     # k_tally (+ NCCL kernel)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, tot, prof_ms, prof_launch, trials = timed_region(P, 0 if P > 1 else 1)
     clk = clocks.stop() if rank == 0 else None
-    sh.set_profiling(0)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    single = None
+    if P > 1:
+        ms1, tot1, prof_ms, prof_launch, trials = timed_region(1, 1)
+        single = {"value": world * n * args.steps / (ms1 * 1e-3), "unit": "showers/s", "ms_per_step": ms1 / args.steps,
+                  "note": "the same K steps as ONE batch on one stream: the region the per-kernel times, roofline and fp64 figures come from"}
+        launches_main = tot["n_launches"]
+        tot = dict(tot1, n_launches=launches_main)          # identical showers: only the launch count differs
     tally_host = tally.cpu().numpy()
 
     # ---- end-to-end through the public host API: pinned host primaries in, tallies out, every step
     e2e_steps = max(1, min(args.steps, 3))
+    step(base_id, host_np, P)            # untimed: host-staging buffers of every engine handle at full size
     barrier()
     e0.record()
     for k in range(e2e_steps):
-        step(base_id, host_np)
+        step(base_id, host_np, P)
         _ = tally.cpu()
     e1.record()
     barrier()
@@ -277,30 +306,6 @@ def ours(args):
         t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
-
-    # ---- extra (N = 1 only): the same step as `parts` concurrent sub-batches (Shower.run_arrays_split: one engine handle,
-    # stream and host thread per part).  Kept out of `value`: per-launch kernel times overlap there, and the roofline
-    # above is defined on launches that own the GPU.
-    conc = None
-    if world == 1 and args.parts > 1:
-        def split_step():
-            bs = sh.run_arrays_split(*devp, parts=args.parts, capacity=capacity, first_shower_id=base_id)
-            tally.zero_()
-            sh.tally_batches(bs, tally)
-            return bs
-        split_step()                                            # warm-up: peer engine tables, stacks, scratch growth
-        split_step()
-        barrier()
-        e0.record()
-        for k in range(e2e_steps):
-            bs = split_step()
-        e1.record()
-        barrier()
-        ms_c = e0.elapsed_time(e1)
-        conc = {"parts": args.parts, "value": n * e2e_steps / (ms_c * 1e-3), "unit": "showers/s", "ms_per_step": ms_c / e2e_steps,
-                "steps": e2e_steps, "records_per_step": sum(b.n for b in bs),
-                "tally_records": float(tally.cpu().numpy()[capi.TALLY_COUNT:capi.TALLY_COUNT + 7].sum()),
-                "api": "Shower.run_arrays_split(device primaries) + Shower.tally_batches"}
 
     if rank != 0:
         if world > 1:
@@ -337,7 +342,7 @@ def ours(args):
         "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "material": MATERIAL, "pid": PID, "E0_GeV": E0, "E_min_GeV": EMIN,
-                   "primaries_per_gpu": n, "parallelism": f"{world} x independent shower shards, tallies all-reduced",
+                   "primaries_per_gpu": n, "parallelism": f"{world} x independent shower shards, tallies all-reduced" + (f"; each shard stepped as {P} concurrent sub-batches (streams)" if P > 1 else ""),
                    "seed": SEED, "maxF": "regenerated (oracle.findmax, B=300)",
                    "l2": f"working set {capacity * rl.RECORD_BYTES / 1e9:.1f} GB of stack per GPU >> 126 MB L2 (no flush needed)",
                    "stack_capacity_records": capacity},
@@ -352,6 +357,7 @@ def ours(args):
                      "launches": prof_launch[dom], "avg_launch_ms": dom_ms / max(prof_launch[dom], 1),
                      "algorithmic_bytes_per_launch": dom_bytes / max(prof_launch[dom], 1),
                      "share_of_step": dom_ms / step_ms_total if step_ms_total else None,
+                     "timed_region": ("single-stream pass (single_stream): the main region runs %d sub-batches concurrently and its launches overlap" % P) if P > 1 else "main",
                      "note": "the step is FP64-pipe / divergence bound, not HBM bound (SURVEY.md 8d): see fp64"},
         "fp64": {"kernel": dom, "achieved_tflops": dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0,
                  "peak_tflops": fp64_peak, "frac": (dom_flops / (dom_ms * 1e-3) / 1e12 / fp64_peak) if dom_ms and fp64_peak else None,
@@ -362,12 +368,12 @@ def ours(args):
         "trials_by_process": trials,
         "e2e": {"value": world * n * e2e_steps / (ms_e2e * 1e-3), "unit": "showers/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": int(tally_host.nbytes + 8 * 16), "steps": e2e_steps,
-                "api": "Shower.run_arrays(host arrays) + Shower.tally + tally.cpu()"},
+                "api": ("Shower.run_arrays_split(host arrays, parts=%d)" % P if P > 1 else "Shower.run_arrays(host arrays)") + " + Shower.tally_batches + tally.cpu()"},
         "gpu_launches": tot["n_launches"],
         "clocks": clk,
         "tally_check": {"records": float(tally_host[capi.TALLY_COUNT:capi.TALLY_COUNT + 7].sum()),
                         "expected": world * tot["n_particles"] / K},
-        "concurrent": conc,
+        "single_stream": single,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -384,7 +390,7 @@ def main():
     ap.add_argument("--primaries", type=int, default=100_000, help="primaries per GPU per step")
     ap.add_argument("--cpu-showers", type=int, default=0, help="size of the CPU-baseline sample (0 = 8 x cores: about 15-20 s of CPU work on all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parts", type=int, default=2, help="extra measurement: the step as this many concurrent sub-batches (0/1 = skip)")
+    ap.add_argument("--parts", type=int, default=2, help="sub-batches of a step stepped concurrently on their own engine handle / stream / host thread (1 = one batch, one stream)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
