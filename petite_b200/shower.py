@@ -710,6 +710,11 @@ class Shower:
         return self.run_arrays(*self._pack_primaries(primaries), GlobalMS=GlobalMS, capacity=capacity,
                                first_shower_id=first_shower_id)
 
+    def generate_showers_split(self, primaries, parts=2, GlobalMS=True, capacity=None, first_shower_id=None):
+        """``generate_showers`` as ``parts`` concurrent sub-batches (:meth:`run_arrays_split`) -> list of :class:`ShowerBatch`."""
+        return self.run_arrays_split(*self._pack_primaries(primaries), parts=parts, GlobalMS=GlobalMS, capacity=capacity,
+                                     first_shower_id=first_shower_id)
+
     def generate_shower(self, p0, VB=False, GlobalMS=True):
         """One primary -> list of all particles of its shower, primary first (shower.py:603-708)."""
         if VB:
