@@ -211,12 +211,12 @@ def ours(args):
     P = max(1, args.parts)
 
     def step(first_id, arrays, parts=1):
-        if parts > 1:                     # concurrent sub-batches: one engine handle, stream and host thread per part
-            bs = sh.run_arrays_split(*arrays, parts=parts, capacity=capacity, first_shower_id=first_id)
+        tally.zero_()
+        if parts > 1:                     # concurrent sub-batches: one engine handle, stream and host thread per part,
+            bs = sh.run_arrays_split(*arrays, parts=parts, capacity=capacity, first_shower_id=first_id, tally=tally)   # tallied per part
         else:
             bs = [sh.run_arrays(*arrays, capacity=capacity, first_shower_id=first_id)]
-        tally.zero_()
-        sh.tally_batches(bs, tally)
+            sh.tally_batches(bs, tally)
         if world > 1:
             dist.all_reduce(tally)        # the only collective: 8 KB of tallies over NVLink
         return bs
@@ -368,7 +368,7 @@ def ours(args):
         "trials_by_process": trials,
         "e2e": {"value": world * n * e2e_steps / (ms_e2e * 1e-3), "unit": "showers/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": int(tally_host.nbytes + 8 * 16), "steps": e2e_steps,
-                "api": ("Shower.run_arrays_split(host arrays, parts=%d)" % P if P > 1 else "Shower.run_arrays(host arrays)") + " + Shower.tally_batches + tally.cpu()"},
+                "api": ("Shower.run_arrays_split(host arrays, parts=%d)" % P if P > 1 else "Shower.run_arrays(host arrays)") + " + pb_tally + tally.cpu()"},
         "gpu_launches": tot["n_launches"],
         "clocks": clk,
         "tally_check": {"records": float(tally_host[capi.TALLY_COUNT:capi.TALLY_COUNT + 7].sum()),

@@ -511,12 +511,15 @@ class Shower:
             self._pool = ThreadPoolExecutor(max_workers=parts)
         return [self] + peers[: parts - 1], streams[:parts]
 
-    def run_arrays_split(self, p, r, w, m, pid, flags, parts=2, GlobalMS=True, capacity=None, first_shower_id=None):
+    def run_arrays_split(self, p, r, w, m, pid, flags, parts=2, GlobalMS=True, capacity=None, first_shower_id=None, tally=None):
         """``run_arrays`` over ``parts`` contiguous sub-batches stepped CONCURRENTLY: one engine handle, one stack, one
         CUDA stream and one host thread per part (handles are independent, include/petite_b200.h).  Every wave kernel
         is a persistent grid whose last CTAs finish late (the longest track / tile of the wave) and the shrinking tail
         of a batch is latency-bound; a second batch in flight fills both.  Showers are keyed by (seed, shower id) and
         part k starts at ``first_shower_id + offset_k``, so the particles are those of the single-batch call.
+
+        ``tally`` (torch float64[TALLY_SIZE] on this GPU, zeroed by the caller): every part adds its ``pb_tally`` to it on
+        its own stream as soon as it is done, i.e. while the other part is still in its narrow last waves.
 
         Stream semantics are those of a synchronous call on the caller's current stream: the parts start after the
         work already queued there and the current stream waits for all of them.  -> list of :class:`ShowerBatch`."""
@@ -527,7 +530,10 @@ class Shower:
             first_shower_id = self._next_shower_id
             self._next_shower_id += n
         if parts == 1:
-            return [self.run_arrays(p, r, w, m, pid, flags, GlobalMS=GlobalMS, capacity=capacity, first_shower_id=first_shower_id)]
+            b = self.run_arrays(p, r, w, m, pid, flags, GlobalMS=GlobalMS, capacity=capacity, first_shower_id=first_shower_id)
+            if tally is not None:
+                self.tally(b, tally)
+            return [b]
         engines, streams = self._ensure_peers(parts)
         bounds = [n * k // parts for k in range(parts + 1)]
         cap = None if capacity is None else int(capacity) // parts + (1 << 16)
@@ -541,6 +547,8 @@ class Shower:
                 streams[k].wait_event(start)
                 b = engines[k].run_arrays(p[sl], r[sl], w[sl], m[sl], pid[sl], flags[sl], GlobalMS=GlobalMS, capacity=cap,
                                           first_shower_id=first_shower_id + bounds[k])
+                if tally is not None:
+                    engines[k].tally(b, tally)
                 done = torch.cuda.Event()
                 done.record(streams[k])
             return b, done

@@ -100,6 +100,10 @@ def test_concurrent_sub_batches_match_single_batch():
         assert np.array_equal(x, y)
     t_two = sh.tally_batches(parts).cpu().numpy()
     assert np.allclose(t_one, t_two, rtol=1e-12, atol=0)
+    import torch
+    t_in = torch.zeros_like(sh.tally(parts[0]))
+    sh.run_arrays_split(*arrays, parts=2, first_shower_id=500, tally=t_in)       # tallied inside, per part and stream
+    assert np.allclose(t_one, t_in.cpu().numpy(), rtol=1e-12, atol=0)
     assert sum(p.n for p in parts) == one.n
     # device-resident primaries, three parts
     import torch
