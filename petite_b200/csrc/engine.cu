@@ -69,6 +69,7 @@ struct MapInfo {
   double invB;               // 1 / B (points per sweep): wgt = jac / B
   double log_E0, inv_dlog;   // geometric-grid guess for the row look-up
   int ninc[4];
+  double dninc[4];           // ninc as doubles (the trial multiplies by it twice: no int->fp64 conversion in the loop)
   int off[4];
 };
 struct Tables {
@@ -666,14 +667,14 @@ __device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, cons
   double jac = 1.0;
 #pragma unroll
   for (int d = 0; d < DIM; ++d) {
-    int ninc = mi.ninc[d];
-    double yn = D[d] * ninc;
-    int iy = min((int)yn, ninc - 1);
+    const double dn = mi.dninc[d];
+    double yn = D[d] * dn;
+    int iy = min((int)yn, mi.ninc[d] - 1);
     const double* gd = g + mi.off[d];
     double g0 = gd[iy], g1 = gd[iy + 1];
     double inc = g1 - g0;
     x[d] = __dadd_rn(g0, __dmul_rn(inc, yn - iy));
-    jac *= inc * ninc;
+    jac *= inc * dn;
   }
   double f;
   if (DIM == 4) {
@@ -1706,7 +1707,7 @@ extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int 
   PB_CUDA(e, cudaSetDevice(e->device));
   MapInfo mi{};
   int stride = 0;
-  for (int d = 0; d < dim; ++d) { mi.ninc[d] = ninc[d]; mi.off[d] = stride; stride += ninc[d] + 1; }
+  for (int d = 0; d < dim; ++d) { mi.ninc[d] = ninc[d]; mi.dninc[d] = (double)ninc[d]; mi.off[d] = stride; stride += ninc[d] + 1; }
   int padded = (stride + 15) / 16 * 16;          // rows start 128-byte aligned; TMA bulk size multiple of 16 B
   if (padded > GRID_SMEM_DOUBLES) { e->err = "map row larger than the shared-memory staging buffer"; return PB_ERR_ARG; }
   std::vector<double> host((size_t)padded * nE, 0.0);
