@@ -281,7 +281,9 @@ class DarkShower(Shower):
         self._dark_capacity = capacity
 
     def generate_dark_showers(self, sm_batch):
-        """Dark pass over a :class:`ShowerBatch` that is still resident on this object's stack -> :class:`DarkBatch`."""
+        """Dark pass over a :class:`ShowerBatch` that is still resident on its stack -> :class:`DarkBatch`.  The batch may
+        live on another engine handle's stack (a part of :meth:`Shower.run_arrays_split`): the stack is caller-owned device
+        memory, and the dark tables only exist on this object's engine, so the pass always runs here."""
         active = [p for p in self.active_processes if p in _CODE]
         mask = 0
         for p in active:
@@ -290,7 +292,9 @@ class DarkShower(Shower):
         t = self._dark_stack
         dk = capi.pb_stack(t["p0"].data_ptr(), t["r0w"].data_ptr(), t["pf"].data_ptr(), t["rf"].data_ptr(),
                            t["key"].data_ptr(), t["meta"].data_ptr(), t["aux"].data_ptr(), self._dark_capacity)
-        sm = self._stack_struct()
+        ts = sm_batch._t
+        sm = capi.pb_stack(ts["p0"].data_ptr(), ts["r0w"].data_ptr(), ts["pf"].data_ptr(), ts["rf"].data_ptr(),
+                           ts["key"].data_ptr(), ts["meta"].data_ptr(), ts["aux"].data_ptr(), int(ts["p0"].shape[0]))
         cnt = capi.pb_counters()
         stream = self._torch.cuda.current_stream(self._device).cuda_stream
         capi.check(self._engine, capi.lib.pb_run_dark(self._engine, C.byref(sm), sm_batch.n, mask, C.byref(dk), C.byref(cnt),

@@ -126,3 +126,24 @@ def test_dark_yield_statistics_vs_oracle():
     Emax_gpu = per_shower(h["shower"], h["p0"][:, 0], n_gpu, np.max)
     Emax_orc = np.array([np.max([v.p0[0] for v in vs]) for _, vs in ref if vs])
     assert ks_2samp(Emax_gpu, Emax_orc).pvalue > 0.01
+
+
+def test_dark_pass_over_concurrent_sub_batches():
+    """Parts of run_arrays_split live on other engine handles' stacks; the dark pass over each of them (on the DarkShower's
+    own engine, which holds the dark tables) gives the dark vectors of the single-batch run."""
+    ds = dark_shower("graphite", 0.03)
+    prims = primaries(11, 3.0, 24)
+    one = ds.generate_showers(prims, first_shower_id=9100)
+    d_one = ds.generate_dark_showers(one)
+    h = d_one.to_host()
+    ref_n, ref_w, ref_E = d_one.n, np.sort(h["weight"]), np.sort(h["p0"][:, 0])
+    parts = ds.generate_showers_split(prims, parts=2, first_shower_id=9100)
+    assert parts[0]._owner is not parts[1]._owner and sum(p.n for p in parts) == one.n
+    ws, Es, n = [], [], 0
+    for part in parts:
+        d = ds.generate_dark_showers(part)
+        hh = d.to_host()
+        n += d.n; ws.append(hh["weight"].copy()); Es.append(hh["p0"][:, 0].copy())
+    assert n == ref_n
+    assert np.array_equal(np.sort(np.concatenate(ws)), ref_w)
+    assert np.array_equal(np.sort(np.concatenate(Es)), ref_E)
