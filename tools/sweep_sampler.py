@@ -1,11 +1,15 @@
-"""Tuning + safety sweep of the accept/reject sampler variants (one process, one engine per configuration; the knobs are
-read from the environment by pb_create): for every (PB_SAMPLE_STREAM, PB_SAMPLE_G, PB_SAMPLE_TOKENS, PB_SAMPLE_CHUNK)
+"""Tuning + safety sweep of the accept/reject sampler (one process, one engine per configuration; the knobs are read from
+the environment by pb_create).  A configuration is "stream,G,tokens,chunk": only G (PB_SAMPLE_G, lanes per sample) still
+exists in the tree - the other three drove the streaming sampler of commit a5882b6, whose sweeps are kept in
+profiles/r01f/sweep_stream_v*.log.  For every configuration
 
-  1. correctness: 2 000 showers of config 2 must give the SAME records and trial counts as the reference configuration
-     (tile kernel, G = 8) - the draws are counter-based, so any schedule has to reproduce them bit for bit;
-  2. timing: config 2 at 1e5 primaries, CUDA events, per-step and per-kernel (profiling level 1).
+  1. correctness: 2 000 showers of config 2 must give the SAME records and trial counts as the first configuration - the
+     draws are counter-based, so any schedule has to reproduce them bit for bit;
+  2. timing: config 2 at 1e5 primaries, CUDA events, per-step and per-kernel (SWEEP_PROFILING=1: the two loop kernels,
+     2: every kernel).
 
-    python tools/sweep_sampler.py [n_timing] > gpurun_out/sweep_sampler.log
+    python tools/sweep_sampler.py [n_timing] [stream,G,tokens,chunk ...] > gpurun_out/sweep_sampler.log
+    PETITE_B200_LIB=variants/libpb_X.so python tools/sweep_sampler.py ...      # compile-time variants: tools/sweep_variants.sh
 """
 import os, sys, json
 import numpy as np, torch
