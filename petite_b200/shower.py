@@ -535,7 +535,8 @@ class Shower:
                 self.tally(b, tally)
             return [b]
         engines, streams = self._ensure_peers(parts)
-        bounds = [n * k // parts for k in range(parts + 1)]
+        from .distributed import shard             # the same contiguous partition as across ranks (tests/test_distributed_cpu.py)
+        bounds = [shard(n, k, parts)[0] for k in range(parts)] + [n]
         cap = None if capacity is None else int(capacity) // parts + (1 << 16)
         cur = torch.cuda.current_stream(self._device)
         start = torch.cuda.Event()

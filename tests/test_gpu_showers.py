@@ -94,7 +94,7 @@ def test_concurrent_sub_batches_match_single_batch():
     a = signature(one)
     t_one = sh.tally(one).cpu().numpy()
     parts = sh.run_arrays_split(*arrays, parts=2, first_shower_id=500)
-    assert [b.n_primaries for b in parts] == [32, 33] and parts[0]._owner is not parts[1]._owner
+    assert [b.n_primaries for b in parts] == [33, 32] and parts[0]._owner is not parts[1]._owner
     b = signature(parts[0]) + signature(parts[1])
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
