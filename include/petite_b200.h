@@ -61,7 +61,7 @@ typedef struct pb_config {
 } pb_config;
 
 /* Structure-of-arrays particle stack in HBM (the Particle list of shower.py:621, particle.py:50-175).
- * One record = 4 x double4 + 32 bytes of ids = 160 B.  Records [0, n_primaries) are the primaries, daughters
+ * One record = 4 x double4 + 32 bytes of ids + 8 bytes of counters = 168 B.  Records [0, n_primaries) are the primaries, daughters
  * are appended wave by wave; record order within a wave is not the reference's creation order (host
  * side restores it from parent/child links, see petite_b200/shower.py). */
 typedef struct pb_stack {
@@ -69,8 +69,10 @@ typedef struct pb_stack {
   double* r0w;     /* [dev] capacity x 4 : x, y, z at creation, weight          (particle._r0, ids['weight']) */
   double* pf;      /* [dev] capacity x 4 : four-momentum after propagation      (particle._pf) */
   double* rf;      /* [dev] capacity x 4 : position after propagation, 4th = 0  (particle._rf) */
-  uint32_t* key;   /* [dev] capacity x 2 : Philox particle key */
-  int32_t* meta;   /* [dev] capacity x 4 : pid, parent slot (-1 primary), gen<<16 | child_bit<<15 | flags<<8 | process, shower id */
+  int32_t* ids;    /* [dev] capacity x 8 : pid, parent slot (-1 primary), gen<<16 | child_bit<<15 | flags<<8 | process, shower id,
+                                           Philox particle key (2 words), weight again (the two halves of the double): one
+                                           32-byte sector per record carries everything the wave kernels need besides the
+                                           four-vectors */
   int32_t* aux;    /* [dev] capacity x 2 : accept/reject trials used, dE/dx sub-steps taken */
   int64_t capacity;
 } pb_stack;
@@ -227,8 +229,15 @@ enum pb_probe {
   PB_PROBE_MCS = 3,      /* in: n x 9: p4[4], dist_m, m_lepton, u_sign, z1, z2 ... see tests; out: n x 4 */
   PB_PROBE_KIN = 4,      /* in: n x 8: E, mass, x[4], u_az, pad;          out: n x 8 two four-vectors (parent along z) */
   PB_PROBE_PHILOX = 5,   /* in: n x 6 (as doubles): key0,key1,c0,stream,c2,c3; out: n x 2 doubles */
-  PB_PROBE_HOTMATH = 6   /* in: n x 4: x_log (> 0), x_exp in [1/20, 1/6], theta, u in [0,1);
+  PB_PROBE_HOTMATH = 6,  /* in: n x 4: x_log (> 0), x_exp in [1/20, 1/6], theta, u in [0,1);
                             out: n x 7: hot_log, hot_exp_neg_step, sin, cos (theta), sin, cos (2 pi u), fast_rcp(x_log) */
+  PB_PROBE_MCS_FAST = 7, /* the folded multiple-scattering form of the sub-step loop; in / out as PB_PROBE_MCS (particle mass = m_lepton) */
+  PB_PROBE_SUBSTEP = 8,  /* ONE iteration of the dE/dx + MCS loop exactly as k_loop runs it (shower.py:559-581).
+                            in: n x 12: pid, E, px, py, pz, x, y, z, key0, key1, sub-step index, multiple scattering on/off;
+                            out: n x 10: loop ended (1) / sub-step applied (0), E, px, py, pz, x, y, z, delta_z, next index */
+  PB_PROBE_DARKKIN = 9   /* dark-vector four-momentum in the parent frame (kinematics.py:43-68, 134-183, 267-299); process =
+                            DarkBrem / DarkMuonBrem / DarkAnn / DarkComp.  in: n x 10: E, mV, x[4], u1, u2, Pe, cos(theta_e);
+                            out: n x 4 */
 };
 int pb_probe(pb_engine e, int what, int process, const double* in, int64_t n, int in_stride, double* out, int out_stride);
 

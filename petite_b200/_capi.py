@@ -33,7 +33,7 @@ class pb_config(C.Structure):
 
 class pb_stack(C.Structure):
     _fields_ = [("p0", C.c_void_p), ("r0w", C.c_void_p), ("pf", C.c_void_p), ("rf", C.c_void_p),
-                ("key", C.c_void_p), ("meta", C.c_void_p), ("aux", C.c_void_p), ("capacity", C.c_int64)]
+                ("ids", C.c_void_p), ("aux", C.c_void_p), ("capacity", C.c_int64)]
 
 
 class pb_primaries(C.Structure):
@@ -99,7 +99,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 PB_OK, PB_ERR_CUDA, PB_ERR_ARG, PB_ERR_CAPACITY, PB_ERR_STATE, PB_ERR_NO_SAMPLE = 0, -1, -2, -3, -4, -5
 PB_FLAG_SHORT_LIVED, PB_FLAG_NO_SAMPLE = 1, 2
-PROBE_DSIGMA, PROBE_NSIGMA, PROBE_MAP, PROBE_MCS, PROBE_KIN, PROBE_PHILOX, PROBE_HOTMATH = range(7)
+PROBE_DSIGMA, PROBE_NSIGMA, PROBE_MAP, PROBE_MCS, PROBE_KIN, PROBE_PHILOX, PROBE_HOTMATH, PROBE_MCS_FAST, PROBE_SUBSTEP, PROBE_DARKKIN = range(10)
 
 
 class EngineError(RuntimeError):

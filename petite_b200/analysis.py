@@ -25,8 +25,8 @@ def detector_cut(batch, owner, detector_positions, detector_radius, method="Samp
     nd = len(z)
     lo, hi = (-np.inf, np.inf) if energy_cut is None else (float(energy_cut[0]), float(energy_cut[1]))
     t = batch._t
-    st = capi.pb_stack(t["p0"].data_ptr(), t["r0w"].data_ptr(), t["pf"].data_ptr(), t["rf"].data_ptr(), t["key"].data_ptr(),
-                       t["meta"].data_ptr(), t["aux"].data_ptr(), t["p0"].shape[0])
+    from .shower import stack_struct
+    st = stack_struct(t)
     wpass, wall = np.zeros(nd), np.zeros(1)
     want_mask = method in ("Sample", "SampleW")
     mask = torch.zeros((max(batch.n, 1), nd), dtype=torch.uint8, device=t["p0"].device) if want_mask else None

@@ -38,7 +38,13 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #define PB_SAMPLE_MINB 4
 #endif
 #ifndef PB_SAMPLE_MINB_SM
-#define PB_SAMPLE_MINB_SM 5
+#define PB_SAMPLE_MINB_SM 5              // SM-pass kernel (no dark integrands): ~96 registers
+#endif
+#ifndef PB_SAMPLE_MINB_T
+#define PB_SAMPLE_MINB_T 3               // kernels evaluating T > 1 trials per lane and round trade occupancy for ILP
+#endif
+#ifndef PB_SAMPLE_MINB_SM_T
+#define PB_SAMPLE_MINB_SM_T 3
 #endif
 #ifndef PB_FIN_MINB
 #define PB_FIN_MINB 8                    // 64 registers, 8 CTAs per SM: measured 17.8 -> 15.3 ms per step (10: 15.7, 12: 16.2, uncapped 94 registers: 17.8) although it spills 92 B
@@ -55,6 +61,12 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #endif
 #ifndef PB_LOOP_MINB
 #define PB_LOOP_MINB 6
+#endif
+#ifndef PB_SAMPLE_G_DEFAULT
+#define PB_SAMPLE_G_DEFAULT 4
+#endif
+#ifndef PB_SAMPLE_T_DEFAULT
+#define PB_SAMPLE_T_DEFAULT 1
 #endif
 constexpr int TILE = PB_TILE;               // samples per tile
 constexpr int SAMPLE_THREADS = PB_SAMPLE_THREADS;
@@ -98,9 +110,19 @@ struct DarkCand {            // candidate dark emissions of one pb_run_dark call
 
 struct Stack {
   double* p0; double* r0w; double* pf; double* rf;
-  uint2* key; int4* meta; int2* aux;
+  int4* ids;                 // 2 x int4 per record: (pid, parent, info, shower), (key.x, key.y, weight lo, weight hi) - ONE 32-byte
+                             // sector holds everything k_emit / k_finalize / k_loop need besides the four-vectors
+  int2* aux;
   long long capacity;
 };
+__device__ __forceinline__ int4 ld_meta(const Stack& S, long long s) { return S.ids[2 * s]; }
+__device__ __forceinline__ int4 ld_kw(const Stack& S, long long s) { return S.ids[2 * s + 1]; }       // key + weight
+__device__ __forceinline__ uint2 kw_key(int4 kw) { return make_uint2((uint32_t)kw.x, (uint32_t)kw.y); }
+__device__ __forceinline__ double kw_weight(int4 kw) { return __hiloint2double(kw.w, kw.z); }
+__device__ __forceinline__ void st_ids(Stack& S, long long s, int4 meta, uint2 key, double w) {
+  S.ids[2 * s] = meta;
+  S.ids[2 * s + 1] = make_int4((int)key.x, (int)key.y, __double2loint(w), __double2hiint(w));
+}
 
 // Wave bookkeeping kept on the device so that waves can be enqueued back to back without a host round trip.
 struct WaveState {
@@ -241,6 +263,40 @@ __device__ __forceinline__ void store_track_setup(const Tables& T, Stack& S, lon
   rfp[1] = make_double2(0.0, 0.0);
 }
 
+// One iteration of the dE/dx + multiple-scattering loop (shower.py:559-581) on a track: true = the loop ends here (energy
+// below threshold, or the hard scatter was drawn), false = one sub-step was applied.  Shared by k_loop and PB_PROBE_SUBSTEP.
+__device__ __forceinline__ bool substep(const Material& M, const Tables& T, Track& t, int ms_e) {
+  if (!(t.p.E >= t.pmin)) return true;                                // loop condition (shower.py:559)
+  double ns = nsigma_hinted(T.sp[t.sp], t.hint, t.p.E);                // sum over the species' processes (shower.py:357-368)
+  double mfp = (ns <= 0.0) ? 1.0e12 : kCmToM * fast_rcp(ns);          // shower.py:386-389
+  D2 u = draw2(t.key, (uint32_t)t.it, ST_SUBSTEP);
+  double iv = fast_rcp(6.0 + 14.0 * u.b);                             // delta_z = mfp / U(6, 20); delta_z / mfp = 1 / U
+  t.delta_z = mfp * iv;
+  if (u.a > hot_exp_neg_step(iv)) return true;                        // hard scatter (shower.py:564)
+  // lose_energy (particle.py:143-153) with |p| carried along the track instead of recomputed
+  double Eu = t.p.E - M.dEdx * t.delta_z;
+  if (Eu <= t.mass) Eu = t.mass;
+  double p3f = sqrt(__dsub_rn(__dmul_rn(Eu, Eu), __dmul_rn(t.mass, t.mass)));
+  if (p3f > 0.0) {
+    double r = p3f * t.ipn;
+    t.p = V4{Eu, t.p.x * r, t.p.y * r, t.p.z * r};
+    t.pn = p3f;
+    double inv = fast_rcp(p3f);
+    t.ipn = inv;
+    double s = t.delta_z * inv;
+    t.rx += t.p.x * s; t.ry += t.p.y * s; t.rz += t.p.z * s;
+    if (ms_e) {
+      McsDraw d = mcs_draw(t.key, (uint32_t)t.it, 0);
+      t.p = mcs_fast(M, t.p, p3f, inv, M.rho * (t.delta_z * (1.0 / kCmToM)), t.iKp, d.sign, d.radial, d.uphi);
+    }
+  } else {
+    t.p = V4{t.mass, 0.0, 0.0, 0.0};
+    t.pn = 0.0; t.ipn = 0.0;
+  }
+  ++t.it;
+  return false;
+}
+
 // First kernel of every wave: turn what the previous wave appended (stack tail, list sizes) into this wave's extent.
 // Idempotent when it has to pause (status 3), so the host can grow the scratch and re-enqueue the same wave.
 __global__ void k_wave_begin(Work W) {
@@ -278,7 +334,7 @@ constexpr int LOOP_CHUNK = 32;
 struct LoopBuf {                 // one chunk of track records: p0, r0w, track set-up (rf), ids
   double2 v[5][LOOP_CHUNK];
   int4 meta[LOOP_CHUNK];
-  uint2 key[LOOP_CHUNK];
+  int4 kw[LOOP_CHUNK];
   int idx[LOOP_CHUNK];
 };
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -325,8 +381,8 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       cp_async16(&B.v[0][lane], p0p); cp_async16(&B.v[1][lane], p0p + 1);
       cp_async16(&B.v[2][lane], r0p); cp_async16(&B.v[3][lane], r0p + 1);
       cp_async16(&B.v[4][lane], sup);
-      cp_async16(&B.meta[lane], S.meta + s);
-      cp_async8(&B.key[lane], S.key + s);
+      cp_async16(&B.meta[lane], S.ids + 2 * s);
+      cp_async16(&B.kw[lane], S.ids + 2 * s + 1);
       B.idx[lane] = pre_idx;
     }
     cnt_fly = pre_cnt;
@@ -363,7 +419,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
         t.p = V4{a0.x, a0.y, a1.x, a1.y};
         t.rx = b0.x; t.ry = b0.y; t.rz = b1.x;
         int4 meta = B.meta[e];
-        t.key = B.key[e];
+        t.key = kw_key(B.kw[e]);
         int pid = meta.x;
         t.mass = pid_mass(pid); t.iKp = 1e-3;
         if (meta.y < 0) { t.mass = prim_mass[begin + cur]; t.iKp = t.mass / (1e3 * pid_mass(pid)); }
@@ -380,38 +436,8 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     // ---- one sub-step for every live lane
     bool done = false;
     if (cur >= 0) {
-      if (!(t.p.E >= t.pmin)) done = true;                               // loop condition (shower.py:559)
-      else {
-        double ns = nsigma_hinted(T.sp[t.sp], t.hint, t.p.E);              // sum over the species' processes (shower.py:357-368)
-        double mfp = (ns <= 0.0) ? 1.0e12 : kCmToM * fast_rcp(ns);        // shower.py:386-389
-        D2 u = draw2(t.key, (uint32_t)t.it, ST_SUBSTEP);
-        double iv = fast_rcp(6.0 + 14.0 * u.b);                           // delta_z = mfp / U(6, 20); delta_z / mfp = 1 / U
-        t.delta_z = mfp * iv;
-        if (u.a > hot_exp_neg_step(iv)) done = true;                      // hard scatter (shower.py:564)
-        else {
-          // lose_energy (particle.py:143-153) with |p| carried along the track instead of recomputed
-          double Eu = t.p.E - M.dEdx * t.delta_z;
-          if (Eu <= t.mass) Eu = t.mass;
-          double p3f = sqrt(__dsub_rn(__dmul_rn(Eu, Eu), __dmul_rn(t.mass, t.mass)));
-          if (p3f > 0.0) {
-            double r = p3f * t.ipn;
-            t.p = V4{Eu, t.p.x * r, t.p.y * r, t.p.z * r};
-            t.pn = p3f;
-            double inv = fast_rcp(p3f);
-            t.ipn = inv;
-            double s = t.delta_z * inv;
-            t.rx += t.p.x * s; t.ry += t.p.y * s; t.rz += t.p.z * s;
-            if (ms_e) {
-              McsDraw d = mcs_draw(t.key, (uint32_t)t.it, 0);
-              t.p = mcs_fast(M, t.p, p3f, inv, M.rho * (t.delta_z * (1.0 / kCmToM)), t.iKp, d.sign, d.radial, d.uphi);
-            }
-          } else {
-            t.p = V4{t.mass, 0.0, 0.0, 0.0};
-            t.pn = 0.0; t.ipn = 0.0;
-          }
-          ++t.it; ++c_sub;
-        }
-      }
+      done = substep(M, T, t, ms_e);
+      if (!done) ++c_sub;
     }
     if (done) {
       long long s = begin + cur;
@@ -441,8 +467,8 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
     const bool charged = j < n_charged;
     int i = charged ? order_c[j] : order_n[j - n_charged];
     long long s = begin + i;
-    int4 meta = S.meta[s];
-    uint2 key = S.key[s];
+    int4 meta = ld_meta(S, s);
+    uint2 key = kw_key(ld_kw(S, s));
     int pid = meta.x;
     int flags = (meta.z >> 8) & 0x7f;
     double mass = (meta.y < 0) ? prim_mass[s] : pid_mass(pid);
@@ -587,8 +613,9 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
 // wave's stack records directly, the dark pass goes through its candidate list.
 struct SampleIO {
   const double* E4;        // incoming energy of entry i at E4[4*i]
-  const uint2* key;        // particle keys
-  const int* key_index;    // entry i uses key[key_index[i]] (nullptr: key[i])
+  const uint2* key;        // particle keys: the key of entry / record k sits at key[k * key_stride + key_off]
+  int key_stride, key_off; // (1, 0) for a plain key array; (4, 2) for the ids records of a stack
+  const int* key_index;    // entry i uses record key_index[i] (nullptr: record off + i)
   int* ntr;                // trials used by entry i at ntr[i * ntr_stride]; -1 if the sampler gave up
   int ntr_stride;
   const WaveState* ws;     // SM pass: entry i is stack slot ws->begin + i (E4/key/ntr then point at slot 0)
@@ -607,7 +634,7 @@ __global__ void __launch_bounds__(256) k_bucket_fill(Work W, SampleIO io, int n_
     double E = 0.0; uint2 key = make_uint2(0, 0);
     if (sampled) {
       E = io.E4[4 * (off + (size_t)i)];
-      key = io.key[io.key_index ? (size_t)io.key_index[i] : off + (size_t)i];
+      key = io.key[(io.key_index ? (size_t)io.key_index[i] : off + (size_t)i) * io.key_stride + io.key_off];
     }
     unsigned peers = __match_any_sync(__activemask(), b);        // lanes of this warp that share the bucket
     int leader = __ffs(peers) - 1;
@@ -645,68 +672,101 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
 
-// One accept/reject trial: Philox doubles D[0..dim] = y_0..y_{dim-1}, u_accept; map y -> x through the staged
-// grid (vegas AdaptiveMap: x = g[i] + (g[i+1]-g[i]) * (y*ninc - i), jac = prod ninc*(g[i+1]-g[i])); accept iff
-// max_F * u < (jac / B) * f(x)  (shower.py:453-459).
-template <int DIM, int FAM>
-__device__ __forceinline__ bool trial(const Material& M, const MapInfo& mi, const double* __restrict__ g, int proc,
-                                      double E, const SampleConst& sc, double maxF, uint2 key, uint32_t t, double* x) {
-  double D[DIM + 2];
-  if (DIM == 4) {          // two calls: four map coordinates, and the accept uniform from the calls' 2 x 24 spare bits
-    uint32_t s0, s1;
-    D2 d0 = draw2s(key, t, ST_VEGAS, 0, proc, s0), d1 = draw2s(key, t, ST_VEGAS, 1, proc, s1);
-    D[0] = d0.a; D[1] = d0.b; D[2] = d1.a; D[3] = d1.b;
-    D[4] = u48(s0, s1);
-  } else {
+// T accept/reject trials (indices t0 .. t0 + T - 1 of one sample) evaluated by ONE lane in straight-line code: the T
+// dependency chains interleave (the register file holds too few warps to hide an FP64 chain by thread-level parallelism
+// alone).  Per trial: Philox doubles D[0..dim] = y_0..y_{dim-1}, u_accept; map y -> x through the staged grid (vegas
+// AdaptiveMap: x = g[i] + (g[i+1]-g[i]) * (y*ninc - i), jac = prod ninc*(g[i+1]-g[i])); accept iff
+// max_F * u < (jac / B) * f(x)  (shower.py:453-459).  Returns the accept mask (bit k = trial t0 + k) and the point of the
+// LOWEST accepted trial in x.  FAM: -1 = every sampled process, 2 = the SM pass (4-D folded forms + the five 1-D SM processes).
+template <int DIM, int FAM, int T>
+__device__ __forceinline__ unsigned trial_block(const Material& M, const MapInfo& mi, const double* __restrict__ g, int proc,
+                                                double E, const SampleConst& sc, double maxF, uint2 key, uint32_t t0, double* x) {
+  double D[T][DIM + 2];      // the uniforms PLUS ONE (doubles in [1, 2)): consumed as fma(D, s, -s) == (D - 1) * s, bit for bit
 #pragma unroll
-    for (int j = 0; j < (DIM + 2) / 2; ++j) {
-      D2 d = draw2(key, t, ST_VEGAS, j, proc);
-      D[2 * j] = d.a; D[2 * j + 1] = d.b;
+  for (int k = 0; k < T; ++k) {
+    const uint32_t t = t0 + k;
+    uint32_t s0, s1;
+    if (DIM == 4) {          // two calls: four map coordinates, and the accept uniform from the calls' 2 x 24 spare bits
+      D2 d0 = draw2s_p1(key, t, ST_VEGAS, 0, proc, s0), d1 = draw2s_p1(key, t, ST_VEGAS, 1, proc, s1);
+      D[k][0] = d0.a; D[k][1] = d0.b; D[k][2] = d1.a; D[k][3] = d1.b;
+      D[k][4] = u48p1(s0, s1);
+    } else {
+#pragma unroll
+      for (int j = 0; j < (DIM + 2) / 2; ++j) {
+        D2 d = draw2s_p1(key, t, ST_VEGAS, j, proc, s0);
+        D[k][2 * j] = d.a; D[k][2 * j + 1] = d.b;
+      }
     }
   }
-  double jac = 1.0;
+  double xx[T][4], jac[T];
+#pragma unroll
+  for (int k = 0; k < T; ++k) { jac[k] = 1.0; xx[k][0] = 0.0; xx[k][1] = 0.0; xx[k][2] = 0.0; xx[k][3] = 0.0; }
 #pragma unroll
   for (int d = 0; d < DIM; ++d) {
     const double dn = mi.dninc[d];
-    double yn = D[d] * dn;
-    int iy = min((int)yn, mi.ninc[d] - 1);
+    const int nm1 = mi.ninc[d] - 1;
     const double* gd = g + mi.off[d];
-    double g0 = gd[iy], g1 = gd[iy + 1];
-    double inc = g1 - g0;
-    x[d] = __dadd_rn(g0, __dmul_rn(inc, yn - iy));
-    jac *= inc * dn;
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+      double yn = fma(D[k][d], dn, -dn);        // y * ninc
+      int iy = min((int)yn, nm1);
+      double g0 = gd[iy], g1 = gd[iy + 1];
+      double inc = g1 - g0;
+      xx[k][d] = __dadd_rn(g0, __dmul_rn(inc, yn - iy));
+      jac[k] *= inc * dn;
+    }
   }
-  double f;
+  double f[T];
   if (DIM == 4) {
-    if (proc == P_PAIRPROD) f = ds_pairprod_fast(sc, E, x);
-    else f = ds_brem_fast(M, sc, E, proc == P_BREM ? kMe : kMmu, x);
-  } else if (FAM == 1) {
-    switch (proc) {            // the five 1-D SM processes only
-      case P_COMP: f = ds_compton(M, E, 0.0, x[0]); break;
-      case P_ANN: f = ds_annihilation(E, 0.0, M.Eg_min, x[0]); break;
-      case P_MOLLER: f = ds_moller(E, M.Ee_min, x[0]); break;
-      case P_BHABHA: f = ds_bhabha(E, M.Ee_min, x[0]); break;
-      default: f = ds_muone(E, M.Ee_min, x[0]); break;
+    if (proc == P_PAIRPROD) {
+#pragma unroll
+      for (int k = 0; k < T; ++k) f[k] = ds_pairprod_fast(sc, E, xx[k]);
+    } else {
+      const double ml = (proc == P_BREM) ? kMe : kMmu;
+#pragma unroll
+      for (int k = 0; k < T; ++k) f[k] = ds_brem_fast(M, sc, E, ml, xx[k]);
+    }
+  } else if (FAM == 2) {       // the five 1-D SM processes only
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+      switch (proc) {
+        case P_COMP: f[k] = ds_compton(M, E, 0.0, xx[k][0]); break;
+        case P_ANN: f[k] = ds_annihilation(E, 0.0, M.Eg_min, xx[k][0]); break;
+        case P_MOLLER: f[k] = ds_moller(E, M.Ee_min, xx[k][0]); break;
+        case P_BHABHA: f[k] = ds_bhabha(E, M.Ee_min, xx[k][0]); break;
+        default: f[k] = ds_muone(E, M.Ee_min, xx[k][0]); break;
+      }
     }
   } else if (DIM == 3) {
-    f = ds_darkbrem_fast(M, sc, E, proc == P_DARKBREM ? kMe : kMmu, x);      // the two 3-D processes
+    const double ml = (proc == P_DARKBREM) ? kMe : kMmu;
+#pragma unroll
+    for (int k = 0; k < T; ++k) f[k] = ds_darkbrem_fast(M, sc, E, ml, xx[k]);      // the two 3-D processes
   } else {
-    f = dsigma(M, proc, E, x);
+#pragma unroll
+    for (int k = 0; k < T; ++k) f[k] = dsigma(M, proc, E, xx[k]);
   }
-  return maxF * D[DIM] < (jac * mi.invB) * f;
+  unsigned am = 0;
+#pragma unroll
+  for (int k = T - 1; k >= 0; --k) {
+    if (fma(maxF, D[k][DIM], -maxF) < (jac[k] * mi.invB) * f[k]) {   // max_F * u
+      am |= 1u << k;
+      x[0] = xx[k][0]; x[1] = xx[k][1]; x[2] = xx[k][2]; x[3] = xx[k][3];
+    }
+  }
+  return am;
 }
 
-// Persistent sampling kernel.  G lanes cooperate on one sample: lane l of the group evaluates trial r*G + l in
-// round r and the lowest accepted trial wins - identical to the reference's sequential first-accept rule because
-// every trial's uniforms are a pure function of (particle key, trial index).  Groups pull the next sample of the
-// tile from a shared cursor as soon as they finish.
-__host__ __device__ constexpr int proc_family(int p) {
-  return (p == P_BREM || p == P_PAIRPROD || p == P_MUONBREM) ? 0 : (p < P_DARKBREM ? 1 : 2);
-}
+// Persistent sampling kernel.  G lanes cooperate on one sample and every lane evaluates T consecutive trials per round:
+// lane l of the group evaluates trials (r G + l) T .. (r G + l) T + T - 1 in round r and the lowest accepted trial wins -
+// identical to the reference's sequential first-accept rule because every trial's uniforms are a pure function of
+// (particle key, trial index).  Groups pull the next sample of the tile from a shared cursor as soon as they finish.
+__host__ __device__ constexpr bool proc_is_sm(int p) { return p < P_DARKBREM; }
+__host__ __device__ constexpr bool proc_is_4d(int p) { return p == P_BREM || p == P_PAIRPROD || p == P_MUONBREM; }
 
-template <int G, int FAM>
-__global__ void __launch_bounds__(SAMPLE_THREADS, (FAM == 0 || FAM == 1) ? PB_SAMPLE_MINB_SM : PB_SAMPLE_MINB)
-k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, SampleIO io, Work W) {
+template <int G, int FAM, int T>
+__global__ void __launch_bounds__(SAMPLE_THREADS, (FAM == 2) ? (T > 1 ? PB_SAMPLE_MINB_SM_T : PB_SAMPLE_MINB_SM) : (T > 1 ? PB_SAMPLE_MINB_T : PB_SAMPLE_MINB))
+k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, SampleIO io, Work W) {
+  const Tables& Tb = T_;
   __shared__ __align__(128) double s_grid[GRID_SMEM_DOUBLES];
   __shared__ __align__(16) double s_E[TILE], s_cb[TILE], s_cc[TILE], s_cd[TILE];   // per-entry energy and sampler constants
   __shared__ __align__(16) uint2 s_key[TILE];
@@ -724,14 +784,13 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
   const size_t off = io.ws ? (size_t)io.ws->begin : 0;
   __syncthreads();
   for (;;) {
-    if (threadIdx.x == 0) { s_tile = atomicAdd(&W.ctrl[FAM < 0 ? 1 : 4 + FAM], 1); s_cursor = 0; }
+    if (threadIdx.x == 0) { s_tile = atomicAdd(&W.ctrl[1], 1); s_cursor = 0; }
     __syncthreads();
     int tile = s_tile;
     if (tile >= W.ctrl[0]) break;
     int bucket = W.tile_bucket[tile], tstart = W.tile_start[tile], tcount = W.tile_count[tile];
     int proc = bucket / LU_MAX, lu = bucket % LU_MAX;
-    if (FAM >= 0 && proc_family(proc) != FAM) { __syncthreads(); continue; }     // another family's kernel takes this tile
-    const MapInfo& mi = T.map[proc];
+    const MapInfo& mi = Tb.map[proc];
     if (threadIdx.x == 0) {
       uint32_t bytes = (uint32_t)mi.stride * 8u;
       mbar_expect_tx(&s_bar, bytes);
@@ -744,10 +803,10 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
       s_E[k] = Ek;
       s_key[k] = W.skey[tstart + k];
       s_idx[k] = W.sorted[tstart + k];
-      if (proc == P_PAIRPROD || proc == P_BREM || proc == P_MUONBREM) {
+      if (proc_is_4d(proc)) {
         SampleConst c = (proc == P_PAIRPROD) ? pairprod_const(M, Ek) : brem_const(M, Ek, proc == P_BREM ? kMe : kMmu);
         s_cb[k] = c.b; s_cc[k] = c.c; s_cd[k] = c.d;
-      } else if (FAM != 1 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) {
+      } else if (FAM != 2 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) {
         SampleConst c = darkbrem_const(M, Ek, proc == P_DARKBREM ? kMe : kMmu);
         s_cb[k] = c.b; s_cc[k] = c.c; s_cd[k] = c.e;          // |p|, tconv, 1/|p|
       }
@@ -756,7 +815,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
     mbar_wait(&s_bar, phase);
     phase ^= 1;
     __syncthreads();
-    const long long max_trials = M.max_trials;
+    const uint32_t max_trials = (uint32_t)min(M.max_trials, 0xffffff00LL);
     // group state
     int cur = -1;          // entry index, -1 = need a new one, -2 = tile exhausted
     double E = 0.0; uint2 key = make_uint2(0, 0);
@@ -766,7 +825,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
       if (cur == -1) {
         int j = 0;
         if (sub == 0) j = atomicAdd(&s_cursor, 1);
-        j = __shfl_sync(gmask, j, gbase);
+        if (G > 1) j = __shfl_sync(gmask, j, gbase);
         if (j < tcount) {
           cur = s_idx[j];
           E = s_E[j];
@@ -775,14 +834,14 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
           if (proc == P_PAIRPROD) sc = SampleConst{E - 2 * kMe, s_cb[j], s_cc[j], s_cd[j], 0.0};
           else if (proc == P_BREM) sc = SampleConst{E - kMe - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMe * kMe};
           else if (proc == P_MUONBREM) sc = SampleConst{E - kMmu - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMmu * kMmu};
-          else if (FAM != 1 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) sc = SampleConst{0.0, s_cb[j], s_cc[j], M.i2mT, s_cd[j]};
+          else if (FAM != 2 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) sc = SampleConst{0.0, s_cb[j], s_cc[j], M.i2mT, s_cd[j]};
         } else cur = -2;
       }
       // ---- drain help.  Once the tile's cursor is exhausted a group that finishes has nothing left to fetch; instead of
       // idling until the slowest sample of the warp is accepted (the geometric tail: 1 sample in 200 needs > 100 trials) it
       // joins a sample that is still open in its warp.  The open samples ("owners", k of them) share the idle groups evenly:
       // idle group i helps owner i mod k as that sample's (1 + i / k)-th group, with the owner's state fetched by shuffles
-      // (the helper's own registers are dead), and the m groups on a sample cover trials next_t .. next_t + m G - 1 of the
+      // (the helper's own registers are dead), and the m groups on a sample cover trials next_t .. next_t + m G T - 1 of the
       // round.  Trial indices, not lanes, define the draws, so the first accepted INDEX wins whoever evaluated it.
       const unsigned own = __ballot_sync(0xffffffffu, sub == 0 && cur >= 0);
       const unsigned idl = __ballot_sync(0xffffffffu, sub == 0 && cur == -2);
@@ -809,37 +868,40 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T, S
         peers = __match_any_sync(0xffffffffu, cur);
       }
       double x[4] = {0.0, 0.0, 0.0, 0.0};
-      bool acc = false;
-      const uint32_t code = r * G + sub;                  // my trial of this round, relative to next_t
-      const uint32_t t = next_t + code;
-      if (cur >= 0 && (long long)t < max_trials) {
-        if (FAM == 0) acc = trial<4, 0>(M, mi, s_grid, proc, E, sc, maxF, key, t, x);
-        else if (FAM == 1) acc = trial<1, 1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x);
-        else switch (mi.dim) {
-          case 4: acc = trial<4, -1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
-          case 3: acc = trial<3, -1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
-          default: acc = trial<1, -1>(M, mi, s_grid, proc, E, sc, maxF, key, t, x); break;
+      unsigned am = 0;
+      const uint32_t code0 = (r * G + sub) * T;           // my first trial of this round, relative to next_t
+      const uint32_t t0 = next_t + code0;
+      if (cur >= 0 && t0 < max_trials) {
+        if (FAM == 2) {
+          if (proc_is_4d(proc)) am = trial_block<4, 2, T>(M, mi, s_grid, proc, E, sc, maxF, key, t0, x);
+          else am = trial_block<1, 2, T>(M, mi, s_grid, proc, E, sc, maxF, key, t0, x);
+        } else switch (mi.dim) {
+          case 4: am = trial_block<4, -1, T>(M, mi, s_grid, proc, E, sc, maxF, key, t0, x); break;
+          case 3: am = trial_block<3, -1, T>(M, mi, s_grid, proc, E, sc, maxF, key, t0, x); break;
+          default: am = trial_block<1, -1, T>(M, mi, s_grid, proc, E, sc, maxF, key, t0, x); break;
         }
+        if (T > 1 && max_trials - t0 < (uint32_t)T) am &= (1u << (max_trials - t0)) - 1u;      // trials at or beyond max_trials do not exist
       }
-      uint32_t best;                                      // lowest accepted trial of my sample in this round
-      if (help) best = __reduce_min_sync(peers, acc ? code : 0xffffffffu);
-      else {
-        const unsigned gb = __ballot_sync(0xffffffffu, acc) & gmask;
-        best = gb ? (uint32_t)(__ffs(gb) - 1 - gbase) : 0xffffffffu;
+      const uint32_t mine = am ? code0 + (uint32_t)(__ffs(am) - 1) : 0xffffffffu;
+      uint32_t best = mine;                               // lowest accepted trial of my sample in this round
+      if (help) best = __reduce_min_sync(peers, mine);
+      else if (G > 1) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
       }
       if (cur >= 0) {
         if (best != 0xffffffffu) {
-          if (acc && code == best) {
+          if (mine == best) {
             double2* xo = reinterpret_cast<double2*>(W.xs + 4 * (size_t)cur);
             xo[0] = make_double2(x[0], x[1]); xo[1] = make_double2(x[2], x[3]);
-            int ntr = (int)(t + 1);
+            int ntr = (int)(next_t + best + 1);
             io.ntr[(off + (size_t)cur) * io.ntr_stride] = ntr;
             c_trials += ntr; c_samples += 1;
           }
           cur = -1;
         } else {
-          next_t += m * G;
-          if ((long long)next_t >= max_trials) {           // "No Sample Found" (shower.py:460-461)
+          next_t += m * (G * T);
+          if (next_t >= max_trials) {                      // "No Sample Found" (shower.py:460-461)
             if (sub == 0 && !helper) {
               io.ntr[(off + (size_t)cur) * io.ntr_stride] = -1;
               W.bucket[cur] = P_NONE * LU_MAX;
@@ -894,7 +956,7 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     int i = wave_order ? j : W.sorted[j];
     int bucket = W.bucket[i];
     proc = bucket / LU_MAX;
-    if (proc == P_NONE && S.aux[begin + i].x < 0) S.meta[begin + i].z |= (PB_FLAG_NO_SAMPLE << 8);   // sampler gave up
+    if (proc == P_NONE && S.aux[begin + i].x < 0) S.ids[2 * (begin + i)].z |= (PB_FLAG_NO_SAMPLE << 8);   // sampler gave up
     if (proc != P_NONE) {
       slot = begin + i;
       const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * slot);
@@ -903,9 +965,8 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       V4 pf{a0.x, a0.y, a1.x, a1.y};
       rx = b0.x; ry = b0.y; rz = b1.x;
       double mass = b1.y;
-      meta = S.meta[slot];
-      key = S.key[slot];
-      wgt = S.r0w[4 * slot + 3];
+      meta = ld_meta(S, slot);
+      { int4 kw = ld_kw(S, slot); key = kw_key(kw); wgt = kw_weight(kw); }
       int pid = meta.x;
       if (proc == P_SMDECAY) {                                     // pi0 -> gamma gamma (particle.py:391-409)
         D2 u = draw2(key, 0, ST_DECAY, 0, P_SMDECAY);
@@ -965,8 +1026,7 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       double2* r0p = reinterpret_cast<double2*>(S.r0w + 4 * dst);
       p0p[0] = make_double2(d.E, d.x); p0p[1] = make_double2(d.y, d.z);
       r0p[0] = make_double2(rx, ry);   r0p[1] = make_double2(rz, wgt);
-      S.key[dst] = child_key(key, bit);
-      S.meta[dst] = make_int4(bit ? pid_b : pid_a, (int)slot, pack_info(gen, bit, 0, proc), meta.w);
+      st_ids(S, dst, make_int4(bit ? pid_b : pid_a, (int)slot, pack_info(gen, bit, 0, proc), meta.w), child_key(key, bit), wgt);
       if (bit ? ch_b : ch_a) {
         next_c[ci++] = (int)(dst - next_begin);
         store_track_setup(T, S, dst, bit ? pid_b : pid_a, d.E, d.x, d.y, d.z);
@@ -985,8 +1045,7 @@ __global__ void k_init_primaries(const __grid_constant__ Tables T, Stack S, Work
   for (int k = 0; k < 4; ++k) S.p0[4 * i + k] = p[4 * i + k];
   for (int k = 0; k < 3; ++k) S.r0w[4 * i + k] = r[3 * i + k];
   S.r0w[4 * i + 3] = w[i];
-  S.key[i] = root_key(seed, first_id + (unsigned long long)i);
-  S.meta[i] = make_int4(pid[i], -1, pack_info(0, 0, flags[i], P_INPUT), (int)i);
+  st_ids(S, i, make_int4(pid[i], -1, pack_info(0, 0, flags[i], P_INPUT), (int)i), root_key(seed, first_id + (unsigned long long)i), w[i]);
   const bool ch = is_charged(pid[i]) && !(flags[i] & PB_FLAG_SHORT_LIVED);
   unsigned long long old = atomicAdd(&W.tail[1], ch ? 1ull : (1ull << 32));
   if (ch) {
@@ -1021,14 +1080,14 @@ k_dark_prepare(const __grid_constant__ Material M, const __grid_constant__ Table
   int nc = 0;
   int c_proc[2]; double c_wg[2]; V4 c_pf[2]; int c_bucket[2];
   if (s < n) {
-    int4 meta = S.meta[s];
+    int4 meta = ld_meta(S, s);
     int pid = meta.x;
     const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
     double2 a0 = p0p[0], a1 = p0p[1];
     V4 p0{a0.x, a0.y, a1.x, a1.y};
     double E0 = p0.E;
     double mass = S.rf[4 * s + 3];
-    uint2 key = S.key[s];
+    uint2 key = kw_key(ld_kw(S, s));
     const double pre = M.g_e * M.g_e / (4 * kPi * kAlpha);
     int procs[2] = {-1, -1};
     if (pid == 11) procs[0] = P_DARKBREM;
@@ -1144,9 +1203,10 @@ k_dark_emit(const __grid_constant__ Material M, Stack S, Stack O, Work W, DarkCa
       double2 b0 = rfp[0], b1 = rfp[1];
       rx = b0.x; ry = b0.y; rz = b1.x;
       double mass = b1.y;
-      meta = S.meta[slot];
-      key = S.key[slot];
-      double w0 = S.r0w[4 * (size_t)slot + 3];
+      meta = ld_meta(S, slot);
+      int4 kw = ld_kw(S, slot);
+      key = kw_key(kw);
+      double w0 = kw_weight(kw);
       const double mV = M.mV, me = kMe;
       double E = pf.E;
       if (proc == P_BSMDECAY) {
@@ -1203,9 +1263,8 @@ k_dark_emit(const __grid_constant__ Material M, Stack S, Stack O, Work W, DarkCa
     pfp[0] = make_double2(v.E, v.x); pfp[1] = make_double2(v.y, v.z);
     r0p[0] = make_double2(rx, ry);   r0p[1] = make_double2(rz, wgt);
     rfp[0] = make_double2(rx, ry);   rfp[1] = make_double2(rz, M.mV);
-    O.key[dst] = child_key(key, 16u + (uint32_t)proc);
     int gen = ((meta.z >> 16) & 0xffff) + 1;
-    O.meta[dst] = make_int4(4900022, slot, pack_info(gen, proc == P_BSMDECAY ? 1 : 0, 0, proc), meta.w);
+    st_ids(O, dst, make_int4(4900022, slot, pack_info(gen, proc == P_BSMDECAY ? 1 : 0, 0, proc), meta.w), child_key(key, 16u + (uint32_t)proc), wgt);
     O.aux[dst] = make_int2(ntr, 0);
   }
 }
@@ -1346,7 +1405,7 @@ __global__ void __launch_bounds__(256) k_tally(Stack S, long long first, long lo
     const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
     double2 a0 = p0p[0], a1 = p0p[1];
     double w = S.r0w[4 * s + 3];
-    int sp = species_of(S.meta[s].x);
+    int sp = species_of(S.ids[2 * s].x);
 #pragma unroll
     for (int k = 0; k < PB_TALLY_NSPECIES; ++k)
       if (sp == k) { cnt[k] += 1.0; ws[k] += w; wes[k] += w * a0.x; }
@@ -1484,6 +1543,36 @@ __global__ void k_probe(const __grid_constant__ Material M, const __grid_constan
       hot_sincos_2pi(a[3], &o[4], &o[5]);
       o[6] = fast_rcp(a[0]);
     } break;
+    case PB_PROBE_MCS_FAST: {   // in as PB_PROBE_MCS; the particle's mass is m_lepton
+      V4 p{a[0], a[1], a[2], a[3]};
+      double pn = norm3_nofma(p.x, p.y, p.z);
+      V4 q = (pn > 0) ? mcs_fast(M, p, pn, fast_rcp(pn), M.rho * (a[4] * (1.0 / kCmToM)), 1e-3, a[6], sqrt(a[7] * a[7] + a[8] * a[8]), a[9]) : p;
+      o[0] = q.E; o[1] = q.x; o[2] = q.y; o[3] = q.z;
+    } break;
+    case PB_PROBE_SUBSTEP: {    // the track set-up of k_loop's refill (and of store_track_setup), then one substep()
+      Track t;
+      int pid = (int)a[0];
+      t.p = V4{a[1], a[2], a[3], a[4]};
+      t.rx = a[5]; t.ry = a[6]; t.rz = a[7];
+      t.key = make_uint2((uint32_t)a[8], (uint32_t)a[9]);
+      t.it = (int)a[10];
+      t.mass = pid_mass(pid); t.iKp = 1e-3;
+      t.pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), t.mass);
+      t.sp = species_index(pid);
+      t.pn = norm3_nofma(t.p.x, t.p.y, t.p.z); t.ipn = 1.0 / t.pn;
+      t.hint = nsigma_locate(T.sp[t.sp], t.p.E);
+      t.delta_z = 0.0;
+      bool done = substep(M, T, t, (int)a[11]);
+      o[0] = done ? 1.0 : 0.0; o[1] = t.p.E; o[2] = t.p.x; o[3] = t.p.y; o[4] = t.p.z; o[5] = t.rx; o[6] = t.ry; o[7] = t.rz;
+      o[8] = t.delta_z; o[9] = (double)t.it;
+    } break;
+    case PB_PROBE_DARKKIN: {    // in: E, mV, x[4], u1, u2, Pe, cte
+      V4 v{0, 0, 0, 0};
+      if (process == P_DARKBREM || process == P_DARKMUONBREM) v = kin_darkbrem_V(a[0], a[1], a + 2, a[6]);
+      else if (process == P_DARKANN) v = kin_darkann_V(a[0], a[1], a[2]);
+      else if (process == P_DARKCOMP) v = kin_compton_bound_V(a[0], a[1], a[2], a[8], a[9], a[6], a[7]);
+      o[0] = v.E; o[1] = v.x; o[2] = v.y; o[3] = v.z;
+    } break;
     case PB_PROBE_PHILOX: {
       D2 d = draw2(make_uint2((uint32_t)a[0], (uint32_t)a[1]), (uint32_t)a[2], (uint32_t)a[3], (uint32_t)a[4], (uint32_t)a[5]);
       o[0] = d.a; o[1] = d.b;
@@ -1515,11 +1604,10 @@ struct pb_engine_s {
   void* prim_stage = nullptr; size_t prim_stage_bytes = 0;
   int n_sm = 148;
   int profiling = 0;             // 0 off, 1 = the two dominant kernels only (k_loop, k_sample), 2 = every kernel
-  int sample_group = 4;          // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G; 4 is fastest with drain help)
+  int sample_group = PB_SAMPLE_G_DEFAULT;    // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
+  int sample_trials = PB_SAMPLE_T_DEFAULT;   // trials per lane and round (PB_SAMPLE_T): ILP inside the lane
+  int sample_generic = 0;        // PB_SAMPLE_GENERIC=1: SM pass through the generic kernel (with the dark integrands compiled in)
   int emit_wave_order = 0;       // PB_EMIT_ORDER=1: k_emit walks the wave in record order (coalesced) instead of bucket order
-  int sample_split = 0;          // PB_SAMPLE_SPLIT=1: SM pass with the 4-D and 1-D integrand families as two concurrent kernels (measured: no gain)
-  cudaStream_t side = nullptr;   // second stream for the concurrent family kernel
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   static constexpr int LOOKAHEAD = 8;   // waves enqueued per host synchronisation while the shower tail shrinks
   cudaEvent_t ev[2 * 8] = {};
   cudaEvent_t evp[LOOKAHEAD][2][2] = {};   // lookahead slot x {k_loop, k_sample} x {start, stop}
@@ -1583,11 +1671,9 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   e->cfg = *cfg;
   derive_material(e);
   if (const char* g = getenv("PB_SAMPLE_G")) e->sample_group = atoi(g);
-  if (const char* g = getenv("PB_SAMPLE_SPLIT")) e->sample_split = atoi(g);
+  if (const char* g = getenv("PB_SAMPLE_T")) e->sample_trials = atoi(g);
+  if (const char* g = getenv("PB_SAMPLE_GENERIC")) e->sample_generic = atoi(g);
   if (const char* g = getenv("PB_EMIT_ORDER")) e->emit_wave_order = atoi(g);
-  cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
   size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * (8 + CNT_N) + sizeof(WaveState) + 64;
   if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
   cudaMemset(e->fixed_blob, 0, fixed);
@@ -1627,9 +1713,6 @@ extern "C" void pb_destroy(pb_engine e) {
   for (int i = 0; i < 2 * 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   for (int a = 0; a < pb_engine_s::LOOKAHEAD; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) if (e->evp[a][b][c]) cudaEventDestroy(e->evp[a][b][c]);
   if (e->h_ws) cudaFreeHost(e->h_ws);
-  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-  if (e->ev_join) cudaEventDestroy(e->ev_join);
-  if (e->side) cudaStreamDestroy(e->side);
   delete e;
 }
 
@@ -1727,30 +1810,24 @@ extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int 
 }
 
 static int ensure_cand(pb_engine e, long long ncap);
-// SM pass: one kernel per integrand family (4-D small-angle processes; 1-D two-body processes), so that the hot 4-D
-// kernel is not register-allocated for the dark-brem integrand and keeps 5 CTAs per SM.  The two kernels run
-// CONCURRENTLY (the 1-D one on a side stream): launched back to back on one stream the second drain cost more than
-// the registers gained; side by side the cheap 1-D tiles fill the SMs the 4-D kernel's tail leaves idle.
-// Dark pass / stand-alone sampling: one generic launch.
-static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream, bool sm_families = false) {
-  if (sm_families && e->sample_group == 8 && e->sample_split && e->side) {
-    const int g5 = std::max(1, std::min(e->n_sm * PB_SAMPLE_MINB_SM, grid * 2));
-    cudaEventRecord(e->ev_fork, stream);
-    cudaStreamWaitEvent(e->side, e->ev_fork, 0);
-    k_sample<8, 0><<<g5, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work);
-    k_sample<8, 1><<<g5, SAMPLE_THREADS, 0, e->side>>>(e->mat, e->tab, io, e->work);
-    cudaEventRecord(e->ev_join, e->side);
-    cudaStreamWaitEvent(stream, e->ev_join, 0);
-    return;
-  }
-  switch (e->sample_group) {
-    case 1: k_sample<1, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    case 2: k_sample<2, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    case 16: k_sample<16, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    case 32: k_sample<32, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    case 8: k_sample<8, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-    default: k_sample<4, -1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); break;
-  }
+// SM pass: a kernel instantiated without the dark integrands (fewer registers, one more CTA per SM); dark pass and
+// stand-alone sampling: the generic instantiation.  (G, T) = lanes per sample x trials per lane and round.
+template <int FAM>
+static void launch_sample_fam(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream) {
+  const int G = e->sample_group, T = e->sample_trials;
+#define PB_LS(g, t) if (G == g && T == t) { k_sample<g, FAM, t><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); return; }
+  PB_LS(4, 1) PB_LS(2, 2) PB_LS(1, 2) PB_LS(4, 2) PB_LS(2, 1) PB_LS(8, 1) PB_LS(1, 4) PB_LS(2, 4) PB_LS(1, 1)
+#undef PB_LS
+  k_sample<PB_SAMPLE_G_DEFAULT, FAM, PB_SAMPLE_T_DEFAULT><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work);
+}
+static int sample_grid(pb_engine e, long long n, bool sm_pass) {
+  const int T = e->sample_trials;
+  const int minb = sm_pass ? (T > 1 ? PB_SAMPLE_MINB_SM_T : PB_SAMPLE_MINB_SM) : (T > 1 ? PB_SAMPLE_MINB_T : PB_SAMPLE_MINB);
+  return (int)std::max<long long>(1, std::min<long long>((long long)e->n_sm * minb, (n + 31) / 32 + 1));
+}
+static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream, bool sm_pass = false) {
+  if (sm_pass && !e->sample_generic) launch_sample_fam<2>(e, grid, io, stream);
+  else launch_sample_fam<-1>(e, grid, io, stream);
 }
 
 // index lists live apart from the other scratch: growing them must keep their contents (a paused wave still needs them)
@@ -1803,7 +1880,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
   if (e->species_dirty) { int rcs = build_species_tables(e); if (rcs != PB_OK) return rcs; }
   int B = e->tab.map[P_BREM].B;
   e->mat.max_trials = (long long)std::min<double>((double)e->cfg.max_sweeps * (double)B, 4.0e9);
-  Stack S{st->p0, st->r0w, st->pf, st->rf, (uint2*)st->key, (int4*)st->meta, (int2*)st->aux, st->capacity};
+  Stack S{st->p0, st->r0w, st->pf, st->rf, (int4*)st->ids, (int2*)st->aux, st->capacity};
   long long launches = 0;
   // ---- primaries: host SoA -> device staging -> stack records [0, n0)
   size_t stage_bytes = (size_t)n0 * (sizeof(double) * (4 + 3 + 1 + 1) + sizeof(int) * 2);
@@ -1892,7 +1969,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     const unsigned g128 = (unsigned)((bound + 127) / 128);
     const unsigned g256 = (unsigned)((bound + 255) / 256);
     const int lg = (int)std::min<long long>((long long)e->n_sm * PB_LOOP_MINB, (bound + 4 * 8 - 1) / (4 * 8));
-    const int sg = (int)std::min<long long>((long long)e->n_sm * PB_SAMPLE_MINB, (bound + 31) / 32 + 1);
+    const int sg = sample_grid(e, bound, true);
     for (int j = 0; j < K; ++j) {
       k_wave_begin<<<1, 1, 0, stream>>>(e->work);
       tick(PB_K_PROPAGATE, j);
@@ -1902,11 +1979,10 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
       tock(PB_K_FINALIZE, j); tick(PB_K_SCAN, j);
       k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
       tock(PB_K_SCAN, j); tick(PB_K_FILL, j);
-      SampleIO io{S.pf, S.key, nullptr, reinterpret_cast<int*>(S.aux), 2, e->work.ws};
+      SampleIO io{S.pf, reinterpret_cast<const uint2*>(S.ids), 4, 2, nullptr, reinterpret_cast<int*>(S.aux), 2, e->work.ws};
       k_bucket_fill<<<g256, 256, 0, stream>>>(e->work, io, -1);
       tock(PB_K_FILL, j); tick(PB_K_SAMPLE, j);
       launch_sample(e, sg, io, stream, true);
-      if (e->sample_split) ++launches;
       tock(PB_K_SAMPLE, j); tick(PB_K_EMIT, j);
       k_emit<<<g128, 128, 0, stream>>>(e->mat, e->tab, S, e->work, e->emit_wave_order);
       tock(PB_K_EMIT, j);
@@ -2010,8 +2086,8 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
   int B = 300;
   for (int p = P_DARKBREM; p <= P_DARKMUONBREM; ++p) if (e->tab.map[p].grid) { B = e->tab.map[p].B; break; }
   e->mat.max_trials = (long long)std::min<double>((double)e->cfg.max_sweeps * (double)B, 4.0e9);
-  Stack S{sm->p0, sm->r0w, sm->pf, sm->rf, (uint2*)sm->key, (int4*)sm->meta, (int2*)sm->aux, sm->capacity};
-  Stack O{dk->p0, dk->r0w, dk->pf, dk->rf, (uint2*)dk->key, (int4*)dk->meta, (int2*)dk->aux, dk->capacity};
+  Stack S{sm->p0, sm->r0w, sm->pf, sm->rf, (int4*)sm->ids, (int2*)sm->aux, sm->capacity};
+  Stack O{dk->p0, dk->r0w, dk->pf, dk->rf, (int4*)dk->ids, (int2*)dk->aux, dk->capacity};
   long long ncap = std::max<long long>(2 * n_sm, 1);
   int rc = ensure_work(e, ncap);
   if (rc != PB_OK) return rc;
@@ -2043,11 +2119,10 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
     tick(PB_K_SCAN);
     k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
     tock(PB_K_SCAN); tick(PB_K_FILL);
-    SampleIO io{e->cand.pf, S.key, e->cand.slot, e->cand.ntr, 1, nullptr};
+    SampleIO io{e->cand.pf, reinterpret_cast<const uint2*>(S.ids), 4, 2, e->cand.slot, e->cand.ntr, 1, nullptr};
     k_bucket_fill<<<(unsigned)((n_cand + 255) / 256), 256, 0, stream>>>(e->work, io, n_cand);
     tock(PB_K_FILL); tick(PB_K_SAMPLE);
-    int sg = (int)std::min<long long>((long long)e->n_sm * PB_SAMPLE_MINB, (n_cand + 31) / 32 + 1);
-    launch_sample(e, sg, io, stream);
+    launch_sample(e, sample_grid(e, n_cand, false), io, stream);
     tock(PB_K_SAMPLE); tick(PB_K_EMIT);
     k_dark_emit<<<(unsigned)((n_cand + 127) / 128), 128, 0, stream>>>(e->mat, S, O, e->work, e->cand, n_cand);
     tock(PB_K_EMIT);
@@ -2111,9 +2186,9 @@ extern "C" int pb_draw_samples(pb_engine e, int process, const double* E, int64_
   PB_CUDA(e, cudaMemsetAsync(e->work.xs, 0, sizeof(double) * 4 * n, stream));
   k_prepare_draws<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->tab, e->work, e->cand, dkeys, dE, (int)n, process, lu_key, seed, first_id);
   k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
-  SampleIO io{e->cand.pf, dkeys, nullptr, e->cand.ntr, 1, nullptr};
+  SampleIO io{e->cand.pf, dkeys, 1, 0, nullptr, e->cand.ntr, 1, nullptr};
   k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, io, (int)n);
-  launch_sample(e, (int)std::min<long long>((long long)e->n_sm * PB_SAMPLE_MINB, (n + 31) / 32 + 1), io, stream);
+  launch_sample(e, sample_grid(e, n, false), io, stream);
   cudaError_t c = cudaMemcpyAsync(x_out, e->work.xs, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, stream);
   if (c == cudaSuccess && ntr_out) c = cudaMemcpyAsync(ntr_out, e->cand.ntr, sizeof(int) * n, cudaMemcpyDeviceToHost, stream);
   if (c == cudaSuccess) c = cudaStreamSynchronize(stream);
@@ -2146,7 +2221,7 @@ extern "C" int pb_detector_cut(pb_engine e, const pb_stack* st, int64_t first, i
   if (!e || !st || !z_det || n_det < 1 || n_det > MAX_DET || n < 0 || first < 0 || first + n > st->capacity) return PB_ERR_ARG;
   PB_CUDA(e, cudaSetDevice(e->device));
   cudaStream_t stream = (cudaStream_t)stream_;
-  Stack S{st->p0, st->r0w, st->pf, st->rf, (uint2*)st->key, (int4*)st->meta, (int2*)st->aux, st->capacity};
+  Stack S{st->p0, st->r0w, st->pf, st->rf, (int4*)st->ids, (int2*)st->aux, st->capacity};
   DetPlanes D{};
   D.n = n_det;
   for (int k = 0; k < n_det; ++k) D.z[k] = z_det[k];
@@ -2215,7 +2290,7 @@ extern "C" int pb_tally(pb_engine e, const pb_stack* st, int64_t first, int64_t 
   if (!e || !st || !tally || n < 0 || first < 0 || first + n > st->capacity) return PB_ERR_ARG;
   if (n == 0) return PB_OK;
   PB_CUDA(e, cudaSetDevice(e->device));
-  Stack S{st->p0, st->r0w, st->pf, st->rf, (uint2*)st->key, (int4*)st->meta, (int2*)st->aux, st->capacity};
+  Stack S{st->p0, st->r0w, st->pf, st->rf, (int4*)st->ids, (int2*)st->aux, st->capacity};
   int grid = (int)std::min<long long>((n + 255) / 256, (long long)e->n_sm * 3);
   cudaFuncSetAttribute(k_tally, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * PB_TALLY_SIZE * (int)sizeof(double));
   k_tally<<<grid, 256, 8 * PB_TALLY_SIZE * sizeof(double), (cudaStream_t)stream_>>>(S, first, n, tally);

@@ -290,8 +290,9 @@ __device__ __forceinline__ double ds_brem_fast(const Material& M, const SampleCo
   double d = s.b * (x[1] + x[2]);
   double dp = s.b * (x[1] - x[2]);
   double epp = ep - w;
+  // branch-free: the kinematic mask selects at the end, so that the T trials a lane evaluates per round stay one basic block
+  // (ILP); outside the mask the arithmetic below runs on garbage (possibly Inf / NaN) and is discarded
   bool ok = (Egmin < w) && (w < ep - ml) && (ml < epp) && (epp < ep) && (d > 0.0) && (dp > 0.0);
-  if (!ok) return 0.0;
   double cph = cospi(2.0 * x[3] - 1.0);           // cos((x4 - 1/2) 2 pi)
   double d2 = d * d, dp2 = dp * dp;
   double od = 1 + d2, odp = 1 + dp2;
@@ -303,7 +304,8 @@ __device__ __forceinline__ double ds_brem_fast(const Material& M, const SampleCo
   double io = fast_rcp(od * odp);
   double i1 = odp * io, i2 = od * io;             // 1/od, 1/odp
   double T = d2 * (i1 * i1) + dp2 * (i2 * i2) + (w * w) * (0.5 * s.c * iepp) * (d2 + dp2) * io - (epp * s.c + ep * iepp) * ddc * io;
-  return s.d * (epp * d * dp) * fast_rcp(w * den * den) * T;
+  double f = s.d * (epp * d * dp) * fast_rcp(w * den * den) * T;
+  return ok ? f : 0.0;
 }
 
 __device__ __forceinline__ SampleConst pairprod_const(const Material& M, double w) {
@@ -324,7 +326,6 @@ __device__ __forceinline__ double ds_pairprod_fast(const SampleConst& s, double 
   double dm = s.b * (x[1] - x[2]);
   double epm = w - epp;
   bool ok = (me < epm) && (epm < w) && (me < epp) && (epp < w) && (dm > 0.0) && (dp > 0.0);
-  if (!ok) return 0.0;
   double cph = cospi(2.0 * x[3]);
   double dp2 = dp * dp, dm2 = dm * dm;
   double op = 1.0 + dp2, om = 1.0 + dm2;
@@ -336,7 +337,8 @@ __device__ __forceinline__ double ds_pairprod_fast(const SampleConst& s, double 
   double io = fast_rcp(op * om);
   double i1 = om * io, i2 = op * io;
   double T = -dp2 * (i1 * i1) - dm2 * (i2 * i2) + (w * w) * (0.5 * ie) * (dp2 + dm2) * io + (epp * epp + epm * epm) * ie * ddc * io;
-  return s.d * (epp * epm * dp * dm) * fast_rcp(den * den) * T;
+  double f = s.d * (epp * epm * dp * dm) * fast_rcp(den * den) * T;
+  return ok ? f : 0.0;
 }
 
 // all_processes.py:625-742 (dsigma_compton_dCT); mV > 0 is DarkComp.

@@ -18,7 +18,7 @@ from . import _capi as capi
 from . import constants as K
 from . import tables as tb
 from .particle import Particle, meson_twobody_branchingratios
-from .shower import Shower, ShowerBatch, LinearTable
+from .shower import Shower, ShowerBatch, LinearTable, stack_struct, new_stack
 
 dark_process_codes = ["DarkBrem", "DarkAnn", "DarkComp", "TwoBody_BSMDecay", "DarkMuonBrem"]
 dimensionalities_dark = {"DarkComp": 1, "DarkBrem": 3, "DarkAnn": 1, "DarkMuonBrem": 3}
@@ -48,7 +48,7 @@ class DarkBatch:
     def to_host(self):
         if self._host is None:
             n = self.n
-            t = {k: v[:n].cpu().numpy() for k, v in self._t.items()}
+            t = {k: v[:n].cpu().numpy() for k, v in self._t.items() if k != "ids"}
             info = t["meta"][:, 2]
             self._host = dict(p0=t["p0"], r0=t["r0w"][:, :3], weight=t["r0w"][:, 3], parent=t["meta"][:, 1],
                               process=info & 0xFF, shower=t["meta"][:, 3], ntrials=t["aux"][:, 0],
@@ -164,22 +164,37 @@ class DarkShower(Shower):
     def _setup_path(self):
         return self._dict_dir + f"dark_setup_{self._target_material}_mV{tb.mv_tag(self._mV_estimator)}.npz"
 
+    def _setup_matches(self, path):
+        """The cached tables depend on the ACTUAL mV (annihilation / Compton thresholds and bound cross-sections) and on Zeff,
+        not only on (material, mV_estimator): the reference recomputes those parts on every construction
+        (dark_shower.py:254-275, 311-399).  A cache is used only if its recorded meta equals this object's."""
+        try:
+            meta = np.load(path)["meta"]
+        except Exception:
+            return False
+        want = (self._mV, self._mV_estimator, self._resonant_annihilation_energy, self._compton_threshold_energy, self.Zeff)
+        got = (meta[0], meta[1], meta[2], meta[3], meta[6])
+        return all(abs(a - b) <= 1e-12 * max(abs(a), abs(b), 1e-300) for a, b in zip(want, got))
+
     def _load_setup(self):
         path = self._setup_path()
-        if not os.path.exists(path):
-            # the reference writes its caches into dict_dir and fails on a read-only one (SURVEY Q-3); fall back to a
-            # per-user cache directory instead
-            alt = os.path.join(os.path.expanduser(os.environ.get("PETITE_B200_CACHE", "~/.cache/petite_b200")), os.path.basename(path))
-            if os.path.exists(alt):
-                path = alt
-            else:
-                from . import dark_setup
-                print("Weights not previously calculated, calculating now...")
-                try:
-                    path = dark_setup.build(self, path)
-                except OSError:
-                    os.makedirs(os.path.dirname(alt), exist_ok=True)
-                    path = dark_setup.build(self, alt)
+        cache_dir = os.path.expanduser(os.environ.get("PETITE_B200_CACHE", "~/.cache/petite_b200"))
+        exact = self._mV == self._mV_estimator and self.Zeff == 29.508
+        name = os.path.basename(path) if exact else os.path.basename(path)[:-4] + f"_m{self._mV:.9g}_Zeff{self.Zeff:.9g}.npz"
+        candidates = ([path] if exact else []) + [os.path.join(cache_dir, name)]
+        path = next((c for c in candidates if os.path.exists(c) and self._setup_matches(c)), None)
+        if path is None:
+            # the reference writes its caches into dict_dir and fails on a read-only one (SURVEY Q-3); tables for a
+            # non-default (mV, Zeff) and read-only dict_dirs go to a per-user cache directory instead
+            from . import dark_setup
+            print("Weights not previously calculated, calculating now...")
+            try:
+                if not exact:
+                    raise OSError("non-default mV / Zeff: per-user cache")
+                path = dark_setup.build(self, candidates[0])
+            except OSError:
+                os.makedirs(cache_dir, exist_ok=True)
+                path = dark_setup.build(self, candidates[-1])
         z = np.load(path)
         self._weights = {k: LinearTable(z[f"weights/{k}"][:, 0], z[f"weights/{k}"][:, 1]) for k in _WEIGHT_ORDER}
         self._brem_elec_numerical_weight, self._brem_positron_numerical_weight = self._weights["brem_elec"], self._weights["brem_positron"]
@@ -273,11 +288,7 @@ class DarkShower(Shower):
         torch = self._torch
         dev = torch.device("cuda", self._device)
         self._dark_stack = None
-        f64 = lambda: torch.empty((capacity, 4), dtype=torch.float64, device=dev)
-        self._dark_stack = {"p0": f64(), "r0w": f64(), "pf": f64(), "rf": f64(),
-                            "key": torch.empty((capacity, 2), dtype=torch.int32, device=dev),
-                            "meta": torch.empty((capacity, 4), dtype=torch.int32, device=dev),
-                            "aux": torch.zeros((capacity, 2), dtype=torch.int32, device=dev)}
+        self._dark_stack = new_stack(torch, dev, capacity)
         self._dark_capacity = capacity
 
     def generate_dark_showers(self, sm_batch):
@@ -290,11 +301,8 @@ class DarkShower(Shower):
             mask |= 1 << _CODE[p]
         self._ensure_dark_stack(2 * sm_batch.n + 1024)
         t = self._dark_stack
-        dk = capi.pb_stack(t["p0"].data_ptr(), t["r0w"].data_ptr(), t["pf"].data_ptr(), t["rf"].data_ptr(),
-                           t["key"].data_ptr(), t["meta"].data_ptr(), t["aux"].data_ptr(), self._dark_capacity)
-        ts = sm_batch._t
-        sm = capi.pb_stack(ts["p0"].data_ptr(), ts["r0w"].data_ptr(), ts["pf"].data_ptr(), ts["rf"].data_ptr(),
-                           ts["key"].data_ptr(), ts["meta"].data_ptr(), ts["aux"].data_ptr(), int(ts["p0"].shape[0]))
+        dk = stack_struct(t)
+        sm = stack_struct(sm_batch._t)
         cnt = capi.pb_counters()
         stream = self._torch.cuda.current_stream(self._device).cuda_stream
         capi.check(self._engine, capi.lib.pb_run_dark(self._engine, C.byref(sm), sm_batch.n, mask, C.byref(dk), C.byref(cnt),
@@ -308,9 +316,7 @@ class DarkShower(Shower):
         torch = self._torch
         if out is None:
             out = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=torch.device("cuda", self._device))
-        t = self._dark_stack
-        st = capi.pb_stack(t["p0"].data_ptr(), t["r0w"].data_ptr(), t["pf"].data_ptr(), t["rf"].data_ptr(),
-                           t["key"].data_ptr(), t["meta"].data_ptr(), t["aux"].data_ptr(), self._dark_capacity)
+        st = stack_struct(dark_batch._t)        # the batch's own stack (it may predate a regrow of this object's)
         stream = torch.cuda.current_stream(self._device).cuda_stream
         capi.check(self._engine, capi.lib.pb_tally(self._engine, C.byref(st), 0, dark_batch.n, C.c_void_p(out.data_ptr()),
                                                    C.c_void_p(stream)))

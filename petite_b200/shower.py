@@ -10,6 +10,7 @@ New, batched entry point: :meth:`Shower.generate_showers` steps many independent
 returns a :class:`ShowerBatch` (structure-of-arrays view of the device stack).
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -49,6 +50,21 @@ class LinearTable:
         return out if out.ndim else np.float64(out)
 
 
+def stack_struct(t):
+    """``pb_stack`` over a dict of stack tensors (capacity = their length)."""
+    return capi.pb_stack(t["p0"].data_ptr(), t["r0w"].data_ptr(), t["pf"].data_ptr(), t["rf"].data_ptr(),
+                         t["ids"].data_ptr(), t["aux"].data_ptr(), int(t["p0"].shape[0]))
+
+
+def new_stack(torch, dev, capacity):
+    """Stack tensors for ``capacity`` records.  ``meta`` (pid, parent, info, shower) and ``key`` are views into the packed
+    32-byte ``ids`` records (include/petite_b200.h)."""
+    f64 = lambda: torch.empty((capacity, 4), dtype=torch.float64, device=dev)
+    ids = torch.empty((capacity, 8), dtype=torch.int32, device=dev)
+    return {"p0": f64(), "r0w": f64(), "pf": f64(), "rf": f64(), "ids": ids, "meta": ids[:, 0:4], "key": ids[:, 4:6],
+            "aux": torch.zeros((capacity, 2), dtype=torch.int32, device=dev)}
+
+
 class ShowerBatch:
     """Result of a batched run: the filled part of the particle stack, still on the GPU (torch tensors).
 
@@ -74,7 +90,7 @@ class ShowerBatch:
     def to_host(self):
         if self._host is None:
             n = self.n
-            t = {k: v[:n].cpu().numpy() for k, v in self._t.items()}
+            t = {k: v[:n].cpu().numpy() for k, v in self._t.items() if k != "ids"}
             meta = t["meta"]
             info = meta[:, 2]
             self._host = dict(
@@ -171,7 +187,10 @@ class Shower:
             raise RuntimeError("petite_b200 needs a CUDA device: the shower path has no CPU fallback")
         self._torch = torch
         self._device = torch.cuda.current_device() if device is None else int(device)
-        self._seed = 0 if seed is None else int(seed)
+        # seed=None: fresh entropy, as the reference leaves NumPy's global generator unseeded (shower.py:140-142); the
+        # value actually used is exposed as ``self.seed`` so that a run can be reproduced
+        self._seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.seed = self._seed
         self._next_shower_id = 0
         self.set_dict_dir(dict_dir)
         self.set_target_material(target_material)
@@ -382,15 +401,7 @@ class Shower:
         torch = self._torch
         dev = torch.device("cuda", self._device)
         self._stack_tensors = None   # release before allocating the bigger one
-        self._stack_tensors = {
-            "p0": torch.empty((capacity, 4), dtype=torch.float64, device=dev),
-            "r0w": torch.empty((capacity, 4), dtype=torch.float64, device=dev),
-            "pf": torch.empty((capacity, 4), dtype=torch.float64, device=dev),
-            "rf": torch.empty((capacity, 4), dtype=torch.float64, device=dev),
-            "key": torch.empty((capacity, 2), dtype=torch.int32, device=dev),
-            "meta": torch.empty((capacity, 4), dtype=torch.int32, device=dev),
-            "aux": torch.zeros((capacity, 2), dtype=torch.int32, device=dev),
-        }
+        self._stack_tensors = new_stack(torch, dev, capacity)
         self._stack_capacity = capacity
 
     def estimate_records(self, energies, pids):
@@ -436,9 +447,7 @@ class Shower:
         return p, r, w, m, pid, fl
 
     def _stack_struct(self):
-        t = self._stack_tensors
-        return capi.pb_stack(t["p0"].data_ptr(), t["r0w"].data_ptr(), t["pf"].data_ptr(), t["rf"].data_ptr(),
-                             t["key"].data_ptr(), t["meta"].data_ptr(), t["aux"].data_ptr(), self._stack_capacity)
+        return stack_struct(self._stack_tensors)
 
     def run_arrays(self, p, r, w, m, pid, flags, GlobalMS=True, capacity=None, first_shower_id=None):
         """Lowest-level entry: SoA primaries -> :class:`ShowerBatch` (one ``pb_run_showers`` call).
@@ -446,6 +455,9 @@ class Shower:
         The six arrays are either all host NumPy arrays (copied to the GPU inside the call) or all torch CUDA
         tensors already resident in HBM (float64 / int32, contiguous)."""
         n = len(pid)
+        if n == 0:
+            self._ensure_stack(1024)
+            return ShowerBatch(self, self._stack_tensors, 0, capi.pb_counters().as_dict(), 0, first_shower_id or 0)
         on_device = not isinstance(p, np.ndarray)
         if on_device:
             arrs = [p, r, w, m, pid, flags]
@@ -480,7 +492,7 @@ class Shower:
             # pilot estimate too small (heavy-tailed batch): one retry with twice the room; showers depend only on
             # (seed, shower id), so the rerun reproduces the same particles
             self._pilot = None
-            return self.run_arrays(p, r, w, m, pid, flags, GlobalMS=GlobalMS, capacity=2 * self._stack_capacity,
+            return self.run_arrays(p, r, w, m, pid, flags, GlobalMS=GlobalMS, capacity=2 * int(capacity),
                                    first_shower_id=first_shower_id)
         capi.check(self._engine, rc)
         return ShowerBatch(self, t, cnt.n_particles, cnt.as_dict(), n, first_shower_id)
@@ -592,7 +604,7 @@ class Shower:
         torch = self._torch
         if out is None:
             out = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=torch.device("cuda", self._device))
-        st = self._stack_struct()
+        st = stack_struct(batch._t)             # the batch's own stack (it may predate a regrow of this object's)
         stream = torch.cuda.current_stream(self._device).cuda_stream
         capi.check(self._engine, capi.lib.pb_tally(self._engine, C.byref(st), 0, batch.n, C.c_void_p(out.data_ptr()),
                                                    C.c_void_p(stream)))
@@ -708,6 +720,7 @@ class Shower:
         t = self._stack_tensors
         for name, arr in (("p0", p0), ("pf", pf), ("r0w", r0w), ("rf", rf), ("meta", meta), ("key", key)):
             t[name][:n].copy_(torch.from_numpy(np.ascontiguousarray(arr)))
+        t["ids"][:n, 6:8].copy_(torch.from_numpy(np.ascontiguousarray(r0w[:, 3]).view(np.int32).reshape(n, 2)))   # packed weight
         t["aux"][:n].zero_()
         b = ShowerBatch(self, t, n, {}, 1, 0)
         b.reference_order = lambda: (np.arange(n), np.array([0, n]))      # the list IS the reference order

@@ -224,7 +224,7 @@ def load_dark_drate(dict_dir, mV, material):
         if mV in d and material in d[mV]:
             out = {}
             for name, tab in d[mV][material].items():
-                keys = list(tab.keys())
+                keys = sorted(tab.keys(), key=float)      # k_dark_prepare binary-searches the energies: ascending order
                 out[name] = (np.array([float(k) for k in keys]),
                              np.stack([np.asarray(tab[k], dtype=np.float64) for k in keys]))
             return out

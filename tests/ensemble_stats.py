@@ -23,6 +23,14 @@ CONFIGS = {
     # (~300 trials per emission, 6.6e3 emissions per shower) is too slow for a fixture and is covered by the replay tests instead
     "c5_mu_lead": dict(material="lead", pid=13, E0=100.0, mass=0.1056583755, E_min=0.010, seed=20261017, n_oracle=160, mV=None),
 }
+# Ensembles made by the UNMODIFIED reference in stream mode (tests/golden/make_ensemble_ref.py -> ensemble_ref.npz); config 5
+# includes its dark pass (DarkMuonBrem first, as BASELINE.json lists the active processes)
+REF_CONFIGS = {
+    "c2_gamma_lead": dict(CONFIGS["c2_gamma_lead"], n_ref=500),
+    "c1_e_graphite": dict(CONFIGS["c1_e_graphite"], n_ref=500),
+    "c3_dark_graphite": dict(CONFIGS["c3_dark_graphite"], n_ref=200, active=["DarkBrem", "DarkAnn", "DarkComp"]),
+    "c5_mu_lead_dark": dict(CONFIGS["c5_mu_lead"], n_ref=200, mV=0.030, active=["DarkMuonBrem", "DarkBrem", "DarkAnn", "DarkComp"]),
+}
 SPEC_EDGES = np.logspace(-2, 1, 9)       # 8 bins, 10 MeV .. 10 GeV
 
 

@@ -14,6 +14,7 @@ Everything recorded here is computed by the reference's own functions:
     particle.npz     Particle.lose_energy / rotation_matrix / two_body_decay
     nsigma.npz       Shower._NSigma*, get_mfp, thresholds for graphite and lead
     showers.npz      whole generate_shower runs (stream mode, seeded) - multiplicities, ids, four-vectors
+    dark_kinematics.npz  l_to_lV_fourvecs / compton_fourvecs_boundelectron / radiative_return_fourvecs of kinematics.py
 """
 import os
 import pickle
@@ -349,6 +350,52 @@ def golden_dark(rng):
     np.savez_compressed(os.path.join(HERE, "dark.npz"), **out)
 
 
+def golden_dark_kinematics(rng):
+    """The three dark-vector kinematics (kinematics.py:43-68, 134-183, 267-299) at points drawn through the shipped dark maps;
+    rows = [E, mV, x[4], u1, u2, Pe, cos(theta_e)] -> V four-vector in the parent frame.  The azimuth uniforms the functions
+    draw from numpy's global stream are recorded by re-seeding (np.random.uniform(0, 2 pi) = 2 pi * random())."""
+    out = {}
+    for mV in (0.003, 0.03):
+        from petite_b200.tables import mv_tag
+        dk = np.load(DATA + f"dark_maps_mV{mv_tag(mV)}.npz")
+        for P, pid, mass in (("DarkBrem", 11, m_electron), ("DarkMuonBrem", 13, m_muon), ("DarkAnn", -11, m_electron), ("DarkComp", 22, 0.0)):
+            E, ninc, G = dk[f"{P}/E"], dk[f"{P}/ninc"], dk[f"{P}/grid"]
+            inp, res = [], []
+            for ie in (10, 40, 70, 99):
+                grid = split_grid(G[ie], ninc)
+                x, _ = map_points(grid, rng.random((24, len(grid))))
+                for xi in x:
+                    Einc = float(E[ie]) * float(rng.uniform(0.9, 1.0))
+                    p = Particle([Einc, 0, 0, np.sqrt(Einc ** 2 - mass ** 2)], [0, 0, 0], {"PID": pid, "mass": mass})
+                    seed = int(rng.integers(1 << 30))
+                    np.random.seed(seed)
+                    u1, u2 = np.random.random(), np.random.random()
+                    np.random.seed(seed)
+                    Pe, cte = 0.0, 0.0
+                    if P in ("DarkBrem", "DarkMuonBrem"):
+                        if xi[0] * Einc <= mV:
+                            continue
+                        v = kin.l_to_lV_fourvecs(p, xi, mV=mV)[1]
+                    elif P == "DarkAnn":
+                        if 2 * m_electron * (Einc + m_electron) <= mV ** 2:
+                            continue
+                        v = kin.radiative_return_fourvecs(p, xi, mV=mV)[1]
+                    else:
+                        Pe, cte = float(1e-3 * rng.random()), float(rng.uniform(-1, 1))
+                        ss = m_electron ** 2 + 2 * Einc * (np.sqrt(m_electron ** 2 + Pe ** 2) - cte * Pe)
+                        if (ss - mV ** 2 + m_electron ** 2) / (2 * np.sqrt(ss)) < m_electron:
+                            continue
+                        v = kin.compton_fourvecs_boundelectron(p, xi, mV=mV, Pe=Pe, cte=cte)[1]
+                    if not np.all(np.isfinite(np.asarray(v, dtype=float))):
+                        continue
+                    inp.append([Einc, mV] + list(np.pad(xi, (0, 4 - len(xi)))) + [u1, u2, Pe, cte])
+                    res.append(list(np.asarray(v, dtype=float)))
+            out[f"{mv_tag(mV)}/{P}/in"] = np.array(inp, dtype=float)
+            out[f"{mv_tag(mV)}/{P}/out"] = np.array(res, dtype=float)
+            print("dark kinematics", mV, P, len(inp))
+    np.savez_compressed(os.path.join(HERE, "dark_kinematics.npz"), **out)
+
+
 def golden_detector(rng):
     """shower.detector_cut (shower.py:825-864) on a random particle list."""
     from PETITE.shower import detector_cut
@@ -377,6 +424,9 @@ if __name__ == "__main__":
     if "--detector-only" in sys.argv:
         golden_detector(rng)
         sys.exit(0)
+    if "--darkkin-only" in sys.argv:
+        golden_dark_kinematics(np.random.default_rng(20261018))
+        sys.exit(0)
     if "--dark-only" in sys.argv:
         golden_dark(rng)
         sys.exit(0)
@@ -388,6 +438,7 @@ if __name__ == "__main__":
     golden_showers()
     golden_dark(rng)
     golden_detector(rng)
+    golden_dark_kinematics(np.random.default_rng(20261018))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -218,3 +218,127 @@ def test_multiple_scattering_vs_reference_golden(golden, material):
     tol = 1e-12 * pn + 4 * 2.3e-16 * gamma2 * dtheta * pn
     assert np.all(np.max(np.abs(got - want), axis=1) <= tol)
     assert np.array_equal(got[:, 0], want[:, 0])                                           # energy untouched
+
+
+@pytest.mark.parametrize("material", ["graphite", "lead"])
+def test_mcs_fast_vs_reference_golden(golden, material):
+    """The folded multiple-scattering form the sub-step loop runs (mcs_fast: 2 divisions, constant-memory log / sincos kernels,
+    branch-free reciprocals) against moliere.get_scattered_momentum_fast of the unmodified reference - same golden vectors and
+    the same condition-number bound as the plain form above (the reference's own value carries the gamma^2-amplified rounding
+    of m beta / sqrt(1 - beta^2); mcs_fast itself never forms that difference)."""
+    from petite_b200 import _capi as capi
+    g = golden("mcs")
+    sh = shower(material)
+    Z = 6 if material == "graphite" else 82
+    sel = g["inp"][:, 10] == Z
+    a, want = g["inp"][sel][:, :10], g["out"][sel]
+    got = probe(sh, capi.PROBE_MCS_FAST, 0, a, 4)
+    plain = probe(sh, capi.PROBE_MCS, 0, a, 4)
+    pn = np.linalg.norm(a[:, 1:4], axis=1)
+    gamma2 = (a[:, 0] / a[:, 5]) ** 2
+    dtheta = np.linalg.norm(np.cross(want[:, 1:], a[:, 1:4]), axis=1) / pn ** 2
+    tol = 1e-12 * pn + 4 * 2.3e-16 * gamma2 * dtheta * pn
+    assert np.all(np.max(np.abs(got - want), axis=1) <= tol)
+    assert np.array_equal(got[:, 0], want[:, 0])
+    # against the plain GPU form (no gamma^2 term on either side): re-association only
+    worst = float(np.max(np.max(np.abs(got - plain), axis=1) / pn))
+    print("mcs_fast vs mcs_apply, max |dp| / |p| =", worst)
+    assert worst < 5e-14
+
+
+@pytest.mark.parametrize("mV", [0.003, 0.03])
+def test_dark_kinematics_vs_reference_golden(golden, mV):
+    """kin_darkbrem_V / kin_darkann_V / kin_compton_bound_V against l_to_lV_fourvecs, radiative_return_fourvecs and
+    compton_fourvecs_boundelectron of the unmodified reference (kinematics.py:43-68, 267-299, 134-183).  Bound: 1e-12 of the
+    vector's largest component; the radiative-return x1 = 1 - (u umax)^(2 / beta) (2 / beta ~ 40) turns a 2-ulp difference
+    between libdevice's and libm's pow into 4e-16 / x1, the bound-electron boost 1 / sqrt(1 - b0^2) amplifies by gamma0^2."""
+    from petite_b200 import _capi as capi
+    from petite_b200.tables import mv_tag
+    from tests.test_gpu_dark import dark_shower
+    g = golden("dark_kinematics")
+    ds = dark_shower("graphite", mV)
+    me, alpha = 510.998950e-6, 1.0 / 137.035999
+    for P, code in (("DarkBrem", 8), ("DarkMuonBrem", 11), ("DarkAnn", 9), ("DarkComp", 10)):
+        a, want = g[f"{mv_tag(mV)}/{P}/in"], g[f"{mv_tag(mV)}/{P}/out"]
+        got = probe(ds, capi.PROBE_DARKKIN, code, a, 4)
+        scale = np.max(np.abs(want), axis=1)
+        err = np.max(np.abs(got - want), axis=1) / scale
+        tol = np.full(len(a), 1e-12)
+        if P == "DarkAnn":
+            s = 2 * me * (me + a[:, 0])
+            beta = (2 * alpha / np.pi) * (np.log(s / me ** 2) - 1)
+            x1 = 1 - (a[:, 2] * (1 - mV ** 2 / s) ** (beta / 2)) ** (2 / beta)
+            tol = tol + 2e-15 / x1
+        if P == "DarkComp":
+            Eg, Pe, cte = a[:, 0], a[:, 8], a[:, 9]
+            b0 = np.sqrt(Eg ** 2 + 2 * cte * Eg * Pe + Pe ** 2) / (Eg + np.sqrt(me ** 2 + Pe ** 2))
+            tol = tol + 4 * 2.3e-16 / (1 - b0 ** 2)
+        print(P, mV, "max err / tol", float(np.max(err / tol)), "max err", float(np.max(err)))
+        assert np.all(err <= tol), (P, float(np.max(err / tol)))
+
+
+@pytest.mark.parametrize("material", ["graphite", "lead"])
+def test_substep_vs_oracle(material):
+    """ONE iteration of the dE/dx + multiple-scattering loop exactly as k_loop runs it (substep(): per-species summed n*sigma
+    table with a hint, fast_rcp, hot_exp_neg_step, carried |p|, mcs_fast) against the oracle's statement of
+    shower.py:559-581 (libm, term-by-term n*sigma sums, lose_energy + get_scattered_momentum_fast) on 24 000 random tracks:
+    the loop decision (hard scatter / below threshold / step) must be IDENTICAL, the state within the multiple-scattering
+    condition bound.  Reports the margin of the closest hard-scatter decision."""
+    import math
+    from petite_b200 import _capi as capi
+    from oracle.shower import OracleShower
+    from oracle.draws import CounterDraws
+    from oracle import physics as phy, consts as OC
+    sh = shower(material)
+    o = OracleShower(None, material, 0.010, rng="counter")
+    rng = np.random.default_rng(77)
+    n = 8000
+    rows, exp = [], []
+    for pid in (11, -11, 13):
+        m = OC.MASS[pid]
+        pmin = max(o.min_calc[pid], o.min_energy, m)
+        E = np.where(rng.random(n) < 0.05, pmin * rng.uniform(0.5, 1.0, n), pmin * 10 ** rng.uniform(0, np.log10(100.0 / pmin), n))
+        if pid == 13:
+            E = np.maximum(E, m * 1.0001)
+        d = rng.normal(size=(n, 3))
+        small = rng.random(n) < 0.5                      # shower particles are collimated along z
+        d[small, :2] *= 1e-3
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        r = rng.normal(size=(n, 3))
+        keys = rng.integers(0, 2 ** 32, size=(n, 2))
+        it = rng.integers(0, 60, n)
+        for k in range(n):
+            pn = math.sqrt(max(E[k] ** 2 - m ** 2, 0.0))
+            p4 = [float(E[k]), pn * d[k, 0], pn * d[k, 1], pn * d[k, 2]]
+            rows.append([pid] + p4 + list(r[k]) + [float(keys[k, 0]), float(keys[k, 1]), float(it[k]), 1.0])
+            dr = CounterDraws((int(keys[k, 0]), int(keys[k, 1])))
+            if not p4[0] >= pmin:
+                exp.append([1.0] + p4 + list(r[k]) + [0.0, 0.0, 1.0])
+                continue
+            mfp = o.get_mfp(pid, p4[0])
+            u_hard, u_dz = dr.substep(int(it[k]))
+            dz = mfp / (6 + 14 * u_dz)
+            margin = abs(u_hard - math.exp(-dz / mfp))
+            if u_hard > math.exp(-dz / mfp):
+                exp.append([1.0] + p4 + list(r[k]) + [dz, margin, 1.0])
+                continue
+            pf = phy.lose_energy(p4, m, o.dEdx * 0.1 * dz)
+            pnf = phy.norm3(pf[1:])
+            rf = [r[k, j] + pf[1 + j] / pnf * dz for j in range(3)] if pnf > 0 else list(r[k])
+            pf = o._mcs(pf, dz, m, dr, int(it[k]))
+            exp.append([0.0] + list(pf) + rf + [dz, margin, (p4[0] / m) ** 2])
+    a, exp = np.array(rows), np.array(exp)
+    got = probe(sh, capi.PROBE_SUBSTEP, 0, a, 10)
+    flips = int(np.sum(got[:, 0] != exp[:, 0]))
+    live = exp[:, 9] > 0
+    print(material, "sub-steps", len(a), "decision flips", flips, "closest hard-scatter margin", float(np.min(exp[live, 9])))
+    assert flips == 0
+    st = exp[:, 0] == 0
+    pn = np.linalg.norm(exp[st, 2:5], axis=1)
+    assert np.all(np.abs(got[st, 1] - exp[st, 1]) <= 1e-13 * exp[st, 1])                       # energy
+    assert np.all(np.abs(got[st, 8] - exp[st, 8]) <= 1e-13 * exp[st, 8])                       # delta_z
+    assert np.all(np.max(np.abs(got[st, 5:8] - exp[st, 5:8]), axis=1) <= 1e-13 * np.maximum(1.0, np.max(np.abs(exp[st, 5:8]), axis=1)))
+    dth = np.linalg.norm(np.cross(got[st, 2:5], a[st, 2:5]), axis=1) / np.maximum(pn, 1e-300) ** 2
+    tol = 1e-12 * pn + 4 * 2.3e-16 * exp[st, 10] * dth * pn
+    assert np.all(np.max(np.abs(got[st, 2:5] - exp[st, 2:5]), axis=1) <= tol + 1e-300)
+    assert np.array_equal(got[st, 9], a[st, 10] + 1)

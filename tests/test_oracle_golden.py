@@ -134,3 +134,23 @@ def test_stream_mode_shower_equals_reference(golden, case):
         scale = np.maximum(np.max(np.abs(want), axis=1, keepdims=True), 1e-300)
         # ulp-level differences are amplified by the reference's own ill-conditioned acos(pz/|p|) (particle.py:181)
         assert np.max(np.abs(arr - want) / scale) < 1e-6, name
+
+
+def test_dark_kinematics(golden):
+    """oracle.physics kin_darkbrem / kin_darkann / kin_compton_bound against l_to_lV_fourvecs, radiative_return_fourvecs and
+    compton_fourvecs_boundelectron of the unmodified reference (tests/golden/make_golden.py golden_dark_kinematics)."""
+    g = golden("dark_kinematics")
+    n = 0
+    for key in [k for k in g.files if k.endswith("/in")]:
+        tag, P, _ = key.split("/")
+        for a, want in zip(g[key], g[f"{tag}/{P}/out"]):
+            E, mV, x, u1, u2, Pe, cte = a[0], a[1], a[2:6], a[6], a[7], a[8], a[9]
+            if P in ("DarkBrem", "DarkMuonBrem"):
+                v = phy.kin_darkbrem(E, m_muon if "Muon" in P else m_electron, x, u1, mV)[1]
+            elif P == "DarkAnn":
+                v = phy.kin_darkann(E, x, mV)[1]
+            else:
+                v = phy.kin_compton_bound(E, x, mV, Pe, cte, u1, u2)[1]
+            assert np.all(np.abs(np.array(v) - want) <= 1e-12 * np.max(np.abs(want))), (P, a, v, want)
+            n += 1
+    assert n > 600

@@ -1,14 +1,14 @@
 """Tuning + safety sweep of the accept/reject sampler (one process, one engine per configuration; the knobs are read from
-the environment by pb_create).  A configuration is "stream,G,tokens,chunk": only G (PB_SAMPLE_G, lanes per sample) still
-exists in the tree - the other three drove the streaming sampler of commit a5882b6, whose sweeps are kept in
-profiles/r01f/sweep_stream_v*.log.  For every configuration
+the environment by pb_create).  A configuration is "G,T,generic": G = lanes per sample (PB_SAMPLE_G), T = trials per lane
+and round (PB_SAMPLE_T), generic = 1 runs the SM pass through the kernel that also carries the dark integrands
+(PB_SAMPLE_GENERIC).  For every configuration
 
   1. correctness: 2 000 showers of config 2 must give the SAME records and trial counts as the first configuration - the
      draws are counter-based, so any schedule has to reproduce them bit for bit;
   2. timing: config 2 at 1e5 primaries, CUDA events, per-step and per-kernel (SWEEP_PROFILING=1: the two loop kernels,
      2: every kernel).
 
-    python tools/sweep_sampler.py [n_timing] [stream,G,tokens,chunk ...] > gpurun_out/sweep_sampler.log
+    python tools/sweep_sampler.py [n_timing] [G,T,generic ...] > gpurun_out/sweep_sampler.log
     PETITE_B200_LIB=variants/libpb_X.so python tools/sweep_sampler.py ...      # compile-time variants: tools/sweep_variants.sh
 """
 import os, sys, json
@@ -18,7 +18,7 @@ from petite_b200.shower import Shower
 
 DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "data", "")
 N_T = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
-CONFIGS = [(0, g, 0, 0) for g in (8, 4, 2, 16)]
+CONFIGS = [(4, 1, 1), (4, 1, 0), (2, 2, 0), (1, 2, 0), (4, 2, 0)]
 if len(sys.argv) > 2:
     CONFIGS = [tuple(int(v) for v in c.split(",")) for c in sys.argv[2:]]
 
@@ -40,9 +40,8 @@ def digest(sh):
 
 dev = torch.device("cuda", 0)
 ref = None
-for stream, G, tok, chunk in CONFIGS:
-    os.environ["PB_SAMPLE_STREAM"], os.environ["PB_SAMPLE_G"], os.environ["PB_SAMPLE_TOKENS"] = str(stream), str(G), str(tok)
-    os.environ["PB_SAMPLE_CHUNK"] = str(chunk)
+for G, T, generic in CONFIGS:
+    os.environ["PB_SAMPLE_G"], os.environ["PB_SAMPLE_T"], os.environ["PB_SAMPLE_GENERIC"] = str(G), str(T), str(generic)
     sh = Shower(DATA, "lead", 0.010, seed=20261017)
     d = digest(sh)
     if ref is None:
@@ -62,7 +61,7 @@ for stream, G, tok, chunk in CONFIGS:
         e1.record(); torch.cuda.synchronize()
         pr = sh.get_profile()
         ms.append(e0.elapsed_time(e1)); ks.append(pr["ms"]["k_sample"]); kl.append(pr["ms"]["k_loop"])
-    print(json.dumps({"stream": stream, "G": G, "tokens": tok, "chunk": chunk, "same_as_reference": bool(same), "records": d[0]["n_particles"],
+    print(json.dumps({"G": G, "T": T, "generic": generic, "lib": os.path.basename(os.environ.get("PETITE_B200_LIB", "default")), "same_as_reference": bool(same), "records": d[0]["n_particles"],
                       "trials": d[0]["n_trials"], "step_ms": round(min(ms), 2), "k_sample_ms": round(min(ks), 2),
                       "k_loop_ms": round(min(kl), 2), "other": {k: round(v, 2) for k, v in pr["ms"].items() if v and k not in ("k_sample", "k_loop")}, "showers_per_s": round(N_T / min(ms) * 1e3)}), flush=True)
     del sh, b, cal, devp
