@@ -235,11 +235,29 @@ enum pb_probe {
   PB_PROBE_SUBSTEP = 8,  /* ONE iteration of the dE/dx + MCS loop exactly as k_loop runs it (shower.py:559-581).
                             in: n x 12: pid, E, px, py, pz, x, y, z, key0, key1, sub-step index, multiple scattering on/off;
                             out: n x 10: loop ended (1) / sub-step applied (0), E, px, py, pz, x, y, z, delta_z, next index */
-  PB_PROBE_DARKKIN = 9   /* dark-vector four-momentum in the parent frame (kinematics.py:43-68, 134-183, 267-299); process =
+  PB_PROBE_DARKKIN = 9,  /* dark-vector four-momentum in the parent frame (kinematics.py:43-68, 134-183, 267-299); process =
                             DarkBrem / DarkMuonBrem / DarkAnn / DarkComp.  in: n x 10: E, mV, x[4], u1, u2, Pe, cos(theta_e);
                             out: n x 4 */
+  PB_PROBE_PROPAGATE = 10 /* propagate_particle (shower.py:509-601) of single particles with the engine's draw protocol.
+                            in: n x 12: pid, E, px, py, pz, x, y, z, mass, key0, key1, multiple scattering on/off;
+                            out: n x 9: pf[4], rf[3], sub-steps, 1 if propagated (0: below threshold, untouched) */
 };
 int pb_probe(pb_engine e, int what, int process, const double* in, int64_t n, int in_stride, double* out, int out_stride);
+
+/* Replay (parity mode): n independent particle-steps - propagate_particle (shower.py:509-601), the process choice (:665-698),
+ * draw_sample's accept/reject loop (:451-459), kinematics and rotation (:467-507) - run by the wave kernels' own device
+ * functions, with every random number taken from a TAPE recorded from a reference run instead of the Philox protocol.
+ * The tape of step i is tape[tape_off[i] .. tape_off[i+1]) and holds, in the reference's consumption order:
+ *   charged: per loop iteration  random(), uniform(6, 20) [, sign, z1, z2, uniform(0, 2 pi) / 2 pi  if a sub-step was applied
+ *            with multiple scattering on];  then the final step  random() [, sign, z1, z2, u_phi];
+ *   photon:  random() (free path);
+ *   then the process choice uniform, then per tested trial  y_0 .. y_{dim-1}, u_accept,  then the kinematics azimuth uniform
+ *   (two uniforms for a short-lived decay instead of all of the above).
+ * particles [host]: n x 10 doubles: pid, E, px, py, pz, x, y, z, mass, flags (1 = multiple scattering on, 2 = short-lived).
+ * out [host]: n x 32 doubles: 0 status (0 ok, 1 tape ran out, 2 tape not used up, 3 no sample), 1 sub-steps, 2 process code,
+ *   3 trials, 4-7 pf, 8-10 rf, 11 kept daughters (bit 0 / bit 1), 12 pid_a, 13-16 p_a, 17 pid_b, 18-21 p_b, 22-25 sampled x,
+ *   26 tape entries consumed, 27 weight factor, 28 propagated (1) / below threshold (0). */
+int pb_replay(pb_engine e, int64_t n, const double* particles, const double* tape, const int64_t* tape_off, double* out);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,7 @@ SIGNATURES = {
     "pb_get_profile": (C.c_int, [pb_engine, C.POINTER(pb_profile)]),
     "pb_measure_fp64_peak": (C.c_int, [pb_engine, c_double_p]),
     "pb_probe": (C.c_int, [pb_engine, C.c_int, C.c_int, c_double_p, C.c_int64, C.c_int, c_double_p, C.c_int]),
+    "pb_replay": (C.c_int, [pb_engine, C.c_int64, c_double_p, c_double_p, C.POINTER(C.c_int64), c_double_p]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(lib, _name)
@@ -99,7 +100,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 PB_OK, PB_ERR_CUDA, PB_ERR_ARG, PB_ERR_CAPACITY, PB_ERR_STATE, PB_ERR_NO_SAMPLE = 0, -1, -2, -3, -4, -5
 PB_FLAG_SHORT_LIVED, PB_FLAG_NO_SAMPLE = 1, 2
-PROBE_DSIGMA, PROBE_NSIGMA, PROBE_MAP, PROBE_MCS, PROBE_KIN, PROBE_PHILOX, PROBE_HOTMATH, PROBE_MCS_FAST, PROBE_SUBSTEP, PROBE_DARKKIN = range(10)
+PROBE_DSIGMA, PROBE_NSIGMA, PROBE_MAP, PROBE_MCS, PROBE_KIN, PROBE_PHILOX, PROBE_HOTMATH, PROBE_MCS_FAST, PROBE_SUBSTEP, PROBE_DARKKIN, PROBE_PROPAGATE = range(11)
 
 
 class EngineError(RuntimeError):

@@ -44,7 +44,7 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #define PB_SAMPLE_MINB_T 3               // kernels evaluating T > 1 trials per lane and round trade occupancy for ILP
 #endif
 #ifndef PB_SAMPLE_MINB_SM_T
-#define PB_SAMPLE_MINB_SM_T 3
+#define PB_SAMPLE_MINB_SM_T 5            // T = 2: 100 registers; measured (4, 2): minb 3 / 4 / 5 -> 62.5 / 57.3 / 57.0 ms per step, (4, 1): 62.3
 #endif
 #ifndef PB_FIN_MINB
 #define PB_FIN_MINB 8                    // 64 registers, 8 CTAs per SM: measured 17.8 -> 15.3 ms per step (10: 15.7, 12: 16.2, uncapped 94 registers: 17.8) although it spills 92 B
@@ -66,7 +66,10 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #define PB_SAMPLE_G_DEFAULT 4
 #endif
 #ifndef PB_SAMPLE_T_DEFAULT
-#define PB_SAMPLE_T_DEFAULT 1
+#define PB_SAMPLE_T_DEFAULT 2            // SM pass: two trials per lane and round (ILP)
+#endif
+#ifndef PB_SAMPLE_T_DARK_DEFAULT
+#define PB_SAMPLE_T_DARK_DEFAULT 1       // generic kernel (dark pass, stand-alone sampling)
 #endif
 constexpr int TILE = PB_TILE;               // samples per tile
 constexpr int SAMPLE_THREADS = PB_SAMPLE_THREADS;
@@ -134,6 +137,7 @@ struct WaveState {
   int status;                // 0 running, 1 finished (empty wave), 2 stack capacity exhausted, 3 scratch too small (host grows it)
   int waves, max_wave;
   int work_cap, order_cap;   // capacities of the per-wave scratch / of each index list
+  int iters, pad;            // k_wave_begin calls of this run (= wave-kernel sequences launched, the last ones empty)
 };
 
 struct Work {            // per-wave scratch, sized to the widest wave seen so far
@@ -255,22 +259,51 @@ struct Track {
 
 // Track set-up computed where the particle is created (k_emit / k_init_primaries, all lanes busy) instead of at refill
 // time inside k_loop (3 of 32 lanes busy): |p| and the species-table hint, parked in the record's not-yet-used rf slot.
-__device__ __forceinline__ void store_track_setup(const Tables& T, Stack& S, long long slot, int pid, double E, double px,
-                                                  double py, double pz) {
+__device__ __forceinline__ void store_track_setup(const Material& M, const Tables& T, Stack& S, long long slot, int pid, double mass,
+                                                  double E, double px, double py, double pz) {
   int h = nsigma_locate(T.sp[species_index(pid)], E);
+  double pn = norm3_nofma(px, py, pz);
+  double pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), mass);           // shower.py:532-533
   double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * slot);
-  rfp[0] = make_double2(norm3_nofma(px, py, pz), __hiloint2double(0, h));
-  rfp[1] = make_double2(0.0, 0.0);
+  rfp[0] = make_double2(pn, __hiloint2double(0, h));
+  rfp[1] = make_double2(pmin, 1.0 / pn);
 }
+
+// ---- draw sources.  Every decision function below takes its random numbers from a "draw source": PhiloxDraws is the engine's
+// protocol (each draw a pure function of (particle key, index, stream)); TapeDraws (replay mode, pb_replay) hands out
+// the numbers a REFERENCE run consumed, in the reference's own order, so that the same device code can be
+// driven by the reference's uniform stream.
+struct PhiloxDraws {
+  uint2 key;
+  __device__ __forceinline__ D2 substep(uint32_t it) { D2 u = draw2(key, it, ST_SUBSTEP); return D2{u.a, 6.0 + 14.0 * u.b}; }   // u_hard, U(6, 20)
+  __device__ __forceinline__ McsDraw mcs(uint32_t it, uint32_t pc) { return mcs_draw(key, it, pc); }
+  __device__ __forceinline__ double final_u() { return draw2(key, 0, ST_FINAL).a; }
+  __device__ __forceinline__ double choice_u() { return draw2(key, 0, ST_CHOICE).a; }
+  __device__ __forceinline__ double kin_u(int proc) { return draw2(key, 0, ST_KIN, 0, proc).a; }
+  __device__ __forceinline__ D2 decay_u(int proc) { return draw2(key, 0, ST_DECAY, 0, proc); }
+};
+struct TapeDraws {             // sequential reader; `over` is set if the tape runs out (a decision differed from the recording)
+  const double* t; long long pos, end; bool over;
+  __device__ __forceinline__ double next() { if (pos >= end) { over = true; return 0.5; } return t[pos++]; }
+  __device__ __forceinline__ D2 substep(uint32_t) { double a = next(), b = next(); return D2{a, b}; }                 // random(), uniform(6, 20)
+  __device__ __forceinline__ McsDraw mcs(uint32_t, uint32_t) {                                                       // choice, gauss, gauss, uniform(0, 2 pi) / 2 pi
+    McsDraw d; d.sign = next(); double z1 = next(), z2 = next(); d.radial = sqrt(z1 * z1 + z2 * z2); d.uphi = next(); return d;
+  }
+  __device__ __forceinline__ double final_u() { return next(); }
+  __device__ __forceinline__ double choice_u() { return next(); }
+  __device__ __forceinline__ double kin_u(int) { return next(); }
+  __device__ __forceinline__ D2 decay_u(int) { double a = next(), b = next(); return D2{a, b}; }
+};
 
 // One iteration of the dE/dx + multiple-scattering loop (shower.py:559-581) on a track: true = the loop ends here (energy
 // below threshold, or the hard scatter was drawn), false = one sub-step was applied.  Shared by k_loop and PB_PROBE_SUBSTEP.
-__device__ __forceinline__ bool substep(const Material& M, const Tables& T, Track& t, int ms_e) {
+template <class DS>
+__device__ __forceinline__ bool substep(const Material& M, const Tables& T, Track& t, int ms_e, DS& ds) {
   if (!(t.p.E >= t.pmin)) return true;                                // loop condition (shower.py:559)
   double ns = nsigma_hinted(T.sp[t.sp], t.hint, t.p.E);                // sum over the species' processes (shower.py:357-368)
   double mfp = (ns <= 0.0) ? 1.0e12 : kCmToM * fast_rcp(ns);          // shower.py:386-389
-  D2 u = draw2(t.key, (uint32_t)t.it, ST_SUBSTEP);
-  double iv = fast_rcp(6.0 + 14.0 * u.b);                             // delta_z = mfp / U(6, 20); delta_z / mfp = 1 / U
+  D2 u = ds.substep((uint32_t)t.it);
+  double iv = fast_rcp(u.b);                                          // delta_z = mfp / U(6, 20); delta_z / mfp = 1 / U
   t.delta_z = mfp * iv;
   if (u.a > hot_exp_neg_step(iv)) return true;                        // hard scatter (shower.py:564)
   // lose_energy (particle.py:143-153) with |p| carried along the track instead of recomputed
@@ -286,7 +319,7 @@ __device__ __forceinline__ bool substep(const Material& M, const Tables& T, Trac
     double s = t.delta_z * inv;
     t.rx += t.p.x * s; t.ry += t.p.y * s; t.rz += t.p.z * s;
     if (ms_e) {
-      McsDraw d = mcs_draw(t.key, (uint32_t)t.it, 0);
+      McsDraw d = ds.mcs((uint32_t)t.it, 0);
       t.p = mcs_fast(M, t.p, p3f, inv, M.rho * (t.delta_z * (1.0 / kCmToM)), t.iKp, d.sign, d.radial, d.uphi);
     }
   } else {
@@ -299,8 +332,11 @@ __device__ __forceinline__ bool substep(const Material& M, const Tables& T, Trac
 
 // First kernel of every wave: turn what the previous wave appended (stack tail, list sizes) into this wave's extent.
 // Idempotent when it has to pause (status 3), so the host can grow the scratch and re-enqueue the same wave.
-__global__ void k_wave_begin(Work W) {
+// Inside the wave-loop graph (pb_run_showers) it also drives the WHILE node: the loop goes on as long as this wave is a real one.
+__device__ __forceinline__ void wave_begin(Work& W) {
   WaveState& ws = *W.ws;
+  ws.iters += 1;
+  if (ws.iters > (1 << 20)) ws.status = 4;                 // safety net for the device-side loop: no shower has a million waves
   if (ws.status != 0 && ws.status != 3) { ws.n = 0; ws.n_charged = 0; return; }
   unsigned long long tail = W.tail[0], lists = W.tail[1];
   long long begin = ws.status == 3 ? ws.begin : ws.end;
@@ -320,6 +356,11 @@ __global__ void k_wave_begin(Work W) {
   W.tail[1] = 0;
   W.ctrl[1] = 0; W.ctrl[2] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0;
 }
+__global__ void k_wave_begin(Work W) { wave_begin(W); }
+__global__ void k_wave_begin_cond(Work W, cudaGraphConditionalHandle h) {
+  wave_begin(W);
+  cudaGraphSetConditional(h, W.ws->status == 0 ? 1u : 0u);     // status 1 / 2 / 3: this iteration's kernels find n = 0, then the loop ends
+}
 
 // Sub-step loop of propagate_particle, charged species only.  Persistent warps pull 32-entry chunks of the wave's charged
 // list; a lane that finishes its track (hard scatter drawn, or energy below threshold) stores it and immediately
@@ -332,7 +373,7 @@ __global__ void k_wave_begin(Work W) {
 // double buffer in shared memory -> consumed with shared-memory reads.
 constexpr int LOOP_CHUNK = 32;
 struct LoopBuf {                 // one chunk of track records: p0, r0w, track set-up (rf), ids
-  double2 v[5][LOOP_CHUNK];
+  double2 v[6][LOOP_CHUNK];
   int4 meta[LOOP_CHUNK];
   int4 kw[LOOP_CHUNK];
   int idx[LOOP_CHUNK];
@@ -380,7 +421,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       const double2* sup = reinterpret_cast<const double2*>(S.rf + 4 * s);     // store_track_setup
       cp_async16(&B.v[0][lane], p0p); cp_async16(&B.v[1][lane], p0p + 1);
       cp_async16(&B.v[2][lane], r0p); cp_async16(&B.v[3][lane], r0p + 1);
-      cp_async16(&B.v[4][lane], sup);
+      cp_async16(&B.v[4][lane], sup); cp_async16(&B.v[5][lane], sup + 1);
       cp_async16(&B.meta[lane], S.ids + 2 * s);
       cp_async16(&B.kw[lane], S.ids + 2 * s + 1);
       B.idx[lane] = pre_idx;
@@ -415,7 +456,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
         const LoopBuf& B = buf[which];
         const int e = pos + rank;
         cur = B.idx[e];
-        double2 a0 = B.v[0][e], a1 = B.v[1][e], b0 = B.v[2][e], b1 = B.v[3][e], s0 = B.v[4][e];
+        double2 a0 = B.v[0][e], a1 = B.v[1][e], b0 = B.v[2][e], b1 = B.v[3][e], s0 = B.v[4][e], s1 = B.v[5][e];
         t.p = V4{a0.x, a0.y, a1.x, a1.y};
         t.rx = b0.x; t.ry = b0.y; t.rz = b1.x;
         int4 meta = B.meta[e];
@@ -423,9 +464,9 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
         int pid = meta.x;
         t.mass = pid_mass(pid); t.iKp = 1e-3;
         if (meta.y < 0) { t.mass = prim_mass[begin + cur]; t.iKp = t.mass / (1e3 * pid_mass(pid)); }
-        t.pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), t.mass);   // shower.py:532-533
+        t.pmin = s1.x;                                                           // store_track_setup
         t.sp = species_index(pid);
-        t.pn = s0.x; t.ipn = 1.0 / s0.x;
+        t.pn = s0.x; t.ipn = s1.y;
         t.hint = __double2loint(s0.y);
         t.delta_z = 0.0; t.it = 0;
       }
@@ -436,7 +477,8 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     // ---- one sub-step for every live lane
     bool done = false;
     if (cur >= 0) {
-      done = substep(M, T, t, ms_e);
+      PhiloxDraws ds{t.key};
+      done = substep(M, T, t, ms_e, ds);
       if (!done) ++c_sub;
     }
     if (done) {
@@ -453,8 +495,86 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   if (lane == 0 && c_sub) atomicAdd(&W.counters[CNT_SUBSTEPS], c_sub);
 }
 
-// Per particle of the wave (charged list first, then the rest): final partial step of a charged track or the
-// photon's free path, process choice, sample_scattering threshold and map look-up key -> bucket + histogram.
+// Second half of propagate_particle + the process choice for ONE particle: the final partial step of a charged track
+// (shower.py:583-598) or the photon's free path (:538-553), then np.random.choice over the species' processes (:665-698) and the
+// sample_scattering threshold (:469).  In: the state the sub-step loop left (charged) or the creation state (neutral).
+// Returns the bucket (process * LU_MAX + map row; P_NONE: no hard scatter; P_SMDECAY: short-lived).
+template <class DS>
+__device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, DS& ds, bool charged, int pid, int flags, double mass,
+                                            double E_start, double delta_z, int ms_e, V4& p, double& rx, double& ry, double& rz, bool& stepped) {
+  int bucket = P_NONE * LU_MAX;
+  const int cls = pid_class(pid);
+  stepped = false;
+  if (charged) {
+    double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
+    if (!(E_start < pmin)) {                                            // shower.py:534-536: otherwise untouched
+      stepped = true;
+      int tb[3];
+      species_tables(pid, tb);
+      double distC = ds.final_u();                                      // shower.py:583-598
+      double last;
+      if (p.E < pmin) last = distC * delta_z;
+      else {
+        double lE = log(p.E);
+        double ns = nsigma_log(T.ns[tb[0]], lE, p.E) + nsigma_log(T.ns[tb[1]], lE, p.E);
+        if (tb[2] >= 0) ns += nsigma_log(T.ns[tb[2]], lE, p.E);
+        double mfp = mfp_from(ns);
+        last = mfp * log(1.0 / (1.0 + (exp(-delta_z / mfp) - 1) * distC));
+      }
+      p = lose_energy(p, mass, M.dEdx * last);
+      double pn = norm3_nofma(p.x, p.y, p.z);
+      if (pn > 0.0) {
+        double sc = last / pn;
+        rx += p.x * sc; ry += p.y * sc; rz += p.z * sc;
+        if (ms_e) {                                                     // SURVEY Q-12: electron mass here
+          McsDraw d = ds.mcs(MCS_FINAL_INDEX, 0);
+          p = mcs_scatter(M, p, pn, M.rho * (last / kCmToM), kMe, mass, d);
+        }
+      }
+    }
+  } else {
+    if (flags & PB_FLAG_SHORT_LIVED) {
+      bucket = P_SMDECAY * LU_MAX;                                      // particle.py:391-409, decays in k_emit
+    } else if (pid == 22) {
+      double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
+      if (!(p.E < pmin)) {                                              // shower.py:538-553 (MS_g is always False)
+        stepped = true;
+        double lE = log(p.E);
+        double mfp = mfp_from(nsigma_log(T.ns[P_PAIRPROD], lE, p.E) + nsigma_log(T.ns[P_COMP], lE, p.E));
+        double distC = ds.final_u();
+        double dist = mfp * log(1.0 / (1.0 - distC));
+        double pn = norm3_nofma(p.x, p.y, p.z);
+        rx += p.x / pn * dist; ry += p.y / pn * dist; rz += p.z / pn * dist;
+      }
+    }
+  }
+  if (cls >= 0 && !(flags & PB_FLAG_SHORT_LIVED)) {
+    // process choice (shower.py:665-698) and the sample_scattering threshold (shower.py:469)
+    double Ef = p.E;
+    int cand[3]; double c[3]; int nc;
+    if (pid == 11) { cand[0] = P_BREM; cand[1] = P_MOLLER; nc = 2; }
+    else if (pid == -11) { cand[0] = P_BREM; cand[1] = P_ANN; cand[2] = P_BHABHA; nc = 3; }
+    else if (pid == 22) { cand[0] = P_PAIRPROD; cand[1] = P_COMP; nc = 2; }
+    else { cand[0] = P_MUONE; cand[1] = P_MUONBREM; nc = 2; }
+    double SC = 0.0;
+    const double lEf = log(Ef);
+    for (int k = 0; k < nc; ++k) { c[k] = nsigma_log(T.ns[cand[k]], lEf, Ef); SC += c[k]; }
+    if (!(SC == 0.0 || SC != SC)) {
+      double u = ds.choice_u();
+      // np.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
+      double cdf[3]; double acc = 0.0;
+      for (int k = 0; k < nc; ++k) { acc += c[k] / SC; cdf[k] = acc; }
+      int pick = nc - 1;
+      for (int k = nc - 1; k >= 0; --k) if (u < cdf[k] / acc) pick = k;
+      int proc = cand[pick];
+      double thr = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
+      if (!(Ef <= thr)) bucket = proc * LU_MAX + lookup_row(T.map[proc], lEf, Ef);
+    }
+  }
+  return bucket;
+}
+
+// Per particle of the wave (charged list first, then the rest): finalize_one -> bucket + histogram.
 __global__ void PB_FIN_BOUNDS
 k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
            const double* __restrict__ prim_mass, int ms_e) {
@@ -468,94 +588,32 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
     int i = charged ? order_c[j] : order_n[j - n_charged];
     long long s = begin + i;
     int4 meta = ld_meta(S, s);
-    uint2 key = kw_key(ld_kw(S, s));
+    PhiloxDraws ds{kw_key(ld_kw(S, s))};
     int pid = meta.x;
     int flags = (meta.z >> 8) & 0x7f;
     double mass = (meta.y < 0) ? prim_mass[s] : pid_mass(pid);
-    int bucket = P_NONE * LU_MAX;
-    int cls = pid_class(pid);
     V4 p; double rx, ry, rz;
     int nsub = 0;
+    double delta_z = 0.0, E_start = 0.0;
     if (charged) {
       const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * s);
       const double2* rfp = reinterpret_cast<const double2*>(S.rf + 4 * s);
       double2 a0 = pfp[0], a1 = pfp[1], b0 = rfp[0], b1 = rfp[1];
       p = V4{a0.x, a0.y, a1.x, a1.y};
       rx = b0.x; ry = b0.y; rz = b1.x;
-      double delta_z = b1.y;
+      delta_z = b1.y;
       nsub = S.aux[s].y;
-      const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
-      double E_start = p0p[0].x;
-      double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
-      if (!(E_start < pmin)) {                                            // shower.py:534-536: otherwise untouched
-        c_steps += 1;
-        int tb[3];
-        species_tables(pid, tb);
-        double distC = draw2(key, 0, ST_FINAL).a;                         // shower.py:583-598
-        double last;
-        if (p.E < pmin) last = distC * delta_z;
-        else {
-          double lE = log(p.E);
-          double ns = nsigma_log(T.ns[tb[0]], lE, p.E) + nsigma_log(T.ns[tb[1]], lE, p.E);
-          if (tb[2] >= 0) ns += nsigma_log(T.ns[tb[2]], lE, p.E);
-          double mfp = mfp_from(ns);
-          last = mfp * log(1.0 / (1.0 + (exp(-delta_z / mfp) - 1) * distC));
-        }
-        p = lose_energy(p, mass, M.dEdx * last);
-        double pn = norm3_nofma(p.x, p.y, p.z);
-        if (pn > 0.0) {
-          double sc = last / pn;
-          rx += p.x * sc; ry += p.y * sc; rz += p.z * sc;
-          if (ms_e) {                                                     // SURVEY Q-12: electron mass here
-            McsDraw d = mcs_draw(key, MCS_FINAL_INDEX, 0);
-            p = mcs_scatter(M, p, pn, M.rho * (last / kCmToM), kMe, mass, d);
-          }
-        }
-      }
+      E_start = S.p0[4 * s];
     } else {
       const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
       const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
       double2 a0 = p0p[0], a1 = p0p[1], b0 = r0p[0], b1 = r0p[1];
       p = V4{a0.x, a0.y, a1.x, a1.y};
       rx = b0.x; ry = b0.y; rz = b1.x;
-      if (flags & PB_FLAG_SHORT_LIVED) {
-        bucket = P_SMDECAY * LU_MAX;                                      // particle.py:391-409, decays in k_emit
-      } else if (pid == 22) {
-        double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
-        if (!(p.E < pmin)) {                                              // shower.py:538-553 (MS_g is always False)
-          c_steps += 1;
-          double lE = log(p.E);
-          double mfp = mfp_from(nsigma_log(T.ns[P_PAIRPROD], lE, p.E) + nsigma_log(T.ns[P_COMP], lE, p.E));
-          double distC = draw2(key, 0, ST_FINAL).a;
-          double dist = mfp * log(1.0 / (1.0 - distC));
-          double pn = norm3_nofma(p.x, p.y, p.z);
-          rx += p.x / pn * dist; ry += p.y / pn * dist; rz += p.z / pn * dist;
-        }
-      }
     }
-    if (cls >= 0 && !(flags & PB_FLAG_SHORT_LIVED)) {
-      // process choice (shower.py:665-698) and the sample_scattering threshold (shower.py:469)
-      double Ef = p.E;
-      int cand[3]; double c[3]; int nc;
-      if (pid == 11) { cand[0] = P_BREM; cand[1] = P_MOLLER; nc = 2; }
-      else if (pid == -11) { cand[0] = P_BREM; cand[1] = P_ANN; cand[2] = P_BHABHA; nc = 3; }
-      else if (pid == 22) { cand[0] = P_PAIRPROD; cand[1] = P_COMP; nc = 2; }
-      else { cand[0] = P_MUONE; cand[1] = P_MUONBREM; nc = 2; }
-      double SC = 0.0;
-      const double lEf = log(Ef);
-      for (int k = 0; k < nc; ++k) { c[k] = nsigma_log(T.ns[cand[k]], lEf, Ef); SC += c[k]; }
-      if (!(SC == 0.0 || SC != SC)) {
-        double u = draw2(key, 0, ST_CHOICE).a;
-        // np.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
-        double cdf[3]; double acc = 0.0;
-        for (int k = 0; k < nc; ++k) { acc += c[k] / SC; cdf[k] = acc; }
-        int pick = nc - 1;
-        for (int k = nc - 1; k >= 0; --k) if (u < cdf[k] / acc) pick = k;
-        int proc = cand[pick];
-        double thr = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
-        if (!(Ef <= thr)) bucket = proc * LU_MAX + lookup_row(T.map[proc], lEf, Ef);
-      }
-    }
+    bool stepped;
+    const int bucket = finalize_one(M, T, ds, charged, pid, flags, mass, E_start, delta_z, ms_e, p, rx, ry, rz, stepped);
+    if (stepped) c_steps += 1;
     double2* pfp = reinterpret_cast<double2*>(S.pf + 4 * s);
     double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * s);
     pfp[0] = make_double2(p.E, p.x); pfp[1] = make_double2(p.y, p.z);
@@ -934,6 +992,33 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
   }
 }
 
+// Hard scatter or decay of ONE particle: sampled point -> two four-vectors in the parent frame (kinematics.py) -> lab frame
+// (particle.py:176-185, shower.py:471-480), PDG ids of the two products (shower.py:77-96) and the weight factor (decays).
+template <class DS>
+__device__ __forceinline__ void scatter_products(int proc, int pid, V4 pf, double mass, const double* x, DS& ds,
+                                                 V4& da, V4& db, int& pid_a, int& pid_b, double& wfac) {
+  wfac = 1.0;
+  if (proc == P_SMDECAY) {                                     // pi0 -> gamma gamma (particle.py:391-409)
+    D2 u = ds.decay_u(P_SMDECAY);
+    two_body_decay(pf, mass, 0.0, 0.0, u.a, u.b, &da, &db);
+    pid_a = 22; pid_b = 22;
+    wfac = 0.98823;                                            // particle.py:40 meson_decay_dict[111]
+    return;
+  }
+  double u_az = ds.kin_u(proc);
+  double E0 = pf.E;
+  switch (proc) {                                              // shower.py:77-96
+    case P_BREM: case P_MUONBREM: kin_brem(E0, mass, x, u_az, &da, &db); pid_a = pid; pid_b = 22; break;
+    case P_PAIRPROD: kin_pairprod(E0, x, u_az, &da, &db); pid_a = -11; pid_b = 11; break;
+    case P_COMP: kin_compton(E0, 0.0, x[0], u_az, &da, &db); pid_a = 11; pid_b = 22; break;
+    case P_ANN: kin_annihilation(E0, 0.0, x[0], u_az, &da, &db); pid_a = 22; pid_b = 22; break;
+    case P_MOLLER: case P_BHABHA: kin_ee(E0, x[0], u_az, &da, &db); pid_a = pid; pid_b = 11; break;
+    case P_MUONE: kin_mue(E0, x[0], u_az, &da, &db); pid_a = pid; pid_b = 11; break;
+  }
+  Rot R = rotation_to(pf);                                     // shower.py:471,479-480
+  da = rotate(R, da); db = rotate(R, db);
+}
+
 // Kinematics + rotation + daughter append, in bucket order (warps are process-coherent).
 __global__ void PB_EMIT_BOUNDS
 k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, int wave_order) {
@@ -968,28 +1053,13 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       meta = ld_meta(S, slot);
       { int4 kw = ld_kw(S, slot); key = kw_key(kw); wgt = kw_weight(kw); }
       int pid = meta.x;
-      if (proc == P_SMDECAY) {                                     // pi0 -> gamma gamma (particle.py:391-409)
-        D2 u = draw2(key, 0, ST_DECAY, 0, P_SMDECAY);
-        two_body_decay(pf, mass, 0.0, 0.0, u.a, u.b, &da, &db);
-        pid_a = 22; pid_b = 22;
-        wgt *= 0.98823;                                            // particle.py:40 meson_decay_dict[111]
-      } else {
-        const double2* xp = reinterpret_cast<const double2*>(W.xs + 4 * (size_t)i);
-        double2 x01 = xp[0], x23 = xp[1];
-        double x[4] = {x01.x, x01.y, x23.x, x23.y};
-        double u_az = draw2(key, 0, ST_KIN, 0, proc).a;
-        double E0 = pf.E;
-        switch (proc) {                                            // shower.py:77-96
-          case P_BREM: case P_MUONBREM: kin_brem(E0, mass, x, u_az, &da, &db); pid_a = pid; pid_b = 22; break;
-          case P_PAIRPROD: kin_pairprod(E0, x, u_az, &da, &db); pid_a = -11; pid_b = 11; break;
-          case P_COMP: kin_compton(E0, 0.0, x[0], u_az, &da, &db); pid_a = 11; pid_b = 22; break;
-          case P_ANN: kin_annihilation(E0, 0.0, x[0], u_az, &da, &db); pid_a = 22; pid_b = 22; break;
-          case P_MOLLER: case P_BHABHA: kin_ee(E0, x[0], u_az, &da, &db); pid_a = pid; pid_b = 11; break;
-          case P_MUONE: kin_mue(E0, x[0], u_az, &da, &db); pid_a = pid; pid_b = 11; break;
-        }
-        Rot R = rotation_to(pf);                                   // shower.py:471,479-480
-        da = rotate(R, da); db = rotate(R, db);
-      }
+      const double2* xp = reinterpret_cast<const double2*>(W.xs + 4 * (size_t)i);
+      double x[4] = {0.0, 0.0, 0.0, 0.0};
+      if (proc != P_SMDECAY) { double2 x01 = xp[0], x23 = xp[1]; x[0] = x01.x; x[1] = x01.y; x[2] = x23.x; x[3] = x23.y; }
+      PhiloxDraws ds{key};
+      double wfac;
+      scatter_products(proc, pid, pf, mass, x, ds, da, db, pid_a, pid_b, wfac);
+      wgt *= wfac;
       keep_a = da.E > M.min_energy;                                // shower.py:704-706
       keep_b = db.E > M.min_energy;
     }
@@ -1029,7 +1099,7 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       st_ids(S, dst, make_int4(bit ? pid_b : pid_a, (int)slot, pack_info(gen, bit, 0, proc), meta.w), child_key(key, bit), wgt);
       if (bit ? ch_b : ch_a) {
         next_c[ci++] = (int)(dst - next_begin);
-        store_track_setup(T, S, dst, bit ? pid_b : pid_a, d.E, d.x, d.y, d.z);
+        store_track_setup(M, T, S, dst, bit ? pid_b : pid_a, pid_mass(bit ? pid_b : pid_a), d.E, d.x, d.y, d.z);
       } else next_n[ni++] = (int)(dst - next_begin);
       ++dst;
     }
@@ -1037,8 +1107,9 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   }   // grid-stride loop
 }
 
-__global__ void k_init_primaries(const __grid_constant__ Tables T, Stack S, Work W, const double* __restrict__ p, const double* __restrict__ r,
-                                 const double* __restrict__ w, const int* __restrict__ pid, const int* __restrict__ flags,
+__global__ void k_init_primaries(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
+                                 const double* __restrict__ p, const double* __restrict__ r, const double* __restrict__ w,
+                                 const double* __restrict__ mass, const int* __restrict__ pid, const int* __restrict__ flags,
                                  long long n, unsigned long long seed, unsigned long long first_id) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1050,7 +1121,7 @@ __global__ void k_init_primaries(const __grid_constant__ Tables T, Stack S, Work
   unsigned long long old = atomicAdd(&W.tail[1], ch ? 1ull : (1ull << 32));
   if (ch) {
     W.list[2][(int)(old & 0xffffffffu)] = (int)i;          // parity 1: the first k_wave_begin flips 0 -> 1
-    store_track_setup(T, S, i, pid[i], p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+    store_track_setup(M, T, S, i, pid[i], mass[i], p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
   } else W.list[3][(int)(old >> 32)] = (int)i;
 }
 
@@ -1094,7 +1165,7 @@ k_dark_prepare(const __grid_constant__ Material M, const __grid_constant__ Table
     else if (pid == -11) { procs[0] = P_DARKBREM; procs[1] = P_DARKANN; }
     else if (pid == 22) procs[0] = P_DARKCOMP;
     else if (pid == 13 || pid == -13) procs[0] = P_DARKMUONBREM;
-    else if (pid == 111) procs[0] = P_BSMDECAY;
+    else if (pid == 111 || pid == 221 || pid == 331) procs[0] = P_BSMDECAY;        // pi0, eta, eta' -> gamma V (dark_shower.py:633-638)
     // the reference visits active_processes in list order; host code restores that order, here DarkBrem < DarkAnn
     for (int k = 0; k < 2; ++k) {
       int proc = procs[k];
@@ -1103,7 +1174,8 @@ k_dark_prepare(const __grid_constant__ Material M, const __grid_constant__ Table
       int wt = -1;                                                      // weight / drate table
       if (proc == P_BSMDECAY) {
         double r = M.mV / mass;
-        if (!(r >= 1.0)) { double q = 1.0 - r * r; wg = 2 * M.eps * M.eps * (q * q * q) * 0.98823; }
+        const double br = pid == 111 ? 0.98823 : (pid == 221 ? 0.3936 : 0.02307);      // particle.py:40-48 meson_twobody_branchingratios
+        if (!(r >= 1.0)) { double q = 1.0 - r * r; wg = 2 * M.eps * M.eps * (q * q * q) * br; }
       } else {
         double thr = D.min_E[proc - P_DARKBREM];
         if (E0 < thr) continue;
@@ -1480,6 +1552,89 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
   if (r == 12345.678) out[0] = r;
 }
 
+// ------------------------------------------------------------------------------------------ replay (parity mode)
+// One complete particle-step per thread - sub-step loop, final step, process choice, accept/reject sampling, kinematics - through
+// the SAME device functions the wave kernels call (substep, finalize_one, the sampler's integrand forms, scatter_products), with
+// every random number taken from a tape recorded from a reference run (TapeDraws).  A step that makes the reference's decisions
+// consumes exactly its tape segment.
+constexpr int REPLAY_IN = 10, REPLAY_OUT = 32;
+__global__ void k_replay(const __grid_constant__ Material M, const __grid_constant__ Tables T, long long n, const double* __restrict__ in,
+                         const double* __restrict__ tape, const long long* __restrict__ tape_off, double* __restrict__ out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* a = in + i * REPLAY_IN;
+  double* o = out + i * REPLAY_OUT;
+  TapeDraws ds{tape, tape_off[i], tape_off[i + 1], false};
+  const int pid = (int)a[0];
+  const double mass = a[8];
+  const int fl = (int)a[9];
+  const int ms_e = fl & 1, flags = (fl & 2) ? PB_FLAG_SHORT_LIVED : 0;
+  const bool charged = is_charged(pid) && !flags;
+  V4 p{a[1], a[2], a[3], a[4]};
+  double rx = a[5], ry = a[6], rz = a[7], delta_z = 0.0;
+  int nsub = 0;
+  if (charged) {                                                  // k_loop: track set-up, then substep() until the loop ends
+    Track t;
+    t.p = p; t.rx = rx; t.ry = ry; t.rz = rz;
+    t.key = make_uint2(0, 0); t.it = 0;
+    t.mass = mass; t.iKp = mass / (1e3 * pid_mass(pid));
+    t.pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), t.mass);
+    t.sp = species_index(pid);
+    t.pn = norm3_nofma(p.x, p.y, p.z); t.ipn = 1.0 / t.pn;
+    t.hint = nsigma_locate(T.sp[t.sp], p.E);
+    t.delta_z = 0.0;
+    while (!substep(M, T, t, ms_e, ds) && !ds.over) {}
+    p = t.p; rx = t.rx; ry = t.ry; rz = t.rz; delta_z = t.delta_z; nsub = t.it;
+  }
+  bool stepped;
+  int bucket = finalize_one(M, T, ds, charged, pid, flags, mass, a[1], delta_z, ms_e, p, rx, ry, rz, stepped);
+  int proc = bucket / LU_MAX, lu = bucket % LU_MAX;
+  double x[4] = {0.0, 0.0, 0.0, 0.0};
+  long long ntr = 0;
+  int status = 0;
+  if (proc < N_SAMPLED) {                                         // k_sample: sequential first-accept over the recorded trials
+    const MapInfo& mi = T.map[proc];
+    const double* g = mi.grid + (size_t)lu * mi.stride;
+    const double maxF = mi.maxF[lu] * M.fudge, E = p.E;
+    SampleConst sc{0, 0, 0, 0, 0};
+    if (proc == P_PAIRPROD) sc = pairprod_const(M, E);
+    else if (proc == P_BREM || proc == P_MUONBREM) sc = brem_const(M, E, proc == P_BREM ? kMe : kMmu);
+    bool found = false;
+    while (!found && !ds.over && ntr < M.max_trials) {
+      ++ntr;
+      double jac = 1.0, xx[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int d = 0; d < mi.dim; ++d) {
+        double yn = ds.next() * mi.dninc[d];
+        int iy = min((int)yn, mi.ninc[d] - 1);
+        double g0 = g[mi.off[d] + iy], g1 = g[mi.off[d] + iy + 1];
+        double inc = g1 - g0;
+        xx[d] = __dadd_rn(g0, __dmul_rn(inc, yn - iy));
+        jac *= inc * mi.dninc[d];
+      }
+      double u = ds.next();
+      double f;
+      if (proc == P_PAIRPROD) f = ds_pairprod_fast(sc, E, xx);
+      else if (proc == P_BREM || proc == P_MUONBREM) f = ds_brem_fast(M, sc, E, proc == P_BREM ? kMe : kMmu, xx);
+      else f = dsigma(M, proc, E, xx);
+      if (!ds.over && maxF * u < (jac * mi.invB) * f) { found = true; x[0] = xx[0]; x[1] = xx[1]; x[2] = xx[2]; x[3] = xx[3]; }
+    }
+    if (!found) { status = 3; proc = P_NONE; }
+  }
+  V4 da{0, 0, 0, 0}, db{0, 0, 0, 0};
+  int pid_a = 0, pid_b = 0;
+  double wfac = 1.0;
+  if (proc != P_NONE && proc != P_INPUT) scatter_products(proc, pid, p, mass, x, ds, da, db, pid_a, pid_b, wfac);
+  if (ds.over) status = 1;
+  else if (ds.pos != ds.end && status == 0) status = 2;
+  o[0] = status; o[1] = nsub; o[2] = proc; o[3] = (double)ntr;
+  o[4] = p.E; o[5] = p.x; o[6] = p.y; o[7] = p.z; o[8] = rx; o[9] = ry; o[10] = rz;
+  o[11] = (da.E > M.min_energy ? 1 : 0) + (db.E > M.min_energy ? 2 : 0);                   // daughters kept (shower.py:704-706)
+  o[12] = pid_a; o[13] = da.E; o[14] = da.x; o[15] = da.y; o[16] = da.z;
+  o[17] = pid_b; o[18] = db.E; o[19] = db.x; o[20] = db.y; o[21] = db.z;
+  o[22] = x[0]; o[23] = x[1]; o[24] = x[2]; o[25] = x[3];
+  o[26] = (double)(ds.pos - tape_off[i]); o[27] = wfac; o[28] = stepped ? 1.0 : 0.0;
+}
+
 // ------------------------------------------------------------------------------------------ probes (tests)
 __global__ void k_probe(const __grid_constant__ Material M, const __grid_constant__ Tables T, int what, int process,
                         const double* __restrict__ in, long long n, int is, double* __restrict__ out, int os) {
@@ -1562,9 +1717,36 @@ __global__ void k_probe(const __grid_constant__ Material M, const __grid_constan
       t.pn = norm3_nofma(t.p.x, t.p.y, t.p.z); t.ipn = 1.0 / t.pn;
       t.hint = nsigma_locate(T.sp[t.sp], t.p.E);
       t.delta_z = 0.0;
-      bool done = substep(M, T, t, (int)a[11]);
+      PhiloxDraws ds{t.key};
+      bool done = substep(M, T, t, (int)a[11], ds);
       o[0] = done ? 1.0 : 0.0; o[1] = t.p.E; o[2] = t.p.x; o[3] = t.p.y; o[4] = t.p.z; o[5] = t.rx; o[6] = t.ry; o[7] = t.rz;
       o[8] = t.delta_z; o[9] = (double)t.it;
+    } break;
+    case PB_PROBE_PROPAGATE: {  // propagate_particle (shower.py:509-601) of one particle with the engine's own draws
+      // in: pid, E, px, py, pz, x, y, z, mass, key0, key1, multiple scattering on/off; out: pf[4], rf[3], sub-steps, propagated
+      const int pid = (int)a[0];
+      const double mass = a[8];
+      const int ms = (int)a[11];
+      PhiloxDraws ds{make_uint2((uint32_t)a[9], (uint32_t)a[10])};
+      V4 p{a[1], a[2], a[3], a[4]};
+      double rx = a[5], ry = a[6], rz = a[7], delta_z = 0.0;
+      int nsub = 0;
+      const bool charged = is_charged(pid);
+      if (charged) {
+        Track t;
+        t.p = p; t.rx = rx; t.ry = ry; t.rz = rz; t.key = ds.key; t.it = 0;
+        t.mass = mass; t.iKp = mass / (1e3 * pid_mass(pid));
+        t.pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), t.mass);
+        t.sp = species_index(pid);
+        t.pn = norm3_nofma(p.x, p.y, p.z); t.ipn = 1.0 / t.pn;
+        t.hint = nsigma_locate(T.sp[t.sp], p.E);
+        t.delta_z = 0.0;
+        while (!substep(M, T, t, ms, ds)) {}
+        p = t.p; rx = t.rx; ry = t.ry; rz = t.rz; delta_z = t.delta_z; nsub = t.it;
+      }
+      bool stepped;
+      finalize_one(M, T, ds, charged, pid, 0, mass, a[1], delta_z, ms, p, rx, ry, rz, stepped);
+      o[0] = p.E; o[1] = p.x; o[2] = p.y; o[3] = p.z; o[4] = rx; o[5] = ry; o[6] = rz; o[7] = nsub; o[8] = stepped ? 1.0 : 0.0;
     } break;
     case PB_PROBE_DARKKIN: {    // in: E, mV, x[4], u1, u2, Pe, cte
       V4 v{0, 0, 0, 0};
@@ -1606,12 +1788,19 @@ struct pb_engine_s {
   int profiling = 0;             // 0 off, 1 = the two dominant kernels only (k_loop, k_sample), 2 = every kernel
   int sample_group = PB_SAMPLE_G_DEFAULT;    // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
   int sample_trials = PB_SAMPLE_T_DEFAULT;   // trials per lane and round (PB_SAMPLE_T): ILP inside the lane
+  int sample_trials_dark = PB_SAMPLE_T_DARK_DEFAULT;   // the same for the generic kernel (PB_SAMPLE_T_DARK)
   int sample_generic = 0;        // PB_SAMPLE_GENERIC=1: SM pass through the generic kernel (with the dark integrands compiled in)
   int emit_wave_order = 0;       // PB_EMIT_ORDER=1: k_emit walks the wave in record order (coalesced) instead of bucket order
   static constexpr int LOOKAHEAD = 8;   // waves enqueued per host synchronisation while the shower tail shrinks
   cudaEvent_t ev[2 * 8] = {};
   cudaEvent_t evp[LOOKAHEAD][2][2] = {};   // lookahead slot x {k_loop, k_sample} x {start, stop}
   WaveState* h_ws = nullptr;             // pinned read-back of the device wave state (+ tail)
+  // host-free wave loop: one CUDA graph = WHILE node around the seven wave kernels, condition set on the device
+  int use_graph = 1;                     // PB_GRAPH=0: stream launches with a host synchronisation per (growing) wave
+  cudaGraph_t wave_graph = nullptr;
+  cudaGraphExec_t wave_exec = nullptr;
+  cudaStream_t cap_stream = nullptr;     // capture stream for building the graph body
+  std::vector<unsigned char> graph_sig;  // kernel arguments the instantiated graph was built with
   pb_profile prof{};
   std::string err;
 };
@@ -1672,8 +1861,10 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   derive_material(e);
   if (const char* g = getenv("PB_SAMPLE_G")) e->sample_group = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_T")) e->sample_trials = atoi(g);
+  if (const char* g = getenv("PB_SAMPLE_T_DARK")) e->sample_trials_dark = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_GENERIC")) e->sample_generic = atoi(g);
   if (const char* g = getenv("PB_EMIT_ORDER")) e->emit_wave_order = atoi(g);
+  if (const char* g = getenv("PB_GRAPH")) e->use_graph = atoi(g);
   size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * (8 + CNT_N) + sizeof(WaveState) + 64;
   if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
   cudaMemset(e->fixed_blob, 0, fixed);
@@ -1713,6 +1904,9 @@ extern "C" void pb_destroy(pb_engine e) {
   for (int i = 0; i < 2 * 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   for (int a = 0; a < pb_engine_s::LOOKAHEAD; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) if (e->evp[a][b][c]) cudaEventDestroy(e->evp[a][b][c]);
   if (e->h_ws) cudaFreeHost(e->h_ws);
+  if (e->wave_exec) cudaGraphExecDestroy(e->wave_exec);
+  if (e->wave_graph) cudaGraphDestroy(e->wave_graph);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   delete e;
 }
 
@@ -1814,14 +2008,14 @@ static int ensure_cand(pb_engine e, long long ncap);
 // stand-alone sampling: the generic instantiation.  (G, T) = lanes per sample x trials per lane and round.
 template <int FAM>
 static void launch_sample_fam(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream) {
-  const int G = e->sample_group, T = e->sample_trials;
+  const int G = e->sample_group, T = (FAM == 2) ? e->sample_trials : e->sample_trials_dark;
 #define PB_LS(g, t) if (G == g && T == t) { k_sample<g, FAM, t><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); return; }
   PB_LS(4, 1) PB_LS(2, 2) PB_LS(1, 2) PB_LS(4, 2) PB_LS(2, 1) PB_LS(8, 1) PB_LS(1, 4) PB_LS(2, 4) PB_LS(1, 1)
 #undef PB_LS
-  k_sample<PB_SAMPLE_G_DEFAULT, FAM, PB_SAMPLE_T_DEFAULT><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work);
+  k_sample<4, FAM, 1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work);
 }
 static int sample_grid(pb_engine e, long long n, bool sm_pass) {
-  const int T = e->sample_trials;
+  const int T = sm_pass && !e->sample_generic ? e->sample_trials : e->sample_trials_dark;
   const int minb = sm_pass ? (T > 1 ? PB_SAMPLE_MINB_SM_T : PB_SAMPLE_MINB_SM) : (T > 1 ? PB_SAMPLE_MINB_T : PB_SAMPLE_MINB);
   return (int)std::max<long long>(1, std::min<long long>((long long)e->n_sm * minb, (n + 31) / 32 + 1));
 }
@@ -1865,6 +2059,60 @@ static int ensure_work(pb_engine e, long long n) {
   e->work.tile_start = (int*)p; p += (size_t)max_tiles * 4;
   e->work.tile_count = (int*)p;
   e->work_n = cap;
+  return PB_OK;
+}
+
+// The wave loop as ONE graph launch: WHILE(condition) { wave_begin (sets the condition); loop; finalize; scan; fill; sample; emit }.
+// Every wave kernel is grid-stride / persistent over the device-side wave size, so the grids are fixed (a multiple of the SM
+// count); kernel arguments are baked into the graph, which is rebuilt when any of them changes (new stack, grown scratch,
+// new tables or configuration).  Measured: 1.45 us per kernel node vs 3.3 us per stream launch + 12 us per host
+// synchronisation (profiles/r02_summary.md).
+static int ensure_wave_graph(pb_engine e, const Stack& S, int ms_flag) {
+  std::vector<unsigned char> sig(sizeof(Material) + sizeof(Tables) + sizeof(Stack) + sizeof(Work) + 5 * sizeof(long long));
+  unsigned char* q = sig.data();
+  memcpy(q, &e->mat, sizeof(Material)); q += sizeof(Material);
+  memcpy(q, &e->tab, sizeof(Tables)); q += sizeof(Tables);
+  memcpy(q, &S, sizeof(Stack)); q += sizeof(Stack);
+  memcpy(q, &e->work, sizeof(Work)); q += sizeof(Work);
+  long long extra[5] = {(long long)(uintptr_t)e->prim_mass, ms_flag, e->sample_group * 100 + e->sample_trials, e->sample_generic, e->emit_wave_order};
+  memcpy(q, extra, sizeof(extra));
+  if (e->wave_exec && sig == e->graph_sig) return PB_OK;
+  if (e->wave_exec) { cudaGraphExecDestroy(e->wave_exec); e->wave_exec = nullptr; }
+  if (e->wave_graph) { cudaGraphDestroy(e->wave_graph); e->wave_graph = nullptr; }
+  if (!e->cap_stream) PB_CUDA(e, cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+  PB_CUDA(e, cudaGraphCreate(&e->wave_graph, 0));
+  cudaGraphConditionalHandle h;
+  PB_CUDA(e, cudaGraphConditionalHandleCreate(&h, e->wave_graph, 1, cudaGraphCondAssignDefault));
+  cudaGraphNodeParams np = {};
+  np.type = cudaGraphNodeTypeConditional;
+  np.conditional.handle = h;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t node;
+  PB_CUDA(e, cudaGraphAddNode(&node, e->wave_graph, nullptr, 0, &np));
+  cudaGraph_t body = np.conditional.phGraph_out[0];
+  cudaStream_t cs = e->cap_stream;
+  PB_CUDA(e, cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+  // one full wave of resident CTAs per kernel (occupancy query): a partial second wave of a grid-stride kernel only adds a tail
+  auto resident = [&](const void* fn, int threads) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, 0) != cudaSuccess || nb < 1) nb = 1;
+    return e->n_sm * nb;
+  };
+  const int g_loop = e->n_sm * PB_LOOP_MINB, g_fin = resident((const void*)k_finalize, 128), g_emit = resident((const void*)k_emit, 128),
+            g_fill = resident((const void*)k_bucket_fill, 256);
+  k_wave_begin_cond<<<1, 1, 0, cs>>>(e->work, h);
+  k_loop<<<g_loop, 128, 0, cs>>>(e->mat, e->tab, S, e->work, e->prim_mass, ms_flag);
+  k_finalize<<<g_fin, 128, 0, cs>>>(e->mat, e->tab, S, e->work, e->prim_mass, ms_flag);
+  k_bucket_scan<<<1, 1024, 0, cs>>>(e->work);
+  SampleIO io{S.pf, reinterpret_cast<const uint2*>(S.ids), 4, 2, nullptr, reinterpret_cast<int*>(S.aux), 2, e->work.ws};
+  k_bucket_fill<<<g_fill, 256, 0, cs>>>(e->work, io, -1);
+  launch_sample(e, sample_grid(e, 1LL << 40, true), io, cs, true);
+  k_emit<<<g_emit, 128, 0, cs>>>(e->mat, e->tab, S, e->work, e->emit_wave_order);
+  cudaError_t ce = cudaStreamEndCapture(cs, nullptr);
+  if (ce != cudaSuccess) { e->err = std::string("wave graph capture: ") + cudaGetErrorString(ce); return PB_ERR_CUDA; }
+  PB_CUDA(e, cudaGraphInstantiate(&e->wave_exec, e->wave_graph, 0));
+  e->graph_sig.swap(sig);
   return PB_OK;
 }
 
@@ -1951,7 +2199,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     }
   };
   tick(PB_K_INIT, 0);
-  k_init_primaries<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(e->tab, S, e->work, d_p, d_r, d_w, d_pid, d_fl, n0, seed, first_id);
+  k_init_primaries<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(e->mat, e->tab, S, e->work, d_p, d_r, d_w, e->prim_mass, d_pid, d_fl, n0, seed, first_id);
   tock(PB_K_INIT, 0);
   ++e->prof.launches[PB_K_INIT];
   ++launches;
@@ -1960,7 +2208,30 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
   unsigned long long* htail = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(hws) + sizeof(WaveState));
   long long n_known = n0, n_prev = 0;
   const int ms_flag = global_ms ? 1 : 0;
-  for (;;) {
+  const bool graph = e->use_graph && plevel == 0 && !getenv("PB_LOG_WAVES");
+  while (graph) {
+    // host-free wave loop: the whole shower is one graph launch; the host only comes back if the per-wave scratch has to grow
+    int rcg = ensure_wave_graph(e, S, ms_flag);
+    if (rcg != PB_OK) return rcg;
+    PB_CUDA(e, cudaGraphLaunch(e->wave_exec, stream));
+    PB_CUDA(e, cudaMemcpyAsync(hws, e->work.ws, sizeof(WaveState), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(e, cudaMemcpyAsync(htail, e->work.tail, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(e, cudaStreamSynchronize(stream));
+    if (hws->status == 3) {             // scratch too small for the next wave: grow (contents preserved) and resume it
+      long long need = (long long)std::min<unsigned long long>(htail[0], (unsigned long long)st->capacity) - hws->begin;
+      if (need > 0x3fffffffLL) { e->err = "wave wider than 2^30"; return PB_ERR_CAPACITY; }
+      int rc = ensure_work(e, 2 * need);
+      if (rc != PB_OK) return rc;
+      rc = ensure_order(e, 4 * need, stream);
+      if (rc != PB_OK) return rc;
+      int caps[2] = {(int)std::min<long long>(e->work_n, 0x7fffffff), (int)std::min<long long>(e->order_cap, 0x7fffffff)};
+      PB_CUDA(e, cudaMemcpyAsync(&e->work.ws->work_cap, caps, sizeof(caps), cudaMemcpyHostToDevice, stream));
+      continue;
+    }
+    break;
+  }
+  if (graph) launches += 7LL * hws->iters;
+  while (!graph) {
     // grow phase (or full profiling): one wave per synchronisation; shrinking tail: LOOKAHEAD waves per synchronisation
     const int K = (plevel >= 2 || n_known > n_prev) ? 1 : pb_engine_s::LOOKAHEAD;
     const long long bound = std::max<long long>(K == 1 ? (n_known * 9) / 8 : 2 * n_known, 4096);
@@ -2024,6 +2295,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     e->err = "particle stack capacity exhausted (wave " + std::to_string(waves) + ")";
     return PB_ERR_CAPACITY;
   }
+  if (hws->status == 4) { e->err = "wave loop did not terminate"; return PB_ERR_STATE; }
   unsigned long long cnt[CNT_N];
   PB_CUDA(e, cudaMemcpyAsync(cnt, e->work.counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
   PB_CUDA(e, cudaStreamSynchronize(stream));
@@ -2334,6 +2606,36 @@ extern "C" int pb_probe(pb_engine e, int what, int process, const double* in, in
   cudaError_t c = cudaDeviceSynchronize();
   if (c == cudaSuccess) c = cudaMemcpy(out, dout, sizeof(double) * n * os, cudaMemcpyDeviceToHost);
   cudaFree(din); cudaFree(dout);
+  if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
+  return PB_OK;
+}
+
+extern "C" int pb_replay(pb_engine e, int64_t n, const double* particles, const double* tape, const int64_t* tape_off, double* out) {
+  if (!e || !particles || !tape_off || !out || n <= 0) return PB_ERR_ARG;
+  PB_CUDA(e, cudaSetDevice(e->device));
+  for (int p = 0; p < 8; ++p)
+    if (e->tab.map[p].grid == nullptr || e->tab.ns[p].n == 0) { e->err = "tables not uploaded"; return PB_ERR_STATE; }
+  if (e->species_dirty) { int rcs = build_species_tables(e); if (rcs != PB_OK) return rcs; }
+  e->mat.max_trials = (long long)std::min<double>((double)e->cfg.max_sweeps * (double)e->tab.map[P_BREM].B, 4.0e9);
+  const long long nt = tape_off[n];
+  double *din = nullptr, *dtape = nullptr, *dout = nullptr;
+  long long* doff = nullptr;
+  PB_CUDA(e, cudaMalloc(&din, sizeof(double) * n * REPLAY_IN));
+  PB_CUDA(e, cudaMalloc(&dtape, sizeof(double) * std::max<long long>(nt, 1)));
+  PB_CUDA(e, cudaMalloc(&doff, sizeof(long long) * (n + 1)));
+  PB_CUDA(e, cudaMalloc(&dout, sizeof(double) * n * REPLAY_OUT));
+  cudaStream_t st;
+  PB_CUDA(e, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaError_t c = cudaMemcpyAsync(din, particles, sizeof(double) * n * REPLAY_IN, cudaMemcpyHostToDevice, st);
+  if (c == cudaSuccess && nt > 0) c = cudaMemcpyAsync(dtape, tape, sizeof(double) * nt, cudaMemcpyHostToDevice, st);
+  if (c == cudaSuccess) c = cudaMemcpyAsync(doff, tape_off, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, st);
+  if (c == cudaSuccess) {
+    k_replay<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(e->mat, e->tab, n, din, dtape, doff, dout);
+    c = cudaMemcpyAsync(out, dout, sizeof(double) * n * REPLAY_OUT, cudaMemcpyDeviceToHost, st);
+  }
+  if (c == cudaSuccess) c = cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  cudaFree(din); cudaFree(dtape); cudaFree(doff); cudaFree(dout);
   if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
   return PB_OK;
 }

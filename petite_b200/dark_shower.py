@@ -159,6 +159,9 @@ class DarkShower(Shower):
         self._minimum_calculable_dark_energy = {
             11: {"DarkBrem": b0}, -11: {"DarkBrem": b0, "DarkAnn": self._resonant_annihilation_energy / 1000.0},
             22: {"DarkComp": self._compton_threshold_energy / 1000.0}, 111: {"TwoBody_BSMDecay": -1},
+            # eta, eta': the reference's weight formula covers them (dark_shower.py:633-638) but its threshold table does not
+            # (:236-241), so its GetBSMWeights raises KeyError at :604 for these PIDs; the formula is implemented as written
+            221: {"TwoBody_BSMDecay": -1}, 331: {"TwoBody_BSMDecay": -1},
             13: {"DarkMuonBrem": m0}, -13: {"DarkMuonBrem": m0}}
 
     def _setup_path(self):
@@ -321,6 +324,42 @@ class DarkShower(Shower):
         capi.check(self._engine, capi.lib.pb_tally(self._engine, C.byref(st), 0, dark_batch.n, C.c_void_p(out.data_ptr()),
                                                    C.c_void_p(stream)))
         return out
+
+    def draw_dark_sample(self, Einc, LU_Key=-1, process="DarkBrem", VB=False):
+        """One VEGAS accept/reject sample of a dark process at ``Einc`` (dark_shower.py:649-704) -> map variables
+        (+ the trial count if ``VB``).  Batched form: ``draw_samples(energies, process)``."""
+        if process not in dimensionalities_dark:
+            raise Exception("Your process is not in the list")
+        if process not in self._dark_maps:
+            raise Exception("Process String does not match library")
+        x, ntr = self.draw_samples([Einc], process, LU_Key)
+        if ntr[0] < 0:
+            raise Exception("No Sample Found", process, Einc, LU_Key)
+        return np.concatenate([x[0], [ntr[0]]]) if VB else x[0]
+
+    def produce_bsm_particle(self, p0, process, weight=None, VB=False):
+        """One dark vector emitted by ``p0`` through ``process`` (dark_shower.py:721-804): interaction-energy choice, multiple
+        scattering + energy loss down to it, dark sample, V four-vector in the lab, weight = p0's weight x ``weight`` (default:
+        ``GetBSMWeights(p0, process)``, what generate_dark_shower passes).  A one-candidate ``pb_run_dark``.  -> Particle or None."""
+        if process not in dimensionalities_dark:
+            raise Exception("Your process is not in the list")
+        wg = self.GetBSMWeights(p0, process)
+        if not wg > 0.0:
+            return None
+        keep = self.active_processes
+        try:
+            self.active_processes = [process]
+            batch = self.batch_from_particles([p0])
+            dark = self.generate_dark_showers(batch)
+            vs = dark.to_particles([[p0]])[0]
+        finally:
+            self.active_processes = keep
+        if not vs:
+            return None
+        v = vs[0]
+        if weight is not None:
+            v.get_ids()["weight"] = v.get_ids()["weight"] * (float(weight) / wg)
+        return v
 
     def generate_dark_shower(self, ExDir=None, SParams=None):
         """dark_shower.py:806-849: (SM shower, list of dark vectors) for one existing or new SM shower."""

@@ -682,12 +682,70 @@ class Shower:
             out.append(Particle(lab, p0.get_rf(), d))
         return out
 
+    def propagate_particle(self, Part0, Losses=False, MS=False):
+        """Propagate one particle to its next hard scatter (shower.py:509-601): free path for photons, the dE/dx +
+        multiple-scattering sub-step loop for e+-/mu+-.  Mutates ``Part0`` (pf, rf, ended) and returns it, like the reference.
+        The draws are the engine's (Philox key from (seed, next shower id)); ``Losses`` must be False for photons and the
+        target's dE/dx (what generate_shower passes, shower.py:624, 644) for charged particles."""
+        if Part0.get_ended() is True:
+            Part0.set_ended(True)
+            return Part0
+        ids = Part0.get_ids()
+        pid = ids["PID"]
+        charged = abs(pid) in (11, 13)
+        if pid not in _STEPPING_PIDS:
+            raise ValueError(f"PID {pid} is not propagated by the shower path")
+        if charged and (Losses is False or abs(float(Losses) - self._dEdx * 0.1) > 1e-12 * self._dEdx):
+            raise NotImplementedError("charged particles are propagated with the target's dE/dx (Losses = dEdx * 0.1), as generate_shower does")
+        if not charged and Losses is not False:
+            raise NotImplementedError("photons are propagated without energy loss (Losses=False), as generate_shower does")
+        fid = self._next_shower_id
+        self._next_shower_id += 1
+        root = self._root_key(fid)
+        inp = [[pid, *np.asarray(Part0.get_p0(), dtype=float), *np.asarray(Part0.get_r0(), dtype=float), ids["mass"], root[0], root[1], 1.0 if MS else 0.0]]
+        o = self._probe(capi.PROBE_PROPAGATE, 0, inp, 9)[0]
+        if o[8]:
+            Part0.set_pf(np.array(o[0:4]))
+            Part0.set_rf(np.array(o[4:7]))
+        Part0.set_ended(True)
+        return Part0
+
+    def _root_key(self, shower_id):
+        """Philox root key of a shower id (rng.cuh root_key): the first two output words of Philox(counter = id, key = seed)."""
+        M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+        c = [shower_id & MASK, (shower_id >> 32) & MASK, 0, 0xA0]
+        k0, k1 = self._seed & MASK, (self._seed >> 32) & MASK
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [((p1 >> 32) ^ c[1] ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c[3] ^ k1) & MASK, p0 & MASK]
+            k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+        return c[0], c[1]
+
     def _probe(self, what, process, inp, out_cols):
         inp = np.ascontiguousarray(inp, dtype=np.float64)
         out = np.zeros((len(inp), out_cols))
         capi.check(self._engine, capi.lib.pb_probe(self._engine, what, process, capi.dptr(inp), len(inp), inp.shape[1],
                                                    capi.dptr(out), out_cols))
         return out
+
+    def replay(self, particles, tape, tape_off):
+        """Replay mode (``pb_replay``): run ``n`` independent particle-steps - propagation, process choice, accept/reject
+        sampling, kinematics - through the wave kernels' own device functions with every random number taken from a TAPE
+        recorded from a reference run (layout: include/petite_b200.h).  ``particles`` (n, 10): pid, p0[4], r0[3], mass, flags
+        (1 = multiple scattering on, 2 = short-lived); ``tape`` (m,) doubles; ``tape_off`` (n + 1,) segment offsets.
+        -> dict of per-step results (status 0 = the step consumed exactly its tape segment)."""
+        part = np.ascontiguousarray(particles, dtype=np.float64).reshape(-1, 10)
+        tape = np.ascontiguousarray(tape, dtype=np.float64)
+        off = np.ascontiguousarray(tape_off, dtype=np.int64)
+        n = len(part)
+        assert len(off) == n + 1 and off[-1] <= len(tape)
+        out = np.zeros((n, 32))
+        capi.check(self._engine, capi.lib.pb_replay(self._engine, n, capi.dptr(part), capi.dptr(tape if len(tape) else np.zeros(1)),
+                                                    off.ctypes.data_as(C.POINTER(C.c_int64)), capi.dptr(out)))
+        return dict(status=out[:, 0].astype(int), nsub=out[:, 1].astype(int), process=out[:, 2].astype(int), ntrials=out[:, 3].astype(np.int64),
+                    pf=out[:, 4:8], rf=out[:, 8:11], kept=out[:, 11].astype(int), pid_a=out[:, 12].astype(int), p_a=out[:, 13:17],
+                    pid_b=out[:, 17].astype(int), p_b=out[:, 18:22], x=out[:, 22:26], consumed=out[:, 26].astype(np.int64),
+                    weight_factor=out[:, 27], propagated=out[:, 28].astype(int))
 
     def find_max(self, process, n_trials=100, seed=20261017, mT=None):
         """GPU ``do_find_max_work`` (utilities/find_maxes.py:55-119) for this target: -> (max_F (nE,), sigma (nE,))."""

@@ -55,7 +55,7 @@ def _spectrum_chi2(gpu_spec, orc_spec):
 
 # showers per batch: the 100 GeV muon showers keep 7.9e3 records (+ 6.6e3 dark vectors) each, so 1e5 of them are stepped as
 # four batches
-BATCH = {"c5_mu_lead_dark": 25_000}
+BATCH = {"c5_mu_lead_dark": 10_000}
 # oracle-side (counter mode) twin of a reference-side configuration and the observables it holds
 ORACLE_TWIN = {"c2_gamma_lead": ("c2_gamma_lead", SM_KEYS), "c1_e_graphite": ("c1_e_graphite", SM_KEYS),
                "c3_dark_graphite": ("c3_dark_graphite", ["mult", "E_gamma", "z_mean"] + DARK_KEYS), "c5_mu_lead_dark": ("c5_mu_lead", SM_KEYS)}

@@ -87,3 +87,80 @@ def test_detector_cut_vs_reference_golden(golden):
         if tag == "b":                                   # the reference drops energy-cut particles before masking
             m = m[:, g["b/kept"]]
         assert np.array_equal(m, want)
+
+
+def test_propagate_particle_api():
+    """Shower.propagate_particle (shower.py:509-601): mutates and returns the particle; the result is the oracle's propagation
+    with the same Philox key (root key of the shower id the call consumed)."""
+    from petite_b200 import Particle
+    from petite_b200.constants import m_electron
+    from oracle.shower import OracleShower, OParticle
+    from oracle.draws import CounterDraws
+    from oracle.philox import root_key
+    sh = shower("lead", 0.010, seed=21)
+    o = OracleShower(None, "lead", 0.010, seed=21, rng="counter")
+    for pid, E, m in ((11, 3.0, m_electron), (-11, 0.7, m_electron), (22, 2.0, 0.0)):
+        p = Particle([E, 0, 0, np.sqrt(E * E - m * m)], [0.1, 0.2, 0.3], {"PID": pid, "ID": 1, "mass": m})
+        fid = sh._next_shower_id
+        ret = sh.propagate_particle(p, Losses=(sh._dEdx * 0.1 if pid != 22 else False), MS=(pid != 22))
+        assert ret is p and p.get_ended() is True
+        q = OParticle(p.get_p0(), p.get_r0(), PID=pid, ID=1, mass=m)
+        q.draws = CounterDraws(root_key(21, fid))
+        o.propagate(q, o.dEdx * 0.1 if pid != 22 else False, pid != 22)
+        assert np.allclose(p.get_pf(), q.pf, rtol=0, atol=1e-9 * E) and np.allclose(p.get_rf(), q.rf, rtol=0, atol=1e-9)
+        if pid != 22:
+            assert p.get_pf()[0] < E          # energy was lost
+    low = Particle([0.001, 0, 0, 0.00085], [0, 0, 0], {"PID": 11, "ID": 1, "mass": m_electron})
+    sh.propagate_particle(low, Losses=sh._dEdx * 0.1, MS=True)
+    assert np.array_equal(low.get_pf(), low.get_p0()) and low.get_ended()          # below threshold: untouched (shower.py:534-536)
+    with pytest.raises(NotImplementedError):
+        sh.propagate_particle(Particle([1.0, 0, 0, 1.0], [0, 0, 0], {"PID": 11, "ID": 1, "mass": m_electron}), Losses=False)
+
+
+def test_dark_sampling_and_produce_bsm_particle_api():
+    """DarkShower.draw_dark_sample (dark_shower.py:649-704) and produce_bsm_particle (:721-804) on the Python class."""
+    from petite_b200 import Particle
+    from petite_b200.constants import m_electron
+    from tests.test_gpu_dark import dark_shower
+    ds = dark_shower("graphite", 0.03)
+    x = ds.draw_dark_sample(5.0, process="DarkBrem")
+    assert x.shape == (3,) and 0 < x[0] < 1 and x[1] < 0.31
+    xv = ds.draw_dark_sample(5.0, process="DarkBrem", VB=True)
+    assert xv.shape == (4,) and xv[3] >= 1
+    assert ds.draw_dark_sample(5.0, process="DarkAnn").shape == (1,)
+    with pytest.raises(Exception):
+        ds.draw_dark_sample(5.0, process="Brem")
+    p = Particle([5.0, 0, 0, np.sqrt(25 - m_electron ** 2)], [0, 0, 0.5], {"PID": 11, "ID": 3, "mass": m_electron, "weight": 0.5})
+    v = ds.produce_bsm_particle(p, "DarkBrem")
+    wg = ds.GetBSMWeights(p, "DarkBrem")
+    ids = v.get_ids()
+    assert ids["PID"] == 4900022 and ids["parent_ID"] == 3 and ids["ID"] == 6 and ids["generation_process"] == "DarkBrem"
+    assert abs(ids["weight"] - 0.5 * wg) <= 1e-12 * wg
+    assert 0.03 <= v.get_p0()[0] <= 5.0
+    v2 = ds.produce_bsm_particle(p, "DarkBrem", weight=2 * wg)
+    assert abs(v2.get_ids()["weight"] - wg) <= 1e-12 * wg
+    assert ds.produce_bsm_particle(p, "DarkAnn") is None                          # an electron has no annihilation weight
+
+
+def test_eta_two_body_bsm_decay():
+    """eta / eta' -> gamma V (dark_shower.py:633-638, particle.py meson_decay_dict): weight 2 eps^2 (1 - mV^2/m^2)^3 BR, V on its
+    mass shell, energy inside the two-body range of the boosted parent."""
+    from petite_b200 import Particle
+    from petite_b200.constants import MASS
+    from tests.test_gpu_dark import dark_shower
+    ds = dark_shower("graphite", 0.03)
+    for pid, br in ((221, 0.3936), (331, 0.02307), (111, 0.98823)):
+        m = MASS[pid]
+        E = 4.0
+        p = Particle([E, 0.0, 0.0, np.sqrt(E * E - m * m)], [0, 0, 0], {"PID": pid, "ID": 1, "mass": m, "stability": "short-lived"})
+        sm, vs = ds.generate_dark_shower(ExDir=[p])
+        assert len(vs) == 1
+        v = vs[0]
+        w = 2 * ds.kinetic_mixing ** 2 * (1 - (ds._mV / m) ** 2) ** 3 * br
+        assert abs(v.get_ids()["weight"] - w) <= 1e-14 * w and v.get_ids()["generation_process"] == "TwoBody_BSMDecay"
+        pv = np.asarray(v.get_p0())
+        assert abs(pv[0] ** 2 - pv[1:] @ pv[1:] - ds._mV ** 2) < 1e-9
+        Ecm = (m * m + ds._mV ** 2) / (2 * m)
+        pcm = np.sqrt(Ecm ** 2 - ds._mV ** 2)
+        g, b = E / m, np.sqrt(1 - (m / E) ** 2)
+        assert g * (Ecm - b * pcm) - 1e-9 <= pv[0] <= g * (Ecm + b * pcm) + 1e-9

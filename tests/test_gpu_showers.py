@@ -204,3 +204,33 @@ def test_tally_matches_host_histograms():
         eb = np.clip(np.floor((np.log10(h["p0"][sel][:, 0]) + 3) * (64 / 6)).astype(int), 0, 63)
         assert np.array_equal(t[capi.TALLY_EHIST + k * 64: capi.TALLY_EHIST + (k + 1) * 64], np.bincount(eb, minlength=64))
     assert t[capi.TALLY_COUNT:capi.TALLY_COUNT + 7].sum() == b.n
+
+
+@pytest.mark.parametrize("name,n", [("c1_e_graphite", 1_000), ("c2_gamma_lead", 10_000)])
+def test_exact_decisions_at_1e3_1e4_showers(golden, name, n):
+    """EXACT equality with the oracle at BASELINE scale: configuration 1 in full (1e3 showers) and the first 1e4 showers of
+    configuration 2 (tests/golden/exact_showers.npz, made by the CPU oracle in counter mode, make_exact_fixture.py).  Per shower:
+    multiplicity, sum of accept/reject trials, sum of dE/dx sub-steps and the histogram of generation processes.  The hot-loop
+    forms (fast_rcp, hot_log, hot_exp_neg_step, mcs_fast, folded integrands, per-species summed n*sigma tables) are <= 2 ulp away
+    from the oracle's libm path, so a hard-scatter / process / accept decision CAN flip when a uniform lands within ~1e-15 of a
+    threshold; this test measures how often (expected flips at this size: ~1e-7) and demands zero."""
+    import torch
+    from tests import ensemble_stats as es
+    from tests.test_gpu_ensemble import _run
+    cfg = es.CONFIGS[name]
+    g = golden("exact_showers")
+    sh = shower(cfg["material"], cfg["E_min"], seed=cfg["seed"])
+    es.REF_CONFIGS.setdefault(name, cfg)
+    batch = _run(sh, name, n, first_id=0)
+    t, m = batch._t, batch.n
+    sid = t["meta"][:m, 3].long()
+    mult = torch.bincount(sid, minlength=n).cpu().numpy()
+    ntr = torch.bincount(sid, weights=t["aux"][:m, 0].double(), minlength=n).cpu().numpy().astype(np.int64)
+    nsub = torch.bincount(sid, weights=t["aux"][:m, 1].double(), minlength=n).cpu().numpy().astype(np.int64)
+    proc = (t["meta"][:m, 2] & 0xFF).long()
+    hist = torch.bincount(sid * 16 + proc, minlength=16 * n).reshape(n, 16).cpu().numpy()
+    bad = (mult != g[f"{name}/mult"]) | (ntr != g[f"{name}/ntrials"]) | (nsub != g[f"{name}/nsub"]) | np.any(hist != g[f"{name}/proc_hist"], axis=1)
+    decisions = int(g[f"{name}/ntrials"].sum() + g[f"{name}/nsub"].sum() + 2 * g[f"{name}/mult"].sum())
+    print(name, "showers", n, "records", m, "decisions ~", decisions, "showers with any difference:", int(bad.sum()),
+          "-> flip rate <", (int(bad.sum()) + 1) / decisions)
+    assert not bad.any(), (np.nonzero(bad)[0][:10], mult[bad][:5], g[f"{name}/mult"][bad][:5])
