@@ -49,7 +49,7 @@ CONFIGS = {
             material="lead", pid=0, E0=0.0, mass=0.0, mV=0.010, active=["DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=10_000, data=DATA400, cpu=1),
     5: dict(workload="Muon dark shower: 100 GeV mu- through lead, MuonBrem/MuonE/DarkMuonBrem + multiple scattering, m_V=30 MeV, 1e5 primaries "
                      "(BASELINE.json configs[4])",
-            material="lead", pid=13, E0=100.0, mass=M_MU, mV=0.030, active=["DarkMuonBrem", "DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=20_000, cpu=1),
+            material="lead", pid=13, E0=100.0, mass=M_MU, mV=0.030, active=["DarkMuonBrem", "DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=10_000, cpu=1),
 }
 CFG = CONFIGS[2]
 

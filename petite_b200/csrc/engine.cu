@@ -75,14 +75,20 @@ constexpr int TILE = PB_TILE;               // samples per tile
 constexpr int SAMPLE_THREADS = PB_SAMPLE_THREADS;
 constexpr int GRID_SMEM_DOUBLES = 4096;     // >= padded stride of a 4-D map row (3964 -> 3968)
 
-struct NSigmaTable { const double4* node; double xmin, xmax; double log_x0, inv_dlog; int n; int pad; };   // node = (x, y, slope to next, 0)
+// Coarse look-up ("which node can E belong to at most") keyed by the top bits of the IEEE representation: key(E) = hi32(E) >> 14 is
+// monotone in E > 0 and splits every octave into 64 bins; coarse[key(E) - key0] = searchsorted_left(x, upper edge of the bin) is an
+// UPPER bound of searchsorted_left(x, E), and walking it down to the first node below E gives the exact index after one or two
+// L1-resident loads - no logarithm, no binary search, no rounding question (integer compares only).
+constexpr int COARSE_SHIFT = 14;
+struct Coarse { const int* ub; int key0, nb; };
+struct NSigmaTable { const double4* node; double xmin, xmax; Coarse c; int n; int pad; };   // node = (x, y, slope to next, 0)
 struct MapInfo {
   const double* grid;   // nE rows, `stride` doubles each (padded to a multiple of 16 doubles)
   const double* E;
   const double* maxF;
   int nE, dim, stride, B;
   double invB;               // 1 / B (points per sweep): wgt = jac / B
-  double log_E0, inv_dlog;   // geometric-grid guess for the row look-up
+  Coarse c;                  // coarse look-up over the row energies
   int ninc[4];
   double dninc[4];           // ninc as doubles (the trial multiplies by it twice: no int->fp64 conversion in the loop)
   int off[4];
@@ -142,13 +148,14 @@ struct WaveState {
 
 struct Work {            // per-wave scratch, sized to the widest wave seen so far
   int* bucket;           // [n] bucket of particle (begin + i)
-  int* sorted;           // [n] wave-local indices in bucket order
+  int2* sorted;          // [n] (wave-local index, bucket) in bucket order: k_emit reads ONE coalesced array instead of sorted -> bucket
   double* xs;            // [n x 4] accepted sample (map variables)
   double* sE;            // [n] incoming energy, gathered into bucket order by k_bucket_fill (contiguous per tile)
   uint2* skey;           // [n] particle key, likewise
   int* hist;             // [NBUCKET]
   int* offsets;          // [NBUCKET + 1]
   int* cursor;           // [NBUCKET]
+  int* tile_base;        // [NBUCKET + 1] exclusive prefix of the per-bucket tile counts (k_bucket_scan); k_bucket_fill expands it into:
   int* tile_bucket;      // [max_tiles]
   int* tile_start;
   int* tile_count;
@@ -158,6 +165,8 @@ struct Work {            // per-wave scratch, sized to the widest wave seen so f
   struct WaveState* ws;  // device-resident wave bookkeeping (lets the host enqueue several waves per synchronisation)
   unsigned long long* tail;      // [0] stack tail (next free record); [1] = (n_neutral_next << 32) | n_charged_next
   unsigned long long* counters;  // [CNT_N]: steps, substeps, samples, trials, no_sample, overflow, per-process trials/samples
+  unsigned long long* tlog;      // measurement aid (PB_TILE_LOG): per tile of ONE chosen wave {start ns, end ns, bucket << 32 | count, SM}; else nullptr
+  int tlog_wave, tlog_cap;
 };
 
 enum { CNT_STEPS = 0, CNT_SUBSTEPS, CNT_SAMPLES, CNT_TRIALS, CNT_NOSAMPLE, CNT_OVERFLOW, CNT_PROC_TRIALS = 8,
@@ -185,15 +194,13 @@ __device__ __forceinline__ int nsigma_locate(const NSigmaTable& T, double E) {
   }
   return min(max(lo, 1), T.n - 1);
 }
-// same result as nsigma_locate, starting from the geometric-grid guess (all shipped tables are geomspace grids;
-// the two fix-up loops make it exact for any increasing grid)
-__device__ __forceinline__ int nsigma_locate_log(const NSigmaTable& T, double logE, double E) {
-  int n = T.n;
-  if (n < 2) return 1;
-  double g = (logE - T.log_x0) * T.inv_dlog;
-  int hi = (g > 0.0) ? ((g < (double)(n - 1)) ? (int)g + 1 : n - 1) : 1;
-  hi = min(max(hi, 1), n - 1);
-  while (hi < n - 1 && __ldg(reinterpret_cast<const double*>(&T.node[hi])) < E) ++hi;
+__device__ __forceinline__ int coarse_ub(const Coarse& c, double E) {
+  int b = (__double2hiint(E) >> COARSE_SHIFT) - c.key0;
+  return __ldg(c.ub + min(max(b, 0), c.nb - 1));
+}
+// same result as nsigma_locate through the coarse table (exact for any increasing grid of positive energies)
+__device__ __forceinline__ int nsigma_locate_c(const NSigmaTable& T, double E) {
+  int hi = coarse_ub(T.c, E);
   while (hi > 1 && !(__ldg(reinterpret_cast<const double*>(&T.node[hi - 1])) < E)) --hi;
   return hi;
 }
@@ -225,19 +232,20 @@ __device__ __forceinline__ void species_tables(int pid, int* t) {
 __device__ __forceinline__ int species_index(int pid) { return pid == 11 ? 0 : (pid == -11 ? 1 : 2); }
 __device__ __forceinline__ double mfp_from(double ns) { return (ns <= 0.0) ? 1.0e12 : kCmToM / ns; }   // shower.py:386-389
 
-__device__ __forceinline__ double nsigma_log(const NSigmaTable& T, double logE, double E) {
+__device__ __forceinline__ double nsigma_c(const NSigmaTable& T, double E) {
   if (T.n < 2) return 0.0;
-  return nsigma_at(T, nsigma_locate_log(T, logE, E), E);
+  if (!(E >= T.xmin && E <= T.xmax)) return (E == E) ? 0.0 : E;
+  int hi = coarse_ub(T.c, E);
+  double4 nd = ld_node(&T.node[hi - 1]);
+  while (hi > 1 && !(nd.x < E)) { --hi; nd = ld_node(&T.node[hi - 1]); }
+  return __dadd_rn(__dmul_rn(nd.z, E - nd.x), nd.y);
 }
 
-// SURVEY Q-1: argmin |E_i - E| + 1, clamped to the last row (shower.py:416-426).  lo = first row with E_row >= E is
-// found from the geometric-grid guess plus exact fix-up loops.
-__device__ __forceinline__ int lookup_row(const MapInfo& m, double logE, double E) {
+// SURVEY Q-1: argmin |E_i - E| + 1, clamped to the last row (shower.py:416-426).  lo = first row with E_row >= E comes from the
+// coarse table (upper bound) walked down.
+__device__ __forceinline__ int lookup_row(const MapInfo& m, double E) {
   int n = m.nE;
-  double g = (logE - m.log_E0) * m.inv_dlog;
-  int lo = (g > 0.0) ? ((g < (double)n) ? (int)g + 1 : n) : 0;
-  lo = min(max(lo, 0), n);
-  while (lo < n && __ldg(m.E + lo) < E) ++lo;
+  int lo = coarse_ub(m.c, E);
   while (lo > 0 && !(__ldg(m.E + lo - 1) < E)) --lo;
   int best;
   if (lo <= 0) best = 0;
@@ -261,7 +269,8 @@ struct Track {
 // time inside k_loop (3 of 32 lanes busy): |p| and the species-table hint, parked in the record's not-yet-used rf slot.
 __device__ __forceinline__ void store_track_setup(const Material& M, const Tables& T, Stack& S, long long slot, int pid, double mass,
                                                   double E, double px, double py, double pz) {
-  int h = nsigma_locate(T.sp[species_index(pid)], E);
+  const NSigmaTable& Ts = T.sp[species_index(pid)];
+  int h = Ts.n >= 2 ? coarse_ub(Ts.c, E) : 1;          // an upper bound of the node index: nsigma_hinted walks it down (exactly) at the first sub-step
   double pn = norm3_nofma(px, py, pz);
   double pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), mass);           // shower.py:532-533
   double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * slot);
@@ -515,9 +524,8 @@ __device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, 
       double last;
       if (p.E < pmin) last = distC * delta_z;
       else {
-        double lE = log(p.E);
-        double ns = nsigma_log(T.ns[tb[0]], lE, p.E) + nsigma_log(T.ns[tb[1]], lE, p.E);
-        if (tb[2] >= 0) ns += nsigma_log(T.ns[tb[2]], lE, p.E);
+        double ns = nsigma_c(T.ns[tb[0]], p.E) + nsigma_c(T.ns[tb[1]], p.E);
+        if (tb[2] >= 0) ns += nsigma_c(T.ns[tb[2]], p.E);
         double mfp = mfp_from(ns);
         last = mfp * log(1.0 / (1.0 + (exp(-delta_z / mfp) - 1) * distC));
       }
@@ -539,8 +547,7 @@ __device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, 
       double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
       if (!(p.E < pmin)) {                                              // shower.py:538-553 (MS_g is always False)
         stepped = true;
-        double lE = log(p.E);
-        double mfp = mfp_from(nsigma_log(T.ns[P_PAIRPROD], lE, p.E) + nsigma_log(T.ns[P_COMP], lE, p.E));
+        double mfp = mfp_from(nsigma_c(T.ns[P_PAIRPROD], p.E) + nsigma_c(T.ns[P_COMP], p.E));
         double distC = ds.final_u();
         double dist = mfp * log(1.0 / (1.0 - distC));
         double pn = norm3_nofma(p.x, p.y, p.z);
@@ -557,8 +564,7 @@ __device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, 
     else if (pid == 22) { cand[0] = P_PAIRPROD; cand[1] = P_COMP; nc = 2; }
     else { cand[0] = P_MUONE; cand[1] = P_MUONBREM; nc = 2; }
     double SC = 0.0;
-    const double lEf = log(Ef);
-    for (int k = 0; k < nc; ++k) { c[k] = nsigma_log(T.ns[cand[k]], lEf, Ef); SC += c[k]; }
+    for (int k = 0; k < nc; ++k) { c[k] = nsigma_c(T.ns[cand[k]], Ef); SC += c[k]; }
     if (!(SC == 0.0 || SC != SC)) {
       double u = ds.choice_u();
       // np.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
@@ -568,7 +574,7 @@ __device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, 
       for (int k = nc - 1; k >= 0; --k) if (u < cdf[k] / acc) pick = k;
       int proc = cand[pick];
       double thr = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
-      if (!(Ef <= thr)) bucket = proc * LU_MAX + lookup_row(T.map[proc], lEf, Ef);
+      if (!(Ef <= thr)) bucket = proc * LU_MAX + lookup_row(T.map[proc], Ef);
     }
   }
   return bucket;
@@ -656,14 +662,10 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
   for (int k = 0; k < PER; ++k) {
     int b = t * PER + k;
     W.offsets[b] = cbase;
-    for (int j = 0; j < til[k]; ++j) {
-      W.tile_bucket[tbase + j] = b;
-      W.tile_start[tbase + j] = cbase + j * TILE;
-      W.tile_count[tbase + j] = min(TILE, cnt[k] - j * TILE);
-    }
+    W.tile_base[b] = tbase;          // the tile table itself is written by k_bucket_fill (wide), one thread per tile
     cbase += cnt[k]; tbase += til[k];
   }
-  if (t == 1023) { W.offsets[NBUCKET] = cbase; W.ctrl[0] = tbase; W.ctrl[1] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0; }
+  if (t == 1023) { W.offsets[NBUCKET] = cbase; W.tile_base[NBUCKET] = tbase; W.ctrl[0] = tbase; W.ctrl[1] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0; }
   if (t == 0) W.ctrl[2] = 0;
 }
 
@@ -686,6 +688,17 @@ __global__ void __launch_bounds__(256) k_bucket_fill(Work W, SampleIO io, int n_
   const int n = n_explicit < 0 ? W.ws->n : n_explicit;
   const int lane = threadIdx.x & 31;
   const size_t off = io.ws ? (size_t)io.ws->begin : 0;
+  // tile table: tile t belongs to the bucket b with tile_base[b] <= t < tile_base[b + 1] (binary search over the 4097-entry prefix)
+  const int n_tiles = W.ctrl[0];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+    int lo = 0, hi = NBUCKET;                       // last b with tile_base[b] <= t
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (W.tile_base[mid] <= t) lo = mid; else hi = mid; }
+    const int j = t - W.tile_base[lo];
+    const int start = W.offsets[lo] + j * TILE;
+    W.tile_bucket[t] = lo;
+    W.tile_start[t] = start;
+    W.tile_count[t] = min(TILE, W.offsets[lo + 1] - start);
+  }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int b = W.bucket[i];
     const bool sampled = b < N_SAMPLED * LU_MAX;
@@ -700,7 +713,7 @@ __global__ void __launch_bounds__(256) k_bucket_fill(Work W, SampleIO io, int n_
     if (lane == leader) base = atomicAdd(&W.cursor[b], __popc(peers));
     base = __shfl_sync(peers, base, leader);
     int pos = W.offsets[b] + base + __popc(peers & ((1u << lane) - 1u));
-    W.sorted[pos] = i;
+    W.sorted[pos] = make_int2(i, b);
     if (sampled) { W.sE[pos] = E; W.skey[pos] = key; }
   }
 }
@@ -849,6 +862,8 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
     int bucket = W.tile_bucket[tile], tstart = W.tile_start[tile], tcount = W.tile_count[tile];
     int proc = bucket / LU_MAX, lu = bucket % LU_MAX;
     const MapInfo& mi = Tb.map[proc];
+    const bool tlog = W.tlog != nullptr && threadIdx.x == 0 && io.ws != nullptr && io.ws->waves == W.tlog_wave && tile < W.tlog_cap;
+    if (tlog) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); W.tlog[4 * tile] = t; }
     if (threadIdx.x == 0) {
       uint32_t bytes = (uint32_t)mi.stride * 8u;
       mbar_expect_tx(&s_bar, bytes);
@@ -860,7 +875,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
       double Ek = W.sE[tstart + k];
       s_E[k] = Ek;
       s_key[k] = W.skey[tstart + k];
-      s_idx[k] = W.sorted[tstart + k];
+      s_idx[k] = W.sorted[tstart + k].x;
       if (proc_is_4d(proc)) {
         SampleConst c = (proc == P_PAIRPROD) ? pairprod_const(M, Ek) : brem_const(M, Ek, proc == P_BREM ? kMe : kMmu);
         s_cb[k] = c.b; s_cc[k] = c.c; s_cd[k] = c.d;
@@ -963,6 +978,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
             if (sub == 0 && !helper) {
               io.ntr[(off + (size_t)cur) * io.ntr_stride] = -1;
               W.bucket[cur] = P_NONE * LU_MAX;
+              W.xs[4 * (size_t)cur] = __longlong_as_double(0x7ff8000000000000LL);     // NaN sample: the emit kernels skip this entry
               c_trials += (unsigned long long)max_trials; c_fail += 1;
             }
             cur = -1;
@@ -984,6 +1000,12 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
     }
     c_trials = 0; c_samples = 0; c_fail = 0;
     __syncthreads();   // everyone is done with s_grid (and the counters) before the next tile overwrites it
+    if (tlog) {
+      unsigned long long t; unsigned sm;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      W.tlog[4 * tile + 1] = t; W.tlog[4 * tile + 2] = ((unsigned long long)bucket << 32) | (unsigned)tcount; W.tlog[4 * tile + 3] = ((unsigned long long)s_ptrials << 16) | sm;
+    }
     if (threadIdx.x == 0) {
       if (s_ptrials) { atomicAdd(&W.counters[CNT_TRIALS], s_ptrials); atomicAdd(&W.counters[CNT_PROC_TRIALS + proc], s_ptrials); }
       if (s_psamples) { atomicAdd(&W.counters[CNT_SAMPLES], s_psamples); atomicAdd(&W.counters[CNT_PROC_SAMPLES + proc], s_psamples); }
@@ -1038,10 +1060,19 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   uint2 key = make_uint2(0, 0);
   double wgt = 0.0, rx = 0, ry = 0, rz = 0;
   if (j < n) {
-    int i = wave_order ? j : W.sorted[j];
-    int bucket = W.bucket[i];
+    int i, bucket;
+    if (wave_order) { i = j; bucket = W.bucket[i]; }
+    else { int2 ib = W.sorted[j]; i = ib.x; bucket = ib.y; }
     proc = bucket / LU_MAX;
-    if (proc == P_NONE && S.aux[begin + i].x < 0) S.ids[2 * (begin + i)].z |= (PB_FLAG_NO_SAMPLE << 8);   // sampler gave up
+    double2 x01 = make_double2(0.0, 0.0), x23 = make_double2(0.0, 0.0);
+    if (proc < N_SAMPLED) {
+      const double2* xp = reinterpret_cast<const double2*>(W.xs + 4 * (size_t)i);
+      x01 = xp[0]; x23 = xp[1];
+      if (x01.x != x01.x) {                                          // the sampler gave up ("No Sample Found", shower.py:460-461)
+        S.ids[2 * (begin + i)].z |= (PB_FLAG_NO_SAMPLE << 8);
+        proc = P_NONE;
+      }
+    }
     if (proc != P_NONE) {
       slot = begin + i;
       const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * slot);
@@ -1053,9 +1084,7 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       meta = ld_meta(S, slot);
       { int4 kw = ld_kw(S, slot); key = kw_key(kw); wgt = kw_weight(kw); }
       int pid = meta.x;
-      const double2* xp = reinterpret_cast<const double2*>(W.xs + 4 * (size_t)i);
-      double x[4] = {0.0, 0.0, 0.0, 0.0};
-      if (proc != P_SMDECAY) { double2 x01 = xp[0], x23 = xp[1]; x[0] = x01.x; x[1] = x01.y; x[2] = x23.x; x[3] = x23.y; }
+      double x[4] = {x01.x, x01.y, x23.x, x23.y};
       PhiloxDraws ds{key};
       double wfac;
       scatter_products(proc, pid, pf, mass, x, ds, da, db, pid_a, pid_b, wfac);
@@ -1181,8 +1210,7 @@ k_dark_prepare(const __grid_constant__ Material M, const __grid_constant__ Table
         if (E0 < thr) continue;
         if (proc == P_DARKCOMP) {
           if (E0 < M.min_calc[2]) continue;
-          double lE = log(E0);
-          wg = pre * loglog_eval(D.nsdark_comp, E0) / (nsigma_log(T.ns[P_PAIRPROD], lE, E0) + nsigma_log(T.ns[P_COMP], lE, E0));
+          wg = pre * loglog_eval(D.nsdark_comp, E0) / (nsigma_c(T.ns[P_PAIRPROD], E0) + nsigma_c(T.ns[P_COMP], E0));
         } else {
           wt = (proc == P_DARKBREM) ? (pid == 11 ? 0 : 1) : (proc == P_DARKANN ? 2 : 3);
           wg = pre * nsigma_eval(D.w[wt], E0);
@@ -1228,7 +1256,7 @@ k_dark_prepare(const __grid_constant__ Material M, const __grid_constant__ Table
         }
         double E = pf.E;
         if ((proc == P_DARKANN && E <= M.E_res_ann) || (proc == P_DARKCOMP && E <= M.E_thr_comp)) bucket = P_BSMDECAY * LU_MAX + 1;
-        else bucket = proc * LU_MAX + lookup_row(T.map[proc], log(E), E);
+        else bucket = proc * LU_MAX + lookup_row(T.map[proc], E);
       }
       c_proc[nc] = proc; c_wg[nc] = wg; c_pf[nc] = pf; c_bucket[nc] = bucket;
       ++nc;
@@ -1263,8 +1291,10 @@ k_dark_emit(const __grid_constant__ Material M, Stack S, Stack O, Work W, DarkCa
   int4 meta = make_int4(0, 0, 0, 0);
   uint2 key = make_uint2(0, 0);
   if (j < n_cand) {
-    int i = W.sorted[j];
-    int bucket = W.bucket[i];
+    const int2 ib = W.sorted[j];
+    const int i = ib.x;
+    int bucket = ib.y;
+    if (bucket / LU_MAX < N_SAMPLED && C.ntr[i] < 0) bucket = P_NONE * LU_MAX;      // the sampler gave up on this candidate
     if (bucket / LU_MAX != P_NONE) {
       slot = C.slot[i]; proc = C.proc[i]; ntr = C.ntr[i];
       double wg = C.wg[i];
@@ -1353,7 +1383,7 @@ k_prepare_draws(const __grid_constant__ Tables T, Work W, DarkCand C, uint2* key
   C.ntr[i] = 0;
   keys[i] = root_key(seed, first_id + (unsigned long long)i);
   const MapInfo& mi = T.map[process];
-  int lu = (lu_key < 0 || lu_key > mi.nE) ? lookup_row(mi, log(Ei), Ei) : min(lu_key, mi.nE - 1);
+  int lu = (lu_key < 0 || lu_key > mi.nE) ? lookup_row(mi, Ei) : min(lu_key, mi.nE - 1);
   int bucket = process * LU_MAX + lu;
   W.bucket[i] = bucket;
   atomicAdd(&W.hist[bucket], 1);
@@ -1803,6 +1833,7 @@ struct pb_engine_s {
   std::vector<unsigned char> graph_sig;  // kernel arguments the instantiated graph was built with
   pb_profile prof{};
   std::string err;
+  std::string tlog_path;
 };
 
 #define PB_CUDA(e, call)                                                                         \
@@ -1865,7 +1896,18 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   if (const char* g = getenv("PB_SAMPLE_GENERIC")) e->sample_generic = atoi(g);
   if (const char* g = getenv("PB_EMIT_ORDER")) e->emit_wave_order = atoi(g);
   if (const char* g = getenv("PB_GRAPH")) e->use_graph = atoi(g);
-  size_t fixed = sizeof(int) * (NBUCKET * 3 + 1 + 16) + sizeof(unsigned long long) * (8 + CNT_N) + sizeof(WaveState) + 64;
+  if (const char* g = getenv("PB_TILE_LOG")) {            // "<file>:<wave>": per-tile timeline of k_sample in that wave of every run (appended)
+    std::string v(g);
+    size_t c = v.rfind(':');
+    if (c != std::string::npos) {
+      e->tlog_path = v.substr(0, c);
+      e->work.tlog_wave = atoi(v.c_str() + c + 1);
+      e->work.tlog_cap = 1 << 17;
+      if (cudaMalloc(&e->work.tlog, sizeof(unsigned long long) * 4 * (size_t)e->work.tlog_cap) != cudaSuccess) e->work.tlog = nullptr;
+      else cudaMemset(e->work.tlog, 0, sizeof(unsigned long long) * 4 * (size_t)e->work.tlog_cap);
+    }
+  }
+  size_t fixed = sizeof(int) * (NBUCKET * 4 + 2 + 16) + sizeof(unsigned long long) * (8 + CNT_N) + sizeof(WaveState) + 64;
   if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
   cudaMemset(e->fixed_blob, 0, fixed);
   for (int i = 0; i < 2 * 8; ++i) cudaEventCreate(&e->ev[i]);
@@ -1876,6 +1918,7 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   e->work.hist = (int*)p; p += NBUCKET * sizeof(int);
   e->work.offsets = (int*)p; p += (NBUCKET + 1) * sizeof(int);
   e->work.cursor = (int*)p; p += NBUCKET * sizeof(int);
+  e->work.tile_base = (int*)p; p += (NBUCKET + 1) * sizeof(int);
   e->work.ctrl = (int*)p; p += 16 * sizeof(int);
   p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
   e->work.ws = (WaveState*)p;
@@ -1904,10 +1947,33 @@ extern "C" void pb_destroy(pb_engine e) {
   for (int i = 0; i < 2 * 8; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   for (int a = 0; a < pb_engine_s::LOOKAHEAD; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) if (e->evp[a][b][c]) cudaEventDestroy(e->evp[a][b][c]);
   if (e->h_ws) cudaFreeHost(e->h_ws);
+  if (e->work.tlog) cudaFree(e->work.tlog);
   if (e->wave_exec) cudaGraphExecDestroy(e->wave_exec);
   if (e->wave_graph) cudaGraphDestroy(e->wave_graph);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   delete e;
+}
+
+// Coarse look-up table over an increasing grid of positive energies (struct Coarse): ub[b] = searchsorted_left(x, upper edge of bin
+// key0 + b), optionally clipped to [lo_clip, hi_clip] (the interpolation tables use scipy's clip(., 1, n - 1)).
+static int build_coarse(pb_engine e, const double* x, int n, int lo_clip, int hi_clip, Coarse* out) {
+  *out = Coarse{nullptr, 0, 0};
+  if (n < 1 || !(x[0] > 0.0)) return PB_OK;
+  auto key = [](double v) { int64_t b; memcpy(&b, &v, 8); return (int)(b >> 32) >> COARSE_SHIFT; };
+  const int key0 = key(x[0]), nb = key(x[n - 1]) - key0 + 1;
+  std::vector<int> ub((size_t)nb);
+  for (int b = 0; b < nb; ++b) {
+    int64_t bits = (int64_t)(key0 + b + 1) << (32 + COARSE_SHIFT);       // smallest double of the next bin
+    double edge; memcpy(&edge, &bits, 8);
+    int s = (int)(std::lower_bound(x, x + n, edge) - x);
+    ub[b] = std::min(std::max(s, lo_clip), hi_clip);
+  }
+  int* d = nullptr;
+  PB_CUDA(e, cudaMalloc(&d, sizeof(int) * (size_t)nb));
+  e->owned.push_back(d);
+  PB_CUDA(e, cudaMemcpy(d, ub.data(), sizeof(int) * (size_t)nb, cudaMemcpyHostToDevice));
+  *out = Coarse{d, key0, nb};
+  return PB_OK;
 }
 
 extern "C" int pb_upload_nsigma(pb_engine e, int id, const double* E, const double* y, int n) {
@@ -1922,9 +1988,11 @@ extern "C" int pb_upload_nsigma(pb_engine e, int id, const double* E, const doub
   PB_CUDA(e, cudaMalloc(&d, sizeof(double) * node.size()));
   e->owned.push_back(d);
   PB_CUDA(e, cudaMemcpy(d, node.data(), sizeof(double) * node.size(), cudaMemcpyHostToDevice));
-  double lx0 = (n > 1 && E[0] > 0) ? log(E[0]) : 0.0;
-  double idl = (n > 1 && E[0] > 0 && E[n - 1] > E[0]) ? (double)(n - 1) / log(E[n - 1] / E[0]) : 0.0;
-  e->tab.ns[id] = NSigmaTable{(const double4*)d, n ? E[0] : 0.0, n ? E[n - 1] : 0.0, lx0, idl, n, 0};
+  if (n >= 2 && !(E[0] > 0.0)) { e->err = "n*sigma tables need positive energies"; return PB_ERR_ARG; }
+  for (int i = 1; i < n; ++i) if (!(E[i] >= E[i - 1])) { e->err = "n*sigma table energies must not decrease"; return PB_ERR_ARG; }
+  Coarse c;
+  { int rcc = build_coarse(e, E, n >= 2 ? n : 0, 1, n - 1, &c); if (rcc != PB_OK) return rcc; }
+  e->tab.ns[id] = NSigmaTable{(const double4*)d, n ? E[0] : 0.0, n ? E[n - 1] : 0.0, c, n >= 2 ? n : 0, 0};
   e->ns_x[id].assign(E, E + n);
   e->ns_y[id].assign(y, y + n);
   e->species_dirty = true;
@@ -1971,7 +2039,9 @@ static int build_species_tables(pb_engine e) {
     PB_CUDA(e, cudaMalloc(&d, sizeof(double) * node.size()));
     e->owned.push_back(d);
     PB_CUDA(e, cudaMemcpy(d, node.data(), sizeof(double) * node.size(), cudaMemcpyHostToDevice));
-    e->tab.sp[sp] = NSigmaTable{(const double4*)d, m ? u[0] : 0.0, m ? u[m - 1] : 0.0, 0.0, 0.0, m, 0};
+    Coarse c;
+    { int rcc = build_coarse(e, u.data(), m >= 2 ? m : 0, 1, m - 1, &c); if (rcc != PB_OK) return rcc; }
+    e->tab.sp[sp] = NSigmaTable{(const double4*)d, m ? u[0] : 0.0, m ? u[m - 1] : 0.0, c, m >= 2 ? m : 0, 0};
   }
   e->species_dirty = false;
   return PB_OK;
@@ -1997,8 +2067,9 @@ extern "C" int pb_upload_maps(pb_engine e, int process, const double* grid, int 
   PB_CUDA(e, cudaMemcpy(dE, E_inc, sizeof(double) * nE, cudaMemcpyHostToDevice));
   PB_CUDA(e, cudaMemcpy(dE + nE, max_F, sizeof(double) * nE, cudaMemcpyHostToDevice));
   mi.grid = d; mi.E = dE; mi.maxF = dE + nE; mi.nE = nE; mi.dim = dim; mi.stride = padded; mi.B = neval; mi.invB = 1.0 / (double)neval;
-  mi.log_E0 = (E_inc[0] > 0) ? log(E_inc[0]) : 0.0;
-  mi.inv_dlog = (nE > 1 && E_inc[0] > 0 && E_inc[nE - 1] > E_inc[0]) ? (double)(nE - 1) / log(E_inc[nE - 1] / E_inc[0]) : 0.0;
+  if (!(E_inc[0] > 0.0)) { e->err = "map energies must be positive"; return PB_ERR_ARG; }
+  for (int r = 1; r < nE; ++r) if (!(E_inc[r] >= E_inc[r - 1])) { e->err = "map energies must not decrease"; return PB_ERR_ARG; }
+  { int rcc = build_coarse(e, E_inc, nE, 0, nE, &mi.c); if (rcc != PB_OK) return rcc; }
   e->tab.map[process] = mi;
   return PB_OK;
 }
@@ -2047,14 +2118,14 @@ static int ensure_work(pb_engine e, long long n) {
   long long cap = std::max<long long>(n * 5 / 4, 1 << 16);
   if (e->work_blob) { cudaFree(e->work_blob); e->work_blob = nullptr; }
   long long max_tiles = cap / TILE + N_SAMPLED * LU_MAX + 1;
-  size_t bytes = (size_t)cap * (4 + 4 + 32 + 8 + 8) + (size_t)max_tiles * 12 + 256;
+  size_t bytes = (size_t)cap * (4 + 8 + 32 + 8 + 8) + (size_t)max_tiles * 12 + 256;
   PB_CUDA(e, cudaMalloc(&e->work_blob, bytes));
   char* p = (char*)e->work_blob;
   e->work.xs = (double*)p; p += (size_t)cap * 32;
   e->work.sE = (double*)p; p += (size_t)cap * 8;
   e->work.skey = (uint2*)p; p += (size_t)cap * 8;
+  e->work.sorted = (int2*)p; p += (size_t)cap * 8;
   e->work.bucket = (int*)p; p += (size_t)cap * 4;
-  e->work.sorted = (int*)p; p += (size_t)cap * 4;
   e->work.tile_bucket = (int*)p; p += (size_t)max_tiles * 4;
   e->work.tile_start = (int*)p; p += (size_t)max_tiles * 4;
   e->work.tile_count = (int*)p;
@@ -2290,6 +2361,12 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     n_known = hws->n;
   }
   for (int k = 1; k < PB_K_N; ++k) e->prof.launches[k] = hws->waves;
+  if (e->work.tlog && !e->tlog_path.empty()) {
+    std::vector<unsigned long long> h(4 * (size_t)e->work.tlog_cap);
+    if (cudaMemcpy(h.data(), e->work.tlog, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+      if (FILE* f = fopen(e->tlog_path.c_str(), "ab")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+    cudaMemset(e->work.tlog, 0, h.size() * 8);
+  }
   long long end = hws->end, waves = hws->waves, max_wave = hws->max_wave, tot_charged = hws->tot_charged;
   if (hws->status == 2) {
     e->err = "particle stack capacity exhausted (wave " + std::to_string(waves) + ")";
@@ -2321,7 +2398,7 @@ static int upload_table(pb_engine e, const double* x, const double* y, int n, NS
   PB_CUDA(e, cudaMalloc(&d, sizeof(double) * node.size()));
   e->owned.push_back(d);
   PB_CUDA(e, cudaMemcpy(d, node.data(), sizeof(double) * node.size(), cudaMemcpyHostToDevice));
-  *out = NSigmaTable{(const double4*)d, n ? x[0] : 0.0, n ? x[n - 1] : 0.0, 0.0, 0.0, n, 0};
+  *out = NSigmaTable{(const double4*)d, n ? x[0] : 0.0, n ? x[n - 1] : 0.0, Coarse{nullptr, 0, 0}, n, 0};   // dark tables (log10 nodes): binary search
   return PB_OK;
 }
 
@@ -2597,6 +2674,7 @@ extern "C" int pb_measure_fp64_peak(pb_engine e, double* tflops) {
 extern "C" int pb_probe(pb_engine e, int what, int process, const double* in, int64_t n, int is, double* out, int os) {
   if (!e || !in || !out || n <= 0) return PB_ERR_ARG;
   PB_CUDA(e, cudaSetDevice(e->device));
+  if (e->species_dirty) { int rcs = build_species_tables(e); if (rcs != PB_OK) return rcs; }     // PB_PROBE_SUBSTEP / PROPAGATE read Tables::sp
   double *din = nullptr, *dout = nullptr;
   PB_CUDA(e, cudaMalloc(&din, sizeof(double) * n * is));
   PB_CUDA(e, cudaMalloc(&dout, sizeof(double) * n * os));

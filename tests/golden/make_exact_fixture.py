@@ -42,9 +42,12 @@ def _one(args):
 
 def main():
     workers = int(sys.argv[sys.argv.index("--workers") + 1]) if "--workers" in sys.argv else os.cpu_count()
-    out = {}
+    path = os.path.join(ROOT, "tests", "golden", "exact_showers.npz")
+    out = dict(np.load(path)) if os.path.exists(path) and "--fresh" not in sys.argv else {}     # finished cases are kept
     with Pool(workers) as pool:
         for name, n in CASES.items():
+            if f"{name}/mult" in out and len(out[f"{name}/mult"]) == n:
+                continue
             t0 = time.time()
             rows = pool.map(_one, [(name, i) for i in range(n)], chunksize=8)
             out[f"{name}/mult"] = np.array([r[0] for r in rows], dtype=np.int64)
@@ -52,7 +55,7 @@ def main():
             out[f"{name}/nsub"] = np.array([r[2] for r in rows], dtype=np.int64)
             out[f"{name}/proc_hist"] = np.stack([r[3] for r in rows])
             print(name, n, f"{time.time() - t0:.0f} s", "mean multiplicity", out[f"{name}/mult"].mean(), flush=True)
-            np.savez_compressed(os.path.join(ROOT, "tests", "golden", "exact_showers.npz"), **out)
+            np.savez_compressed(path, **out)
 
 
 if __name__ == "__main__":
