@@ -259,6 +259,20 @@ int pb_probe(pb_engine e, int what, int process, const double* in, int64_t n, in
  *   26 tape entries consumed, 27 weight factor, 28 propagated (1) / below threshold (0). */
 int pb_replay(pb_engine e, int64_t n, const double* particles, const double* tape, const int64_t* tape_off, double* out);
 
+/* Dark set-up quadratures: the integrals DarkShower.__init__ computes with scipy.integrate.quad - the cumulative
+ * interaction integrals II(E) (src/PETITE/shower.py:298-320), the emission weights (dark_shower.py:337-399) and the dRate/dE bins
+ * (dark_shower.py:454-493) - one GPU thread per integral, through a restatement of QUADPACK's QAGS (epsabs = epsrel = 1.49e-8,
+ * limit = 50, the scipy defaults; petite_b200/csrc/quadpack.cuh) so that the subdivision and extrapolation decisions, and with them
+ * the reference's numbers, are reproduced.  Tables are linear interpolants with a fill value outside their range (scipy interp1d).
+ *   kind 0: f(E) = table[tab](E)                                                                  (shower.py:305-320)
+ *   kind 1: f(E) = 10^table[tab](log10 E) / dEdx_cm * exp(-sum_k (table[surv_k](Ei) - table[surv_k](E)) / dEdx_m / cmtom), 0 if the
+ *           sum is negative or E > Ei, and 0 if `cut` and the first factor is below 1e-18       (dark_shower.py:311-335)
+ * ier [host, optional]: QUADPACK's ier * 1000 + number of sub-intervals used. */
+typedef struct pb_quad_call { int32_t kind, tab, surv[3], cut; double Ei, a, b; } pb_quad_call;
+int pb_quad_batch(pb_engine e, int n_tabs, const int32_t* tab_n, const double* const* tab_x, const double* const* tab_y,
+                  const double* tab_fill, double dEdx_GeV_per_m, const pb_quad_call* calls, int64_t n, double* result,
+                  double* abserr, int32_t* ier);
+
 #ifdef __cplusplus
 }
 #endif

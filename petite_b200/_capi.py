@@ -92,6 +92,8 @@ SIGNATURES = {
     "pb_measure_fp64_peak": (C.c_int, [pb_engine, c_double_p]),
     "pb_probe": (C.c_int, [pb_engine, C.c_int, C.c_int, c_double_p, C.c_int64, C.c_int, c_double_p, C.c_int]),
     "pb_replay": (C.c_int, [pb_engine, C.c_int64, c_double_p, c_double_p, C.POINTER(C.c_int64), c_double_p]),
+    "pb_quad_batch": (C.c_int, [pb_engine, C.c_int, c_int32_p, C.POINTER(c_double_p), C.POINTER(c_double_p), c_double_p, C.c_double,
+                                C.c_void_p, C.c_int64, c_double_p, c_double_p, c_int32_p]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(lib, _name)

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "engine.cu")
 OUT = os.path.join(HERE, "libpetite_b200.so")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("physics.cuh", "rng.cuh")] + \
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("physics.cuh", "rng.cuh", "quadpack.cuh")] + \
        [os.path.join(HERE, "..", "include", "petite_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

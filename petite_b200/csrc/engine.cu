@@ -23,6 +23,7 @@
 
 #include "../../include/petite_b200.h"
 #include "physics.cuh"
+#include "quadpack.cuh"
 
 namespace pb {
 
@@ -45,6 +46,12 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #endif
 #ifndef PB_SAMPLE_MINB_SM_T
 #define PB_SAMPLE_MINB_SM_T 5            // T = 2: 100 registers; measured (4, 2): minb 3 / 4 / 5 -> 62.5 / 57.3 / 57.0 ms per step, (4, 1): 62.3
+#endif
+#ifndef PB_SAMPLE_MINB_DB
+#define PB_SAMPLE_MINB_DB 4              // dark-brem family kernel (FAM = 3)
+#endif
+#ifndef PB_SAMPLE_T_DB_DEFAULT
+#define PB_SAMPLE_T_DB_DEFAULT 2
 #endif
 #ifndef PB_FIN_MINB
 #define PB_FIN_MINB 8                    // 64 registers, 8 CTAs per SM: measured 17.8 -> 15.3 ms per step (10: 15.7, 12: 16.2, uncapped 94 registers: 17.8) although it spills 92 B
@@ -155,7 +162,10 @@ struct Work {            // per-wave scratch, sized to the widest wave seen so f
   int* hist;             // [NBUCKET]
   int* offsets;          // [NBUCKET + 1]
   int* cursor;           // [NBUCKET]
-  int* tile_base;        // [NBUCKET + 1] exclusive prefix of the per-bucket tile counts (k_bucket_scan); k_bucket_fill expands it into:
+  int* tile_base;        // [2][NBUCKET + 1] exclusive prefix of the per-bucket tile counts (k_bucket_scan), heavy buckets (class 0: their
+                         // tiles come first) and the others (class 1); k_bucket_fill expands it into the tile table:
+  int* tile_sz;          // [NBUCKET] samples per tile of the bucket in this wave (cost-normalised, see k_bucket_scan)
+  unsigned long long* bstat;   // [NBUCKET][2] accepted samples and trials the sampler has spent in the bucket so far (all waves, all runs)
   int* tile_bucket;      // [max_tiles]
   int* tile_start;
   int* tile_count;
@@ -634,38 +644,81 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
   if ((threadIdx.x & 31) == 0 && c_steps) atomicAdd(&W.counters[CNT_STEPS], c_steps);
 }
 
-// Exclusive scan over NBUCKET bins + tile table; one CTA of 1024 threads, NBUCKET/1024 bins per thread.
+// Exclusive scan over NBUCKET bins + tile bookkeeping; one CTA of 1024 threads, NBUCKET/1024 bins per thread.
+// Tiles are COST-normalised: the accept/reject cost of a sample differs by an order of magnitude between buckets (10 GeV photons
+// in lead: Brem / PairProd rows need 12-40 trials per sample, the annihilation rows 100-170), and a 192-sample tile of such a row
+// used to run 300-500 us at the end of a launch whose other CTAs had finished (profiles/r02_summary.md, tile timeline).  The engine
+// therefore keeps, per bucket, the samples and trials spent so far (bstat), sizes a bucket's tiles so that every tile of the launch
+// costs about as many trials (TILE samples for a bucket at or below the launch's average trials per sample, proportionally fewer
+// above it), and puts the tiles of the heavy buckets (more than twice the average) at the front of the tile table.  Scheduling only: the samples themselves
+// are a pure function of (particle key, trial index).
+constexpr int TILE_MIN = 32;
 __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
   constexpr int PER = NBUCKET / 1024;
-  __shared__ int s_cnt[1024], s_til[1024];
+  __shared__ int s_cnt[1024], s_t0[1024], s_t1[1024];
+  __shared__ float s_w[32], s_c[32];
   int t = threadIdx.x;
-  int cnt[PER], til[PER];
-  int csum = 0, tsum = 0;
+  int cnt[PER], til[PER], heavy[PER];
+  float avg[PER];
+  // expected trials per sample of every bucket (16 until the bucket has a history) and of this launch as a whole
+  float wsum = 0.f, csamp = 0.f;
   for (int k = 0; k < PER; ++k) {
     int b = t * PER + k;
     int c = W.hist[b];
-    cnt[k] = c;
-    til[k] = (b < N_SAMPLED * LU_MAX) ? (c + TILE - 1) / TILE : 0;
-    csum += c; tsum += til[k];
+    cnt[k] = c; avg[k] = 16.f;
+    if (b < N_SAMPLED * LU_MAX) {
+      const unsigned long long ns = W.bstat[2 * b], nt = W.bstat[2 * b + 1];
+      if (ns >= 64) avg[k] = fmaxf((float)nt / (float)ns, 1.f);
+      wsum += avg[k] * (float)c; csamp += (float)c;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) { wsum += __shfl_down_sync(0xffffffffu, wsum, o); csamp += __shfl_down_sync(0xffffffffu, csamp, o); }
+  if ((t & 31) == 0) { s_w[t >> 5] = wsum; s_c[t >> 5] = csamp; }
+  __syncthreads();
+  float wall = 0.f, call = 0.f;
+  for (int k = 0; k < 32; ++k) { wall += s_w[k]; call += s_c[k]; }
+  const float avg_all = call > 0.f ? wall / call : 16.f;
+  // tile sizes relative to the launch average: a tile of any bucket costs about TILE x avg_all trials; the buckets more than twice as
+  // expensive per sample as the average go first
+  int csum = 0, t0sum = 0, t1sum = 0;
+  for (int k = 0; k < PER; ++k) {
+    int b = t * PER + k;
+    int c = cnt[k];
+    til[k] = 0; heavy[k] = 0;
+    if (b < N_SAMPLED * LU_MAX) {
+      int tsz = TILE;
+      if (avg[k] > avg_all) tsz = max(TILE_MIN, min(TILE, (int)((float)TILE * avg_all / avg[k]) & ~31));
+      W.tile_sz[b] = tsz;
+      til[k] = (c + tsz - 1) / tsz;
+      heavy[k] = avg[k] > 2.f * avg_all;
+    }
+    csum += c;
+    if (heavy[k]) t0sum += til[k]; else t1sum += til[k];
     W.hist[b] = 0;
     W.cursor[b] = 0;
   }
-  s_cnt[t] = csum; s_til[t] = tsum;
+  s_cnt[t] = csum; s_t0[t] = t0sum; s_t1[t] = t1sum;
   __syncthreads();
   for (int o = 1; o < 1024; o <<= 1) {           // Hillis-Steele inclusive scan
-    int a = (t >= o) ? s_cnt[t - o] : 0, b = (t >= o) ? s_til[t - o] : 0;
+    int a = 0, b = 0, c = 0;
+    if (t >= o) { a = s_cnt[t - o]; b = s_t0[t - o]; c = s_t1[t - o]; }
     __syncthreads();
-    s_cnt[t] += a; s_til[t] += b;
+    s_cnt[t] += a; s_t0[t] += b; s_t1[t] += c;
     __syncthreads();
   }
-  int cbase = s_cnt[t] - csum, tbase = s_til[t] - tsum;
+  int cbase = s_cnt[t] - csum, t0base = s_t0[t] - t0sum, t1base = s_t1[t] - t1sum;
+  int* tb0 = W.tile_base; int* tb1 = W.tile_base + NBUCKET + 1;
   for (int k = 0; k < PER; ++k) {
     int b = t * PER + k;
     W.offsets[b] = cbase;
-    W.tile_base[b] = tbase;          // the tile table itself is written by k_bucket_fill (wide), one thread per tile
-    cbase += cnt[k]; tbase += til[k];
+    tb0[b] = t0base; tb1[b] = t1base;          // the tile table itself is written by k_bucket_fill (wide), one thread per tile
+    cbase += cnt[k];
+    if (heavy[k]) t0base += til[k]; else t1base += til[k];
   }
-  if (t == 1023) { W.offsets[NBUCKET] = cbase; W.tile_base[NBUCKET] = tbase; W.ctrl[0] = tbase; W.ctrl[1] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0; }
+  if (t == 1023) {
+    W.offsets[NBUCKET] = cbase; tb0[NBUCKET] = t0base; tb1[NBUCKET] = t1base;
+    W.ctrl[0] = t0base + t1base; W.ctrl[1] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0;
+  }
   if (t == 0) W.ctrl[2] = 0;
 }
 
@@ -689,15 +742,17 @@ __global__ void __launch_bounds__(256) k_bucket_fill(Work W, SampleIO io, int n_
   const int lane = threadIdx.x & 31;
   const size_t off = io.ws ? (size_t)io.ws->begin : 0;
   // tile table: tile t belongs to the bucket b with tile_base[b] <= t < tile_base[b + 1] (binary search over the 4097-entry prefix)
-  const int n_tiles = W.ctrl[0];
+  const int n_tiles = W.ctrl[0], n_heavy = W.tile_base[NBUCKET];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
-    int lo = 0, hi = NBUCKET;                       // last b with tile_base[b] <= t
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (W.tile_base[mid] <= t) lo = mid; else hi = mid; }
-    const int j = t - W.tile_base[lo];
-    const int start = W.offsets[lo] + j * TILE;
+    const int* tb = t < n_heavy ? W.tile_base : W.tile_base + NBUCKET + 1;      // heavy buckets' tiles first
+    const int u = t < n_heavy ? t : t - n_heavy;
+    int lo = 0, hi = NBUCKET;                       // last b with tb[b] <= u
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (tb[mid] <= u) lo = mid; else hi = mid; }
+    const int tsz = W.tile_sz[lo];
+    const int start = W.offsets[lo] + (u - tb[lo]) * tsz;
     W.tile_bucket[t] = lo;
     W.tile_start[t] = start;
-    W.tile_count[t] = min(TILE, W.offsets[lo + 1] - start);
+    W.tile_count[t] = min(tsz, W.offsets[lo + 1] - start);
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int b = W.bucket[i];
@@ -748,7 +803,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // alone).  Per trial: Philox doubles D[0..dim] = y_0..y_{dim-1}, u_accept; map y -> x through the staged grid (vegas
 // AdaptiveMap: x = g[i] + (g[i+1]-g[i]) * (y*ninc - i), jac = prod ninc*(g[i+1]-g[i])); accept iff
 // max_F * u < (jac / B) * f(x)  (shower.py:453-459).  Returns the accept mask (bit k = trial t0 + k) and the point of the
-// LOWEST accepted trial in x.  FAM: -1 = every sampled process, 2 = the SM pass (4-D folded forms + the five 1-D SM processes).
+// LOWEST accepted trial in x.  FAM: -1 = every sampled process, 2 = the SM pass (4-D folded forms + the five 1-D SM processes),
+// 3 = the dark-bremsstrahlung family (DarkBrem, DarkMuonBrem: the 3-D folded form only).
 template <int DIM, int FAM, int T>
 __device__ __forceinline__ unsigned trial_block(const Material& M, const MapInfo& mi, const double* __restrict__ g, int proc,
                                                 double E, const SampleConst& sc, double maxF, uint2 key, uint32_t t0, double* x) {
@@ -834,9 +890,10 @@ __device__ __forceinline__ unsigned trial_block(const Material& M, const MapInfo
 __host__ __device__ constexpr bool proc_is_sm(int p) { return p < P_DARKBREM; }
 __host__ __device__ constexpr bool proc_is_4d(int p) { return p == P_BREM || p == P_PAIRPROD || p == P_MUONBREM; }
 
+// family_mode (FAM == -1 only): 1 = leave the dark-brem tiles to the FAM = 3 launch of the same pass (own tile cursor, ctrl[4])
 template <int G, int FAM, int T>
-__global__ void __launch_bounds__(SAMPLE_THREADS, (FAM == 2) ? (T > 1 ? PB_SAMPLE_MINB_SM_T : PB_SAMPLE_MINB_SM) : (T > 1 ? PB_SAMPLE_MINB_T : PB_SAMPLE_MINB))
-k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, SampleIO io, Work W) {
+__global__ void __launch_bounds__(SAMPLE_THREADS, (FAM == 2) ? (T > 1 ? PB_SAMPLE_MINB_SM_T : PB_SAMPLE_MINB_SM) : (FAM == 3) ? PB_SAMPLE_MINB_DB : (T > 1 ? PB_SAMPLE_MINB_T : PB_SAMPLE_MINB))
+k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, SampleIO io, Work W, int family_mode) {
   const Tables& Tb = T_;
   __shared__ __align__(128) double s_grid[GRID_SMEM_DOUBLES];
   __shared__ __align__(16) double s_E[TILE], s_cb[TILE], s_cc[TILE], s_cd[TILE];   // per-entry energy and sampler constants
@@ -855,12 +912,16 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
   const size_t off = io.ws ? (size_t)io.ws->begin : 0;
   __syncthreads();
   for (;;) {
-    if (threadIdx.x == 0) { s_tile = atomicAdd(&W.ctrl[1], 1); s_cursor = 0; }
+    if (threadIdx.x == 0) { s_tile = atomicAdd(&W.ctrl[(FAM == -1 && family_mode == 1) ? 4 : 1], 1); s_cursor = 0; }
     __syncthreads();
     int tile = s_tile;
     if (tile >= W.ctrl[0]) break;
     int bucket = W.tile_bucket[tile], tstart = W.tile_start[tile], tcount = W.tile_count[tile];
     int proc = bucket / LU_MAX, lu = bucket % LU_MAX;
+    {
+      const bool db = proc == P_DARKBREM || proc == P_DARKMUONBREM;
+      if ((FAM == 3 && !db) || (FAM == -1 && family_mode == 1 && db)) { __syncthreads(); continue; }     // the other launch's tile
+    }
     const MapInfo& mi = Tb.map[proc];
     const bool tlog = W.tlog != nullptr && threadIdx.x == 0 && io.ws != nullptr && io.ws->waves == W.tlog_wave && tile < W.tlog_cap;
     if (tlog) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); W.tlog[4 * tile] = t; }
@@ -876,7 +937,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
       s_E[k] = Ek;
       s_key[k] = W.skey[tstart + k];
       s_idx[k] = W.sorted[tstart + k].x;
-      if (proc_is_4d(proc)) {
+      if (FAM != 3 && proc_is_4d(proc)) {
         SampleConst c = (proc == P_PAIRPROD) ? pairprod_const(M, Ek) : brem_const(M, Ek, proc == P_BREM ? kMe : kMmu);
         s_cb[k] = c.b; s_cc[k] = c.c; s_cd[k] = c.d;
       } else if (FAM != 2 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) {
@@ -904,7 +965,8 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
           E = s_E[j];
           key = s_key[j];
           next_t = 0;
-          if (proc == P_PAIRPROD) sc = SampleConst{E - 2 * kMe, s_cb[j], s_cc[j], s_cd[j], 0.0};
+          if (FAM == 3) sc = SampleConst{0.0, s_cb[j], s_cc[j], M.i2mT, s_cd[j]};
+          else if (proc == P_PAIRPROD) sc = SampleConst{E - 2 * kMe, s_cb[j], s_cc[j], s_cd[j], 0.0};
           else if (proc == P_BREM) sc = SampleConst{E - kMe - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMe * kMe};
           else if (proc == P_MUONBREM) sc = SampleConst{E - kMmu - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMmu * kMmu};
           else if (FAM != 2 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) sc = SampleConst{0.0, s_cb[j], s_cc[j], M.i2mT, s_cd[j]};
@@ -948,6 +1010,8 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
         if (FAM == 2) {
           if (proc_is_4d(proc)) am = trial_block<4, 2, T>(M, mi, s_grid, proc, E, sc, maxF, key, t0, x);
           else am = trial_block<1, 2, T>(M, mi, s_grid, proc, E, sc, maxF, key, t0, x);
+        } else if (FAM == 3) {
+          am = trial_block<3, 3, T>(M, mi, s_grid, proc, E, sc, maxF, key, t0, x);
         } else switch (mi.dim) {
           case 4: am = trial_block<4, -1, T>(M, mi, s_grid, proc, E, sc, maxF, key, t0, x); break;
           case 3: am = trial_block<3, -1, T>(M, mi, s_grid, proc, E, sc, maxF, key, t0, x); break;
@@ -1007,8 +1071,8 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
       W.tlog[4 * tile + 1] = t; W.tlog[4 * tile + 2] = ((unsigned long long)bucket << 32) | (unsigned)tcount; W.tlog[4 * tile + 3] = ((unsigned long long)s_ptrials << 16) | sm;
     }
     if (threadIdx.x == 0) {
-      if (s_ptrials) { atomicAdd(&W.counters[CNT_TRIALS], s_ptrials); atomicAdd(&W.counters[CNT_PROC_TRIALS + proc], s_ptrials); }
-      if (s_psamples) { atomicAdd(&W.counters[CNT_SAMPLES], s_psamples); atomicAdd(&W.counters[CNT_PROC_SAMPLES + proc], s_psamples); }
+      if (s_ptrials) { atomicAdd(&W.counters[CNT_TRIALS], s_ptrials); atomicAdd(&W.counters[CNT_PROC_TRIALS + proc], s_ptrials); atomicAdd(&W.bstat[2 * bucket + 1], s_ptrials); }
+      if (s_psamples) { atomicAdd(&W.counters[CNT_SAMPLES], s_psamples); atomicAdd(&W.counters[CNT_PROC_SAMPLES + proc], s_psamples); atomicAdd(&W.bstat[2 * bucket], s_psamples); }
       s_ptrials = 0; s_psamples = 0;
     }
   }
@@ -1064,25 +1128,26 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     if (wave_order) { i = j; bucket = W.bucket[i]; }
     else { int2 ib = W.sorted[j]; i = ib.x; bucket = ib.y; }
     proc = bucket / LU_MAX;
-    double2 x01 = make_double2(0.0, 0.0), x23 = make_double2(0.0, 0.0);
-    if (proc < N_SAMPLED) {
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0, x01 = a0, x23 = a0;
+    if (proc != P_NONE) {
+      // every load of this particle is issued here, behind the one coalesced (index, bucket) read: two levels of memory latency
+      slot = begin + i;
+      const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * slot);
+      const double2* rfp = reinterpret_cast<const double2*>(S.rf + 4 * slot);
       const double2* xp = reinterpret_cast<const double2*>(W.xs + 4 * (size_t)i);
-      x01 = xp[0]; x23 = xp[1];
+      a0 = pfp[0]; a1 = pfp[1]; b0 = rfp[0]; b1 = rfp[1];
+      if (proc < N_SAMPLED) { x01 = xp[0]; x23 = xp[1]; }
+      meta = ld_meta(S, slot);
+      { int4 kw = ld_kw(S, slot); key = kw_key(kw); wgt = kw_weight(kw); }
       if (x01.x != x01.x) {                                          // the sampler gave up ("No Sample Found", shower.py:460-461)
-        S.ids[2 * (begin + i)].z |= (PB_FLAG_NO_SAMPLE << 8);
+        S.ids[2 * slot].z = meta.z | (PB_FLAG_NO_SAMPLE << 8);
         proc = P_NONE;
       }
     }
     if (proc != P_NONE) {
-      slot = begin + i;
-      const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * slot);
-      const double2* rfp = reinterpret_cast<const double2*>(S.rf + 4 * slot);
-      double2 a0 = pfp[0], a1 = pfp[1], b0 = rfp[0], b1 = rfp[1];
       V4 pf{a0.x, a0.y, a1.x, a1.y};
       rx = b0.x; ry = b0.y; rz = b1.x;
       double mass = b1.y;
-      meta = ld_meta(S, slot);
-      { int4 kw = ld_kw(S, slot); key = kw_key(kw); wgt = kw_weight(kw); }
       int pid = meta.x;
       double x[4] = {x01.x, x01.y, x23.x, x23.y};
       PhiloxDraws ds{key};
@@ -1665,6 +1730,47 @@ __global__ void k_replay(const __grid_constant__ Material M, const __grid_consta
   o[26] = (double)(ds.pos - tape_off[i]); o[27] = wfac; o[28] = stepped ? 1.0 : 0.0;
 }
 
+// ------------------------------------------------------------------------------------------ dark set-up quadratures (row f-3)
+// The integrals DarkShower.__init__ computes with scipy.integrate.quad (dark_shower.py:311-399, 454-493; shower.py:298-354), one
+// thread per integral, through the QAGS restatement in quadpack.cuh.  Tables are evaluated like scipy's interp1d (linear,
+// fill value outside): the same +, -, *, / as the host twin petite_b200.shower.LinearTable, never contracted.
+struct QuadTab { const double* x; const double* y; int n; int pad; double fill; };
+struct QuadTabs { const QuadTab* t; double dEdx_m; };
+__device__ __forceinline__ double quad_lin(const QuadTab& T, double v) {
+  int lo = 0, hi = T.n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (T.x[mid] < v) lo = mid + 1; else hi = mid; }      // searchsorted(side='left')
+  hi = min(max(lo, 1), T.n - 1);
+  lo = hi - 1;
+  double slope = __ddiv_rn(__dsub_rn(T.y[hi], T.y[lo]), __dsub_rn(T.x[hi], T.x[lo]));
+  double out = __dadd_rn(__dmul_rn(slope, __dsub_rn(v, T.x[lo])), T.y[lo]);
+  return (v < T.x[0] || v > T.x[T.n - 1]) ? T.fill : out;
+}
+struct QuadIntegrand {
+  const QuadTab* t; pb_quad_call c; double dEdx_m;
+  __device__ double operator()(double E) const {
+    if (c.kind == 0) return quad_lin(t[c.tab], E);                          // shower.py:298-320: the n*sigma table itself
+    // dark_shower.py:311-335: n*sigma_dark(E) / dEdx * survival(E, Ei)
+    double v = pow(10.0, quad_lin(t[c.tab], log10(E)));                     // dark_shower.py:31-46 (log-log table)
+    if (c.cut && v < 1.0e-18) return 0.0;
+    double d = 0.0;                                                        // shower.py:322-354: sum over the species' processes
+    for (int k = 0; k < 3; ++k)
+      if (c.surv[k] >= 0) d = __dadd_rn(d, __dsub_rn(quad_lin(t[c.surv[k]], c.Ei), quad_lin(t[c.surv[k]], E)));
+    if (d < 0.0 || E > c.Ei) return 0.0;
+    const double dEdx_cm = __dmul_rn(dEdx_m, kCmToM);
+    return __dmul_rn(__ddiv_rn(v, dEdx_cm), exp(__ddiv_rn(__ddiv_rn(-d, dEdx_m), kCmToM)));
+  }
+};
+__global__ void __launch_bounds__(64) k_quad(QuadTabs T, const pb_quad_call* __restrict__ calls, long long n, double* __restrict__ result,
+                                             double* __restrict__ abserr, int* __restrict__ ier) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  QuadIntegrand f{T.t, calls[i], T.dEdx_m};
+  pbq::QagsOut o = pbq::qags(f, f.c.a, f.c.b, 1.49e-8, 1.49e-8);           // scipy.integrate.quad defaults
+  result[i] = o.result;
+  if (abserr) abserr[i] = o.abserr;
+  if (ier) ier[i] = o.ier * 1000 + o.last;
+}
+
 // ------------------------------------------------------------------------------------------ probes (tests)
 __global__ void k_probe(const __grid_constant__ Material M, const __grid_constant__ Tables T, int what, int process,
                         const double* __restrict__ in, long long n, int is, double* __restrict__ out, int os) {
@@ -1819,6 +1925,8 @@ struct pb_engine_s {
   int sample_group = PB_SAMPLE_G_DEFAULT;    // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
   int sample_trials = PB_SAMPLE_T_DEFAULT;   // trials per lane and round (PB_SAMPLE_T): ILP inside the lane
   int sample_trials_dark = PB_SAMPLE_T_DARK_DEFAULT;   // the same for the generic kernel (PB_SAMPLE_T_DARK)
+  int sample_trials_db = PB_SAMPLE_T_DB_DEFAULT;       // the same for the dark-brem family kernel (PB_SAMPLE_T_DB)
+  int sample_split_db = 1;                             // PB_SAMPLE_SPLIT_DB=0: dark pass through one generic launch
   int sample_generic = 0;        // PB_SAMPLE_GENERIC=1: SM pass through the generic kernel (with the dark integrands compiled in)
   int emit_wave_order = 0;       // PB_EMIT_ORDER=1: k_emit walks the wave in record order (coalesced) instead of bucket order
   static constexpr int LOOKAHEAD = 8;   // waves enqueued per host synchronisation while the shower tail shrinks
@@ -1894,6 +2002,8 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   if (const char* g = getenv("PB_SAMPLE_T")) e->sample_trials = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_T_DARK")) e->sample_trials_dark = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_GENERIC")) e->sample_generic = atoi(g);
+  if (const char* g = getenv("PB_SAMPLE_T_DB")) e->sample_trials_db = atoi(g);
+  if (const char* g = getenv("PB_SAMPLE_SPLIT_DB")) e->sample_split_db = atoi(g);
   if (const char* g = getenv("PB_EMIT_ORDER")) e->emit_wave_order = atoi(g);
   if (const char* g = getenv("PB_GRAPH")) e->use_graph = atoi(g);
   if (const char* g = getenv("PB_TILE_LOG")) {            // "<file>:<wave>": per-tile timeline of k_sample in that wave of every run (appended)
@@ -1907,7 +2017,7 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
       else cudaMemset(e->work.tlog, 0, sizeof(unsigned long long) * 4 * (size_t)e->work.tlog_cap);
     }
   }
-  size_t fixed = sizeof(int) * (NBUCKET * 4 + 2 + 16) + sizeof(unsigned long long) * (8 + CNT_N) + sizeof(WaveState) + 64;
+  size_t fixed = sizeof(int) * (NBUCKET * 6 + 3 + 16) + sizeof(unsigned long long) * (8 + CNT_N + 2 * NBUCKET) + sizeof(WaveState) + 64;
   if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
   cudaMemset(e->fixed_blob, 0, fixed);
   for (int i = 0; i < 2 * 8; ++i) cudaEventCreate(&e->ev[i]);
@@ -1915,10 +2025,12 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   char* p = (char*)e->fixed_blob;
   e->work.tail = (unsigned long long*)p; p += 8 * sizeof(unsigned long long);
   e->work.counters = (unsigned long long*)p; p += CNT_N * sizeof(unsigned long long);
+  e->work.bstat = (unsigned long long*)p; p += 2 * NBUCKET * sizeof(unsigned long long);
   e->work.hist = (int*)p; p += NBUCKET * sizeof(int);
   e->work.offsets = (int*)p; p += (NBUCKET + 1) * sizeof(int);
   e->work.cursor = (int*)p; p += NBUCKET * sizeof(int);
-  e->work.tile_base = (int*)p; p += (NBUCKET + 1) * sizeof(int);
+  e->work.tile_base = (int*)p; p += 2 * (NBUCKET + 1) * sizeof(int);
+  e->work.tile_sz = (int*)p; p += NBUCKET * sizeof(int);
   e->work.ctrl = (int*)p; p += 16 * sizeof(int);
   p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
   e->work.ws = (WaveState*)p;
@@ -2078,21 +2190,26 @@ static int ensure_cand(pb_engine e, long long ncap);
 // SM pass: a kernel instantiated without the dark integrands (fewer registers, one more CTA per SM); dark pass and
 // stand-alone sampling: the generic instantiation.  (G, T) = lanes per sample x trials per lane and round.
 template <int FAM>
-static void launch_sample_fam(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream) {
-  const int G = e->sample_group, T = (FAM == 2) ? e->sample_trials : e->sample_trials_dark;
-#define PB_LS(g, t) if (G == g && T == t) { k_sample<g, FAM, t><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work); return; }
+static void launch_sample_fam(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream, int family_mode) {
+  const int G = e->sample_group, T = (FAM == 2) ? e->sample_trials : (FAM == 3 ? e->sample_trials_db : e->sample_trials_dark);
+#define PB_LS(g, t) if (G == g && T == t) { k_sample<g, FAM, t><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work, family_mode); return; }
   PB_LS(4, 1) PB_LS(2, 2) PB_LS(1, 2) PB_LS(4, 2) PB_LS(2, 1) PB_LS(8, 1) PB_LS(1, 4) PB_LS(2, 4) PB_LS(1, 1)
 #undef PB_LS
-  k_sample<4, FAM, 1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work);
+  k_sample<4, FAM, 1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work, family_mode);
 }
-static int sample_grid(pb_engine e, long long n, bool sm_pass) {
-  const int T = sm_pass && !e->sample_generic ? e->sample_trials : e->sample_trials_dark;
-  const int minb = sm_pass ? (T > 1 ? PB_SAMPLE_MINB_SM_T : PB_SAMPLE_MINB_SM) : (T > 1 ? PB_SAMPLE_MINB_T : PB_SAMPLE_MINB);
+static int sample_grid(pb_engine e, long long n, bool sm_pass, bool db = false) {
+  const int T = db ? e->sample_trials_db : (sm_pass && !e->sample_generic ? e->sample_trials : e->sample_trials_dark);
+  const int minb = db ? PB_SAMPLE_MINB_DB : (sm_pass ? (T > 1 ? PB_SAMPLE_MINB_SM_T : PB_SAMPLE_MINB_SM) : (T > 1 ? PB_SAMPLE_MINB_T : PB_SAMPLE_MINB));
   return (int)std::max<long long>(1, std::min<long long>((long long)e->n_sm * minb, (n + 31) / 32 + 1));
 }
-static void launch_sample(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream, bool sm_pass = false) {
-  if (sm_pass && !e->sample_generic) launch_sample_fam<2>(e, grid, io, stream);
-  else launch_sample_fam<-1>(e, grid, io, stream);
+// SM pass: the FAM = 2 kernel (no dark integrands: fewer registers, one more CTA per SM).  Dark pass / stand-alone sampling: the
+// dark-brem tiles (3-D folded form, ~70-300 trials per sample: 90 % of a dark pass) go to the FAM = 3 kernel and everything else to
+// the generic one, two launches over the same tile table with their own cursors (PB_SAMPLE_SPLIT_DB=0: one generic launch).
+static void launch_sample(pb_engine e, long long n, const SampleIO& io, cudaStream_t stream, bool sm_pass = false) {
+  if (sm_pass && !e->sample_generic) { launch_sample_fam<2>(e, sample_grid(e, n, true), io, stream, 0); return; }
+  if (sm_pass || !e->sample_split_db) { launch_sample_fam<-1>(e, sample_grid(e, n, sm_pass), io, stream, 0); return; }
+  launch_sample_fam<3>(e, sample_grid(e, n, false, true), io, stream, 0);
+  launch_sample_fam<-1>(e, sample_grid(e, n, false), io, stream, 1);
 }
 
 // index lists live apart from the other scratch: growing them must keep their contents (a paused wave still needs them)
@@ -2117,7 +2234,7 @@ static int ensure_work(pb_engine e, long long n) {
   if (n <= e->work_n) return PB_OK;
   long long cap = std::max<long long>(n * 5 / 4, 1 << 16);
   if (e->work_blob) { cudaFree(e->work_blob); e->work_blob = nullptr; }
-  long long max_tiles = cap / TILE + N_SAMPLED * LU_MAX + 1;
+  long long max_tiles = cap / TILE_MIN + N_SAMPLED * LU_MAX + 1;
   size_t bytes = (size_t)cap * (4 + 8 + 32 + 8 + 8) + (size_t)max_tiles * 12 + 256;
   PB_CUDA(e, cudaMalloc(&e->work_blob, bytes));
   char* p = (char*)e->work_blob;
@@ -2178,7 +2295,7 @@ static int ensure_wave_graph(pb_engine e, const Stack& S, int ms_flag) {
   k_bucket_scan<<<1, 1024, 0, cs>>>(e->work);
   SampleIO io{S.pf, reinterpret_cast<const uint2*>(S.ids), 4, 2, nullptr, reinterpret_cast<int*>(S.aux), 2, e->work.ws};
   k_bucket_fill<<<g_fill, 256, 0, cs>>>(e->work, io, -1);
-  launch_sample(e, sample_grid(e, 1LL << 40, true), io, cs, true);
+  launch_sample(e, 1LL << 40, io, cs, true);
   k_emit<<<g_emit, 128, 0, cs>>>(e->mat, e->tab, S, e->work, e->emit_wave_order);
   cudaError_t ce = cudaStreamEndCapture(cs, nullptr);
   if (ce != cudaSuccess) { e->err = std::string("wave graph capture: ") + cudaGetErrorString(ce); return PB_ERR_CUDA; }
@@ -2324,7 +2441,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
       SampleIO io{S.pf, reinterpret_cast<const uint2*>(S.ids), 4, 2, nullptr, reinterpret_cast<int*>(S.aux), 2, e->work.ws};
       k_bucket_fill<<<g256, 256, 0, stream>>>(e->work, io, -1);
       tock(PB_K_FILL, j); tick(PB_K_SAMPLE, j);
-      launch_sample(e, sg, io, stream, true);
+      launch_sample(e, bound, io, stream, true);
       tock(PB_K_SAMPLE, j); tick(PB_K_EMIT, j);
       k_emit<<<g128, 128, 0, stream>>>(e->mat, e->tab, S, e->work, e->emit_wave_order);
       tock(PB_K_EMIT, j);
@@ -2471,7 +2588,7 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
     SampleIO io{e->cand.pf, reinterpret_cast<const uint2*>(S.ids), 4, 2, e->cand.slot, e->cand.ntr, 1, nullptr};
     k_bucket_fill<<<(unsigned)((n_cand + 255) / 256), 256, 0, stream>>>(e->work, io, n_cand);
     tock(PB_K_FILL); tick(PB_K_SAMPLE);
-    launch_sample(e, sample_grid(e, n_cand, false), io, stream);
+    launch_sample(e, n_cand, io, stream);
     tock(PB_K_SAMPLE); tick(PB_K_EMIT);
     k_dark_emit<<<(unsigned)((n_cand + 127) / 128), 128, 0, stream>>>(e->mat, S, O, e->work, e->cand, n_cand);
     tock(PB_K_EMIT);
@@ -2537,7 +2654,7 @@ extern "C" int pb_draw_samples(pb_engine e, int process, const double* E, int64_
   k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
   SampleIO io{e->cand.pf, dkeys, 1, 0, nullptr, e->cand.ntr, 1, nullptr};
   k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, io, (int)n);
-  launch_sample(e, sample_grid(e, n, false), io, stream);
+  launch_sample(e, n, io, stream);
   cudaError_t c = cudaMemcpyAsync(x_out, e->work.xs, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, stream);
   if (c == cudaSuccess && ntr_out) c = cudaMemcpyAsync(ntr_out, e->cand.ntr, sizeof(int) * n, cudaMemcpyDeviceToHost, stream);
   if (c == cudaSuccess) c = cudaStreamSynchronize(stream);
@@ -2715,5 +2832,51 @@ extern "C" int pb_replay(pb_engine e, int64_t n, const double* particles, const 
   cudaStreamDestroy(st);
   cudaFree(din); cudaFree(dtape); cudaFree(doff); cudaFree(dout);
   if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
+  return PB_OK;
+}
+
+extern "C" int pb_quad_batch(pb_engine e, int n_tabs, const int32_t* tab_n, const double* const* tab_x, const double* const* tab_y,
+                             const double* tab_fill, double dEdx_GeV_per_m, const pb_quad_call* calls, int64_t n, double* result,
+                             double* abserr, int32_t* ier) {
+  if (!e || n_tabs < 1 || !tab_n || !tab_x || !tab_y || !tab_fill || !calls || !result || n <= 0) return PB_ERR_ARG;
+  for (int64_t i = 0; i < n; ++i) {
+    const pb_quad_call& c = calls[i];
+    bool ok = c.tab >= 0 && c.tab < n_tabs && (c.kind == 0 || c.kind == 1);
+    for (int k = 0; k < 3 && ok; ++k) ok = c.surv[k] < n_tabs;
+    if (!ok) { e->err = "pb_quad_batch: call " + std::to_string(i) + " refers to a table that does not exist"; return PB_ERR_ARG; }
+  }
+  PB_CUDA(e, cudaSetDevice(e->device));
+  size_t total = 0;
+  for (int k = 0; k < n_tabs; ++k) { if (tab_n[k] < 2) { e->err = "pb_quad_batch: tables need two nodes"; return PB_ERR_ARG; } total += (size_t)tab_n[k]; }
+  std::vector<double> flat(2 * total);
+  std::vector<QuadTab> tabs((size_t)n_tabs);
+  double* d_flat = nullptr; QuadTab* d_tabs = nullptr; pb_quad_call* d_calls = nullptr; double* d_out = nullptr; int* d_ier = nullptr;
+  cudaStream_t st = nullptr;
+  auto cleanup = [&]() { cudaFree(d_flat); cudaFree(d_tabs); cudaFree(d_calls); cudaFree(d_out); cudaFree(d_ier); if (st) cudaStreamDestroy(st); };
+#define PB_Q(call) do { cudaError_t _c = (call); if (_c != cudaSuccess) { e->err = std::string(#call) + ": " + cudaGetErrorString(_c); cleanup(); return PB_ERR_CUDA; } } while (0)
+  PB_Q(cudaMalloc(&d_flat, sizeof(double) * flat.size()));
+  size_t off = 0;
+  for (int k = 0; k < n_tabs; ++k) {
+    memcpy(&flat[off], tab_x[k], sizeof(double) * tab_n[k]);
+    memcpy(&flat[off + tab_n[k]], tab_y[k], sizeof(double) * tab_n[k]);
+    tabs[k] = QuadTab{d_flat + off, d_flat + off + tab_n[k], tab_n[k], 0, tab_fill[k]};
+    off += 2 * (size_t)tab_n[k];
+  }
+  PB_Q(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  PB_Q(cudaMalloc(&d_tabs, sizeof(QuadTab) * tabs.size()));
+  PB_Q(cudaMalloc(&d_calls, sizeof(pb_quad_call) * n));
+  PB_Q(cudaMalloc(&d_out, sizeof(double) * 2 * n));
+  PB_Q(cudaMalloc(&d_ier, sizeof(int) * n));
+  PB_Q(cudaMemcpyAsync(d_flat, flat.data(), sizeof(double) * flat.size(), cudaMemcpyHostToDevice, st));
+  PB_Q(cudaMemcpyAsync(d_tabs, tabs.data(), sizeof(QuadTab) * tabs.size(), cudaMemcpyHostToDevice, st));
+  PB_Q(cudaMemcpyAsync(d_calls, calls, sizeof(pb_quad_call) * n, cudaMemcpyHostToDevice, st));
+  k_quad<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(QuadTabs{d_tabs, dEdx_GeV_per_m}, d_calls, n, d_out, d_out + n, d_ier);
+  PB_Q(cudaGetLastError());
+  PB_Q(cudaMemcpyAsync(result, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (abserr) PB_Q(cudaMemcpyAsync(abserr, d_out + n, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (ier) PB_Q(cudaMemcpyAsync(ier, d_ier, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+  PB_Q(cudaStreamSynchronize(st));
+#undef PB_Q
+  cleanup();
   return PB_OK;
 }

@@ -83,6 +83,19 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(r, e, r);
 }
 
+// Square root without the IEEE routine's special-case branch and slow-path call: MUFU.RSQ64H seed, one Newton step on 1/sqrt(x),
+// one correction of x * r (<= 1 ulp).  Same contract as fast_rcp: finite normal positive arguments; anything else (negative, 0, Inf)
+// yields NaN / garbage, which the branch-free integrands discard through their kinematic mask.
+__device__ __forceinline__ double fast_sqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double h = 0.5 * x;
+  r = fma(r, fma(-h * r, r, 0.5), r);          // r (1 + (1/2 - x r^2 / 2))
+  r = fma(r, fma(-h * r, r, 0.5), r);
+  double s = x * r;
+  return fma(fma(-s, s, x), 0.5 * r, s);       // s + (x - s^2) r / 2
+}
+
 // ---------------------------------------------------------------- hot-loop elementary functions
 // The sub-step loop calls exp, log (twice), sincos and sincospi once per iteration.  libdevice's versions are accurate but
 // ptxas materialises each of their ~60 fp64 polynomial coefficients as a pair of 32-bit immediate moves (24 % of k_loop's
@@ -516,43 +529,45 @@ __device__ __forceinline__ double ff_el_inel_over_t2_fast(const Material& M, dou
   return M.dff_pref * (Gel + Ginel);
 }
 __device__ __forceinline__ double ds_darkbrem_fast(const Material& M, const SampleConst& sc, double Eb, double ml, const double* xx) {
+  // branch-free (the kinematic cuts select at the end): the lanes of a warp sit at independent points, so an early return saves
+  // nothing under SIMT, and straight-line code lets the T trials a lane evaluates per round interleave.  Outside the cuts the
+  // arithmetic runs on garbage (sqrt of a negative number -> NaN) and is discarded.
   const double mV = M.mV, MT = M.mT;
   const double LN10 = 2.302585092994046;
   double x = xx[0];
   double xE = x * Eb;
-  if (!(xE >= mV)) return 0.0;
   double omc = hot_exp10(xx[1]);
   double cth = 1.0 - omc;
   double ttilde = hot_exp10(xx[2]);
   double mV2 = mV * mV, ml2 = ml * ml;
-  double k = sqrt(fabs(xE * xE - mV2));
+  double k = fast_sqrt(fabs(xE * xE - mV2));
   const double p = sc.b;
   double V2 = p * p + k * k - 2 * p * k * cth;
-  double V = sqrt(V2);
+  double V = fast_sqrt(V2);
   double VV = V * V;
   double utilde = -2 * (x * Eb * Eb - k * p * cth) + mV2;
   double Er = (1 - x) * Eb + MT;
   double discr = utilde * utilde + 4 * MT * utilde * Er + 4 * MT * MT * VV;
-  if (!(discr >= 0)) return 0.0;
-  double sq = sqrt(discr);
+  bool ok = (xE >= mV) && (discr >= 0);
+  double sq = fast_sqrt(discr);
   double iden = fast_rcp(2 * Er * Er - 2 * VV);
   double cmn = V * (utilde + 2 * MT * Er);
   double Qp = fabs((cmn + Er * sq) * iden);
   double Qm = fabs((cmn - Er * sq) * iden);
-  double tplus = 2 * MT * (sqrt(MT * MT + Qp * Qp) - MT);
-  double tminus = 2 * MT * (sqrt(MT * MT + Qm * Qm) - MT);
+  double tplus = 2 * MT * (fast_sqrt(MT * MT + Qp * Qp) - MT);
+  double tminus = 2 * MT * (fast_sqrt(MT * MT + Qm * Qm) - MT);
   const double tconv = sc.c, i2MT = sc.d;
   double t = ttilde * tconv;
-  if (!((tplus > tminus) && (t > tminus) && (t < tplus))) return 0.0;
+  ok = ok && (tplus > tminus) && (t > tminus) && (t < tplus);
   double q0 = -t * i2MT;
-  double q = sqrt(t * t * (i2MT * i2MT) + t);
+  double q = fast_sqrt(t * t * (i2MT * i2MT) + t);
   double e3 = Eb + q0 - xE;
   double iV = fast_rcp(V), iq = fast_rcp(q);
   double cthq = -(VV + q * q + ml2 - e3 * e3) * (0.5 * iV * iq);
   double mm = mV2 + 2 * ml2;
   double Y = -t + 2 * q0 * Eb - 2 * q * p * (p - k * cth) * cthq * iV;
   double W = fabs(Y * Y - 4 * q * q * p * p * k * k * (1 - cth * cth) * (1 - cthq * cthq) * (iV * iV));
-  if (!((fabs(cthq) <= 1.0) && (W > 0))) return 0.0;
+  ok = ok && (fabs(cthq) <= 1.0) && (W > 0);
   double iu = fast_rcp(utilde);
   double Am2 = -8 * MT * (4 * Eb * Eb * MT - t * (2 * Eb + MT)) * mm;
   double A1 = 8 * MT * MT * iu;
@@ -563,12 +578,13 @@ __device__ __forceinline__ double ds_darkbrem_fast(const Material& M, const Samp
                            + t * t * (utilde - mV2));
   double A0 = (8 * iu * iu) * (MT * MT * (2 * t * utilde + (t - 4 * Eb * Eb * (x - 1) * (x - 1)) * mm)
                                + 2 * Eb * MT * t * (utilde - (x - 1) * mm));
-  double sW = sqrt(W);
+  double sW = fast_sqrt(W);
   double isW = fast_rcp(sW);
   double phi_int = (A0 + Y * A1 + Am1 * isW + Y * Am2 * (isW * isW * isW)) * (0.5 * i2MT * i2MT);
   double FF = ff_el_inel_over_t2_fast(M, t);
   double Jac = omc * ttilde * (LN10 * LN10);
-  return FF * (kAlpha * kAlpha * kAlpha) * k * Eb * phi_int * (sc.e * iV) * tconv * Jac;
+  double f = FF * (kAlpha * kAlpha * kAlpha) * k * Eb * phi_int * (sc.e * iV) * tconv * Jac;
+  return ok ? f : 0.0;
 }
 
 // radiative_return.py:26-79 + all_processes.py:400-466 (dsigma_radiative_return_du)

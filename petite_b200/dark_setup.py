@@ -9,7 +9,9 @@ bound-electron cross-sections of atomic_annihilation.py / atomic_compton.py) and
     drate/<name>/E|table          10 energy bins of the emission rate per initial energy (dark_shower.py:454-493)
     nsdark/<P>/x|y                log10 nodes of n*sigma_dark(E)                      (dark_shower.py:294-309)
 
-Only ``bound_electron=True`` is supported.  It is set-up code: scalar SciPy quadrature, ~30-60 s per (material, mV).
+Only ``bound_electron=True`` is supported.  The ~6 000 adaptive quadratures run on the GPU (``pb_quad_batch``: QUADPACK's QAGS restated in
+csrc/quadpack.cuh, one thread per integral, a fraction of a second); ``scipy_runner`` evaluates the same calls with
+``scipy.integrate.quad`` as the reference does (30-60 s per (material, mV)) and is the CPU tests' yardstick.
 """
 import numpy as np
 from scipy.integrate import quad
@@ -95,34 +97,100 @@ class _LogLog:
         return 10 ** self._t(np.log10(E))
 
 
-def _cumulative(table, grid):
-    """shower.py:298-320: II(E_i) = int_{E_0}^{E_i} n*sigma dE on the table's own energy grid."""
-    y = np.array([quad(table, grid[0], e, full_output=1)[0] for e in grid])
-    return LinearTable(grid, y)
+# ------------------------------------------------------------------------------------------------ the quadratures
+# Every integral of the set-up is one "call" (struct pb_quad_call, include/petite_b200.h) over a list of linear tables:
+#   kind 0: f(E) = table[tab](E)                                       cumulative interaction integrals, shower.py:298-320
+#   kind 1: f(E) = 10^table[tab](log10 E) / dEdx_cm * survival(E, Ei)   emission rate, dark_shower.py:311-335, shower.py:322-354
+# A "runner" integrates a batch of calls.  The product runner is the GPU (pb_quad_batch: QUADPACK's QAGS restated in
+# csrc/quadpack.cuh, one thread per integral); ``scipy_runner`` evaluates the same calls with scipy.integrate.quad on Python
+# integrands (what the reference does) and is what the CPU tests pin the restatement to.
+CALL_DTYPE = np.dtype([("kind", "<i4"), ("tab", "<i4"), ("surv", "<i4", (3,)), ("cut", "<i4"), ("Ei", "<f8"), ("a", "<f8"), ("b", "<f8")])
 
 
-def build(sh, path):
-    """Compute the set-up tables for ``sh`` (a partly constructed DarkShower) and write them to ``path``."""
+def _call(kind, tab, a, b, Ei=0.0, surv=(), cut=False):
+    c = np.zeros((), dtype=CALL_DTYPE)
+    c["kind"], c["tab"], c["cut"], c["Ei"], c["a"], c["b"] = kind, tab, int(cut), Ei, a, b
+    c["surv"] = (list(surv) + [-1, -1, -1])[:3]
+    return c
+
+
+def integrand(tables, dEdx_m, c):
+    """Python twin of QuadIntegrand (csrc/engine.cu) for one call; ``tables`` = list of LinearTable."""
+    if c["kind"] == 0:
+        t = tables[c["tab"]]
+        return lambda E: t(E)
+    ns, surv, Ei, cut = tables[c["tab"]], [tables[k] for k in c["surv"] if k >= 0], float(c["Ei"]), bool(c["cut"])
+    dEdx_cm = dEdx_m * K.cmtom
+
+    def f(E):
+        v = 10 ** ns(np.log10(E))
+        if cut and v < 1.0e-18:
+            return 0.0
+        d = sum(t(Ei) - t(E) for t in surv)
+        if d < 0.0 or E > Ei:
+            return 0.0
+        return v / dEdx_cm * np.exp(-d / dEdx_m / K.cmtom)
+    return f
+
+
+def scipy_runner(tables, dEdx_m, calls):
+    return np.array([quad(integrand(tables, dEdx_m, c), float(c["a"]), float(c["b"]), full_output=1)[0] for c in calls])
+
+
+def c_abi_runner(fn, engine=None, on_error=None):
+    """Runner over a C entry point with pb_quad_batch's table / call arguments (the engine's, or the host build used by the tests)."""
+    import ctypes as C
+
+    def run(tables, dEdx_m, calls):
+        calls = np.ascontiguousarray(calls, dtype=CALL_DTYPE)
+        n_t = len(tables)
+        xs = [np.ascontiguousarray(t.x, dtype=np.float64) for t in tables]
+        ys = [np.ascontiguousarray(t.y, dtype=np.float64) for t in tables]
+        dp = C.POINTER(C.c_double)
+        px = (dp * n_t)(*[a.ctypes.data_as(dp) for a in xs])
+        py = (dp * n_t)(*[a.ctypes.data_as(dp) for a in ys])
+        tn = np.array([len(a) for a in xs], dtype=np.int32)
+        fill = np.array([float(t.fill_value) for t in tables], dtype=np.float64)
+        out, err, ier = np.zeros(len(calls)), np.zeros(len(calls)), np.zeros(len(calls), dtype=np.int32)
+        args = (n_t, tn.ctypes.data_as(C.POINTER(C.c_int32)), px, py, fill.ctypes.data_as(dp), C.c_double(dEdx_m),
+                C.c_void_p(calls.ctypes.data), C.c_int64(len(calls)), out.ctypes.data_as(dp), err.ctypes.data_as(dp),
+                ier.ctypes.data_as(C.POINTER(C.c_int32)))
+        rc = fn(engine, *args) if engine is not None else fn(*args)
+        if rc != 0:
+            if on_error is not None:
+                on_error(rc)
+            raise RuntimeError(f"quadrature batch failed with code {rc}")
+        run.last_ier = ier
+        return out
+    return run
+
+
+def gpu_runner(sh):
+    from . import _capi as capi
+    return c_abi_runner(capi.lib.pb_quad_batch, sh._engine, on_error=lambda rc: capi.check(sh._engine, rc))
+
+
+def build(sh, path, runner=None):
+    """Compute the set-up tables for ``sh`` (a partly constructed DarkShower) and write them to ``path``.  ``runner`` integrates the
+    batches of quadrature calls; default: the GPU engine of ``sh``."""
+    runner = gpu_runner(sh) if runner is None else runner
     X, t = sh._xsec, sh._nsigma_tables
     nZ, ne = sh.get_n_targets()
     G = K.GeVsqcm2
     dEdx_m = sh._dEdx * 0.1                      # GeV/m
-    dEdx_cm = dEdx_m * K.cmtom                   # GeV/cm
 
-    II = {P: _cumulative(t[P], X[P][:, 0]) for P in ("Brem", "Ann")}
-    II["Moller"] = _cumulative(t["Moller"], t["Moller"].x)
-    II["Bhabha"] = _cumulative(t["Bhabha"], t["Bhabha"].x)
-    II["MuonBrem"] = _cumulative(t["MuonE"], X["MuonBrem"][:, 0])     # SURVEY Q-4: integrates n*sigma_MuonE
-    II["MuonE"] = _cumulative(t["MuonE"], X["MuonE"][:, 0])
-
-    def survive(names):
-        def f(E, Ei):                            # shower.py:322-354
-            d = sum(II[n](Ei) - II[n](E) for n in names)
-            if d < 0.0 or E > Ei:
-                return 0.0
-            return np.exp(-d / dEdx_m / K.cmtom)
-        return f
-    surv_e, surv_p, surv_mu = survive(("Brem", "Moller")), survive(("Brem", "Ann", "Bhabha")), survive(("MuonBrem", "MuonE"))
+    # ---- phase 1 (shower.py:298-320): II(E_i) = int_{E_0}^{E_i} n*sigma dE on the table's own energy grid
+    ii_spec = [("Brem", t["Brem"], X["Brem"][:, 0]), ("Ann", t["Ann"], X["Ann"][:, 0]), ("Moller", t["Moller"], t["Moller"].x),
+               ("Bhabha", t["Bhabha"], t["Bhabha"].x),
+               ("MuonBrem", t["MuonE"], X["MuonBrem"][:, 0]),          # SURVEY Q-4: integrates n*sigma_MuonE
+               ("MuonE", t["MuonE"], X["MuonE"][:, 0])]
+    tabs1 = [tb for _, tb, _ in ii_spec]
+    calls1 = np.array([_call(0, k, float(grid[0]), float(e)) for k, (_, _, grid) in enumerate(ii_spec) for e in grid], dtype=CALL_DTYPE)
+    y1 = runner(tabs1, dEdx_m, calls1)
+    II, pos = {}, 0
+    for name, _, grid in ii_spec:
+        II[name] = LinearTable(np.asarray(grid, dtype=float), y1[pos:pos + len(grid)])
+        pos += len(grid)
 
     DBS, DMB = sh._dark_brem_cross_section, sh._dark_muon_brem_cross_section
     E_res, E_thr = sh._resonant_annihilation_energy, sh._compton_threshold_energy
@@ -131,43 +199,44 @@ def build(sh, path):
     ann_bound = np.column_stack([Ea, [sigma_atomic_annihilation(e, sh._mV, sh.Zeff) for e in Ea]])
     Ec = np.logspace(np.log10(max(mce[22], 0.001 * E_thr)), np.log10(sh._dark_compton_cross_section[-1][0]), 200)
     comp_bound = np.column_stack([Ec, [sigma_atomic_compton(e, sh._mV, sh.Zeff) for e in Ec]])
-
     ns = {"DarkBrem": _LogLog(DBS[:, 0], nZ * G * DBS[:, 1]), "DarkAnn": _LogLog(ann_bound[:, 0], ne * G * ann_bound[:, 1]),
           "DarkComp": _LogLog(comp_bound[:, 0], ne * G * comp_bound[:, 1]), "DarkMuonBrem": _LogLog(DMB[:, 0], nZ * G * DMB[:, 1])}
 
-    def rate(nsig, surv, cut):
-        def f(E, Ei):                            # dark_shower.py:311-335
-            v = nsig(E)
-            if cut and v < 1.0e-18:
-                return 0.0
-            return v / dEdx_cm * surv(E, Ei)
-        return f
-    f_be, f_bp = rate(ns["DarkBrem"], surv_e, True), rate(ns["DarkBrem"], surv_p, True)
-    f_mu, f_an = rate(ns["DarkMuonBrem"], surv_mu, True), rate(ns["DarkAnn"], surv_p, False)
-
-    def weights(f, Es, pid):                     # dark_shower.py:337-399
-        out = []
-        for Ei in Es:
-            brk = Ei - 10 * sh.get_mfp([pid, Ei]) * dEdx_m
-            brk = brk if brk > Es[0] else Es[0]
-            out.append(quad(f, Es[0], brk, args=(Ei), full_output=1)[0] + quad(f, brk, Ei, args=(Ei), full_output=1)[0])
-        return np.column_stack([Es, out])
-
-    def drate(f, Es, pid, floor):                # dark_shower.py:454-493
-        tabs = []
-        for Ei in Es:
-            edges = np.linspace(max(Ei - 10 * sh.get_mfp([pid, Ei]) * dEdx_m, floor), Ei, 11)
-            centres = np.array([(edges[i] + edges[i + 1]) / 2.0 for i in range(10)])
-            tabs.append(np.column_stack([centres, [quad(f, edges[i], edges[i + 1], args=(Ei), full_output=1)[0] for i in range(10)]]))
-        return np.asarray(Es, dtype=float), np.stack(tabs)
-
+    # ---- phase 2 (dark_shower.py:311-399, 454-493): emission weights and dRate/dE bins
+    names2 = ["Brem", "Ann", "Moller", "Bhabha", "MuonBrem", "MuonE"]
+    tabs2 = [II[n] for n in names2] + [ns[P]._t for P in ("DarkBrem", "DarkMuonBrem", "DarkAnn")]
+    iid = {n: k for k, n in enumerate(names2)}
+    nsid = {"DarkBrem": 6, "DarkMuonBrem": 7, "DarkAnn": 8}
+    surv_e, surv_p, surv_mu = [iid["Brem"], iid["Moller"]], [iid["Brem"], iid["Ann"], iid["Bhabha"]], [iid["MuonBrem"], iid["MuonE"]]
     Eb, Em, Ean = DBS[:, 0], DMB[:, 0], ann_bound[:, 0]
-    out = {"meta": np.array([sh._mV, sh._mV_estimator, E_res, E_thr, sh.g_e, sh.kinetic_mixing, sh.Zeff, 1.0]),
-           "weights/brem_elec": weights(f_be, Eb, 11), "weights/brem_positron": weights(f_bp, Eb, -11),
-           "weights/muon_brem": weights(f_mu, Em, 13), "weights/annihilation": weights(f_an, Ean, -11)}
-    for name, (f, Es, pid, floor) in {"brem_elec": (f_be, Eb, 11, Eb[0]), "brem_positron": (f_bp, Eb, -11, Eb[0]),
-                                      "muon_brem": (f_mu, Em, 13, Em[0]), "annihilation": (f_an, Ean, -11, Ean[0])}.items():
-        out[f"drate/{name}/E"], out[f"drate/{name}/table"] = drate(f, Es, pid, floor)
+    rates = {"brem_elec": (nsid["DarkBrem"], surv_e, True, Eb, 11), "brem_positron": (nsid["DarkBrem"], surv_p, True, Eb, -11),
+             "muon_brem": (nsid["DarkMuonBrem"], surv_mu, True, Em, 13), "annihilation": (nsid["DarkAnn"], surv_p, False, Ean, -11)}
+    calls2, layout = [], {}
+    for name, (tab, surv, cut, Es, pid) in rates.items():
+        first = len(calls2)
+        edges_all = []
+        for Ei in Es:                                                    # weights: two pieces, split 10 mean free paths below Ei
+            Ei = float(Ei)
+            reach = 10 * sh.get_mfp([pid, Ei]) * dEdx_m
+            brk = Ei - reach
+            brk = brk if brk > Es[0] else float(Es[0])
+            calls2 += [_call(1, tab, float(Es[0]), brk, Ei, surv, cut), _call(1, tab, brk, Ei, Ei, surv, cut)]
+        for Ei in Es:                                                    # dRate: ten equal bins over the last 10 mean free paths
+            Ei = float(Ei)
+            edges = np.linspace(max(Ei - 10 * sh.get_mfp([pid, Ei]) * dEdx_m, float(Es[0])), Ei, 11)
+            edges_all.append(edges)
+            calls2 += [_call(1, tab, float(edges[i]), float(edges[i + 1]), Ei, surv, cut) for i in range(10)]
+        layout[name] = (first, len(Es), edges_all)
+    y2 = runner(tabs2, dEdx_m, np.array(calls2, dtype=CALL_DTYPE))
+
+    out = {"meta": np.array([sh._mV, sh._mV_estimator, E_res, E_thr, sh.g_e, sh.kinetic_mixing, sh.Zeff, 1.0])}
+    for name, (tab, surv, cut, Es, pid) in rates.items():
+        first, n, edges_all = layout[name]
+        w = y2[first:first + 2 * n].reshape(n, 2)
+        out[f"weights/{name}"] = np.column_stack([Es, w[:, 0] + w[:, 1]])
+        d = y2[first + 2 * n:first + 12 * n].reshape(n, 10)
+        centres = np.array([[(e[i] + e[i + 1]) / 2.0 for i in range(10)] for e in edges_all])
+        out[f"drate/{name}/E"], out[f"drate/{name}/table"] = np.asarray(Es, dtype=float), np.stack([centres, d], axis=2)
     for P, tab in ns.items():
         out[f"nsdark/{P}/x"], out[f"nsdark/{P}/y"] = tab.lx, tab.ly
     md = sh._minimum_calculable_dark_energy

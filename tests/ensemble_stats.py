@@ -31,7 +31,37 @@ REF_CONFIGS = {
     "c3_dark_graphite": dict(CONFIGS["c3_dark_graphite"], n_ref=200, active=["DarkBrem", "DarkAnn", "DarkComp"]),
     "c5_mu_lead_dark": dict(CONFIGS["c5_mu_lead"], n_ref=200, mV=0.030, active=["DarkMuonBrem", "DarkBrem", "DarkAnn", "DarkComp"]),
 }
+# BASELINE config 4: the 400 GeV table set (data_400GeV/, 4-D / 3-D maps retrained here: upstream lost them, tools/make_400GeV.py) and a
+# synthetic beam-dump spectrum into lead, m_V = 10 MeV.  Primaries are i.i.d. draws (beam_dump_primaries), so a reference ensemble on
+# the first n_ref of them and a GPU ensemble on 1e5 of them sample the same distribution.
+REF_CONFIGS["c4_beamdump_lead_dark"] = dict(material="lead", pid=0, E0=400.0, mass=None, E_min=0.010, seed=20261017, n_ref=96, mV=0.010,
+                                            active=["DarkBrem", "DarkAnn", "DarkComp"], data="data_400GeV")
 SPEC_EDGES = np.logspace(-2, 1, 9)       # 8 bins, 10 MeV .. 10 GeV
+
+
+def beam_dump_primaries(n, seed=20261017):
+    """Config 4: 50 % photons resampled from the reference's 120 GeV pi0-photon beam (data_400GeV/Photons_From_Pi0s_120GeV.npy)
+    scaled x (400 / 120) in momentum, 25 % e-, 25 % e+ with dN/dE ~ 1/E on [1, 400] GeV along +z; shuffled, so that any prefix is an
+    i.i.d. sample of the spectrum.  -> (p (n,4), pid (n,), mass (n,))"""
+    import os
+    rng = np.random.default_rng(seed)
+    beam = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data_400GeV", "Photons_From_Pi0s_120GeV.npy"))
+    kind = rng.integers(0, 4, n)                                  # 0, 1: photon; 2: e-; 3: e+
+    g = beam[beam[:, 0] * (400.0 / 120.0) > 0.0016]
+    pg = g[rng.integers(0, len(g), n)] * (400.0 / 120.0)
+    E = np.exp(rng.uniform(np.log(1.0), np.log(400.0), n))
+    pe = np.column_stack([E, np.zeros(n), np.zeros(n), np.sqrt(E ** 2 - m_e ** 2)])
+    p = np.where((kind < 2)[:, None], pg, pe)
+    pid = np.where(kind < 2, 22, np.where(kind == 2, 11, -11)).astype(np.int32)
+    return p, pid, np.where(pid == 22, 0.0, m_e)
+
+
+def config_primaries(cfg, n):
+    """-> (p, pid, mass) arrays of a configuration's first n primaries (mono-energetic along +z, or the config-4 spectrum)."""
+    if cfg["pid"] == 0:
+        return beam_dump_primaries(n, cfg["seed"])
+    E, m = cfg["E0"], cfg["mass"]
+    return np.tile([E, 0.0, 0.0, np.sqrt(E * E - m * m)], (n, 1)), np.full(n, cfg["pid"], dtype=np.int32), np.full(n, m)
 
 
 def summarise_oracle_sm(plist):

@@ -28,11 +28,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 sys.path.insert(0, ROOT)
-from tests.ensemble_stats import REF_CONFIGS, SPEC_EDGES   # noqa: E402
+from tests.ensemble_stats import REF_CONFIGS, SPEC_EDGES, config_primaries   # noqa: E402
 
 REFDIR = "/tmp/petite_refdata/"
+REFDIR_400 = "/tmp/petite_refdata_400GeV/"
 SEED0 = 7_000_000
 _STATE = {}
+_PRIM = {}
 
 
 def _summarise_sm(plist):
@@ -63,12 +65,13 @@ def _engine(name):
         _refstub.import_reference()
         warnings.filterwarnings("ignore")
         cfg = REF_CONFIGS[name]
+        refdir = REFDIR_400 if cfg.get("data") == "data_400GeV" else REFDIR
         if cfg.get("mV") is None:
             from PETITE.shower import Shower
-            _STATE[name] = Shower(REFDIR, cfg["material"], cfg["E_min"])
+            _STATE[name] = Shower(refdir, cfg["material"], cfg["E_min"])
         else:
             from PETITE.dark_shower import DarkShower
-            _STATE[name] = DarkShower(REFDIR, cfg["material"], cfg["E_min"], cfg["mV"],
+            _STATE[name] = DarkShower(refdir, cfg["material"], cfg["E_min"], cfg["mV"],
                                       active_processes=cfg.get("active"))
     return _STATE[name]
 
@@ -78,12 +81,13 @@ def _one(args):
     from PETITE.particle import Particle    # after _engine() installed the stubs in this worker
     cfg = REF_CONFIGS[name]
     s = _engine(name)
-    E, m = cfg["E0"], cfg["mass"]
+    if name not in _PRIM:
+        _PRIM[name] = config_primaries(cfg, cfg["n_ref"])
+    p, pid, mass = _PRIM[name]
     np.random.seed(SEED0 + i)
     random.seed(SEED0 + i)
     t0 = time.time()
-    sm = s.generate_shower(Particle([E, 0.0, 0.0, float(np.sqrt(E * E - m * m))], [0.0, 0.0, 0.0],
-                                    {"PID": cfg["pid"], "ID": 1, "mass": m}))
+    sm = s.generate_shower(Particle([float(v) for v in p[i]], [0.0, 0.0, 0.0], {"PID": int(pid[i]), "ID": 1, "mass": float(mass[i])}))
     row = _summarise_sm(sm)
     if cfg.get("mV") is not None:
         _, vs = s.generate_dark_shower(ExDir=list(sm))
@@ -109,6 +113,8 @@ def main():
     sys.path.insert(0, HERE)
     import make_golden            # builds the reference-format dict_dir from data/*.npz (sm_maps.pkl, dark_maps.pkl)
     make_golden.build_reference_dict_dir()
+    if any(REF_CONFIGS[n].get("data") == "data_400GeV" for n in (only or REF_CONFIGS)):
+        make_golden.build_reference_dict_dir(data=os.path.join(ROOT, "data_400GeV", ""), refdir=REFDIR_400, ref_sub="data_400GeV", materials=["lead"])
     for name, cfg in REF_CONFIGS.items():
         if only and name not in only:
             continue

@@ -45,40 +45,45 @@ DATA = os.path.join(HERE, "..", "..", "data", "")
 REFDIR = "/tmp/petite_refdata/"
 
 
-def build_reference_dict_dir():
-    """Reference-format dict_dir: shipped pickles + sm_maps.pkl / dark_maps.pkl rebuilt from data/*.npz."""
-    os.makedirs(REFDIR, exist_ok=True)
+def build_reference_dict_dir(data=None, refdir=None, ref_sub="data", materials=None):
+    """Reference-format dict_dir: shipped pickles + sm_maps.pkl / dark_maps.pkl rebuilt from <data>/*.npz.  Defaults: the 10 GeV
+    set (data/ -> /tmp/petite_refdata/); ``data=data_400GeV/, ref_sub="data_400GeV"`` builds the 400 GeV one (max_F exists for the
+    materials tools/make_400GeV.py was run for)."""
+    data = DATA if data is None else data
+    refdir = REFDIR if refdir is None else refdir
+    materials = MATERIALS if materials is None else materials
+    os.makedirs(refdir, exist_ok=True)
     import shutil
     for f in ["sm_xsec.pkl", "dark_xsec.pkl"]:
-        if not os.path.exists(REFDIR + f):
-            os.symlink(os.path.join(_refstub.REF_ROOT, "data", f), REFDIR + f)
+        if not os.path.exists(refdir + f):
+            os.symlink(os.path.join(_refstub.REF_ROOT, ref_sub, f), refdir + f)
     for f in ["dark_weights.pkl", "dark_drate.pkl"]:      # the constructors write into these (SURVEY Q-3): real copies
-        if not os.path.exists(REFDIR + f) or os.path.islink(REFDIR + f):
-            if os.path.islink(REFDIR + f):
-                os.unlink(REFDIR + f)
-            shutil.copy(os.path.join(_refstub.REF_ROOT, "data", f), REFDIR + f)
-            os.chmod(REFDIR + f, 0o644)
+        if not os.path.exists(refdir + f) or os.path.islink(refdir + f):
+            if os.path.islink(refdir + f):
+                os.unlink(refdir + f)
+            shutil.copy(os.path.join(_refstub.REF_ROOT, ref_sub, f), refdir + f)
+            os.chmod(refdir + f, 0o644)
 
     def mk(z, mf, procs, pre=""):
         out = {}
         for P in procs:
             E, ninc, G, meta = z[f"{P}/E"], z[f"{P}/ninc"], z[f"{P}/grid"], z[f"{P}/meta"]
-            out[P] = [[float(E[i]), {"neval": int(meta[0]), "max_F": {m: float(mf[f"{pre}{P}/{m}"][i]) for m in MATERIALS},
+            out[P] = [[float(E[i]), {"neval": int(meta[0]), "max_F": {m: float(mf[f"{pre}{P}/{m}"][i]) for m in materials},
                                      "adaptive_map": AdaptiveMapStub(split_grid(G[i], ninc)),
                                      "Eg_min": float(meta[1]), "Ee_min": float(meta[2])}] for i in range(len(E))]
         return out
-    pickle.dump(mk(np.load(DATA + "sm_maps.npz"), np.load(DATA + "sm_maxF.npz"), SM_PROCESSES), open(REFDIR + "sm_maps.pkl", "wb"))
-    dmf = np.load(DATA + "dark_maxF.npz")
+    pickle.dump(mk(np.load(data + "sm_maps.npz"), np.load(data + "sm_maxF.npz"), SM_PROCESSES), open(refdir + "sm_maps.pkl", "wb"))
+    dmf = np.load(data + "dark_maxF.npz")
     dm = {}
-    for f in sorted(os.listdir(DATA)):
-        if f.startswith("dark_maps_mV"):
+    for f in sorted(os.listdir(data)):
+        if f.startswith("dark_maps_mV") and not f.endswith("_shipped.npz"):
             tag = f[len("dark_maps_mV"):-4]
-            dm[float(tag)] = mk(np.load(DATA + f), dmf, DARK_PROCESSES, pre=tag + "/")
+            dm[float(tag)] = mk(np.load(data + f), dmf, DARK_PROCESSES, pre=tag + "/")
             # the reference's default active_processes includes "TwoBody_BSMDecay" and set_dark_samples
             # (dark_shower.py:196-201) looks every active process up in dark_maps.pkl: the lost pickle must have
             # carried such a key.  An empty entry lets the unmodified constructor run.
             dm[float(tag)]["TwoBody_BSMDecay"] = []
-    pickle.dump(dm, open(REFDIR + "dark_maps.pkl", "wb"))
+    pickle.dump(dm, open(refdir + "dark_maps.pkl", "wb"))
 
 
 REF_DS = {"Brem": ap.dsigma_brem_dimensionless, "MuonBrem": ap.dsigma_brem_dimensionless,
