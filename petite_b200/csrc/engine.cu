@@ -50,6 +50,9 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #ifndef PB_SAMPLE_MINB_DB
 #define PB_SAMPLE_MINB_DB 4              // dark-brem family kernel (FAM = 3)
 #endif
+#ifndef PB_SAMPLE_G_DARK_DEFAULT
+#define PB_SAMPLE_G_DARK_DEFAULT 8       // dark pass: ~70-300 trials per sample, wide groups waste little (measured 77 vs 85 ms, config 3)
+#endif
 #ifndef PB_SAMPLE_T_DB_DEFAULT
 #define PB_SAMPLE_T_DB_DEFAULT 2
 #endif
@@ -177,6 +180,7 @@ struct Work {            // per-wave scratch, sized to the widest wave seen so f
   unsigned long long* counters;  // [CNT_N]: steps, substeps, samples, trials, no_sample, overflow, per-process trials/samples
   unsigned long long* tlog;      // measurement aid (PB_TILE_LOG): per tile of ONE chosen wave {start ns, end ns, bucket << 32 | count, SM}; else nullptr
   int tlog_wave, tlog_cap;
+  int tile_norm;                 // 1: cost-normalised tiles, heavy buckets first (k_bucket_scan); 0 (PB_TILE_NORM=0): TILE samples per tile, bucket order
 };
 
 enum { CNT_STEPS = 0, CNT_SUBSTEPS, CNT_SAMPLES, CNT_TRIALS, CNT_NOSAMPLE, CNT_OVERFLOW, CNT_PROC_TRIALS = 8,
@@ -328,7 +332,7 @@ __device__ __forceinline__ bool substep(const Material& M, const Tables& T, Trac
   // lose_energy (particle.py:143-153) with |p| carried along the track instead of recomputed
   double Eu = t.p.E - M.dEdx * t.delta_z;
   if (Eu <= t.mass) Eu = t.mass;
-  double p3f = sqrt(__dsub_rn(__dmul_rn(Eu, Eu), __dmul_rn(t.mass, t.mass)));
+  double p3f = fast_sqrt0(__dsub_rn(__dmul_rn(Eu, Eu), __dmul_rn(t.mass, t.mass)));      // exactly 0 at Eu == mass, as the reference's sqrt
   if (p3f > 0.0) {
     double r = p3f * t.ipn;
     t.p = V4{Eu, t.p.x * r, t.p.y * r, t.p.z * r};
@@ -546,7 +550,8 @@ __device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, 
         rx += p.x * sc; ry += p.y * sc; rz += p.z * sc;
         if (ms_e) {                                                     // SURVEY Q-12: electron mass here
           McsDraw d = ds.mcs(MCS_FINAL_INDEX, 0);
-          p = mcs_scatter(M, p, pn, M.rho * (last / kCmToM), kMe, mass, d);
+          // the folded form the sub-step loop uses (golden-checked against the reference like mcs_apply, test_mcs_fast_vs_reference_golden)
+          p = mcs_fast(M, p, pn, fast_rcp(pn), M.rho * (last * (1.0 / kCmToM)), mass * (1.0 / (1e3 * kMe)), d.sign, d.radial, d.uphi);
         }
       }
     }
@@ -648,9 +653,8 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
 // Tiles are COST-normalised: the accept/reject cost of a sample differs by an order of magnitude between buckets (10 GeV photons
 // in lead: Brem / PairProd rows need 12-40 trials per sample, the annihilation rows 100-170), and a 192-sample tile of such a row
 // used to run 300-500 us at the end of a launch whose other CTAs had finished (profiles/r02_summary.md, tile timeline).  The engine
-// therefore keeps, per bucket, the samples and trials spent so far (bstat), sizes a bucket's tiles so that every tile of the launch
-// costs about as many trials (TILE samples for a bucket at or below the launch's average trials per sample, proportionally fewer
-// above it), and puts the tiles of the heavy buckets (more than twice the average) at the front of the tile table.  Scheduling only: the samples themselves
+// therefore keeps, per bucket, the samples and trials spent so far (bstat), gives the heavy buckets (more than twice the launch's
+// average trials per sample) proportionally smaller tiles and puts those tiles at the front of the tile table.  Scheduling only: the samples themselves
 // are a pure function of (particle key, trial index).
 constexpr int TILE_MIN = 32;
 __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
@@ -678,8 +682,10 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
   float wall = 0.f, call = 0.f;
   for (int k = 0; k < 32; ++k) { wall += s_w[k]; call += s_c[k]; }
   const float avg_all = call > 0.f ? wall / call : 16.f;
-  // tile sizes relative to the launch average: a tile of any bucket costs about TILE x avg_all trials; the buckets more than twice as
-  // expensive per sample as the average go first
+  // the buckets more than twice as expensive per sample as the launch average ("heavy") get proportionally smaller tiles - a heavy
+  // tile then costs about TILE x avg_all trials, like an average one - and go first.  Everything else keeps TILE samples per tile:
+  // shrinking every above-average bucket was measured 15 % slower on the dark pass, whose buckets spread over 30-300 trials per
+  // sample (each tile ends with a drain phase, and small tiles have more of them per sample)
   int csum = 0, t0sum = 0, t1sum = 0;
   for (int k = 0; k < PER; ++k) {
     int b = t * PER + k;
@@ -687,10 +693,10 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
     til[k] = 0; heavy[k] = 0;
     if (b < N_SAMPLED * LU_MAX) {
       int tsz = TILE;
-      if (avg[k] > avg_all) tsz = max(TILE_MIN, min(TILE, (int)((float)TILE * avg_all / avg[k]) & ~31));
+      heavy[k] = W.tile_norm && avg[k] > 2.f * avg_all;
+      if (heavy[k]) tsz = max(TILE_MIN, min(TILE, (int)((float)TILE * avg_all / avg[k]) & ~31));
       W.tile_sz[b] = tsz;
       til[k] = (c + tsz - 1) / tsz;
-      heavy[k] = avg[k] > 2.f * avg_all;
     }
     csum += c;
     if (heavy[k]) t0sum += til[k]; else t1sum += til[k];
@@ -868,6 +874,9 @@ __device__ __forceinline__ unsigned trial_block(const Material& M, const MapInfo
     const double ml = (proc == P_DARKBREM) ? kMe : kMmu;
 #pragma unroll
     for (int k = 0; k < T; ++k) f[k] = ds_darkbrem_fast(M, sc, E, ml, xx[k]);      // the two 3-D processes
+  } else if (FAM == -1 && DIM == 1 && proc == P_DARKANN) {
+#pragma unroll
+    for (int k = 0; k < T; ++k) f[k] = ds_darkann_c(M, sc, E, xx[k][0]);
   } else {
 #pragma unroll
     for (int k = 0; k < T; ++k) f[k] = dsigma(M, proc, E, xx[k]);
@@ -943,6 +952,9 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
       } else if (FAM != 2 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) {
         SampleConst c = darkbrem_const(M, Ek, proc == P_DARKBREM ? kMe : kMmu);
         s_cb[k] = c.b; s_cc[k] = c.c; s_cd[k] = c.e;          // |p|, tconv, 1/|p|
+      } else if (FAM == -1 && proc == P_DARKANN) {
+        SampleConst c = darkann_const(M, Ek);
+        s_cb[k] = c.b; s_cc[k] = c.c; s_cd[k] = c.d;          // beta, u_max, 2 x prefactor
       }
     }
     double maxF = __ldg(mi.maxF + lu) * M.fudge;
@@ -970,6 +982,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
           else if (proc == P_BREM) sc = SampleConst{E - kMe - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMe * kMe};
           else if (proc == P_MUONBREM) sc = SampleConst{E - kMmu - M.Eg_min, s_cb[j], s_cc[j], s_cd[j], kMmu * kMmu};
           else if (FAM != 2 && (proc == P_DARKBREM || proc == P_DARKMUONBREM)) sc = SampleConst{0.0, s_cb[j], s_cc[j], M.i2mT, s_cd[j]};
+          else if (FAM == -1 && proc == P_DARKANN) sc = SampleConst{0.0, s_cb[j], s_cc[j], s_cd[j], (M.mV * M.mV) / (2.0 * kMe * (E + kMe))};
         } else cur = -2;
       }
       // ---- drain help.  Once the tile's cursor is exhausted a group that finishes has nothing left to fetch; instead of
@@ -1783,6 +1796,7 @@ __global__ void k_probe(const __grid_constant__ Material M, const __grid_constan
       if (process >= 32) {      // the folded forms used inside k_sample
         int p = process - 32;
         if (p == P_PAIRPROD) { SampleConst sc = pairprod_const(M, a[0]); o[0] = ds_pairprod_fast(sc, a[0], a + 1); }
+        else if (p == P_DARKANN) { SampleConst sc = darkann_const(M, a[0]); o[0] = ds_darkann_c(M, sc, a[0], a[1]); }
         else if (p == P_DARKBREM || p == P_DARKMUONBREM) {
           double ml = (p == P_DARKBREM) ? kMe : kMmu;
           SampleConst sc = darkbrem_const(M, a[0], ml);
@@ -1833,6 +1847,7 @@ __global__ void k_probe(const __grid_constant__ Material M, const __grid_constan
       hot_sincos(a[2], &o[2], &o[3]);
       hot_sincos_2pi(a[3], &o[4], &o[5]);
       o[6] = fast_rcp(a[0]);
+      if (os >= 10) { o[7] = fast_sqrt0(a[0]); o[8] = fast_rsqrt(a[0]); o[9] = fast_sqrt0(0.0) + fast_sqrt0(-a[0]); }
     } break;
     case PB_PROBE_MCS_FAST: {   // in as PB_PROBE_MCS; the particle's mass is m_lepton
       V4 p{a[0], a[1], a[2], a[3]};
@@ -1924,6 +1939,7 @@ struct pb_engine_s {
   int profiling = 0;             // 0 off, 1 = the two dominant kernels only (k_loop, k_sample), 2 = every kernel
   int sample_group = PB_SAMPLE_G_DEFAULT;    // lanes cooperating on one accept/reject sample (tuning knob, PB_SAMPLE_G)
   int sample_trials = PB_SAMPLE_T_DEFAULT;   // trials per lane and round (PB_SAMPLE_T): ILP inside the lane
+  int sample_group_dark = PB_SAMPLE_G_DARK_DEFAULT;   // lanes per sample in the dark pass / stand-alone sampling (PB_SAMPLE_G_DARK)
   int sample_trials_dark = PB_SAMPLE_T_DARK_DEFAULT;   // the same for the generic kernel (PB_SAMPLE_T_DARK)
   int sample_trials_db = PB_SAMPLE_T_DB_DEFAULT;       // the same for the dark-brem family kernel (PB_SAMPLE_T_DB)
   int sample_split_db = 1;                             // PB_SAMPLE_SPLIT_DB=0: dark pass through one generic launch
@@ -2000,12 +2016,15 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   derive_material(e);
   if (const char* g = getenv("PB_SAMPLE_G")) e->sample_group = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_T")) e->sample_trials = atoi(g);
+  if (const char* g = getenv("PB_SAMPLE_G_DARK")) e->sample_group_dark = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_T_DARK")) e->sample_trials_dark = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_GENERIC")) e->sample_generic = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_T_DB")) e->sample_trials_db = atoi(g);
   if (const char* g = getenv("PB_SAMPLE_SPLIT_DB")) e->sample_split_db = atoi(g);
   if (const char* g = getenv("PB_EMIT_ORDER")) e->emit_wave_order = atoi(g);
   if (const char* g = getenv("PB_GRAPH")) e->use_graph = atoi(g);
+  e->work.tile_norm = 1;
+  if (const char* g = getenv("PB_TILE_NORM")) e->work.tile_norm = atoi(g);
   if (const char* g = getenv("PB_TILE_LOG")) {            // "<file>:<wave>": per-tile timeline of k_sample in that wave of every run (appended)
     std::string v(g);
     size_t c = v.rfind(':');
@@ -2191,9 +2210,10 @@ static int ensure_cand(pb_engine e, long long ncap);
 // stand-alone sampling: the generic instantiation.  (G, T) = lanes per sample x trials per lane and round.
 template <int FAM>
 static void launch_sample_fam(pb_engine e, int grid, const SampleIO& io, cudaStream_t stream, int family_mode) {
-  const int G = e->sample_group, T = (FAM == 2) ? e->sample_trials : (FAM == 3 ? e->sample_trials_db : e->sample_trials_dark);
+  const int G = (FAM == 2) ? e->sample_group : e->sample_group_dark;
+  const int T = (FAM == 2) ? e->sample_trials : (FAM == 3 ? e->sample_trials_db : e->sample_trials_dark);
 #define PB_LS(g, t) if (G == g && T == t) { k_sample<g, FAM, t><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work, family_mode); return; }
-  PB_LS(4, 1) PB_LS(2, 2) PB_LS(1, 2) PB_LS(4, 2) PB_LS(2, 1) PB_LS(8, 1) PB_LS(1, 4) PB_LS(2, 4) PB_LS(1, 1)
+  PB_LS(4, 1) PB_LS(2, 2) PB_LS(1, 2) PB_LS(4, 2) PB_LS(2, 1) PB_LS(8, 1) PB_LS(8, 2) PB_LS(1, 4) PB_LS(2, 4) PB_LS(1, 1)
 #undef PB_LS
   k_sample<4, FAM, 1><<<grid, SAMPLE_THREADS, 0, stream>>>(e->mat, e->tab, io, e->work, family_mode);
 }

@@ -96,6 +96,16 @@ __device__ __forceinline__ double fast_sqrt(double x) {
   return fma(fma(-s, s, x), 0.5 * r, s);       // s + (x - s^2) r / 2
 }
 
+// fast_sqrt with sqrt(x <= 0) = 0 (the reference's sqrt gives exactly 0 at 0, e.g. for a particle that has just stopped)
+__device__ __forceinline__ double fast_sqrt0(double x) { return x > 0.0 ? fast_sqrt(x) : 0.0; }
+__device__ __forceinline__ double fast_rsqrt(double x) {       // 1 / sqrt(x), x finite, normal, positive; <= 1 ulp
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double h = 0.5 * x;
+  r = fma(r, fma(-h * r, r, 0.5), r);
+  return fma(r, fma(-h * r, r, 0.5), r);
+}
+
 // ---------------------------------------------------------------- hot-loop elementary functions
 // The sub-step loop calls exp, log (twice), sincos and sincospi once per iteration.  libdevice's versions are accurate but
 // ptxas materialises each of their ~60 fp64 polynomial coefficients as a pair of 32-bit immediate moves (24 % of k_loop's
@@ -528,7 +538,75 @@ __device__ __forceinline__ double ff_el_inel_over_t2_fast(const Material& M, dou
   double Ginel = M.dff_inel_pref * (r * r) * ((1.0 + t * ((mu_p * mu_p - 1.0) / (4.0 * kMp * kMp))) * fast_rcp(d2 * d2));
   return M.dff_pref * (Gel + Ginel);
 }
-__device__ __forceinline__ double ds_darkbrem_fast(const Material& M, const SampleConst& sc, double Eb, double ml, const double* xx) {
+#ifndef PB_DB_BRANCHFREE
+#define PB_DB_BRANCHFREE 0      // measured (profiles/r02_summary.md): with ~95 % of the dark-brem trials outside the kinematic cuts, a warp
+#endif                          // whose lanes ALL leave early is common enough that the early returns win (config 3: 67.7 vs 85.1 ms)
+#ifndef PB_DB_FASTSQRT
+#define PB_DB_FASTSQRT 1
+#endif
+#if PB_DB_FASTSQRT
+#define DB_SQRT fast_sqrt
+#else
+#define DB_SQRT sqrt
+#endif
+// the same integrand with the kinematic cuts tested as soon as their inputs exist (early returns)
+__device__ __forceinline__ double ds_darkbrem_fast_eo(const Material& M, const SampleConst& sc, double Eb, double ml, const double* xx) {
+  const double mV = M.mV, MT = M.mT;
+  const double LN10 = 2.302585092994046;
+  double x = xx[0];
+  double xE = x * Eb;
+  if (!(xE >= mV)) return 0.0;
+  double omc = hot_exp10(xx[1]);
+  double cth = 1.0 - omc;
+  double ttilde = hot_exp10(xx[2]);
+  double mV2 = mV * mV, ml2 = ml * ml;
+  double k = DB_SQRT(fabs(xE * xE - mV2));
+  const double p = sc.b;
+  double V2 = p * p + k * k - 2 * p * k * cth;
+  double V = DB_SQRT(V2);
+  double VV = V * V;
+  double utilde = -2 * (x * Eb * Eb - k * p * cth) + mV2;
+  double Er = (1 - x) * Eb + MT;
+  double discr = utilde * utilde + 4 * MT * utilde * Er + 4 * MT * MT * VV;
+  if (!(discr >= 0)) return 0.0;
+  double sq = DB_SQRT(discr);
+  double iden = fast_rcp(2 * Er * Er - 2 * VV);
+  double cmn = V * (utilde + 2 * MT * Er);
+  double Qp = fabs((cmn + Er * sq) * iden);
+  double Qm = fabs((cmn - Er * sq) * iden);
+  double tplus = 2 * MT * (DB_SQRT(MT * MT + Qp * Qp) - MT);
+  double tminus = 2 * MT * (DB_SQRT(MT * MT + Qm * Qm) - MT);
+  const double tconv = sc.c, i2MT = sc.d;
+  double t = ttilde * tconv;
+  if (!((tplus > tminus) && (t > tminus) && (t < tplus))) return 0.0;
+  double q0 = -t * i2MT;
+  double q = DB_SQRT(t * t * (i2MT * i2MT) + t);
+  double e3 = Eb + q0 - xE;
+  double iV = fast_rcp(V), iq = fast_rcp(q);
+  double cthq = -(VV + q * q + ml2 - e3 * e3) * (0.5 * iV * iq);
+  double mm = mV2 + 2 * ml2;
+  double Y = -t + 2 * q0 * Eb - 2 * q * p * (p - k * cth) * cthq * iV;
+  double W = fabs(Y * Y - 4 * q * q * p * p * k * k * (1 - cth * cth) * (1 - cthq * cthq) * (iV * iV));
+  if (!((fabs(cthq) <= 1.0) && (W > 0))) return 0.0;
+  double iu = fast_rcp(utilde);
+  double Am2 = -8 * MT * (4 * Eb * Eb * MT - t * (2 * Eb + MT)) * mm;
+  double A1 = 8 * MT * MT * iu;
+  double Am1 = (8 * iu) * (MT * MT * (2 * t * utilde + utilde * utilde
+                                      + 4 * Eb * Eb * (2 * (x - 1) * mm - t * ((x - 2) * x + 2))
+                                      + 2 * t * (-mV2 + 2 * ml2 + t))
+                           - 2 * Eb * MT * t * ((1 - x) * utilde + (x - 2) * (mm + t))
+                           + t * t * (utilde - mV2));
+  double A0 = (8 * iu * iu) * (MT * MT * (2 * t * utilde + (t - 4 * Eb * Eb * (x - 1) * (x - 1)) * mm)
+                               + 2 * Eb * MT * t * (utilde - (x - 1) * mm));
+  double sW = DB_SQRT(W);
+  double isW = fast_rcp(sW);
+  double phi_int = (A0 + Y * A1 + Am1 * isW + Y * Am2 * (isW * isW * isW)) * (0.5 * i2MT * i2MT);
+  double FF = ff_el_inel_over_t2_fast(M, t);
+  double Jac = omc * ttilde * (LN10 * LN10);
+  return FF * (kAlpha * kAlpha * kAlpha) * k * Eb * phi_int * (sc.e * iV) * tconv * Jac;
+}
+
+__device__ __forceinline__ double ds_darkbrem_fast_bf(const Material& M, const SampleConst& sc, double Eb, double ml, const double* xx) {
   // branch-free (the kinematic cuts select at the end): the lanes of a warp sit at independent points, so an early return saves
   // nothing under SIMT, and straight-line code lets the T trials a lane evaluates per round interleave.  Outside the cuts the
   // arithmetic runs on garbage (sqrt of a negative number -> NaN) and is discarded.
@@ -540,27 +618,27 @@ __device__ __forceinline__ double ds_darkbrem_fast(const Material& M, const Samp
   double cth = 1.0 - omc;
   double ttilde = hot_exp10(xx[2]);
   double mV2 = mV * mV, ml2 = ml * ml;
-  double k = fast_sqrt(fabs(xE * xE - mV2));
+  double k = DB_SQRT(fabs(xE * xE - mV2));
   const double p = sc.b;
   double V2 = p * p + k * k - 2 * p * k * cth;
-  double V = fast_sqrt(V2);
+  double V = DB_SQRT(V2);
   double VV = V * V;
   double utilde = -2 * (x * Eb * Eb - k * p * cth) + mV2;
   double Er = (1 - x) * Eb + MT;
   double discr = utilde * utilde + 4 * MT * utilde * Er + 4 * MT * MT * VV;
   bool ok = (xE >= mV) && (discr >= 0);
-  double sq = fast_sqrt(discr);
+  double sq = DB_SQRT(discr);
   double iden = fast_rcp(2 * Er * Er - 2 * VV);
   double cmn = V * (utilde + 2 * MT * Er);
   double Qp = fabs((cmn + Er * sq) * iden);
   double Qm = fabs((cmn - Er * sq) * iden);
-  double tplus = 2 * MT * (fast_sqrt(MT * MT + Qp * Qp) - MT);
-  double tminus = 2 * MT * (fast_sqrt(MT * MT + Qm * Qm) - MT);
+  double tplus = 2 * MT * (DB_SQRT(MT * MT + Qp * Qp) - MT);
+  double tminus = 2 * MT * (DB_SQRT(MT * MT + Qm * Qm) - MT);
   const double tconv = sc.c, i2MT = sc.d;
   double t = ttilde * tconv;
   ok = ok && (tplus > tminus) && (t > tminus) && (t < tplus);
   double q0 = -t * i2MT;
-  double q = fast_sqrt(t * t * (i2MT * i2MT) + t);
+  double q = DB_SQRT(t * t * (i2MT * i2MT) + t);
   double e3 = Eb + q0 - xE;
   double iV = fast_rcp(V), iq = fast_rcp(q);
   double cthq = -(VV + q * q + ml2 - e3 * e3) * (0.5 * iV * iq);
@@ -578,13 +656,21 @@ __device__ __forceinline__ double ds_darkbrem_fast(const Material& M, const Samp
                            + t * t * (utilde - mV2));
   double A0 = (8 * iu * iu) * (MT * MT * (2 * t * utilde + (t - 4 * Eb * Eb * (x - 1) * (x - 1)) * mm)
                                + 2 * Eb * MT * t * (utilde - (x - 1) * mm));
-  double sW = fast_sqrt(W);
+  double sW = DB_SQRT(W);
   double isW = fast_rcp(sW);
   double phi_int = (A0 + Y * A1 + Am1 * isW + Y * Am2 * (isW * isW * isW)) * (0.5 * i2MT * i2MT);
   double FF = ff_el_inel_over_t2_fast(M, t);
   double Jac = omc * ttilde * (LN10 * LN10);
   double f = FF * (kAlpha * kAlpha * kAlpha) * k * Eb * phi_int * (sc.e * iV) * tconv * Jac;
   return ok ? f : 0.0;
+}
+
+__device__ __forceinline__ double ds_darkbrem_fast(const Material& M, const SampleConst& sc, double Eb, double ml, const double* xx) {
+#if PB_DB_BRANCHFREE
+  return ds_darkbrem_fast_bf(M, sc, Eb, ml, xx);
+#else
+  return ds_darkbrem_fast_eo(M, sc, Eb, ml, xx);
+#endif
 }
 
 // radiative_return.py:26-79 + all_processes.py:400-466 (dsigma_radiative_return_du)
@@ -612,6 +698,57 @@ __device__ __forceinline__ double ds_darkann(const Material& M, double Ee, doubl
   double y = mV2 / s;
   double lumi = fl_kf(y / x1, beta) * fl_kf_scaled(x1, beta) * (1.0 / x1) * (2.0 / beta);
   return 2.0 * prefac * lumi;
+}
+
+// ---- the radiative-return integrand as the sampler evaluates it.  Everything that depends on the positron energy alone - s, beta
+// (a logarithm), u_max (a pow), the prefactor (a square root and three divisions) - is computed ONCE per sample (SampleConst:
+// b = beta, c = u_max, d = 2 x prefac, e = mV^2 / s) with the very expressions of ds_darkann; a trial is left with three powers.
+// DarkAnn needs ~300 trials per accepted sample (the flux function is singular at the resonance), 1e9 trials per 2e4 config-3
+// showers.  PB_DARKANN_FASTPOW: a^b as exp(b log a) through the constant-memory log (relative error ~ |b ln a| ulp <= 1e-14
+// here, where libdevice's pow carries a double-double logarithm for <= 2 ulp); differences to ds_darkann are far inside the
+// integrand's own conditioning (tests/test_gpu_probes.py::test_dark_dsigma_vs_reference_golden).
+#ifndef PB_DARKANN_FASTPOW
+#define PB_DARKANN_FASTPOW 1
+#endif
+__device__ __forceinline__ double ann_pow(double a, double b) {
+#if PB_DARKANN_FASTPOW
+  if (!(a > 0.0)) return (a == 0.0) ? (b > 0.0 ? 0.0 : 1.0 / 0.0) : a + b;      // pow(0, b); NaN in -> NaN out
+  return exp(b * hot_log(a));
+#else
+  return pow(a, b);
+#endif
+}
+__device__ __forceinline__ SampleConst darkann_const(const Material& M, double Ee) {
+  const double me = kMe;
+  SampleConst c{0.0, 0.0, 0.0, 0.0, 0.0};
+  double mV2 = M.mV * M.mV;
+  double s = 2.0 * me * (Ee + me);
+  c.a = s;
+  double beta = kf_beta(s);
+  double umax = pow(1.0 - mV2 / s, beta / 2.0);
+  double betaf = sqrt(1.0 - 4.0 * me * me / mV2);
+  double prefac = (4.0 * kPi * kPi) * kAlpha * betaf * (3.0 / 2.0 - betaf * betaf / 2.0) / s * umax;
+  c.b = beta; c.c = umax; c.d = 2.0 * prefac; c.e = mV2 / s;
+  return c;
+}
+__device__ __forceinline__ double ds_darkann_c(const Material& M, const SampleConst& c, double Ee, double u0) {
+  const double me = kMe;
+  const double mV2 = M.mV * M.mV;
+  const double s = 2.0 * me * (Ee + me);          // one multiply-add: cheaper than a fourth staged constant
+  if (s < mV2) return 0.0;
+  const double beta = c.b, umax = c.c;
+  double u = u0 * umax;
+  double x1 = 1.0 - ann_pow(u, 2.0 / beta);
+  double x2 = mV2 / (x1 * s);
+  if (!((x2 < 1.0) && (x1 > 0.0) && (u0 < 1.0))) return 0.0;
+  double y = c.e;
+  // fl_kf(y / x1, beta) * fl_kf_scaled(x1, beta) / x1 * (2 / beta), the two flux factors as in radiative_return.py:26-79
+  double xa = y / x1;
+  if (xa >= 1.0) xa = 1.0 - 1e-10;
+  double fa = (beta / 16.0) * ((8.0 + 3.0 * beta) * ann_pow(1.0 - xa, beta / 2.0 - 1.0) - 4.0 * (1.0 + xa));
+  double fb = (beta / 16.0) * ((8.0 + 3.0 * beta) - 4.0 * (1.0 + x1) * ann_pow(1.0 - x1, 1.0 - beta / 2.0));
+  double lumi = fa * fb * (1.0 / x1) * (2.0 / beta);
+  return c.d * lumi;
 }
 
 __device__ __forceinline__ double dsigma(const Material& M, int proc, double E, const double* x) {
@@ -709,11 +846,11 @@ __device__ __forceinline__ V4 mcs_fast(const Material& M, V4 p4, double pn, doub
   double E2 = E * E;
   double omega = M.mcs_Cw * t * E2 * fast_rcp(pn * pn + M.mcs_c3 * E2);
   double v = omega * (0.5 / (1.0 - F));
-  double th0 = sqrt(chic2 * ((1.0 + v) * hot_log(1.0 + v) * fast_rcp(v) - 1) * (1.0 / (1.0 + F * F)));
+  double th0 = fast_sqrt0(chic2 * ((1.0 + v) * hot_log(1.0 + v) * fast_rcp(v) - 1) * (1.0 / (1.0 + F * F)));
   double theta = sign * (radial * th0) * M.rescale_mcs;
   double vx = p4.x, vy = p4.y, vz = p4.z;
   double ca, sa, vxp;
-  if (vx != 0.0 && vy != 0.0) { double pt2 = vx * vx + vy * vy; double r = rsqrt(pt2); ca = vx * r; sa = -vy * r; vxp = pt2 * r; }
+  if (vx != 0.0 && vy != 0.0) { double pt2 = vx * vx + vy * vy; double r = fast_rsqrt(pt2); ca = vx * r; sa = -vy * r; vxp = pt2 * r; }
   else if (vy != 0.0) { ca = 0.0; sa = 1.0; vxp = -vy; }
   else { ca = 1.0; sa = 0.0; vxp = vx; }
   double cb, sb;
@@ -743,7 +880,7 @@ __device__ __forceinline__ McsDraw mcs_draw(uint2 key, uint32_t index, uint32_t 
   McsDraw d;
   d.sign = (sp & 1u) ? 1.0 : -1.0;
   d.uphi = a.a;
-  d.radial = sqrt(-2.0 * hot_log(1.0 - a.b));
+  d.radial = fast_sqrt0(-2.0 * hot_log(1.0 - a.b));
   return d;
 }
 __device__ __forceinline__ V4 mcs_scatter(const Material& M, V4 p4, double pn, double t, double m_lepton, double mass,

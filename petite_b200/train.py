@@ -99,8 +99,12 @@ class Trainer:
                                                               capi.dptr(n), capi.dptr(I)))
         return d, n, I
 
-    def train(self, process, energies, nitn=30, n_points=1_000_000, alpha=1.0, seed=20261017, verbose=False):
-        """-> (grids (nE, sum(ninc+1)), ninc, integral estimate of the last sweep (nE,))."""
+    def train(self, process, energies, nitn=30, n_points=1_000_000, alpha=1.0, seed=20261017, verbose=False, schedule=None):
+        """-> (grids (nE, sum(ninc+1)), ninc, integral estimate of the last sweep (nE,)).  ``schedule`` = [(iterations, points per
+        iteration, alpha), ...] replaces the single (nitn, n_points, alpha) stage: coarse, strongly damped stages first, then stages with
+        more points and a smaller alpha, whose training data are less noisy per increment (fewer spikes of jac x f, i.e. a smaller
+        max_F for the same integral)."""
+        stages = [(nitn, n_points, alpha)] if schedule is None else list(schedule)
         E = np.asarray(energies, dtype=np.float64)
         dim = tb.PROC_DIM[process]
         ninc = NINC[dim]
@@ -110,15 +114,18 @@ class Trainer:
             for ax, (lo, hi) in enumerate(integration_range(process, e, self.mV, self.Eg_min, self.Ee_min)):
                 grids[k, offs[ax]:offs[ax + 1]] = np.linspace(lo, hi, ninc[ax] + 1)
         I = np.zeros(len(E))
-        for it in range(nitn):
-            d, n, I = self.sweep(process, grids, ninc, E, n_points, seed + it)
-            for k in range(len(E)):
-                for ax in range(dim):
-                    a, b = offs[ax], offs[ax + 1]
-                    grids[k, a:b] = refine(grids[k, a:b], d[k, a:b - 1], n[k, a:b - 1], alpha)
-            if verbose:
-                print(process, "iteration", it, "integral[mid]", I[len(E) // 2], flush=True)
-        _, _, I = self.sweep(process, grids, ninc, E, n_points, seed + nitn)
+        it = 0
+        for nitn_s, n_points, alpha in stages:
+            for _ in range(nitn_s):
+                d, n, I = self.sweep(process, grids, ninc, E, n_points, seed + it)
+                for k in range(len(E)):
+                    for ax in range(dim):
+                        a, b = offs[ax], offs[ax + 1]
+                        grids[k, a:b] = refine(grids[k, a:b], d[k, a:b - 1], n[k, a:b - 1], alpha)
+                if verbose:
+                    print(process, "iteration", it, "integral[mid]", I[len(E) // 2], flush=True)
+                it += 1
+        _, _, I = self.sweep(process, grids, ninc, E, n_points, seed + it)
         return grids, np.array(ninc, dtype=np.int32), I
 
 

@@ -23,11 +23,13 @@ def test_library_exports_every_declared_symbol(built_library):
 def test_capi_struct_layouts(built_library):
     from petite_b200 import _capi
     assert set(_capi.SIGNATURES) >= {"pb_run_showers", "pb_probe"}
-    assert ctypes.sizeof(_capi.pb_stack) == 8 * 8
+    assert ctypes.sizeof(_capi.pb_stack) == 7 * 8            # p0, r0w, pf, rf, ids (packed meta + key + weight), aux, capacity
     assert ctypes.sizeof(_capi.pb_primaries) == 8 * 8
     assert ctypes.sizeof(_capi.pb_profile) == 8 * (8 + 8 + 16 + 16)
     assert ctypes.sizeof(_capi.pb_counters) == 10 * 8
     assert ctypes.sizeof(_capi.pb_config) == 8 * (10 + 5 + 1 + 6 + 1)
+    from petite_b200 import dark_setup
+    assert dark_setup.CALL_DTYPE.itemsize == 48                # struct pb_quad_call: 6 x int32, 3 x double
 
 
 def test_engine_fails_loudly_without_gpu(built_library):

@@ -25,7 +25,7 @@ for c in [int(a) for a in sys.argv[1:]] or [3, 5]:
         row = {"config": c, "sm_showers": n, "sm_records": b.n, "dark_vectors": d.n, "dark_trials": d.counters["n_trials"], "dark_samples": d.counters["n_samples"],
                "pass_ms": e0.elapsed_time(e1), "kernels_ms": {k: round(v, 3) for k, v in pr["ms"].items() if v},
                "trials": {k: v for k, v in pr["trials"].items() if v}, "samples": {k: v for k, v in pr["samples"].items() if v},
-               "T_dark": os.environ.get("PB_SAMPLE_T_DARK", "default"), "G": os.environ.get("PB_SAMPLE_G", "default")}
+               "T_dark": os.environ.get("PB_SAMPLE_T_DARK", "default"), "G": os.environ.get("PB_SAMPLE_G_DARK", "default")}
         if best is None or row["pass_ms"] < best["pass_ms"]:
             best = row
     best["ps_per_trial"] = 1e9 * best["kernels_ms"].get("k_sample", 0.0) / max(best["dark_trials"], 1)
