@@ -657,6 +657,10 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
 // average trials per sample) proportionally smaller tiles and puts those tiles at the front of the tile table.  Scheduling only: the samples themselves
 // are a pure function of (particle key, trial index).
 constexpr int TILE_MIN = 32;
+#ifndef PB_TILE_HEAVY_COST
+#define PB_TILE_HEAVY_COST 4.f
+#endif
+constexpr float TILE_HEAVY_COST = PB_TILE_HEAVY_COST;     // a heavy bucket's tile may cost this many average tiles
 __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
   constexpr int PER = NBUCKET / 1024;
   __shared__ int s_cnt[1024], s_t0[1024], s_t1[1024];
@@ -682,10 +686,21 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
   float wall = 0.f, call = 0.f;
   for (int k = 0; k < 32; ++k) { wall += s_w[k]; call += s_c[k]; }
   const float avg_all = call > 0.f ? wall / call : 16.f;
-  // the buckets more than twice as expensive per sample as the launch average ("heavy") get proportionally smaller tiles - a heavy
-  // tile then costs about TILE x avg_all trials, like an average one - and go first.  Everything else keeps TILE samples per tile:
-  // shrinking every above-average bucket was measured 15 % slower on the dark pass, whose buckets spread over 30-300 trials per
-  // sample (each tile ends with a drain phase, and small tiles have more of them per sample)
+  // share of the launch's expected trials that sits in heavy buckets: rare stragglers (the annihilation rows of an SM wave, < 1 %) get
+  // the special treatment below; when the heavy buckets ARE the work (DarkAnn in a dark pass: 90 %) they are scheduled like any other
+  float hw = 0.f;
+  for (int k = 0; k < PER; ++k) if (avg[k] > 2.f * avg_all && t * PER + k < N_SAMPLED * LU_MAX) hw += avg[k] * (float)cnt[k];
+  for (int o = 16; o > 0; o >>= 1) hw += __shfl_down_sync(0xffffffffu, hw, o);
+  __syncthreads();
+  if ((t & 31) == 0) s_w[t >> 5] = hw;
+  __syncthreads();
+  float hall = 0.f;
+  for (int k = 0; k < 32; ++k) hall += s_w[k];
+  const bool norm = W.tile_norm && hall < 0.25f * wall;
+  // the buckets more than twice as expensive per sample as the launch average ("heavy") go first, with tiles shrunk so that one of
+  // them costs at most TILE_HEAVY_COST average tiles.  Not smaller: a tile ends when its slowest WARP is done, the trial count of a
+  // sample is geometric, and the fewer samples a warp gets the larger the spread between the four warps (normalising every tile to
+  // the average cost was measured 15 % slower on the dark pass of config 3, where DarkAnn needs 300 trials per sample)
   int csum = 0, t0sum = 0, t1sum = 0;
   for (int k = 0; k < PER; ++k) {
     int b = t * PER + k;
@@ -693,8 +708,8 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(Work W) {
     til[k] = 0; heavy[k] = 0;
     if (b < N_SAMPLED * LU_MAX) {
       int tsz = TILE;
-      heavy[k] = W.tile_norm && avg[k] > 2.f * avg_all;
-      if (heavy[k]) tsz = max(TILE_MIN, min(TILE, (int)((float)TILE * avg_all / avg[k]) & ~31));
+      heavy[k] = norm && avg[k] > 2.f * avg_all;
+      if (heavy[k]) tsz = max(TILE_MIN, min(TILE, (int)((float)TILE * TILE_HEAVY_COST * avg_all / avg[k]) & ~31));
       W.tile_sz[b] = tsz;
       til[k] = (c + tsz - 1) / tsz;
     }

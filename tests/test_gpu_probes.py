@@ -154,8 +154,11 @@ def test_dark_dsigma_vs_reference_golden(golden, material, process, code):
         w = u ** (2 / beta)
         x1, y = 1 - w, mV ** 2 / s_
         with np.errstate(all="ignore"):
-            amp = w * (1 / np.maximum(x1, 1e-300) + 1 / np.maximum(x1 - y, 1e-300))
-            ann_tol = 1e-12 + 2.3e-16 * (4 + (2 / beta) * np.abs(np.log(np.maximum(u, 1e-300)))) * np.where(np.isfinite(amp), amp, 0.0) * 4
+            e_pow = 2.3e-16 * (4 + (2 / beta) * np.abs(np.log(np.maximum(u, 1e-300))))            # relative error of the power
+            dx1 = e_pow * w / np.maximum(x1, 1e-300)                                             # ... of x1
+            near = np.maximum(x1, 1e-300) / np.maximum(x1 - y, 1e-300)                           # 1 / (1 - x2)
+            ann_tol = 1e-12 + 4 * (dx1 * (2 + near) + 2 * 2.3e-16 * near)
+            ann_tol = np.where(np.isfinite(ann_tol), ann_tol, 1.0)
     for got in forms:
         assert np.array_equal(got == 0, f == 0)
         for Einc in np.unique(E):
