@@ -46,10 +46,10 @@ CONFIGS = {
             material="graphite", pid=11, E0=10.0, mass=M_E, mV=0.003, active=["DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=100_000, cpu=2),
     4: dict(workload="High-energy dark shower: data_400GeV maps, synthetic beam-dump e+-/gamma spectrum into lead, m_V=10 MeV, 1e5 primaries "
                      "(BASELINE.json configs[3])",
-            material="lead", pid=0, E0=0.0, mass=0.0, mV=0.010, active=["DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=10_000, data=DATA400, cpu=1),
+            material="lead", pid=0, E0=0.0, mass=0.0, mV=0.010, active=["DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=20_000, data=DATA400, cpu=1),
     5: dict(workload="Muon dark shower: 100 GeV mu- through lead, MuonBrem/MuonE/DarkMuonBrem + multiple scattering, m_V=30 MeV, 1e5 primaries "
                      "(BASELINE.json configs[4])",
-            material="lead", pid=13, E0=100.0, mass=M_MU, mV=0.030, active=["DarkMuonBrem", "DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=10_000, cpu=1),
+            material="lead", pid=13, E0=100.0, mass=M_MU, mV=0.030, active=["DarkMuonBrem", "DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=25_000, cpu=1),
 }
 CFG = CONFIGS[2]
 
@@ -325,6 +325,7 @@ def ours(args):
                     eng.tally_dark(d, dtally)
                     tot["n_dark"] += d.n; tot["n_dark_trials"] += d.counters["n_trials"]; tot["n_dark_samples"] += d.counters["n_samples"]
                     tot["n_launches"] += d.counters["n_launches"] + 1
+                    del d                                                  # (a live DarkBatch pins its dark stack)
             if keep:
                 kept = bs
         if world > 1:
@@ -467,6 +468,8 @@ def ours(args):
     if args.fudge_line and rank == 0:
         sh4 = engine(4)
         sh4._stack_tensors, sh4._stack_capacity = sh._stack_tensors, sh._stack_capacity       # same HBM: the runs do not overlap
+        if dark:
+            sh4._dark_stack, sh4._dark_capacity = sh._dark_stack, sh._dark_capacity
         step(devp, 1, eng=sh4)
         torch.cuda.synchronize()
         e0.record()

@@ -1267,8 +1267,8 @@ __device__ __forceinline__ double np_sum10(const double* a) {
 // bin, MCS + energy loss down to it, threshold short-cuts -> candidate (SM slot, process, weight, four-momentum, bucket).
 __global__ void __launch_bounds__(128)
 k_dark_prepare(const __grid_constant__ Material M, const __grid_constant__ Tables T, const __grid_constant__ DarkTables D,
-               Stack S, Work W, DarkCand C, long long n, unsigned active) {
-  long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+               Stack S, Work W, DarkCand C, long long first, long long n, unsigned active) {
+  long long s = first + blockIdx.x * (long long)blockDim.x + threadIdx.x;      // SM records [first, n) of this chunk
   const int lane = threadIdx.x & 31;
   int nc = 0;
   int c_proc[2]; double c_wg[2]; V4 c_pf[2]; int c_bucket[2];
@@ -2583,40 +2583,49 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
   if (!e->dark_ready) { e->err = "dark tables not uploaded"; return PB_ERR_STATE; }
   for (int p = P_DARKBREM; p <= P_DARKMUONBREM; ++p)
     if (((active >> p) & 1u) && e->tab.map[p].grid == nullptr) { e->err = "dark maps not uploaded for an active process"; return PB_ERR_STATE; }
-  if (2 * n_sm > 0x7fffffffLL) { e->err = "too many SM records for one dark pass"; return PB_ERR_CAPACITY; }
+  if (n_sm > 0x7fffffffLL) { e->err = "too many SM records for one dark pass"; return PB_ERR_CAPACITY; }
   int B = 300;
   for (int p = P_DARKBREM; p <= P_DARKMUONBREM; ++p) if (e->tab.map[p].grid) { B = e->tab.map[p].B; break; }
   e->mat.max_trials = (long long)std::min<double>((double)e->cfg.max_sweeps * (double)B, 4.0e9);
   Stack S{sm->p0, sm->r0w, sm->pf, sm->rf, (int4*)sm->ids, (int2*)sm->aux, sm->capacity};
   Stack O{dk->p0, dk->r0w, dk->pf, dk->rf, (int4*)dk->ids, (int2*)dk->aux, dk->capacity};
-  long long ncap = std::max<long long>(2 * n_sm, 1);
+  // The SM records are processed in chunks of at most DARK_CHUNK records, so that the candidate scratch (2 candidates per record
+  // in the worst case: 108 B per record) stays bounded whatever the size of the SM stack; dark vectors are appended chunk after chunk.
+  const long long DARK_CHUNK = 1LL << 25;
+  long long ncap = std::max<long long>(2 * std::min<long long>(n_sm, DARK_CHUNK), 1);
   int rc = ensure_work(e, ncap);
   if (rc != PB_OK) return rc;
   rc = ensure_cand(e, ncap);
   if (rc != PB_OK) return rc;
   const bool prof = e->profiling != 0;
   memset(&e->prof, 0, sizeof(e->prof));
-  bool recorded[8] = {false, false, false, false, false, false, false, false};
-  auto tick = [&](int k) { if (prof) { cudaEventRecord(e->ev[2 * k], stream); recorded[k] = true; } };
-  auto tock = [&](int k) { if (prof) cudaEventRecord(e->ev[2 * k + 1], stream); ++e->prof.launches[k]; };
+  auto tick = [&](int k) { if (prof) cudaEventRecord(e->ev[2 * k], stream); };
+  auto tock = [&](int k) { if (prof) { cudaEventRecord(e->ev[2 * k + 1], stream); } ++e->prof.launches[k]; };
+  auto collect = [&](int k) {        // after a stream synchronise
+    float ms = 0.f;
+    if (prof && cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]) == cudaSuccess) e->prof.ms[k] += ms;
+  };
   unsigned long long tail0[2] = {0ull, 0ull};
   PB_CUDA(e, cudaMemcpyAsync(e->work.tail, tail0, sizeof(tail0), cudaMemcpyHostToDevice, stream));
   PB_CUDA(e, cudaMemsetAsync(e->work.counters, 0, sizeof(unsigned long long) * CNT_N, stream));
   PB_CUDA(e, cudaMemsetAsync(e->work.hist, 0, sizeof(int) * NBUCKET, stream));
-  PB_CUDA(e, cudaMemsetAsync(e->work.ctrl, 0, sizeof(int) * 8, stream));
-  PB_CUDA(e, cudaMemsetAsync(e->cand.count, 0, sizeof(int), stream));
-  long long launches = 0;
-  int n_cand = 0;
-  if (n_sm > 0) {
+  long long launches = 0, cand_total = 0, max_cand = 0;
+  for (long long first = 0; first < n_sm; first += DARK_CHUNK) {
+    const long long last = std::min<long long>(n_sm, first + DARK_CHUNK);
+    int n_cand = 0;
+    PB_CUDA(e, cudaMemsetAsync(e->work.ctrl, 0, sizeof(int) * 8, stream));
+    PB_CUDA(e, cudaMemsetAsync(e->cand.count, 0, sizeof(int), stream));
     tick(PB_K_FINALIZE);
-    k_dark_prepare<<<(unsigned)((n_sm + 127) / 128), 128, 0, stream>>>(e->mat, e->tab, e->dark, S, e->work, e->cand, n_sm, active);
+    k_dark_prepare<<<(unsigned)((last - first + 127) / 128), 128, 0, stream>>>(e->mat, e->tab, e->dark, S, e->work, e->cand, first, last, active);
     tock(PB_K_FINALIZE);
     PB_CUDA(e, cudaMemcpyAsync(&n_cand, e->cand.count, sizeof(int), cudaMemcpyDeviceToHost, stream));
     PB_CUDA(e, cudaStreamSynchronize(stream));
+    collect(PB_K_FINALIZE);
     ++launches;
-  }
-  if (n_cand > 0) {
-    if (n_cand > dk->capacity) { e->err = "dark stack capacity exhausted"; return PB_ERR_CAPACITY; }
+    if (n_cand <= 0) continue;
+    cand_total += n_cand;
+    max_cand = std::max<long long>(max_cand, n_cand);
+    if (cand_total > dk->capacity) { e->err = "dark stack capacity exhausted"; return PB_ERR_CAPACITY; }
     tick(PB_K_SCAN);
     k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
     tock(PB_K_SCAN); tick(PB_K_FILL);
@@ -2628,23 +2637,22 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
     k_dark_emit<<<(unsigned)((n_cand + 127) / 128), 128, 0, stream>>>(e->mat, S, O, e->work, e->cand, n_cand);
     tock(PB_K_EMIT);
     launches += 4;
+    if (prof || first + DARK_CHUNK < n_sm) {          // the scratch is reused by the next chunk
+      PB_CUDA(e, cudaStreamSynchronize(stream));
+      collect(PB_K_SCAN); collect(PB_K_FILL); collect(PB_K_SAMPLE); collect(PB_K_EMIT);
+    }
   }
   unsigned long long tl[2] = {0, 0};
   unsigned long long cnt[CNT_N];
   PB_CUDA(e, cudaMemcpyAsync(tl, e->work.tail, sizeof(tl), cudaMemcpyDeviceToHost, stream));
   PB_CUDA(e, cudaMemcpyAsync(cnt, e->work.counters, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
   PB_CUDA(e, cudaStreamSynchronize(stream));
-  for (int k = 0; k < PB_K_N; ++k) {
-    if (!recorded[k]) continue;
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, e->ev[2 * k], e->ev[2 * k + 1]) == cudaSuccess) e->prof.ms[k] += ms;
-  }
   for (int p = 0; p < 16; ++p) { e->prof.trials[p] = (int64_t)cnt[CNT_PROC_TRIALS + p]; e->prof.samples[p] = (int64_t)cnt[CNT_PROC_SAMPLES + p]; }
   if (out) {
     memset(out, 0, sizeof(*out));
     out->n_particles = (int64_t)std::min<unsigned long long>(tl[0], (unsigned long long)dk->capacity);
-    out->n_steps = n_cand; out->n_samples = (int64_t)cnt[CNT_SAMPLES]; out->n_trials = (int64_t)cnt[CNT_TRIALS];
-    out->n_no_sample = (int64_t)cnt[CNT_NOSAMPLE]; out->n_launches = launches; out->max_wave = n_cand; out->n_waves = 1;
+    out->n_steps = cand_total; out->n_samples = (int64_t)cnt[CNT_SAMPLES]; out->n_trials = (int64_t)cnt[CNT_TRIALS];
+    out->n_no_sample = (int64_t)cnt[CNT_NOSAMPLE]; out->n_launches = launches; out->max_wave = max_cand; out->n_waves = 1;
   }
   if (cnt[CNT_OVERFLOW]) { e->err = "dark stack overflow"; return PB_ERR_CAPACITY; }
   return PB_OK;

@@ -302,14 +302,23 @@ class DarkShower(Shower):
         mask = 0
         for p in active:
             mask |= 1 << _CODE[p]
-        self._ensure_dark_stack(2 * sm_batch.n + 1024)
-        t = self._dark_stack
-        dk = stack_struct(t)
+        # dark-stack capacity: the worst case is two dark vectors per SM record (e+: DarkBrem and DarkAnn), showers make 0.8-1.3 per
+        # record; start from the larger of the current stack and 1.5 n and fall back to the bound if the engine reports it too small
+        # (a DarkBatch of an earlier call keeps ITS stack alive: drop it before the next call if memory is tight)
+        worst = 2 * sm_batch.n + 1024
+        self._ensure_dark_stack(min(worst, max(self._dark_capacity, int(1.5 * sm_batch.n) + 1024)))
         sm = stack_struct(sm_batch._t)
         cnt = capi.pb_counters()
         stream = self._torch.cuda.current_stream(self._device).cuda_stream
-        capi.check(self._engine, capi.lib.pb_run_dark(self._engine, C.byref(sm), sm_batch.n, mask, C.byref(dk), C.byref(cnt),
-                                                      C.c_void_p(stream)))
+        while True:
+            t = self._dark_stack
+            dk = stack_struct(t)
+            rc = capi.lib.pb_run_dark(self._engine, C.byref(sm), sm_batch.n, mask, C.byref(dk), C.byref(cnt), C.c_void_p(stream))
+            if rc == capi.PB_ERR_CAPACITY and self._dark_capacity < worst:
+                self._ensure_dark_stack(worst)
+                continue
+            capi.check(self._engine, rc)
+            break
         b = DarkBatch(t, cnt.n_particles, cnt.as_dict(), sm_batch, active)
         b._mV = self._mV
         return b
