@@ -1969,6 +1969,8 @@ struct pb_engine_s {
   cudaGraph_t wave_graph = nullptr;
   cudaGraphExec_t wave_exec = nullptr;
   cudaStream_t cap_stream = nullptr;     // capture stream for building the graph body
+  cudaStream_t aux_stream = nullptr;     // set-up / probe entry points (find_max, training, probes, peak measurement) run here, not on the
+                                         // default stream: they must not serialise against another handle's wave loop
   std::vector<unsigned char> graph_sig;  // kernel arguments the instantiated graph was built with
   pb_profile prof{};
   std::string err;
@@ -2054,8 +2056,12 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   size_t fixed = sizeof(int) * (NBUCKET * 6 + 3 + 16) + sizeof(unsigned long long) * (8 + CNT_N + 2 * NBUCKET) + sizeof(WaveState) + 64;
   if (cudaMalloc(&e->fixed_blob, fixed) != cudaSuccess) { delete e; return PB_ERR_CUDA; }
   cudaMemset(e->fixed_blob, 0, fixed);
-  for (int i = 0; i < 2 * 8; ++i) cudaEventCreate(&e->ev[i]);
-  for (int a = 0; a < pb_engine_s::LOOKAHEAD; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) cudaEventCreate(&e->evp[a][b][c]);
+  bool ok = cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 * 8 && ok; ++i) ok = cudaEventCreate(&e->ev[i]) == cudaSuccess;
+  for (int a = 0; a < pb_engine_s::LOOKAHEAD && ok; ++a) for (int b = 0; b < 2 && ok; ++b) for (int c = 0; c < 2 && ok; ++c)
+    ok = cudaEventCreate(&e->evp[a][b][c]) == cudaSuccess;
+  if (ok) ok = cudaMallocHost(&e->h_ws, sizeof(WaveState) + 16) == cudaSuccess;
+  if (!ok) { pb_destroy(e); return PB_ERR_CUDA; }
   char* p = (char*)e->fixed_blob;
   e->work.tail = (unsigned long long*)p; p += 8 * sizeof(unsigned long long);
   e->work.counters = (unsigned long long*)p; p += CNT_N * sizeof(unsigned long long);
@@ -2068,7 +2074,6 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   e->work.ctrl = (int*)p; p += 16 * sizeof(int);
   p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
   e->work.ws = (WaveState*)p;
-  cudaMallocHost(&e->h_ws, sizeof(WaveState) + 16);
   *out = e;
   return PB_OK;
 }
@@ -2097,6 +2102,7 @@ extern "C" void pb_destroy(pb_engine e) {
   if (e->wave_exec) cudaGraphExecDestroy(e->wave_exec);
   if (e->wave_graph) cudaGraphDestroy(e->wave_graph);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
   delete e;
 }
 
@@ -2715,10 +2721,10 @@ extern "C" int pb_find_max(pb_engine e, int process, int n_trials, uint64_t seed
   if (mT > 0) m.mT = mT;
   double* d = nullptr;
   PB_CUDA(e, cudaMalloc(&d, sizeof(double) * 2 * mi.nE));
-  k_find_max<<<mi.nE, 128>>>(m, e->tab, process, n_trials, seed, d, d + mi.nE);
-  cudaError_t c = cudaDeviceSynchronize();
-  if (c == cudaSuccess) c = cudaMemcpy(max_out, d, sizeof(double) * mi.nE, cudaMemcpyDeviceToHost);
-  if (c == cudaSuccess) c = cudaMemcpy(sum_out, d + mi.nE, sizeof(double) * mi.nE, cudaMemcpyDeviceToHost);
+  k_find_max<<<mi.nE, 128, 0, e->aux_stream>>>(m, e->tab, process, n_trials, seed, d, d + mi.nE);
+  cudaError_t c = cudaMemcpyAsync(max_out, d, sizeof(double) * mi.nE, cudaMemcpyDeviceToHost, e->aux_stream);
+  if (c == cudaSuccess) c = cudaMemcpyAsync(sum_out, d + mi.nE, sizeof(double) * mi.nE, cudaMemcpyDeviceToHost, e->aux_stream);
+  if (c == cudaSuccess) c = cudaStreamSynchronize(e->aux_stream);
   cudaFree(d);
   if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
   return PB_OK;
@@ -2768,17 +2774,20 @@ extern "C" int pb_train_accumulate(pb_engine e, int process, const double* grid,
   double* d = nullptr;
   PB_CUDA(e, cudaMalloc(&d, sizeof(double) * (3 * rows + 2 * (size_t)nE)));
   double *d_grid = d, *d_d = d + rows, *d_n = d + 2 * rows, *d_E = d + 3 * rows, *d_I = d_E + nE;
-  PB_CUDA(e, cudaMemcpy(d_grid, grid, sizeof(double) * rows, cudaMemcpyHostToDevice));
-  PB_CUDA(e, cudaMemcpy(d_E, E_inc, sizeof(double) * nE, cudaMemcpyHostToDevice));
-  PB_CUDA(e, cudaMemset(d_d, 0, sizeof(double) * (2 * rows)));
-  PB_CUDA(e, cudaMemset(d_I, 0, sizeof(double) * nE));
-  PB_CUDA(e, cudaFuncSetAttribute(k_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int bx = (int)std::max<long long>(1, std::min<long long>(64, n_points / 4096));
-  k_train<<<dim3(bx, nE), 256, smem>>>(m, process, dim, stride, make_int4(nn[0], nn[1], nn[2], nn[3]), d_grid, d_E, n_points, seed, d_d, d_n, d_I);
-  cudaError_t c = cudaDeviceSynchronize();
-  if (c == cudaSuccess) c = cudaMemcpy(d_out, d_d, sizeof(double) * rows, cudaMemcpyDeviceToHost);
-  if (c == cudaSuccess) c = cudaMemcpy(n_out, d_n, sizeof(double) * rows, cudaMemcpyDeviceToHost);
-  if (c == cudaSuccess) c = cudaMemcpy(integral_out, d_I, sizeof(double) * nE, cudaMemcpyDeviceToHost);
+  cudaStream_t st = e->aux_stream;
+  cudaError_t c = cudaMemcpyAsync(d_grid, grid, sizeof(double) * rows, cudaMemcpyHostToDevice, st);
+  if (c == cudaSuccess) c = cudaMemcpyAsync(d_E, E_inc, sizeof(double) * nE, cudaMemcpyHostToDevice, st);
+  if (c == cudaSuccess) c = cudaMemsetAsync(d_d, 0, sizeof(double) * (2 * rows), st);
+  if (c == cudaSuccess) c = cudaMemsetAsync(d_I, 0, sizeof(double) * nE, st);
+  if (c == cudaSuccess) c = cudaFuncSetAttribute(k_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (c == cudaSuccess) {
+    int bx = (int)std::max<long long>(1, std::min<long long>(64, n_points / 4096));
+    k_train<<<dim3(bx, nE), 256, smem, st>>>(m, process, dim, stride, make_int4(nn[0], nn[1], nn[2], nn[3]), d_grid, d_E, n_points, seed, d_d, d_n, d_I);
+    c = cudaMemcpyAsync(d_out, d_d, sizeof(double) * rows, cudaMemcpyDeviceToHost, st);
+  }
+  if (c == cudaSuccess) c = cudaMemcpyAsync(n_out, d_n, sizeof(double) * rows, cudaMemcpyDeviceToHost, st);
+  if (c == cudaSuccess) c = cudaMemcpyAsync(integral_out, d_I, sizeof(double) * nE, cudaMemcpyDeviceToHost, st);
+  if (c == cudaSuccess) c = cudaStreamSynchronize(st);
   cudaFree(d);
   if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
   return PB_OK;
@@ -2817,9 +2826,9 @@ extern "C" int pb_measure_fp64_peak(pb_engine e, double* tflops) {
   const int iters = 1 << 16, blocks = e->n_sm * 8, threads = 256;
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {
-    cudaEventRecord(a);
-    k_fp64_peak<<<blocks, threads>>>(d, iters, 1.0000001, 1e-9);
-    cudaEventRecord(b);
+    cudaEventRecord(a, e->aux_stream);
+    k_fp64_peak<<<blocks, threads, 0, e->aux_stream>>>(d, iters, 1.0000001, 1e-9);
+    cudaEventRecord(b, e->aux_stream);
     cudaEventSynchronize(b);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, a, b);
@@ -2838,11 +2847,13 @@ extern "C" int pb_probe(pb_engine e, int what, int process, const double* in, in
   double *din = nullptr, *dout = nullptr;
   PB_CUDA(e, cudaMalloc(&din, sizeof(double) * n * is));
   PB_CUDA(e, cudaMalloc(&dout, sizeof(double) * n * os));
-  PB_CUDA(e, cudaMemcpy(din, in, sizeof(double) * n * is, cudaMemcpyHostToDevice));
-  PB_CUDA(e, cudaMemset(dout, 0, sizeof(double) * n * os));
-  k_probe<<<(unsigned)((n + 127) / 128), 128>>>(e->mat, e->tab, what, process, din, n, is, dout, os);
-  cudaError_t c = cudaDeviceSynchronize();
-  if (c == cudaSuccess) c = cudaMemcpy(out, dout, sizeof(double) * n * os, cudaMemcpyDeviceToHost);
+  cudaError_t c = cudaMemcpyAsync(din, in, sizeof(double) * n * is, cudaMemcpyHostToDevice, e->aux_stream);
+  if (c == cudaSuccess) c = cudaMemsetAsync(dout, 0, sizeof(double) * n * os, e->aux_stream);
+  if (c == cudaSuccess) {
+    k_probe<<<(unsigned)((n + 127) / 128), 128, 0, e->aux_stream>>>(e->mat, e->tab, what, process, din, n, is, dout, os);
+    c = cudaMemcpyAsync(out, dout, sizeof(double) * n * os, cudaMemcpyDeviceToHost, e->aux_stream);
+  }
+  if (c == cudaSuccess) c = cudaStreamSynchronize(e->aux_stream);
   cudaFree(din); cudaFree(dout);
   if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
   return PB_OK;
