@@ -72,6 +72,9 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #ifndef PB_LOOP_MINB
 #define PB_LOOP_MINB 6
 #endif
+#ifndef PB_LOOP_CAP_DEFAULT
+#define PB_LOOP_CAP_DEFAULT 32           // sub-steps a track may take per k_loop launch before it is carried into the next wave (0: no limit); measured 16 / 32 / 64 / 128 / off: 155.3 / 145.4 / 146.3 / 150.0 / 151.2 ms per config-2 step
+#endif
 #ifndef PB_SAMPLE_G_DEFAULT
 #define PB_SAMPLE_G_DEFAULT 4
 #endif
@@ -148,7 +151,9 @@ struct WaveState {
   long long begin, end;      // stack slots of the current wave
   long long capacity;        // of the particle stack
   long long tot_charged;
-  int n, n_charged;          // size of the current wave, of its charged list
+  int n, n_charged;          // entries of the current wave (new records + carried tracks), size of its charged list
+  int n_new, n_carry;        // new records [begin, begin + n_new) have wave-local index = slot - begin; the carried tracks (sub-step loop
+                             // paused in an earlier wave, see k_loop) follow with local indices n_new .. n - 1, slot = carry list entry
   int parity;                // which pair of index lists the current wave reads
   int status;                // 0 running, 1 finished (empty wave), 2 stack capacity exhausted, 3 scratch too small (host grows it)
   int waves, max_wave;
@@ -175,8 +180,11 @@ struct Work {            // per-wave scratch, sized to the widest wave seen so f
   int* ctrl;             // [0] n_tiles, [1] tile cursor, [2] k_loop chunk cursor
   int* list[4];          // wave-local index lists, two parities x {charged (dE/dx-stepping), everything else}: the wave
                          // reads list[2*parity + k], k_emit builds list[2*(parity^1) + k] for the next wave
+  int* carry[2];         // slots of the tracks carried into the current wave (carry[parity]) / paused in it (carry[parity ^ 1])
+  int loop_cap;          // sub-steps a track may take per launch (power of two; 0 = unlimited): see k_loop
+  int pad_;
   struct WaveState* ws;  // device-resident wave bookkeeping (lets the host enqueue several waves per synchronisation)
-  unsigned long long* tail;      // [0] stack tail (next free record); [1] = (n_neutral_next << 32) | n_charged_next
+  unsigned long long* tail;      // [0] stack tail (next free record); [1] = (n_neutral_next << 32) | n_charged_next; [2] tracks paused by this wave
   unsigned long long* counters;  // [CNT_N]: steps, substeps, samples, trials, no_sample, overflow, per-process trials/samples
   unsigned long long* tlog;      // measurement aid (PB_TILE_LOG): per tile of ONE chosen wave {start ns, end ns, bucket << 32 | count, SM}; else nullptr
   int tlog_wave, tlog_cap;
@@ -187,6 +195,11 @@ enum { CNT_STEPS = 0, CNT_SUBSTEPS, CNT_SAMPLES, CNT_TRIALS, CNT_NOSAMPLE, CNT_O
        CNT_PROC_SAMPLES = 24, CNT_N = 40 };
 
 __device__ __forceinline__ bool is_charged(int pid) { return pid == 11 || pid == -11 || pid == 13 || pid == -13; }
+// stack slot of wave-local entry i (WaveState::n_new)
+__device__ __forceinline__ long long wave_slot(const Work& W, long long begin, int n_new, int parity, int i) {
+  return i < n_new ? begin + i : (long long)W.carry[parity][i - n_new];
+}
+constexpr int AUX_PAUSED = -2;     // aux.x of a track whose sub-step loop was paused in this wave (k_finalize skips it)
 __device__ __forceinline__ int pack_info(int gen, int child_bit, int flags, int process) {
   return (gen << 16) | (child_bit << 15) | ((flags & 0x7f) << 8) | (process & 0xff);
 }
@@ -360,23 +373,23 @@ __device__ __forceinline__ void wave_begin(Work& W) {
   WaveState& ws = *W.ws;
   ws.iters += 1;
   if (ws.iters > (1 << 20)) ws.status = 4;                 // safety net for the device-side loop: no shower has a million waves
-  if (ws.status != 0 && ws.status != 3) { ws.n = 0; ws.n_charged = 0; return; }
-  unsigned long long tail = W.tail[0], lists = W.tail[1];
+  if (ws.status != 0 && ws.status != 3) { ws.n = 0; ws.n_charged = 0; ws.n_new = 0; ws.n_carry = 0; return; }
+  unsigned long long tail = W.tail[0], lists = W.tail[1], carried = W.tail[2];
   long long begin = ws.status == 3 ? ws.begin : ws.end;
   long long end = (long long)min(tail, (unsigned long long)ws.capacity);
-  long long n = end - begin;
+  long long n_new = end - begin, n = n_new + (long long)carried;
   ws.status = 0;
-  if (n <= 0) { ws.status = 1; ws.n = 0; ws.n_charged = 0; return; }
-  if (end + 2 * n > ws.capacity) { ws.status = 2; ws.n = 0; ws.n_charged = 0; return; }
-  if (n > ws.work_cap || 2 * n > ws.order_cap) { ws.status = 3; ws.begin = begin; ws.n = 0; ws.n_charged = 0; return; }
+  if (n <= 0) { ws.status = 1; ws.n = 0; ws.n_charged = 0; ws.n_new = 0; ws.n_carry = 0; return; }
+  if (end + 2 * n > ws.capacity) { ws.status = 2; ws.n = 0; ws.n_charged = 0; ws.n_new = 0; ws.n_carry = 0; return; }
+  if (n > ws.work_cap || 2 * n > ws.order_cap) { ws.status = 3; ws.begin = begin; ws.n = 0; ws.n_charged = 0; ws.n_new = 0; ws.n_carry = 0; return; }
   ws.begin = begin; ws.end = end;
-  ws.n = (int)n;
+  ws.n = (int)n; ws.n_new = (int)n_new; ws.n_carry = (int)carried;
   ws.n_charged = (int)(lists & 0xffffffffull);
   ws.parity ^= 1;
   ws.tot_charged += ws.n_charged;
   ws.waves += 1;
   ws.max_wave = max(ws.max_wave, (int)n);
-  W.tail[1] = 0;
+  W.tail[1] = 0; W.tail[2] = 0;
   W.ctrl[1] = 0; W.ctrl[2] = 0; W.ctrl[4] = 0; W.ctrl[5] = 0; W.ctrl[6] = 0;
 }
 __global__ void k_wave_begin(Work W) { wave_begin(W); }
@@ -395,10 +408,11 @@ __global__ void k_wave_begin_cond(Work W, cudaGraphConditionalHandle h) {
 // the chunk's records copied asynchronously (cp.async / LDGSTS, no registers) into the idle half of a per-warp
 // double buffer in shared memory -> consumed with shared-memory reads.
 constexpr int LOOP_CHUNK = 32;
-struct LoopBuf {                 // one chunk of track records: p0, r0w, track set-up (rf), ids
+struct LoopBuf {                 // one chunk of track records: p0, r0w, track set-up (rf), ids  (a carried track: pf, rf, -, ids, aux)
   double2 v[6][LOOP_CHUNK];
   int4 meta[LOOP_CHUNK];
   int4 kw[LOOP_CHUNK];
+  int2 aux[LOOP_CHUNK];
   int idx[LOOP_CHUNK];
 };
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -409,42 +423,60 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// **Bounded sub-steps per launch (carry-over).**  The sub-step count of a track is geometric (mean ~9, 1 track in 40 above 32, the
+// longest of a million above 150), a track cannot be split, and a wave used to end with its longest track: 50-130 us of idle SMs
+// per launch, and in narrow waves the whole critical path.  With Work::loop_cap = K (a power of two) a track is PAUSED when its
+// sub-step index reaches a multiple of K: its state is stored where the finished state would go (pf, rf with delta_z, aux.y = index,
+// aux.x = AUX_PAUSED), its slot is appended to the carry list of the NEXT wave, and that wave's k_loop resumes it next to its own
+// fresh tracks.  k_finalize skips paused tracks; a carried track that finishes joins the finalize -> bucket -> sample -> emit flow of
+// the wave it finishes in (wave-local index n_new + k, see WaveState).  The draws are indexed by (particle key, sub-step index), so
+// the track is the one an uninterrupted loop would have produced; daughters only appear a wave or two later.
 __global__ void __launch_bounds__(128, PB_LOOP_MINB)
 k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
        const double* __restrict__ prim_mass, int ms_e) {
   __shared__ __align__(16) LoopBuf s_buf[4][2];
   const long long begin = W.ws->begin;
-  const int n_charged = W.ws->n_charged;
-  if (n_charged <= 0) return;
-  const int* __restrict__ order_c = W.list[2 * W.ws->parity];
+  const int n_charged = W.ws->n_charged, n_new = W.ws->n_new;
+  const int n_work = n_charged + W.ws->n_carry;            // fresh charged tracks, then the carried ones
+  if (n_work <= 0) return;
+  const int parity = W.ws->parity;
+  const int* __restrict__ order_c = W.list[2 * parity];
+  const int* __restrict__ carry_in = W.carry[parity];
+  int* __restrict__ carry_out = W.carry[parity ^ 1];
+  const unsigned cap_mask = W.loop_cap > 0 ? (unsigned)W.loop_cap - 1u : 0xffffffffu;
   const int lane = threadIdx.x & 31;
   LoopBuf* buf = s_buf[threadIdx.x >> 5];
   const unsigned lt_mask = (1u << lane) - 1u;
   // small waves: smaller chunks, so that the three chunks every warp holds in its pipeline do not starve the other warps
-  const int chunk = min(LOOP_CHUNK, max(1, n_charged / (3 * (int)(gridDim.x * (blockDim.x / 32)))));
+  const int chunk = min(LOOP_CHUNK, max(1, n_work / (3 * (int)(gridDim.x * (blockDim.x / 32)))));
   // ---- pipeline state (warp-uniform unless noted)
   int which = 0;                 // half of the double buffer being consumed
   int pos = 0, cnt = 0;          // consumed / valid entries of that half
   int cnt_fly = 0;               // valid entries of the chunk being copied into the other half
-  int pre_idx = -1, pre_cnt = 0; // (per lane) list index of the chunk after that, and its size
+  int pre_idx = -1, pre_cnt = 0; // (per lane) wave-local index of the chunk after that, and its size
   int c_raw = 0;                 // (lane 0) cursor of the chunk after that; read one chunk later
   bool dry = false;              // the list is exhausted
   auto fetch_cursor = [&]() { if (lane == 0) c_raw = atomicAdd(&W.ctrl[2], chunk); };
   auto fetch_index = [&]() {     // consumes c_raw, issues the index load
     int c = __shfl_sync(0xffffffffu, c_raw, 0);
-    pre_cnt = min(max(n_charged - c, 0), chunk);
-    pre_idx = (lane < pre_cnt) ? order_c[c + lane] : -1;
+    pre_cnt = min(max(n_work - c, 0), chunk);
+    const int w = c + lane;
+    pre_idx = (lane < pre_cnt) ? (w < n_charged ? order_c[w] : n_new + (w - n_charged)) : -1;
   };
   auto issue_copy = [&](int half) {   // consumes pre_idx, starts the record copies into buf[half]
     LoopBuf& B = buf[half];
     if (lane < pre_cnt) {
-      long long s = begin + pre_idx;
-      const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
-      const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
-      const double2* sup = reinterpret_cast<const double2*>(S.rf + 4 * s);     // store_track_setup
-      cp_async16(&B.v[0][lane], p0p); cp_async16(&B.v[1][lane], p0p + 1);
-      cp_async16(&B.v[2][lane], r0p); cp_async16(&B.v[3][lane], r0p + 1);
-      cp_async16(&B.v[4][lane], sup); cp_async16(&B.v[5][lane], sup + 1);
+      const bool resumed = pre_idx >= n_new;
+      long long s = resumed ? (long long)carry_in[pre_idx - n_new] : begin + pre_idx;
+      const double2* pa = reinterpret_cast<const double2*>((resumed ? S.pf : S.p0) + 4 * s);
+      const double2* pb = reinterpret_cast<const double2*>((resumed ? S.rf : S.r0w) + 4 * s);
+      cp_async16(&B.v[0][lane], pa); cp_async16(&B.v[1][lane], pa + 1);
+      cp_async16(&B.v[2][lane], pb); cp_async16(&B.v[3][lane], pb + 1);
+      if (resumed) cp_async8(&B.aux[lane], S.aux + s);
+      else {
+        const double2* sup = reinterpret_cast<const double2*>(S.rf + 4 * s);     // store_track_setup
+        cp_async16(&B.v[4][lane], sup); cp_async16(&B.v[5][lane], sup + 1);
+      }
       cp_async16(&B.meta[lane], S.ids + 2 * s);
       cp_async16(&B.kw[lane], S.ids + 2 * s + 1);
       B.idx[lane] = pre_idx;
@@ -461,7 +493,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   };
   fetch_cursor(); fetch_index(); fetch_cursor();
   issue_copy(1); fetch_index(); fetch_cursor();
-  int cur = -1;                       // -1: needs a track, -2: no more work
+  int cur = -1;                       // wave-local index of the lane's track; -1: needs a track, -2: no more work
   Track t;
   unsigned long long c_sub = 0;
   for (;;) {
@@ -479,38 +511,53 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
         const LoopBuf& B = buf[which];
         const int e = pos + rank;
         cur = B.idx[e];
-        double2 a0 = B.v[0][e], a1 = B.v[1][e], b0 = B.v[2][e], b1 = B.v[3][e], s0 = B.v[4][e], s1 = B.v[5][e];
+        double2 a0 = B.v[0][e], a1 = B.v[1][e], b0 = B.v[2][e], b1 = B.v[3][e];
         t.p = V4{a0.x, a0.y, a1.x, a1.y};
         t.rx = b0.x; t.ry = b0.y; t.rz = b1.x;
         int4 meta = B.meta[e];
         t.key = kw_key(B.kw[e]);
         int pid = meta.x;
         t.mass = pid_mass(pid); t.iKp = 1e-3;
-        if (meta.y < 0) { t.mass = prim_mass[begin + cur]; t.iKp = t.mass / (1e3 * pid_mass(pid)); }
-        t.pmin = s1.x;                                                           // store_track_setup
+        if (meta.y < 0) {          // a primary: its slot is its index in the call's primary arrays
+          t.mass = prim_mass[cur < n_new ? begin + cur : (long long)carry_in[cur - n_new]];
+          t.iKp = t.mass / (1e3 * pid_mass(pid));
+        }
         t.sp = species_index(pid);
-        t.pn = s0.x; t.ipn = s1.y;
-        t.hint = __double2loint(s0.y);
-        t.delta_z = 0.0; t.it = 0;
+        if (cur < n_new) {         // fresh track: set-up stored at creation (store_track_setup)
+          double2 s0 = B.v[4][e], s1 = B.v[5][e];
+          t.pmin = s1.x;
+          t.pn = s0.x; t.ipn = s1.y;
+          t.hint = __double2loint(s0.y);
+          t.delta_z = 0.0; t.it = 0;
+        } else {                   // carried track: the state k_loop stored when it paused it
+          t.delta_z = b1.y;
+          t.it = B.aux[e].y;
+          t.pmin = fmax(fmax(M.min_calc[pid_class(pid)], M.min_energy), t.mass);
+          // |p| and its reciprocal exactly as substep() carried them (a track is only ever paused after a sub-step): bit-identical resume
+          t.pn = fast_sqrt0(__dsub_rn(__dmul_rn(t.p.E, t.p.E), __dmul_rn(t.mass, t.mass)));
+          t.ipn = t.pn > 0.0 ? fast_rcp(t.pn) : 0.0;
+          t.hint = T.sp[t.sp].n >= 2 ? coarse_ub(T.sp[t.sp].c, t.p.E) : 1;
+        }
       }
       pos += min(__popc(need), avail);
       need = __ballot_sync(0xffffffffu, cur == -1);
     }
     if (__all_sync(0xffffffffu, cur == -2)) break;
     // ---- one sub-step for every live lane
-    bool done = false;
+    bool done = false, pause = false;
     if (cur >= 0) {
       PhiloxDraws ds{t.key};
       done = substep(M, T, t, ms_e, ds);
-      if (!done) ++c_sub;
+      if (!done) { ++c_sub; pause = ((unsigned)t.it & cap_mask) == 0u; }
     }
-    if (done) {
-      long long s = begin + cur;
+    if (done || pause) {
+      long long s = cur < n_new ? begin + cur : (long long)carry_in[cur - n_new];
       double2* pfp = reinterpret_cast<double2*>(S.pf + 4 * s);
       double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * s);
       pfp[0] = make_double2(t.p.E, t.p.x); pfp[1] = make_double2(t.p.y, t.p.z);
       rfp[0] = make_double2(t.rx, t.ry);   rfp[1] = make_double2(t.rz, t.delta_z);
-      S.aux[s] = make_int2(0, t.it);
+      S.aux[s] = make_int2(pause ? AUX_PAUSED : 0, t.it);
+      if (pause) carry_out[(int)atomicAdd(&W.tail[2], 1ull)] = (int)s;
       cur = -1;
     }
   }
@@ -600,14 +647,22 @@ __global__ void PB_FIN_BOUNDS
 k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
            const double* __restrict__ prim_mass, int ms_e) {
   const long long begin = W.ws->begin;
-  const int n = W.ws->n, n_charged = W.ws->n_charged;
-  const int* __restrict__ order_c = W.list[2 * W.ws->parity];
-  const int* __restrict__ order_n = W.list[2 * W.ws->parity + 1];
+  const int n = W.ws->n, n_charged = W.ws->n_charged, n_new = W.ws->n_new, parity = W.ws->parity;
+  const int* __restrict__ order_c = W.list[2 * parity];
+  const int* __restrict__ order_n = W.list[2 * parity + 1];
   unsigned long long c_steps = 0;
+  // entries: the wave's charged list, its other records, then the carried tracks (all charged, wave-local index = their position)
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-    const bool charged = j < n_charged;
-    int i = charged ? order_c[j] : order_n[j - n_charged];
-    long long s = begin + i;
+    const bool charged = j < n_charged || j >= n_new;
+    int i = j < n_charged ? order_c[j] : (j < n_new ? order_n[j - n_charged] : j);
+    long long s = wave_slot(W, begin, n_new, parity, i);
+    if (charged && S.aux[s].x == AUX_PAUSED) {      // sub-step loop paused in this wave (k_loop): nothing to finalize yet
+      const int bucket = P_NONE * LU_MAX;
+      W.bucket[i] = bucket;
+      unsigned peers = __match_any_sync(__activemask(), bucket);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&W.hist[bucket], __popc(peers));
+      continue;
+    }
     int4 meta = ld_meta(S, s);
     PhiloxDraws ds{kw_key(ld_kw(S, s))};
     int pid = meta.x;
@@ -761,7 +816,6 @@ struct SampleIO {
 __global__ void __launch_bounds__(256) k_bucket_fill(Work W, SampleIO io, int n_explicit) {
   const int n = n_explicit < 0 ? W.ws->n : n_explicit;
   const int lane = threadIdx.x & 31;
-  const size_t off = io.ws ? (size_t)io.ws->begin : 0;
   // tile table: tile t belongs to the bucket b with tile_base[b] <= t < tile_base[b + 1] (binary search over the 4097-entry prefix)
   const int n_tiles = W.ctrl[0], n_heavy = W.tile_base[NBUCKET];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
@@ -780,8 +834,9 @@ __global__ void __launch_bounds__(256) k_bucket_fill(Work W, SampleIO io, int n_
     const bool sampled = b < N_SAMPLED * LU_MAX;
     double E = 0.0; uint2 key = make_uint2(0, 0);
     if (sampled) {
-      E = io.E4[4 * (off + (size_t)i)];
-      key = io.key[(io.key_index ? (size_t)io.key_index[i] : off + (size_t)i) * io.key_stride + io.key_off];
+      const size_t rec = io.ws ? (size_t)wave_slot(W, io.ws->begin, io.ws->n_new, io.ws->parity, i) : (size_t)i;   // SM pass: stack slot
+      E = io.E4[4 * rec];
+      key = io.key[(io.key_index ? (size_t)io.key_index[i] : rec) * io.key_stride + io.key_off];
     }
     unsigned peers = __match_any_sync(__activemask(), b);        // lanes of this warp that share the bucket
     int leader = __ffs(peers) - 1;
@@ -933,7 +988,9 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
   unsigned long long c_trials = 0, c_samples = 0, c_fail = 0;
   __shared__ unsigned long long s_ptrials, s_psamples;
   if (threadIdx.x == 0) { mbar_init(&s_bar, 1); s_ptrials = 0; s_psamples = 0; }
-  const size_t off = io.ws ? (size_t)io.ws->begin : 0;
+  const long long w_begin = io.ws ? io.ws->begin : 0;
+  const int w_new = io.ws ? io.ws->n_new : 0x7fffffff, w_par = io.ws ? io.ws->parity : 0;
+  auto rec_of = [&](int i) -> size_t { return io.ws ? (size_t)wave_slot(W, w_begin, w_new, w_par, i) : (size_t)i; };
   __syncthreads();
   for (;;) {
     if (threadIdx.x == 0) { s_tile = atomicAdd(&W.ctrl[(FAM == -1 && family_mode == 1) ? 4 : 1], 1); s_cursor = 0; }
@@ -1060,7 +1117,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
             double2* xo = reinterpret_cast<double2*>(W.xs + 4 * (size_t)cur);
             xo[0] = make_double2(x[0], x[1]); xo[1] = make_double2(x[2], x[3]);
             int ntr = (int)(next_t + best + 1);
-            io.ntr[(off + (size_t)cur) * io.ntr_stride] = ntr;
+            io.ntr[rec_of(cur) * io.ntr_stride] = ntr;
             c_trials += ntr; c_samples += 1;
           }
           cur = -1;
@@ -1068,7 +1125,7 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
           next_t += m * (G * T);
           if (next_t >= max_trials) {                      // "No Sample Found" (shower.py:460-461)
             if (sub == 0 && !helper) {
-              io.ntr[(off + (size_t)cur) * io.ntr_stride] = -1;
+              io.ntr[rec_of(cur) * io.ntr_stride] = -1;
               W.bucket[cur] = P_NONE * LU_MAX;
               W.xs[4 * (size_t)cur] = __longlong_as_double(0x7ff8000000000000LL);     // NaN sample: the emit kernels skip this entry
               c_trials += (unsigned long long)max_trials; c_fail += 1;
@@ -1137,9 +1194,9 @@ __device__ __forceinline__ void scatter_products(int proc, int pid, V4 pf, doubl
 __global__ void PB_EMIT_BOUNDS
 k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, int wave_order) {
   const long long begin = W.ws->begin;
-  const int n = W.ws->n;
-  int* __restrict__ next_c = W.list[2 * (W.ws->parity ^ 1)];
-  int* __restrict__ next_n = W.list[2 * (W.ws->parity ^ 1) + 1];
+  const int n = W.ws->n, n_new = W.ws->n_new, parity = W.ws->parity;
+  int* __restrict__ next_c = W.list[2 * (parity ^ 1)];
+  int* __restrict__ next_n = W.list[2 * (parity ^ 1) + 1];
   const int lane = threadIdx.x & 31;
   // warp-uniform grid-stride loop (the append below uses full-warp shuffles)
   for (int jbase = (blockIdx.x * blockDim.x + threadIdx.x) - lane; jbase < n; jbase += gridDim.x * blockDim.x) {
@@ -1159,7 +1216,7 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0, x01 = a0, x23 = a0;
     if (proc != P_NONE) {
       // every load of this particle is issued here, behind the one coalesced (index, bucket) read: two levels of memory latency
-      slot = begin + i;
+      slot = wave_slot(W, begin, n_new, parity, i);
       const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * slot);
       const double2* rfp = reinterpret_cast<const double2*>(S.rf + 4 * slot);
       const double2* xp = reinterpret_cast<const double2*>(W.xs + 4 * (size_t)i);
@@ -1207,7 +1264,7 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     long long dst = (long long)base + (incl - cnt);
     int ci = (int)(lbase & 0xffffffffu) + (inch - cch);
     int ni = (int)(lbase >> 32) + ((incl - cnt) - (inch - cch));
-    const long long next_begin = begin + n;
+    const long long next_begin = begin + n_new;
     int gen = ((meta.z >> 16) & 0xffff) + 1;
     for (int bit = 0; bit < 2; ++bit) {
       bool keep = bit ? keep_b : keep_a;
@@ -2042,6 +2099,9 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   if (const char* g = getenv("PB_GRAPH")) e->use_graph = atoi(g);
   e->work.tile_norm = 1;
   if (const char* g = getenv("PB_TILE_NORM")) e->work.tile_norm = atoi(g);
+  e->work.loop_cap = PB_LOOP_CAP_DEFAULT;
+  if (const char* g = getenv("PB_LOOP_CAP")) e->work.loop_cap = atoi(g);
+  if (e->work.loop_cap < 0 || (e->work.loop_cap & (e->work.loop_cap - 1))) e->work.loop_cap = 0;      // powers of two only
   if (const char* g = getenv("PB_TILE_LOG")) {            // "<file>:<wave>": per-tile timeline of k_sample in that wave of every run (appended)
     std::string v(g);
     size_t c = v.rfind(':');
@@ -2060,7 +2120,7 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   for (int i = 0; i < 2 * 8 && ok; ++i) ok = cudaEventCreate(&e->ev[i]) == cudaSuccess;
   for (int a = 0; a < pb_engine_s::LOOKAHEAD && ok; ++a) for (int b = 0; b < 2 && ok; ++b) for (int c = 0; c < 2 && ok; ++c)
     ok = cudaEventCreate(&e->evp[a][b][c]) == cudaSuccess;
-  if (ok) ok = cudaMallocHost(&e->h_ws, sizeof(WaveState) + 16) == cudaSuccess;
+  if (ok) ok = cudaMallocHost(&e->h_ws, sizeof(WaveState) + 32) == cudaSuccess;
   if (!ok) { pb_destroy(e); return PB_ERR_CUDA; }
   char* p = (char*)e->fixed_blob;
   e->work.tail = (unsigned long long*)p; p += 8 * sizeof(unsigned long long);
@@ -2258,15 +2318,16 @@ static int ensure_order(pb_engine e, long long n_list, cudaStream_t stream) {
   if (n_list <= e->order_cap) return PB_OK;
   long long cap = std::max<long long>(n_list * 5 / 4, 1 << 16);
   int* blob = nullptr;
-  PB_CUDA(e, cudaMalloc(&blob, sizeof(int) * 4 * (size_t)cap));
+  PB_CUDA(e, cudaMalloc(&blob, sizeof(int) * 6 * (size_t)cap));
   if (e->order_blob) {
-    for (int k = 0; k < 4; ++k)
-      PB_CUDA(e, cudaMemcpyAsync(blob + k * cap, e->work.list[k], sizeof(int) * e->order_cap, cudaMemcpyDeviceToDevice, stream));
+    for (int k = 0; k < 6; ++k)
+      PB_CUDA(e, cudaMemcpyAsync(blob + k * cap, k < 4 ? e->work.list[k] : e->work.carry[k - 4], sizeof(int) * e->order_cap, cudaMemcpyDeviceToDevice, stream));
     PB_CUDA(e, cudaStreamSynchronize(stream));
     cudaFree(e->order_blob);
   }
   e->order_blob = blob;
   for (int k = 0; k < 4; ++k) e->work.list[k] = blob + k * cap;
+  for (int k = 0; k < 2; ++k) e->work.carry[k] = blob + (4 + k) * cap;
   e->order_cap = cap;
   return PB_OK;
 }
@@ -2390,7 +2451,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
   }
   { int rc0 = ensure_order(e, std::max<long long>(2 * n0, 1 << 16), stream); if (rc0 != PB_OK) return rc0; }
   { int rc0 = ensure_work(e, std::max<long long>(2 * n0, 1 << 16)); if (rc0 != PB_OK) return rc0; }
-  unsigned long long tail0[2] = {(unsigned long long)n0, 0ull};
+  unsigned long long tail0[3] = {(unsigned long long)n0, 0ull, 0ull};
   PB_CUDA(e, cudaMemcpyAsync(e->work.tail, tail0, sizeof(tail0), cudaMemcpyHostToDevice, stream));
   PB_CUDA(e, cudaMemsetAsync(e->work.ctrl, 0, sizeof(int) * 8, stream));
   PB_CUDA(e, cudaMemsetAsync(e->work.counters, 0, sizeof(unsigned long long) * CNT_N, stream));
@@ -2444,10 +2505,10 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     if (rcg != PB_OK) return rcg;
     PB_CUDA(e, cudaGraphLaunch(e->wave_exec, stream));
     PB_CUDA(e, cudaMemcpyAsync(hws, e->work.ws, sizeof(WaveState), cudaMemcpyDeviceToHost, stream));
-    PB_CUDA(e, cudaMemcpyAsync(htail, e->work.tail, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(e, cudaMemcpyAsync(htail, e->work.tail, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     PB_CUDA(e, cudaStreamSynchronize(stream));
     if (hws->status == 3) {             // scratch too small for the next wave: grow (contents preserved) and resume it
-      long long need = (long long)std::min<unsigned long long>(htail[0], (unsigned long long)st->capacity) - hws->begin;
+      long long need = (long long)std::min<unsigned long long>(htail[0], (unsigned long long)st->capacity) - hws->begin + (long long)htail[2];
       if (need > 0x3fffffffLL) { e->err = "wave wider than 2^30"; return PB_ERR_CAPACITY; }
       int rc = ensure_work(e, 2 * need);
       if (rc != PB_OK) return rc;
@@ -2489,13 +2550,13 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
       launches += 7;
     }
     PB_CUDA(e, cudaMemcpyAsync(hws, e->work.ws, sizeof(WaveState), cudaMemcpyDeviceToHost, stream));
-    PB_CUDA(e, cudaMemcpyAsync(htail, e->work.tail, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(e, cudaMemcpyAsync(htail, e->work.tail, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     PB_CUDA(e, cudaStreamSynchronize(stream));
     double ms_before[PB_K_N];
     for (int k = 0; k < PB_K_N; ++k) ms_before[k] = e->prof.ms[k];
     collect();
     if (hws->status == 3) {             // scratch too small for the next wave: grow (contents preserved) and resume it
-      long long need = (long long)std::min<unsigned long long>(htail[0], (unsigned long long)st->capacity) - hws->begin;
+      long long need = (long long)std::min<unsigned long long>(htail[0], (unsigned long long)st->capacity) - hws->begin + (long long)htail[2];
       if (need > 0x3fffffffLL) { e->err = "wave wider than 2^30"; return PB_ERR_CAPACITY; }
       int rc = ensure_work(e, 2 * need);
       if (rc != PB_OK) return rc;

@@ -116,13 +116,15 @@ class ShowerBatch:
         rank = np.zeros(n, dtype=np.int64)
         rank[: self.n_primaries] = np.arange(self.n_primaries)
         wave_order = [np.arange(self.n_primaries)]
-        # slots are appended wave by wave, so depth is non-decreasing along the stack
-        bounds = np.searchsorted(depth, np.arange(1, int(depth.max()) + 2 if n else 1))
+        # generation by generation (slots are appended wave by wave, but a track whose sub-step loop was carried over several waves
+        # - engine.cu, k_loop - emits its daughters later than its generation's wave: group by depth explicitly)
+        by_depth = np.argsort(depth, kind="stable")
+        bounds = np.searchsorted(depth[by_depth], np.arange(1, int(depth.max()) + 2 if n else 1))
         b = self.n_primaries
         for e in bounds:
             if e <= b:
                 continue
-            sl = np.arange(b, e)
+            sl = by_depth[b:e]
             key = rank[h["parent"][sl]] * 2 + h["child_bit"][sl]
             o = np.argsort(key, kind="stable")
             rank[sl[o]] = np.arange(len(sl))
