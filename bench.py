@@ -394,15 +394,16 @@ def ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ms, tot, prof_ms, prof_launch, trials = timed_region(P, 0 if P > 1 else 1, K)
+    ms, tot, _, _, _ = timed_region(P, 0, K)              # no per-kernel events: the wave loop runs as one CUDA graph per batch
     clk = clocks.stop() if rank == 0 else None
-    single = None
-    if P > 1:
-        ms1, tot1, prof_ms, prof_launch, trials = timed_region(1, 1, K)
-        single = {"value": n_job * K / (ms1 * 1e-3), "unit": "showers/s", "ms_per_step": ms1 / K,
-                  "note": "the same K steps as ONE batch on one stream: the region the per-kernel times, roofline and fp64 figures come from"}
-        launches_main = tot["n_launches"]
-        tot = dict(tot1, n_launches=launches_main)          # identical showers: only the launch count differs
+    # the same K steps as ONE batch on one stream with CUDA events around the two dominant kernels (profiling level 1 switches the
+    # engine to stream launches, one host synchronisation per growing wave): what the per-kernel, roofline and fp64 figures come from
+    ms1, tot1, prof_ms, prof_launch, trials = timed_region(1, 1, K)
+    single = {"value": n_job * K / (ms1 * 1e-3), "unit": "showers/s", "ms_per_step": ms1 / K,
+              "note": "the same K steps as ONE batch on one stream, stream launches with per-kernel CUDA events: the region the per-kernel times, "
+                      "roofline and fp64 figures come from"}
+    launches_main = tot["n_launches"]
+    tot = dict(tot1, n_launches=launches_main)          # identical showers: only the launch count differs
     tally_host = tally.cpu().numpy()
     dtally_host = dtally.cpu().numpy() if dark else None
 
@@ -549,7 +550,7 @@ def ours(args):
                      "launches": prof_launch[dom], "avg_launch_ms": dom_ms / max(prof_launch[dom], 1),
                      "algorithmic_bytes_per_launch": dom_bytes / max(prof_launch[dom], 1),
                      "share_of_step": dom_ms / step_ms_total if step_ms_total else None,
-                     "timed_region": ("single-stream pass (single_stream): the main region runs %d sub-batches concurrently and its launches overlap" % P) if P > 1 else "main",
+                     "timed_region": "single-stream pass (single_stream): the main region runs the wave loop as a CUDA graph without per-kernel events" + ((", %d sub-batches concurrently" % P) if P > 1 else ""),
                      "note": "the step is FP64-pipe / divergence bound, not HBM bound (SURVEY.md 8d): see fp64"},
         "fp64": {"kernel": dom, "achieved_tflops": dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms else 0.0,
                  "peak_tflops": fp64_peak, "frac": (dom_flops / (dom_ms * 1e-3) / 1e12 / fp64_peak) if dom_ms and fp64_peak else None,

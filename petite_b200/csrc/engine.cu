@@ -656,13 +656,6 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
     const bool charged = j < n_charged || j >= n_new;
     int i = j < n_charged ? order_c[j] : (j < n_new ? order_n[j - n_charged] : j);
     long long s = wave_slot(W, begin, n_new, parity, i);
-    if (charged && S.aux[s].x == AUX_PAUSED) {      // sub-step loop paused in this wave (k_loop): nothing to finalize yet
-      const int bucket = P_NONE * LU_MAX;
-      W.bucket[i] = bucket;
-      unsigned peers = __match_any_sync(__activemask(), bucket);
-      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&W.hist[bucket], __popc(peers));
-      continue;
-    }
     int4 meta = ld_meta(S, s);
     PhiloxDraws ds{kw_key(ld_kw(S, s))};
     int pid = meta.x;
@@ -670,6 +663,7 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
     double mass = (meta.y < 0) ? prim_mass[s] : pid_mass(pid);
     V4 p; double rx, ry, rz;
     int nsub = 0;
+    bool paused = false;
     double delta_z = 0.0, E_start = 0.0;
     if (charged) {
       const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * s);
@@ -678,8 +672,10 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
       p = V4{a0.x, a0.y, a1.x, a1.y};
       rx = b0.x; ry = b0.y; rz = b1.x;
       delta_z = b1.y;
-      nsub = S.aux[s].y;
+      const int2 ax = S.aux[s];
+      nsub = ax.y;
       E_start = S.p0[4 * s];
+      paused = ax.x == AUX_PAUSED;     // sub-step loop paused in this wave (k_loop): nothing to finalize yet, the record stays as k_loop left it
     } else {
       const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
       const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
@@ -687,14 +683,17 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
       p = V4{a0.x, a0.y, a1.x, a1.y};
       rx = b0.x; ry = b0.y; rz = b1.x;
     }
-    bool stepped;
-    const int bucket = finalize_one(M, T, ds, charged, pid, flags, mass, E_start, delta_z, ms_e, p, rx, ry, rz, stepped);
-    if (stepped) c_steps += 1;
-    double2* pfp = reinterpret_cast<double2*>(S.pf + 4 * s);
-    double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * s);
-    pfp[0] = make_double2(p.E, p.x); pfp[1] = make_double2(p.y, p.z);
-    rfp[0] = make_double2(rx, ry);   rfp[1] = make_double2(rz, mass);
-    S.aux[s] = make_int2(0, nsub);
+    int bucket = P_NONE * LU_MAX;
+    if (!paused) {
+      bool stepped;
+      bucket = finalize_one(M, T, ds, charged, pid, flags, mass, E_start, delta_z, ms_e, p, rx, ry, rz, stepped);
+      if (stepped) c_steps += 1;
+      double2* pfp = reinterpret_cast<double2*>(S.pf + 4 * s);
+      double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * s);
+      pfp[0] = make_double2(p.E, p.x); pfp[1] = make_double2(p.y, p.z);
+      rfp[0] = make_double2(rx, ry);   rfp[1] = make_double2(rz, mass);
+      S.aux[s] = make_int2(0, nsub);
+    }
     W.bucket[i] = bucket;
     // warp-aggregated histogram: one atomic per distinct bucket in the warp
     unsigned peers = __match_any_sync(__activemask(), bucket);
@@ -1656,8 +1655,9 @@ __global__ void __launch_bounds__(256) k_tally(Stack S, long long first, long lo
     long long s = first + i;
     const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
     double2 a0 = p0p[0], a1 = p0p[1];
-    double w = S.r0w[4 * s + 3];
-    int sp = species_of(S.ids[2 * s].x);
+    const int4 kw = ld_kw(S, s);                  // pid and weight sit in the record's one 32-byte ids sector (r0w is not touched)
+    double w = kw_weight(kw);
+    int sp = species_of(ld_meta(S, s).x);
 #pragma unroll
     for (int k = 0; k < PB_TALLY_NSPECIES; ++k)
       if (sp == k) { cnt[k] += 1.0; ws[k] += w; wes[k] += w * a0.x; }
