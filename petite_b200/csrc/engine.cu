@@ -647,15 +647,16 @@ __global__ void PB_FIN_BOUNDS
 k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
            const double* __restrict__ prim_mass, int ms_e) {
   const long long begin = W.ws->begin;
-  const int n = W.ws->n, n_charged = W.ws->n_charged, n_new = W.ws->n_new, parity = W.ws->parity;
-  const int* __restrict__ order_c = W.list[2 * parity];
-  const int* __restrict__ order_n = W.list[2 * parity + 1];
+  const int n = W.ws->n, n_charged = W.ws->n_charged, n_new = W.ws->n_new;
+  const int* __restrict__ order_c = W.list[2 * W.ws->parity];
+  const int* __restrict__ order_n = W.list[2 * W.ws->parity + 1];
+  const int* __restrict__ carry = W.carry[W.ws->parity];
   unsigned long long c_steps = 0;
   // entries: the wave's charged list, its other records, then the carried tracks (all charged, wave-local index = their position)
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const bool charged = j < n_charged || j >= n_new;
     int i = j < n_charged ? order_c[j] : (j < n_new ? order_n[j - n_charged] : j);
-    long long s = wave_slot(W, begin, n_new, parity, i);
+    long long s = j < n_new ? begin + i : (long long)carry[j - n_new];
     int4 meta = ld_meta(S, s);
     PhiloxDraws ds{kw_key(ld_kw(S, s))};
     int pid = meta.x;
@@ -675,7 +676,9 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
       const int2 ax = S.aux[s];
       nsub = ax.y;
       E_start = S.p0[4 * s];
-      paused = ax.x == AUX_PAUSED;     // sub-step loop paused in this wave (k_loop): nothing to finalize yet, the record stays as k_loop left it
+      paused = ax.x == AUX_PAUSED;     // sub-step loop paused in this wave (k_loop): nothing to finalize yet, the record stays as k_loop
+                                       // left it.  (Tested AFTER finalize_one: the 2 % of wasted evaluations cost less than a branch that
+                                       // every track would wait on with the latency of this load.)
     } else {
       const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
       const double2* r0p = reinterpret_cast<const double2*>(S.r0w + 4 * s);
@@ -683,10 +686,10 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
       p = V4{a0.x, a0.y, a1.x, a1.y};
       rx = b0.x; ry = b0.y; rz = b1.x;
     }
-    int bucket = P_NONE * LU_MAX;
-    if (!paused) {
-      bool stepped;
-      bucket = finalize_one(M, T, ds, charged, pid, flags, mass, E_start, delta_z, ms_e, p, rx, ry, rz, stepped);
+    bool stepped;
+    int bucket = finalize_one(M, T, ds, charged, pid, flags, mass, E_start, delta_z, ms_e, p, rx, ry, rz, stepped);
+    if (paused) bucket = P_NONE * LU_MAX;
+    else {
       if (stepped) c_steps += 1;
       double2* pfp = reinterpret_cast<double2*>(S.pf + 4 * s);
       double2* rfp = reinterpret_cast<double2*>(S.rf + 4 * s);

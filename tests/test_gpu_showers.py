@@ -234,3 +234,29 @@ def test_exact_decisions_at_1e3_1e4_showers(golden, name, n):
     print(name, "showers", n, "records", m, "decisions ~", decisions, "showers with any difference:", int(bad.sum()),
           "-> flip rate <", (int(bad.sum()) + 1) / decisions)
     assert not bad.any(), (np.nonzero(bad)[0][:10], mult[bad][:5], g[f"{name}/mult"][bad][:5])
+
+
+def test_sub_step_cap_does_not_change_the_showers(monkeypatch):
+    """k_loop pauses a track when its sub-step index reaches a multiple of PB_LOOP_CAP and carries it into the next wave
+    (engine.cu): scheduling only.  The same 400 showers with the cap off, at 4 (almost every track is carried, several times)
+    and at the default must be the same records bit for bit - creation and end-point four-vectors, trial and sub-step counts -
+    in the reference's order, although the waves they are stepped in differ."""
+    from petite_b200.shower import Shower
+    prims = primaries(11, 8.0, 400)
+    runs = {}
+    for cap in ("0", "4", "32"):
+        monkeypatch.setenv("PB_LOOP_CAP", cap)
+        sh = Shower(DATA_DIR, "lead", 0.010, seed=21)
+        b = sh.generate_showers(prims, first_shower_id=300)
+        h = b.to_host()
+        order, offs = b.reference_order()
+        runs[cap] = (b.counters, [h[k][order] for k in ("pid", "p0", "pf", "rf", "ntrials", "nsub", "process")], offs)
+        del sh
+    c0, a0, o0 = runs["0"]
+    for cap in ("4", "32"):
+        c, a, o = runs[cap]
+        assert np.array_equal(o, o0)
+        for x, y in zip(a, a0):
+            assert np.array_equal(x, y), cap
+        assert all(c[k] == c0[k] for k in ("n_particles", "n_steps", "n_substeps", "n_samples", "n_trials"))
+    assert runs["4"][0]["n_waves"] > runs["0"][0]["n_waves"]       # the carried tracks did take extra waves
