@@ -187,7 +187,7 @@ __device__ __forceinline__ void hot_sincos(double x, double* sn, double* cs) {
   if (fabs(x) <= 0.78539816339744828) hot_sincos_kernel(x, sn, cs);
   else sincos(x, sn, cs);                                     // rare: multiple-scattering angles are small
 }
-// sin and cos of 2 pi u, u in [0, 1)
+// sin and cos of 2 pi u, u in [-1/2, 2): exact argument reduction (the reference rounds 2 pi u first: 4e-16 absolute apart)
 __device__ __forceinline__ void hot_sincos_2pi(double u, double* sn, double* cs) {
   double t = 2.0 * u;
   double q = rint(2.0 * t);                                   // quadrant 0..4
@@ -891,11 +891,14 @@ __device__ __forceinline__ V4 mcs_scatter(const Material& M, V4 p4, double pn, d
 // particle.py:176-185: rows of Rz(phi) Ry(theta) taking z-hat onto pf; applied as lab = R v
 struct Rot { double r00, r01, r02, r10, r11, r12, r20, r22; };
 __device__ __forceinline__ Rot rotation_to(V4 pf) {
+  // theta goes through acos as in the reference: for a collimated particle acos(1 - eps) carries an error of ~1e-16 / theta that the
+  // daughters inherit, and fidelity means inheriting the same one.  The azimuth is well conditioned: cos / sin of atan2(py, px) ARE
+  // px / pt, py / pt to an ulp, which saves the atan2 and a full-range sincos (12 % of k_emit's instructions).
   double th = acos(pf.z / norm3_nofma(pf.x, pf.y, pf.z));
-  double ph = atan2(pf.y, pf.x);
-  double ct, st, cp, sp;
-  sincos(th, &st, &ct);
-  sincos(ph, &sp, &cp);
+  double ct, st, cp = 1.0, sp = 0.0;
+  hot_sincos(th, &st, &ct);
+  double pt2 = pf.x * pf.x + pf.y * pf.y;
+  if (pt2 > 0.0) { double r = fast_rsqrt(pt2); cp = pf.x * r; sp = pf.y * r; }     // atan2(0, 0) = 0
   return Rot{ct * cp, -sp, st * cp, ct * sp, cp, st * sp, -st, ct};
 }
 __device__ __forceinline__ V4 rotate(const Rot& R, V4 v) {
@@ -908,14 +911,15 @@ __device__ __forceinline__ double sq(double v) { return v * v; }
 // kinematics.py:10-41 (e_to_egamma_fourvecs): a = outgoing lepton, b = photon
 __device__ __forceinline__ void kin_brem(double ep, double ml, const double* x, double u_az, V4* a, V4* b) {
   double w = EGAMMA_MIN_KIN + x[0] * (ep - ml - EGAMMA_MIN_KIN);
+  // (libdevice cos on purpose: sqrt(1 - ct^2) below amplifies the last bit of ct by 1 / theta^2, and fidelity to the reference's
+  // value means the rounding closest to glibc's; the azimuths are well conditioned and go through the exact-reduction kernel)
   double ct = cos((x[1] + x[2]) / 2);
   double ctp = cos((x[1] - x[2]) * ep / (2 * (ep - w)));
-  double ph = (x[3] - 0.5) * 2.0 * kPi;
   double epp = ep - w;
   double pp = sqrt(epp * epp - ml * ml);
   double sal, cal, sp, cp;
-  sincos(u_az * kTwoPi, &sal, &cal);
-  sincos(ph, &sp, &cp);
+  hot_sincos_2pi(u_az, &sal, &cal);
+  hot_sincos_2pi(x[3] - 0.5, &sp, &cp);            // ph = (x4 - 1/2) 2 pi
   double st = sqrt(1.0 - ct * ct), stp = sqrt(1.0 - ctp * ctp);
   *b = V4{w, w * cal * st, w * sal * st, w * ct};
   *a = V4{epp, pp * (sal * sp * stp + cal * (ctp * st - cp * ct * stp)), pp * (ctp * sal * st - (cp * ct * sal + cal * sp) * stp),
@@ -928,13 +932,11 @@ __device__ __forceinline__ void kin_pairprod(double w, const double* x, double u
   double epp = me + x[0] * (w - 2 * me);
   double ctp = cos(w * (x[1] + x[2]) / (2 * epp));
   double ctm = cos(w * (x[1] - x[2]) / (2 * (w - epp)));
-  double ph = x[3] * 2 * kPi;
   double epm = w - epp;
   double pm = sqrt(epm * epm - me * me), pp = sqrt(epp * epp - me * me);
-  double al = u_az * kTwoPi;
   double sal, cal, spal, cpal;
-  sincos(al, &sal, &cal);
-  sincos(ph + al, &spal, &cpal);
+  hot_sincos_2pi(u_az, &sal, &cal);                // al = 2 pi u
+  hot_sincos_2pi(x[3] + u_az, &spal, &cpal);       // ph + al = 2 pi (x4 + u)
   double stp = sqrt(1.0 - ctp * ctp), stm = sqrt(1.0 - ctm * ctm);
   *a = V4{epp, pp * stp * cal, pp * stp * sal, pp * ctp};
   *b = V4{epm, pm * stm * cpal, pm * stm * spal, pm * ctm};
@@ -952,7 +954,7 @@ __device__ __forceinline__ void kin_compton(double Eg, double mV, double ct, dou
   double g0 = Ee0 / me;
   double b0 = 1.0 / g0 * sqrt(g0 * g0 - 1.0);
   double sp, cp;
-  sincos(u_az * kTwoPi, &sp, &cp);
+  hot_sincos_2pi(u_az, &sp, &cp);
   double st = sqrt(1 - ct * ct);
   *a = V4{g0 * Ee + b0 * g0 * pF * ct, -pF * st * sp, -pF * st * cp, b0 * g0 * Ee + g0 * pF * ct};
   *b = V4{g0 * EV - b0 * g0 * pF * ct, pF * st * sp, pF * st * cp, b0 * g0 * EV - g0 * pF * ct};
@@ -970,7 +972,7 @@ __device__ __forceinline__ void kin_annihilation(double Ee, double mV, double ct
   double g0 = EeCM / me;
   double b0 = 1.0 / g0 * sqrt(g0 * g0 - 1.0);
   double sp, cp;
-  sincos(u_az * kTwoPi, &sp, &cp);
+  hot_sincos_2pi(u_az, &sp, &cp);
   double st = sqrt(1 - ct * ct);
   *a = V4{g0 * Eg - b0 * g0 * pF * ct, -pF * st * sp, -pF * st * cp, b0 * g0 * Eg - g0 * pF * ct};
   *b = V4{g0 * EV + b0 * g0 * pF * ct, pF * st * sp, pF * st * cp, b0 * g0 * EV + g0 * pF * ct};
@@ -985,7 +987,7 @@ __device__ __forceinline__ void kin_ee(double Einc, double ct, double u_az, V4* 
   double g0 = Ee0 / me;
   double b0 = 1.0 / g0 * sqrt(g0 * g0 - 1.0);
   double sp, cp;
-  sincos(u_az * kTwoPi, &sp, &cp);
+  hot_sincos_2pi(u_az, &sp, &cp);
   double st = sqrt(1 - ct * ct);
   *a = V4{g0 * Ee0 + b0 * g0 * pF * ct, -pF * st * sp, -pF * st * cp, b0 * g0 * Ee0 + g0 * pF * ct};
   *b = V4{g0 * Ee0 - b0 * g0 * pF * ct, pF * st * sp, pF * st * cp, b0 * g0 * Ee0 - g0 * pF * ct};
@@ -1003,7 +1005,7 @@ __device__ __forceinline__ void kin_mue(double Einc, double ct, double u_az, V4*
   double g0 = Ee0 / me;
   double b0 = 1.0 / g0 * sqrt(g0 * g0 - 1.0);
   double sp, cp;
-  sincos(u_az * kTwoPi, &sp, &cp);
+  hot_sincos_2pi(u_az, &sp, &cp);
   double st = sqrt(1 - ct * ct);
   *a = V4{g0 * Em0 + b0 * g0 * pm * ct, pm * st * sp, pm * st * cp, b0 * g0 * Em0 + g0 * pm * ct};
   *b = V4{g0 * Ee0 - b0 * g0 * pe * ct, -pe * st * sp, -pe * st * cp, b0 * g0 * Ee0 - g0 * pe * ct};
@@ -1015,7 +1017,7 @@ __device__ __forceinline__ V4 kin_darkbrem_V(double ep, double mV, const double*
   double ct = 1 - pow(10.0, x[1]);
   double k = sqrt(w * w - mV * mV);
   double sal, cal;
-  sincos(u_az * kTwoPi, &sal, &cal);
+  hot_sincos_2pi(u_az, &sal, &cal);
   double st = sqrt(1.0 - ct * ct);
   return V4{w, k * cal * st, k * sal * st, k * ct};
 }
