@@ -550,6 +550,14 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       done = substep(M, T, t, ms_e, ds);
       if (!done) { ++c_sub; pause = ((unsigned)t.it & cap_mask) == 0u; }
     }
+    // tracks created together reach the cap together: one atomic per warp for the carry-list slots
+    const unsigned pmask = __ballot_sync(0xffffffffu, pause);
+    int pbase = 0;
+    if (pmask) {
+      const int leader = __ffs(pmask) - 1;
+      if (lane == leader) pbase = (int)atomicAdd(&W.tail[2], (unsigned long long)__popc(pmask));
+      pbase = __shfl_sync(0xffffffffu, pbase, leader);
+    }
     if (done || pause) {
       long long s = cur < n_new ? begin + cur : (long long)carry_in[cur - n_new];
       double2* pfp = reinterpret_cast<double2*>(S.pf + 4 * s);
@@ -557,7 +565,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       pfp[0] = make_double2(t.p.E, t.p.x); pfp[1] = make_double2(t.p.y, t.p.z);
       rfp[0] = make_double2(t.rx, t.ry);   rfp[1] = make_double2(t.rz, t.delta_z);
       S.aux[s] = make_int2(pause ? AUX_PAUSED : 0, t.it);
-      if (pause) carry_out[(int)atomicAdd(&W.tail[2], 1ull)] = (int)s;
+      if (pause) carry_out[pbase + __popc(pmask & lt_mask)] = (int)s;
       cur = -1;
     }
   }
@@ -817,7 +825,6 @@ struct SampleIO {
 // coalesced, so that k_sample stages a tile with contiguous loads instead of two dependent scattered ones per sample.
 __global__ void __launch_bounds__(256) k_bucket_fill(Work W, SampleIO io, int n_explicit) {
   const int n = n_explicit < 0 ? W.ws->n : n_explicit;
-  const int lane = threadIdx.x & 31;
   // tile table: tile t belongs to the bucket b with tile_base[b] <= t < tile_base[b + 1] (binary search over the 4097-entry prefix)
   const int n_tiles = W.ctrl[0], n_heavy = W.tile_base[NBUCKET];
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
@@ -831,23 +838,49 @@ __global__ void __launch_bounds__(256) k_bucket_fill(Work W, SampleIO io, int n_
     W.tile_start[t] = start;
     W.tile_count[t] = min(tsz, W.offsets[lo + 1] - start);
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int b = W.bucket[i];
-    const bool sampled = b < N_SAMPLED * LU_MAX;
-    double E = 0.0; uint2 key = make_uint2(0, 0);
-    if (sampled) {
-      const size_t rec = io.ws ? (size_t)wave_slot(W, io.ws->begin, io.ws->n_new, io.ws->parity, i) : (size_t)i;   // SM pass: stack slot
-      E = io.E4[4 * rec];
-      key = io.key[(io.key_index ? (size_t)io.key_index[i] : rec) * io.key_stride + io.key_off];
+  // Counting-sort scatter, aggregated per CTA: the kernel used to be bound by the latency of same-address atomics (every warp of a
+  // wide wave bumps the cursors of the same few hot buckets: 65 % of its stall samples waited on that atomic, 7 % of the issue slots
+  // were busy).  A CTA now ranks FILL_CHUNK entries per bucket in shared memory first and makes ONE global atomic per bucket it saw.
+  __shared__ int s_cnt[NBUCKET], s_base[NBUCKET];
+  for (int k = threadIdx.x; k < NBUCKET; k += blockDim.x) s_cnt[k] = 0;
+  __syncthreads();
+  constexpr int FILL_PER = 4;
+  const int chunk = FILL_PER * (int)blockDim.x;
+  for (int c0 = blockIdx.x * chunk; c0 < n; c0 += gridDim.x * chunk) {
+    int b[FILL_PER], r[FILL_PER];
+    double E[FILL_PER]; uint2 key[FILL_PER];
+#pragma unroll
+    for (int e = 0; e < FILL_PER; ++e) {
+      const int i = c0 + e * (int)blockDim.x + (int)threadIdx.x;
+      b[e] = -1; r[e] = 0; E[e] = 0.0; key[e] = make_uint2(0, 0);
+      if (i < n) {
+        b[e] = W.bucket[i];
+        r[e] = atomicAdd(&s_cnt[b[e]], 1);                     // rank among the CTA's entries of this bucket
+        if (b[e] < N_SAMPLED * LU_MAX) {
+          const size_t rec = io.ws ? (size_t)wave_slot(W, io.ws->begin, io.ws->n_new, io.ws->parity, i) : (size_t)i;   // SM pass: stack slot
+          E[e] = io.E4[4 * rec];
+          key[e] = io.key[(io.key_index ? (size_t)io.key_index[i] : rec) * io.key_stride + io.key_off];
+        }
+      }
     }
-    unsigned peers = __match_any_sync(__activemask(), b);        // lanes of this warp that share the bucket
-    int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&W.cursor[b], __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    int pos = W.offsets[b] + base + __popc(peers & ((1u << lane) - 1u));
-    W.sorted[pos] = make_int2(i, b);
-    if (sampled) { W.sE[pos] = E; W.skey[pos] = key; }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < FILL_PER; ++e)
+      if (b[e] >= 0 && r[e] == 0) s_base[b[e]] = atomicAdd(&W.cursor[b[e]], s_cnt[b[e]]);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < FILL_PER; ++e) {
+      if (b[e] < 0) continue;
+      const int i = c0 + e * (int)blockDim.x + (int)threadIdx.x;
+      const int pos = W.offsets[b[e]] + s_base[b[e]] + r[e];
+      W.sorted[pos] = make_int2(i, b[e]);
+      if (b[e] < N_SAMPLED * LU_MAX) { W.sE[pos] = E[e]; W.skey[pos] = key[e]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < FILL_PER; ++e)
+      if (b[e] >= 0 && r[e] == 0) s_cnt[b[e]] = 0;
+    __syncthreads();
   }
 }
 
@@ -1200,9 +1233,11 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   int* __restrict__ next_c = W.list[2 * (parity ^ 1)];
   int* __restrict__ next_n = W.list[2 * (parity ^ 1) + 1];
   const int lane = threadIdx.x & 31;
-  // warp-uniform grid-stride loop (the append below uses full-warp shuffles)
-  for (int jbase = (blockIdx.x * blockDim.x + threadIdx.x) - lane; jbase < n; jbase += gridDim.x * blockDim.x) {
-  const int j = jbase + lane;
+  // CTA-uniform grid-stride loop (the append below uses full-warp shuffles and two CTA barriers)
+  __shared__ int s_tot[4], s_tch[4];
+  __shared__ unsigned long long s_base[4], s_lbase[4];
+  for (int cbase = blockIdx.x * blockDim.x; cbase < n; cbase += gridDim.x * blockDim.x) {
+  const int j = cbase + (int)threadIdx.x;
   V4 da{0, 0, 0, 0}, db{0, 0, 0, 0};
   int pid_a = 0, pid_b = 0, proc = P_NONE;
   bool keep_a = false, keep_b = false;
@@ -1245,7 +1280,8 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       keep_b = db.E > M.min_energy;
     }
   }
-  // warp-aggregated append: one atomic on the stack tail and one on the packed (neutral, charged) list counters per warp
+  // CTA-aggregated append: one atomic on the stack tail and one on the packed (neutral, charged) list counters per CTA (every warp of
+  // the launch used to bump the same two words and wait for the result: 12 % of the kernel's stall samples)
   const bool ch_a = keep_a && is_charged(pid_a), ch_b = keep_b && is_charged(pid_b);
   int cnt = (keep_a ? 1 : 0) + (keep_b ? 1 : 0);
   int cch = (ch_a ? 1 : 0) + (ch_b ? 1 : 0);
@@ -1255,13 +1291,25 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     if (lane >= o) { incl += v; inch += w; }
   }
   int total = __shfl_sync(0xffffffffu, incl, 31), total_ch = __shfl_sync(0xffffffffu, inch, 31);
-  unsigned long long base = 0, lbase = 0;
-  if (lane == 31 && total > 0) {
-    base = atomicAdd(&W.tail[0], (unsigned long long)total);
-    lbase = atomicAdd(&W.tail[1], ((unsigned long long)(total - total_ch) << 32) | (unsigned long long)total_ch);
+  const int wid = threadIdx.x >> 5;
+  if (lane == 0) { s_tot[wid] = total; s_tch[wid] = total_ch; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t_all = 0, c_all = 0;
+    for (int k = 0; k < 4; ++k) { t_all += s_tot[k]; c_all += s_tch[k]; }
+    unsigned long long b0 = 0, l0 = 0;
+    if (t_all > 0) {
+      b0 = atomicAdd(&W.tail[0], (unsigned long long)t_all);
+      l0 = atomicAdd(&W.tail[1], ((unsigned long long)(t_all - c_all) << 32) | (unsigned long long)c_all);
+    }
+    for (int k = 0; k < 4; ++k) {        // per-warp bases: records, and the (neutral << 32 | charged) list positions
+      s_base[k] = b0; s_lbase[k] = l0;
+      b0 += (unsigned long long)s_tot[k];
+      l0 += ((unsigned long long)(s_tot[k] - s_tch[k]) << 32) | (unsigned long long)s_tch[k];
+    }
   }
-  base = __shfl_sync(0xffffffffu, base, 31);
-  lbase = __shfl_sync(0xffffffffu, lbase, 31);
+  __syncthreads();
+  const unsigned long long base = s_base[wid], lbase = s_lbase[wid];
   if (cnt) {
     long long dst = (long long)base + (incl - cnt);
     int ci = (int)(lbase & 0xffffffffu) + (inch - cch);
@@ -2544,7 +2592,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
       k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
       tock(PB_K_SCAN, j); tick(PB_K_FILL, j);
       SampleIO io{S.pf, reinterpret_cast<const uint2*>(S.ids), 4, 2, nullptr, reinterpret_cast<int*>(S.aux), 2, e->work.ws};
-      k_bucket_fill<<<g256, 256, 0, stream>>>(e->work, io, -1);
+      k_bucket_fill<<<(g256 + 3) / 4, 256, 0, stream>>>(e->work, io, -1);          // a CTA ranks 1 024 entries per iteration
       tock(PB_K_FILL, j); tick(PB_K_SAMPLE, j);
       launch_sample(e, bound, io, stream, true);
       tock(PB_K_SAMPLE, j); tick(PB_K_EMIT, j);
@@ -2700,7 +2748,7 @@ extern "C" int pb_run_dark(pb_engine e, const pb_stack* sm, int64_t n_sm, uint32
     k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
     tock(PB_K_SCAN); tick(PB_K_FILL);
     SampleIO io{e->cand.pf, reinterpret_cast<const uint2*>(S.ids), 4, 2, e->cand.slot, e->cand.ntr, 1, nullptr};
-    k_bucket_fill<<<(unsigned)((n_cand + 255) / 256), 256, 0, stream>>>(e->work, io, n_cand);
+    k_bucket_fill<<<(unsigned)((n_cand + 1023) / 1024), 256, 0, stream>>>(e->work, io, n_cand);
     tock(PB_K_FILL); tick(PB_K_SAMPLE);
     launch_sample(e, n_cand, io, stream);
     tock(PB_K_SAMPLE); tick(PB_K_EMIT);
@@ -2766,7 +2814,7 @@ extern "C" int pb_draw_samples(pb_engine e, int process, const double* E, int64_
   k_prepare_draws<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->tab, e->work, e->cand, dkeys, dE, (int)n, process, lu_key, seed, first_id);
   k_bucket_scan<<<1, 1024, 0, stream>>>(e->work);
   SampleIO io{e->cand.pf, dkeys, 1, 0, nullptr, e->cand.ntr, 1, nullptr};
-  k_bucket_fill<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(e->work, io, (int)n);
+  k_bucket_fill<<<(unsigned)((n + 1023) / 1024), 256, 0, stream>>>(e->work, io, (int)n);
   launch_sample(e, n, io, stream);
   cudaError_t c = cudaMemcpyAsync(x_out, e->work.xs, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, stream);
   if (c == cudaSuccess && ntr_out) c = cudaMemcpyAsync(ntr_out, e->cand.ntr, sizeof(int) * n, cudaMemcpyDeviceToHost, stream);
