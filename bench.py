@@ -5,7 +5,9 @@
 
 A "step" is one pass of the hot path over one batch of synthetic primaries.  Default workload: BASELINE.json configs[1], 10 GeV
 photons into lead, E_min = 10 MeV, 1e5 primaries per GPU (weak scaling: every rank steps its own 1e5 showers, shower ids offset
-by rank; ``--scaling strong``: the 1e5 primaries are split over the ranks).  The only collective is one NCCL all-reduce of the
+by rank; ``--scaling strong``: the 1e5 primaries are split over the ranks).  A step is one batch on one stream, the wave loop one CUDA
+graph launch (``--parts 2`` steps it as two concurrent sub-batches: better only for the narrow-wave configurations 1 and 5 since the
+kernel tails were removed in round 2).  The only collective is one NCCL all-reduce of the
 8 KB tally buffer per step.  ``--config`` selects another BASELINE.json configuration (1, 3, 4, 5; the dark configurations run
 their dark pass inside the step and are stepped in sub-batches that fit HBM, tallies only).
 
@@ -38,7 +40,7 @@ M_E, M_MU = 510.998950e-6, 105.6583755e-3
 # (the 100 GeV / 400 GeV showers keep 6-8 thousand records each, so 1e5 of them do not fit HBM at once).
 CONFIGS = {
     1: dict(workload="SM shower: 10 GeV e- into graphite, E_min=0.010 GeV, ./data/ maps, 1e3 primaries (BASELINE.json configs[0])",
-            material="graphite", pid=11, E0=10.0, mass=M_E, mV=None, n=1_000, batch=1_000, cpu=8),
+            material="graphite", pid=11, E0=10.0, mass=M_E, mV=None, n=1_000, batch=1_000, cpu=8, parts=2),
     2: dict(workload="SM shower: 10 GeV photon into lead, E_min=0.010 GeV, 1e5 primaries (BASELINE.json configs[1])",
             material="lead", pid=22, E0=10.0, mass=0.0, mV=None, n=100_000, batch=100_000, cpu=8),
     3: dict(workload="Dark shower: 10 GeV e- into graphite, m_V=3 MeV (lightest trained mass; the literal 1 MeV runs as 1 GeV, SURVEY Q-2), "
@@ -49,7 +51,7 @@ CONFIGS = {
             material="lead", pid=0, E0=0.0, mass=0.0, mV=0.010, active=["DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=20_000, data=DATA400, cpu=1),
     5: dict(workload="Muon dark shower: 100 GeV mu- through lead, MuonBrem/MuonE/DarkMuonBrem + multiple scattering, m_V=30 MeV, 1e5 primaries "
                      "(BASELINE.json configs[4])",
-            material="lead", pid=13, E0=100.0, mass=M_MU, mV=0.030, active=["DarkMuonBrem", "DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=25_000, cpu=1),
+            material="lead", pid=13, E0=100.0, mass=M_MU, mV=0.030, active=["DarkMuonBrem", "DarkBrem", "DarkAnn", "DarkComp"], n=100_000, batch=25_000, cpu=1, parts=2),
 }
 CFG = CONFIGS[2]
 
@@ -294,7 +296,7 @@ def ours(args):
     tally = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=dev)
     dtally = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=dev) if dark else None
 
-    P = max(1, args.parts)
+    P = args.parts if args.parts > 0 else cfg.get("parts", 1)
     COUNT_KEYS = ("n_particles", "n_steps", "n_substeps", "n_samples", "n_trials", "n_launches", "n_waves", "n_charged")
 
     def step(arrays, parts=1, eng=None, keep=False):
@@ -594,7 +596,8 @@ def main():
     ap.add_argument("--primaries", type=int, default=0, help="primaries per GPU per step (weak) / in total (strong); 0 = the configuration's own number")
     ap.add_argument("--cpu-showers", type=int, default=0, help="size of the CPU-baseline sample (0 = per configuration: about 15-30 s of CPU work on all host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parts", type=int, default=2, help="sub-batches of a step stepped concurrently on their own engine handle / stream / host thread (1 = one batch, one stream)")
+    ap.add_argument("--parts", type=int, default=0, help="sub-batches of a step stepped concurrently on their own engine handle / stream / host thread "
+                    "(1 = one batch, one stream; 0 = the configuration's measured best: 1 for the wide-wave configurations 2-4, 2 for the narrow-wave ones 1 and 5)")
     ap.add_argument("--no-history", dest="history", action="store_false", help="skip the e2e_history step (full particle history copied to the host)")
     ap.add_argument("--no-fudge-line", dest="fudge_line", action="store_false", help="skip the maxF_fudge_global=4 line")
     args = ap.parse_args()
