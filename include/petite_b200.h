@@ -231,7 +231,8 @@ enum pb_probe {
   PB_PROBE_PHILOX = 5,   /* in: n x 6 (as doubles): key0,key1,c0,stream,c2,c3; out: n x 2 doubles */
   PB_PROBE_HOTMATH = 6,  /* in: n x 4: x_log (> 0), x_exp in [1/20, 1/6], theta, u in [0,1);
                             out: n x 7: hot_log, hot_exp_neg_step, sin, cos (theta), sin, cos (2 pi u), fast_rcp(x_log)
-                            (out stride >= 10 adds fast_sqrt0(x_log), fast_rsqrt(x_log), fast_sqrt0 at 0 and below) */
+                            (out stride >= 10 adds fast_sqrt0(x_log), fast_rsqrt(x_log), fast_sqrt0 at 0 and below;
+                            out stride >= 12 adds hot_cospi(2 u - 1), hot_cospi(2 u): the azimuth factor of the 4-D sampler integrands) */
   PB_PROBE_MCS_FAST = 7, /* the folded multiple-scattering form of the sub-step loop; in / out as PB_PROBE_MCS (particle mass = m_lepton) */
   PB_PROBE_SUBSTEP = 8,  /* ONE iteration of the dE/dx + MCS loop exactly as k_loop runs it (shower.py:559-581).
                             in: n x 12: pid, E, px, py, pz, x, y, z, key0, key1, sub-step index, multiple scattering on/off;

@@ -73,6 +73,18 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #define PB_LOOP_MINB 6
 #endif
 #ifndef PB_LOOP_CAP_DEFAULT
+#ifndef PB_LOOP_NODE_CACHE
+#define PB_LOOP_NODE_CACHE 0             // 1: k_loop keeps the current n*sigma node in registers (nsigma_cached); measured SLOWER (48.6 vs 47.7 ms per config-2 step: six more live registers at the 80-register cap), kept as an option
+#endif
+#ifndef PB_PREFETCH
+#define PB_PREFETCH 1                    // k_finalize / k_emit: L2 prefetch of the record the thread's NEXT grid-stride iteration gathers
+#endif
+#ifndef PB_LOOP_CG
+#define PB_LOOP_CG 1                     // k_loop's 16-byte record copies bypass L1 (cp.async.cg): the 23 KB of L1 stay with the tables (49.2 -> 48.6 ms per config-2 step)
+#endif
+#ifndef PB_DRAIN_LANES_DEFAULT
+#define PB_DRAIN_LANES_DEFAULT 16        // k_loop: once the charged list is dry, a warp with at most this many live tracks pauses them (carry-over) instead of draining at falling occupancy; 0 = off
+#endif
 #define PB_LOOP_CAP_DEFAULT 32           // sub-steps a track may take per k_loop launch before it is carried into the next wave (0: no limit); measured 16 / 32 / 64 / 128 / off: 155.3 / 145.4 / 146.3 / 150.0 / 151.2 ms per config-2 step
 #endif
 #ifndef PB_SAMPLE_G_DEFAULT
@@ -182,7 +194,7 @@ struct Work {            // per-wave scratch, sized to the widest wave seen so f
                          // reads list[2*parity + k], k_emit builds list[2*(parity^1) + k] for the next wave
   int* carry[2];         // slots of the tracks carried into the current wave (carry[parity]) / paused in it (carry[parity ^ 1])
   int loop_cap;          // sub-steps a track may take per launch (power of two; 0 = unlimited): see k_loop
-  int pad_;
+  int drain_lanes;       // wide waves: live tracks per warp at or below which a warp whose list is dry pauses them (0 = off): see k_loop
   struct WaveState* ws;  // device-resident wave bookkeeping (lets the host enqueue several waves per synchronisation)
   unsigned long long* tail;      // [0] stack tail (next free record); [1] = (n_neutral_next << 32) | n_charged_next; [2] tracks paused by this wave
   unsigned long long* counters;  // [CNT_N]: steps, substeps, samples, trials, no_sample, overflow, per-process trials/samples
@@ -250,6 +262,21 @@ __device__ __forceinline__ double nsigma_hinted(const NSigmaTable& T, int& hi, d
   return __dadd_rn(__dmul_rn(nd.z, E - nd.x), nd.y);
 }
 
+// The same with the node itself carried along the track: energy only decreases, so the node stays the right one until E drops to
+// its lower edge (a few per cent of the sub-steps); the others evaluate from registers instead of waiting on a dependent table
+// load (k_loop's L1 is the 23 KB the shared-memory carve-out leaves, and the record copies stream through it).  Same node, same
+// two roundings: bit-identical to nsigma_hinted.  nx = +Inf marks "not loaded yet".
+__device__ __forceinline__ double nsigma_cached(const NSigmaTable& T, int& hi, double& nx, double& ny, double& nz, double E) {
+  if (T.n < 2) return 0.0;
+  if (!(E >= T.xmin && E <= T.xmax)) return (E == E) ? 0.0 : E;
+  if (!(nx < E)) {
+    double4 nd = ld_node(&T.node[hi - 1]);
+    while (hi > 1 && !(nd.x < E)) { --hi; nd = ld_node(&T.node[hi - 1]); }
+    nx = nd.x; ny = nd.y; nz = nd.z;
+  }
+  return __dadd_rn(__dmul_rn(nz, E - nx), ny);
+}
+
 // tables entering the mean free path of a charged species, in the reference's summation order (shower.py:357-368)
 __device__ __forceinline__ void species_tables(int pid, int* t) {
   if (pid == 11) { t[0] = P_BREM; t[1] = P_MOLLER; t[2] = -1; }
@@ -290,6 +317,9 @@ struct Track {
   uint2 key;
   int sp, hint;    // species table (Tables::sp) and the look-up hint into it
   int it;          // loop iterations done == accepted sub-steps while the loop is alive
+#if PB_LOOP_NODE_CACHE
+  double nx = HUGE_VAL, ny = 0.0, nz = 0.0;   // the table node the hint points at (x, y, slope): valid while nx < E, so the common sub-step loads nothing
+#endif
 };
 
 // Track set-up computed where the particle is created (k_emit / k_init_primaries, all lanes busy) instead of at refill
@@ -336,7 +366,11 @@ struct TapeDraws {             // sequential reader; `over` is set if the tape r
 template <class DS>
 __device__ __forceinline__ bool substep(const Material& M, const Tables& T, Track& t, int ms_e, DS& ds) {
   if (!(t.p.E >= t.pmin)) return true;                                // loop condition (shower.py:559)
+#if PB_LOOP_NODE_CACHE
+  double ns = nsigma_cached(T.sp[t.sp], t.hint, t.nx, t.ny, t.nz, t.p.E);   // sum over the species' processes (shower.py:357-368)
+#else
   double ns = nsigma_hinted(T.sp[t.sp], t.hint, t.p.E);                // sum over the species' processes (shower.py:357-368)
+#endif
   double mfp = (ns <= 0.0) ? 1.0e12 : kCmToM * fast_rcp(ns);          // shower.py:386-389
   D2 u = ds.substep((uint32_t)t.it);
   double iv = fast_rcp(u.b);                                          // delta_z = mfp / U(6, 20); delta_z / mfp = 1 / U
@@ -416,11 +450,16 @@ struct LoopBuf {                 // one chunk of track records: p0, r0w, track s
   int idx[LOOP_CHUNK];
 };
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+#if PB_LOOP_CG
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#else
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // **Bounded sub-steps per launch (carry-over).**  The sub-step count of a track is geometric (mean ~9, 1 track in 40 above 32, the
@@ -437,13 +476,19 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   __shared__ __align__(16) LoopBuf s_buf[4][2];
   const long long begin = W.ws->begin;
   const int n_charged = W.ws->n_charged, n_new = W.ws->n_new;
-  const int n_work = n_charged + W.ws->n_carry;            // fresh charged tracks, then the carried ones
+  const int n_carry = W.ws->n_carry;
+  const int n_work = n_charged + n_carry;                  // the carried tracks first (they resume in full warps), then the fresh charged ones
   if (n_work <= 0) return;
   const int parity = W.ws->parity;
   const int* __restrict__ order_c = W.list[2 * parity];
   const int* __restrict__ carry_in = W.carry[parity];
   int* __restrict__ carry_out = W.carry[parity ^ 1];
   const unsigned cap_mask = W.loop_cap > 0 ? (unsigned)W.loop_cap - 1u : 0xffffffffu;
+  // **Drain pause.**  When the list is dry a warp finishes the <= 32 tracks it holds at falling occupancy: the slowest of 32 geometric
+  // sub-step counts takes ~30 iterations where the work is worth ~8 (a mid-size wave ran 23.6 of 32 lanes, profiles/r02z).  In a wave wide
+  // enough to have filled every warp, a warp that is down to drain_lanes live tracks pauses them like tracks at the cap: the next
+  // wave resumes them FIRST, packed into full warps.  Scheduling only (see the carry-over note above).
+  const int drain_lanes = (W.drain_lanes > 0 && n_work >= 2 * (int)(gridDim.x * blockDim.x)) ? W.drain_lanes : 0;
   const int lane = threadIdx.x & 31;
   LoopBuf* buf = s_buf[threadIdx.x >> 5];
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -461,7 +506,7 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     int c = __shfl_sync(0xffffffffu, c_raw, 0);
     pre_cnt = min(max(n_work - c, 0), chunk);
     const int w = c + lane;
-    pre_idx = (lane < pre_cnt) ? (w < n_charged ? order_c[w] : n_new + (w - n_charged)) : -1;
+    pre_idx = (lane < pre_cnt) ? (w < n_carry ? n_new + w : order_c[w - n_carry]) : -1;
   };
   auto issue_copy = [&](int half) {   // consumes pre_idx, starts the record copies into buf[half]
     LoopBuf& B = buf[half];
@@ -523,6 +568,9 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
           t.iKp = t.mass / (1e3 * pid_mass(pid));
         }
         t.sp = species_index(pid);
+#if PB_LOOP_NODE_CACHE
+        t.nx = HUGE_VAL;     // node not loaded yet
+#endif
         if (cur < n_new) {         // fresh track: set-up stored at creation (store_track_setup)
           double2 s0 = B.v[4][e], s1 = B.v[5][e];
           t.pmin = s1.x;
@@ -545,10 +593,11 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
     if (__all_sync(0xffffffffu, cur == -2)) break;
     // ---- one sub-step for every live lane
     bool done = false, pause = false;
+    const bool drain = dry && __popc(__ballot_sync(0xffffffffu, cur >= 0)) <= drain_lanes;     // warp-uniform
     if (cur >= 0) {
       PhiloxDraws ds{t.key};
       done = substep(M, T, t, ms_e, ds);
-      if (!done) { ++c_sub; pause = ((unsigned)t.it & cap_mask) == 0u; }
+      if (!done) { ++c_sub; pause = drain || ((unsigned)t.it & cap_mask) == 0u; }     // only ever after a sub-step: the launch makes progress on every track
     }
     // tracks created together reach the cap together: one atomic per warp for the carry-list slots
     const unsigned pmask = __ballot_sync(0xffffffffu, pause);
@@ -661,10 +710,32 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
   const int* __restrict__ carry = W.carry[W.ws->parity];
   unsigned long long c_steps = 0;
   // entries: the wave's charged list, its other records, then the carried tracks (all charged, wave-local index = their position)
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+  // The loop is a chain of dependent gathers (list entry -> record sectors -> table nodes; half of the stall samples were long-scoreboard
+  // waits, profiles/r02z): the list entry is read two iterations ahead and the record of the NEXT iteration is prefetched into L2
+  // while this one is computed, so its five sectors arrive with L2 latency instead of HBM's.
+  const int stride = gridDim.x * blockDim.x;
+  auto entry = [&](int jj) { return jj < n_charged ? order_c[jj] : (jj < n_new ? order_n[jj - n_charged] : jj); };
+  const int j0 = blockIdx.x * blockDim.x + threadIdx.x;
+  int i_cur = j0 < n ? entry(j0) : 0, i_nxt = j0 + stride < n ? entry(j0 + stride) : 0;
+  for (int j = j0; j < n; j += stride) {
     const bool charged = j < n_charged || j >= n_new;
-    int i = j < n_charged ? order_c[j] : (j < n_new ? order_n[j - n_charged] : j);
+    const int i = i_cur;
     long long s = j < n_new ? begin + i : (long long)carry[j - n_new];
+#if PB_PREFETCH
+    {
+      const int jn = j + stride;
+      if (jn < n_new) {                          // (carried tracks are few and would need one more dependent load for their slot)
+        const long long sn = begin + i_nxt;
+        prefetch_l2(S.ids + 2 * sn);
+        if (jn < n_charged) { prefetch_l2(S.pf + 4 * sn); prefetch_l2(S.rf + 4 * sn); prefetch_l2(S.aux + sn); prefetch_l2(S.p0 + 4 * sn); }
+        else { prefetch_l2(S.p0 + 4 * sn); prefetch_l2(S.r0w + 4 * sn); }
+      }
+      i_cur = i_nxt;
+      i_nxt = jn + stride < n ? entry(jn + stride) : 0;
+    }
+#else
+    i_cur = j + stride < n ? entry(j + stride) : 0;
+#endif
     int4 meta = ld_meta(S, s);
     PhiloxDraws ds{kw_key(ld_kw(S, s))};
     int pid = meta.x;
@@ -1236,8 +1307,30 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   // CTA-uniform grid-stride loop (the append below uses full-warp shuffles and two CTA barriers)
   __shared__ int s_tot[4], s_tch[4];
   __shared__ unsigned long long s_base[4], s_lbase[4];
-  for (int cbase = blockIdx.x * blockDim.x; cbase < n; cbase += gridDim.x * blockDim.x) {
+  const int stride = gridDim.x * blockDim.x;
+  const int j0 = blockIdx.x * blockDim.x + (int)threadIdx.x;
+  // (index, bucket) read two iterations ahead, the record of the next iteration prefetched into L2 (see k_finalize)
+  int2 ib_cur = (!wave_order && j0 < n) ? W.sorted[j0] : make_int2(0, 0), ib_nxt = (!wave_order && j0 + stride < n) ? W.sorted[j0 + stride] : make_int2(0, 0);
+  for (int cbase = blockIdx.x * blockDim.x; cbase < n; cbase += stride) {
   const int j = cbase + (int)threadIdx.x;
+  const int2 ib_now = ib_cur;
+#if PB_PREFETCH
+  if (!wave_order) {
+    const int jn = j + stride;
+    if (jn < n && ib_nxt.y / LU_MAX != P_NONE) {
+      const int in = ib_nxt.x;
+      if (in < n_new) {
+        const long long sn = begin + in;
+        prefetch_l2(S.pf + 4 * sn); prefetch_l2(S.rf + 4 * sn); prefetch_l2(S.ids + 2 * sn);
+      }
+      prefetch_l2(W.xs + 4 * (size_t)in);
+    }
+    ib_cur = ib_nxt;
+    ib_nxt = jn + stride < n ? W.sorted[jn + stride] : make_int2(0, 0);
+  }
+#else
+  if (!wave_order) ib_cur = j + stride < n ? W.sorted[j + stride] : make_int2(0, 0);
+#endif
   V4 da{0, 0, 0, 0}, db{0, 0, 0, 0};
   int pid_a = 0, pid_b = 0, proc = P_NONE;
   bool keep_a = false, keep_b = false;
@@ -1248,7 +1341,7 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   if (j < n) {
     int i, bucket;
     if (wave_order) { i = j; bucket = W.bucket[i]; }
-    else { int2 ib = W.sorted[j]; i = ib.x; bucket = ib.y; }
+    else { i = ib_now.x; bucket = ib_now.y; }
     proc = bucket / LU_MAX;
     double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0, x01 = a0, x23 = a0;
     if (proc != P_NONE) {
@@ -1643,7 +1736,7 @@ k_find_max(const __grid_constant__ Material M, const __grid_constant__ Tables T,
 __global__ void __launch_bounds__(256)
 k_train(const __grid_constant__ Material M, int process, int dim, int stride, int4 ninc4, const double* __restrict__ grids,
         const double* __restrict__ E_inc, long long n_points, unsigned long long seed, double* __restrict__ d_out,
-        double* __restrict__ n_out, double* __restrict__ integral_out) {
+        double* __restrict__ n_out, double* __restrict__ integral_out, double power) {
   extern __shared__ double s_mem[];
   double* s_grid = s_mem;
   double* s_d = s_mem + stride;
@@ -1674,7 +1767,7 @@ k_train(const __grid_constant__ Material M, int process, int dim, int stride, in
     double f = jac * dsigma(M, process, E, x);
     if (f == f && fabs(f) < 1e300) {
       acc += f;
-      double f2 = f * f;
+      double f2 = (power == 2.0) ? f * f : pow(fabs(f), power);     // training weight |jac f|^p: p = 2 is Lepage's variance criterion
       for (int d = 0; d < dim; ++d) { atomicAdd(&s_d[off[d] + iy[d]], f2); atomicAdd(&s_n[off[d] + iy[d]], 1); }
     }
   }
@@ -1971,6 +2064,7 @@ __global__ void k_probe(const __grid_constant__ Material M, const __grid_constan
       hot_sincos_2pi(a[3], &o[4], &o[5]);
       o[6] = fast_rcp(a[0]);
       if (os >= 10) { o[7] = fast_sqrt0(a[0]); o[8] = fast_rsqrt(a[0]); o[9] = fast_sqrt0(0.0) + fast_sqrt0(-a[0]); }
+      if (os >= 12) { o[10] = hot_cospi(2.0 * a[3] - 1.0); o[11] = hot_cospi(2.0 * a[3]); }
     } break;
     case PB_PROBE_MCS_FAST: {   // in as PB_PROBE_MCS; the particle's mass is m_lepton
       V4 p{a[0], a[1], a[2], a[3]};
@@ -2150,6 +2244,8 @@ extern "C" int pb_create(pb_engine* out, int device, const pb_config* cfg) {
   if (const char* g = getenv("PB_GRAPH")) e->use_graph = atoi(g);
   e->work.tile_norm = 1;
   if (const char* g = getenv("PB_TILE_NORM")) e->work.tile_norm = atoi(g);
+  e->work.drain_lanes = PB_DRAIN_LANES_DEFAULT;
+  if (const char* g = getenv("PB_DRAIN_LANES")) e->work.drain_lanes = std::min(std::max(atoi(g), 0), 32);
   e->work.loop_cap = PB_LOOP_CAP_DEFAULT;
   if (const char* g = getenv("PB_LOOP_CAP")) e->work.loop_cap = atoi(g);
   if (e->work.loop_cap < 0 || (e->work.loop_cap & (e->work.loop_cap - 1))) e->work.loop_cap = 0;      // powers of two only
@@ -2894,7 +2990,9 @@ extern "C" int pb_train_accumulate(pb_engine e, int process, const double* grid,
   if (c == cudaSuccess) c = cudaFuncSetAttribute(k_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (c == cudaSuccess) {
     int bx = (int)std::max<long long>(1, std::min<long long>(64, n_points / 4096));
-    k_train<<<dim3(bx, nE), 256, smem, st>>>(m, process, dim, stride, make_int4(nn[0], nn[1], nn[2], nn[3]), d_grid, d_E, n_points, seed, d_d, d_n, d_I);
+    double power = 2.0;
+    if (const char* g = getenv("PB_TRAIN_POW")) { power = atof(g); if (!(power > 0.0)) power = 2.0; }      // experiment knob (profiles/r02_summary.md 6)
+    k_train<<<dim3(bx, nE), 256, smem, st>>>(m, process, dim, stride, make_int4(nn[0], nn[1], nn[2], nn[3]), d_grid, d_E, n_points, seed, d_d, d_n, d_I, power);
     c = cudaMemcpyAsync(d_out, d_d, sizeof(double) * rows, cudaMemcpyDeviceToHost, st);
   }
   if (c == cudaSuccess) c = cudaMemcpyAsync(n_out, d_n, sizeof(double) * rows, cudaMemcpyDeviceToHost, st);

@@ -204,6 +204,28 @@ __device__ __forceinline__ void hot_sincos_2pi(double u, double* sn, double* cs)
   *cs = ((iq + 1) & 2) ? -co : co;
 }
 
+// cos(pi t), |t| <= 2: the azimuth factor of the two 4-D sampler integrands (once per accept/reject trial).  Exact reduction to
+// |r| <= 1/4, both fdlibm kernels at r * pi (rounded once: <= 1.2e-16 absolute in the argument), quadrant select: <= 2 ulp, half the
+// instructions of libdevice's cospi, which selects each of its coefficients with a pair of FSELs (9 % of k_sample, profiles/r02z).
+__device__ __forceinline__ double hot_cospi(double t) {
+  double a = fabs(t);
+  double q = rint(2.0 * a);                                   // quadrant 0..4
+  double r = fma(q, -0.5, a);                                 // exact
+  double s, c;
+  hot_sincos_kernel(r * kHotMath[32], &s, &c);
+  int iq = (int)q;
+  double v = (iq & 1) ? s : c;                                // cos(x + q pi/2): c, -s, -c, s, c
+  return ((iq + 1) & 2) ? -v : v;
+}
+#ifndef PB_FAST_COSPI
+#define PB_FAST_COSPI 1
+#endif
+#if PB_FAST_COSPI
+#define PB_COSPI hot_cospi
+#else
+#define PB_COSPI cospi
+#endif
+
 // ---------------------------------------------------------------- form factors
 __device__ __forceinline__ double ff_elastic(const Material& M, double t) {  // all_processes.py:99-103
   double den = 1.0 + M.ff_a0sq * t;
@@ -316,7 +338,7 @@ __device__ __forceinline__ double ds_brem_fast(const Material& M, const SampleCo
   // branch-free: the kinematic mask selects at the end, so that the T trials a lane evaluates per round stay one basic block
   // (ILP); outside the mask the arithmetic below runs on garbage (possibly Inf / NaN) and is discarded
   bool ok = (Egmin < w) && (w < ep - ml) && (ml < epp) && (epp < ep) && (d > 0.0) && (dp > 0.0);
-  double cph = cospi(2.0 * x[3] - 1.0);           // cos((x4 - 1/2) 2 pi)
+  double cph = PB_COSPI(2.0 * x[3] - 1.0);        // cos((x4 - 1/2) 2 pi)
   double d2 = d * d, dp2 = dp * dp;
   double od = 1 + d2, odp = 1 + dp2;
   double iepp = fast_rcp(epp);
@@ -349,7 +371,7 @@ __device__ __forceinline__ double ds_pairprod_fast(const SampleConst& s, double 
   double dm = s.b * (x[1] - x[2]);
   double epm = w - epp;
   bool ok = (me < epm) && (epm < w) && (me < epp) && (epp < w) && (dm > 0.0) && (dp > 0.0);
-  double cph = cospi(2.0 * x[3]);
+  double cph = PB_COSPI(2.0 * x[3]);
   double dp2 = dp * dp, dm2 = dm * dm;
   double op = 1.0 + dp2, om = 1.0 + dm2;
   double ie = fast_rcp(epp * epm);

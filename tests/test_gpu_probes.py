@@ -38,7 +38,7 @@ def test_hot_math():
     xexp = rng.uniform(1 / 20, 1 / 6, n); xexp[:2] = [1 / 20, 1 / 6]
     th = np.concatenate([rng.uniform(-np.pi / 4, np.pi / 4, n // 2), rng.normal(0, 1e-4, n // 4), rng.uniform(-50, 50, n // 4)])
     u = rng.random(n); u[:5] = [0.0, 0.25, 0.5, 0.75, 1 - 2.0 ** -52]
-    got = probe(sh, capi.PROBE_HOTMATH, 0, np.column_stack([xlog, xexp, th, u]), 10)
+    got = probe(sh, capi.PROBE_HOTMATH, 0, np.column_stack([xlog, xexp, th, u]), 12)
     ulps = lambda a, b: np.abs(a - b) / np.spacing(np.maximum(np.abs(b), 1e-300))
     assert got[0, 0] == 0.0                                                   # log(1) is exactly 0
     lg = np.log(xlog)
@@ -56,6 +56,16 @@ def test_hot_math():
     assert np.max(np.abs(got[:, 7].astype(L) - np.sqrt(xl)) / np.spacing(np.sqrt(xlog))) <= 1
     assert np.max(np.abs(got[:, 8].astype(L) - 1 / np.sqrt(xl)) / np.spacing(1.0 / np.sqrt(xlog))) <= 1.01
     assert np.all(got[:, 9] == 0.0)
+    # cos(pi t) of the sampler integrands (hot_cospi), t = 2 u - 1 (Brem) and 2 u (PairProd): <= 2 ulp where |cos| is not small, and in
+    # absolute terms everywhere (the reference rounds (u - 1/2) 2 pi first, the kernel reduces exactly)
+    for col, t in ((10, 2.0 * u - 1.0), (11, 2.0 * u)):
+        tl = t.astype(L)
+        exact = np.cos(L(np.pi) * tl + L(1.2246467991473532e-16) * tl)
+        err = np.abs(got[:, col].astype(L) - exact)
+        assert np.max(err) < 2.3e-16
+        big = np.abs(exact) > 0.5
+        assert np.max(err[big] / np.spacing(np.abs(exact[big]).astype(np.float64))) <= 2
+    assert got[0, 10] == -1.0 and got[0, 11] == 1.0 and got[2, 10] == 1.0 and got[2, 11] == -1.0      # u = 0, 1/2: exact
 
 
 def _four_dim_condition(process, E, x):

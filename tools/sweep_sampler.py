@@ -11,7 +11,7 @@ and round (PB_SAMPLE_T), generic = 1 runs the SM pass through the kernel that al
     python tools/sweep_sampler.py [n_timing] [G,T,generic ...] > gpurun_out/sweep_sampler.log
     PETITE_B200_LIB=variants/libpb_X.so python tools/sweep_sampler.py ...      # compile-time variants: tools/sweep_variants.sh
 """
-import os, sys, json
+import os, sys, json, hashlib
 import numpy as np, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from petite_b200.shower import Shower
@@ -61,7 +61,15 @@ for G, T, generic in CONFIGS:
         e1.record(); torch.cuda.synchronize()
         pr = sh.get_profile()
         ms.append(e0.elapsed_time(e1)); ks.append(pr["ms"]["k_sample"]); kl.append(pr["ms"]["k_loop"])
-    print(json.dumps({"G": G, "T": T, "generic": generic, "lib": os.path.basename(os.environ.get("PETITE_B200_LIB", "default")), "same_as_reference": bool(same), "records": d[0]["n_particles"],
+    sh.set_profiling(0)                                            # the wave loop as one CUDA graph (the bench's main region)
+    mg = []
+    for rep in range(3):
+        torch.cuda.synchronize(); e0.record()
+        b = sh.run_arrays(*devp, capacity=cap, first_shower_id=0)
+        e1.record(); torch.cuda.synchronize()
+        mg.append(e0.elapsed_time(e1))
+    sha = hashlib.sha1(b"".join(np.ascontiguousarray(a).tobytes() for a in d[1:])).hexdigest()[:12]
+    print(json.dumps({"drain": os.environ.get("PB_DRAIN_LANES", ""), "graph_step_ms": round(min(mg), 2), "waves": b.counters.get("n_waves"), "digest": sha, "G": G, "T": T, "generic": generic, "lib": os.path.basename(os.environ.get("PETITE_B200_LIB", "default")), "same_as_reference": bool(same), "records": d[0]["n_particles"],
                       "trials": d[0]["n_trials"], "step_ms": round(min(ms), 2), "k_sample_ms": round(min(ks), 2),
                       "k_loop_ms": round(min(kl), 2), "other": {k: round(v, 2) for k, v in pr["ms"].items() if v and k not in ("k_sample", "k_loop")}, "showers_per_s": round(N_T / min(ms) * 1e3)}), flush=True)
     del sh, b, cal, devp
