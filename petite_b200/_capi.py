@@ -84,6 +84,8 @@ SIGNATURES = {
     "pb_find_max": (C.c_int, [pb_engine, C.c_int, C.c_int, C.c_uint64, C.c_double, c_double_p, c_double_p]),
     "pb_train_accumulate": (C.c_int, [pb_engine, C.c_int, c_double_p, C.c_int, C.c_int, c_int32_p, c_double_p, C.c_int64, C.c_uint64,
                                       C.c_double, c_double_p, c_double_p, c_double_p]),
+    "pb_train_accumulate_p": (C.c_int, [pb_engine, C.c_int, c_double_p, C.c_int, C.c_int, c_int32_p, c_double_p, C.c_int64, C.c_uint64,
+                                        C.c_double, C.c_double, c_double_p, c_double_p, c_double_p]),
     "pb_tally": (C.c_int, [pb_engine, C.POINTER(pb_stack), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "pb_detector_cut": (C.c_int, [pb_engine, C.POINTER(pb_stack), C.c_int64, C.c_int64, c_double_p, C.c_int, C.c_double, C.c_double,
                                   C.c_double, C.c_double, c_double_p, c_double_p, C.c_void_p, C.c_void_p]),

@@ -76,9 +76,6 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #ifndef PB_LOOP_NODE_CACHE
 #define PB_LOOP_NODE_CACHE 0             // 1: k_loop keeps the current n*sigma node in registers (nsigma_cached); measured SLOWER (48.6 vs 47.7 ms per config-2 step: six more live registers at the 80-register cap), kept as an option
 #endif
-#ifndef PB_PREFETCH
-#define PB_PREFETCH 1                    // k_finalize / k_emit: L2 prefetch of the record the thread's NEXT grid-stride iteration gathers
-#endif
 #ifndef PB_LOOP_CG
 #define PB_LOOP_CG 1                     // k_loop's 16-byte record copies bypass L1 (cp.async.cg): the 23 KB of L1 stay with the tables (49.2 -> 48.6 ms per config-2 step)
 #endif
@@ -459,7 +456,6 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // **Bounded sub-steps per launch (carry-over).**  The sub-step count of a track is geometric (mean ~9, 1 track in 40 above 32, the
@@ -710,32 +706,10 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
   const int* __restrict__ carry = W.carry[W.ws->parity];
   unsigned long long c_steps = 0;
   // entries: the wave's charged list, its other records, then the carried tracks (all charged, wave-local index = their position)
-  // The loop is a chain of dependent gathers (list entry -> record sectors -> table nodes; half of the stall samples were long-scoreboard
-  // waits, profiles/r02z): the list entry is read two iterations ahead and the record of the NEXT iteration is prefetched into L2
-  // while this one is computed, so its five sectors arrive with L2 latency instead of HBM's.
-  const int stride = gridDim.x * blockDim.x;
-  auto entry = [&](int jj) { return jj < n_charged ? order_c[jj] : (jj < n_new ? order_n[jj - n_charged] : jj); };
-  const int j0 = blockIdx.x * blockDim.x + threadIdx.x;
-  int i_cur = j0 < n ? entry(j0) : 0, i_nxt = j0 + stride < n ? entry(j0 + stride) : 0;
-  for (int j = j0; j < n; j += stride) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
     const bool charged = j < n_charged || j >= n_new;
-    const int i = i_cur;
+    int i = j < n_charged ? order_c[j] : (j < n_new ? order_n[j - n_charged] : j);
     long long s = j < n_new ? begin + i : (long long)carry[j - n_new];
-#if PB_PREFETCH
-    {
-      const int jn = j + stride;
-      if (jn < n_new) {                          // (carried tracks are few and would need one more dependent load for their slot)
-        const long long sn = begin + i_nxt;
-        prefetch_l2(S.ids + 2 * sn);
-        if (jn < n_charged) { prefetch_l2(S.pf + 4 * sn); prefetch_l2(S.rf + 4 * sn); prefetch_l2(S.aux + sn); prefetch_l2(S.p0 + 4 * sn); }
-        else { prefetch_l2(S.p0 + 4 * sn); prefetch_l2(S.r0w + 4 * sn); }
-      }
-      i_cur = i_nxt;
-      i_nxt = jn + stride < n ? entry(jn + stride) : 0;
-    }
-#else
-    i_cur = j + stride < n ? entry(j + stride) : 0;
-#endif
     int4 meta = ld_meta(S, s);
     PhiloxDraws ds{kw_key(ld_kw(S, s))};
     int pid = meta.x;
@@ -1307,30 +1281,8 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   // CTA-uniform grid-stride loop (the append below uses full-warp shuffles and two CTA barriers)
   __shared__ int s_tot[4], s_tch[4];
   __shared__ unsigned long long s_base[4], s_lbase[4];
-  const int stride = gridDim.x * blockDim.x;
-  const int j0 = blockIdx.x * blockDim.x + (int)threadIdx.x;
-  // (index, bucket) read two iterations ahead, the record of the next iteration prefetched into L2 (see k_finalize)
-  int2 ib_cur = (!wave_order && j0 < n) ? W.sorted[j0] : make_int2(0, 0), ib_nxt = (!wave_order && j0 + stride < n) ? W.sorted[j0 + stride] : make_int2(0, 0);
-  for (int cbase = blockIdx.x * blockDim.x; cbase < n; cbase += stride) {
+  for (int cbase = blockIdx.x * blockDim.x; cbase < n; cbase += gridDim.x * blockDim.x) {
   const int j = cbase + (int)threadIdx.x;
-  const int2 ib_now = ib_cur;
-#if PB_PREFETCH
-  if (!wave_order) {
-    const int jn = j + stride;
-    if (jn < n && ib_nxt.y / LU_MAX != P_NONE) {
-      const int in = ib_nxt.x;
-      if (in < n_new) {
-        const long long sn = begin + in;
-        prefetch_l2(S.pf + 4 * sn); prefetch_l2(S.rf + 4 * sn); prefetch_l2(S.ids + 2 * sn);
-      }
-      prefetch_l2(W.xs + 4 * (size_t)in);
-    }
-    ib_cur = ib_nxt;
-    ib_nxt = jn + stride < n ? W.sorted[jn + stride] : make_int2(0, 0);
-  }
-#else
-  if (!wave_order) ib_cur = j + stride < n ? W.sorted[j + stride] : make_int2(0, 0);
-#endif
   V4 da{0, 0, 0, 0}, db{0, 0, 0, 0};
   int pid_a = 0, pid_b = 0, proc = P_NONE;
   bool keep_a = false, keep_b = false;
@@ -1341,7 +1293,7 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   if (j < n) {
     int i, bucket;
     if (wave_order) { i = j; bucket = W.bucket[i]; }
-    else { i = ib_now.x; bucket = ib_now.y; }
+    else { int2 ib = W.sorted[j]; i = ib.x; bucket = ib.y; }
     proc = bucket / LU_MAX;
     double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0, x01 = a0, x23 = a0;
     if (proc != P_NONE) {
@@ -1767,7 +1719,10 @@ k_train(const __grid_constant__ Material M, int process, int dim, int stride, in
     double f = jac * dsigma(M, process, E, x);
     if (f == f && fabs(f) < 1e300) {
       acc += f;
-      double f2 = (power == 2.0) ? f * f : pow(fabs(f), power);     // training weight |jac f|^p: p = 2 is Lepage's variance criterion
+      // training weight |jac f|^p.  p = 2 is Lepage's variance criterion (what vegas trains on); the SAMPLER's figure of merit is
+      // mean / max of jac f, and a larger p flattens the peaks that set max_F (p = 8: 2.3-2.8x the accept rate of the shipped maps,
+      // profiles/r03/exp_train_pow2.log).  Only ratios within an axis matter to the refinement; the clamp keeps the sums finite.
+      double f2 = (power == 2.0) ? f * f : fmin(pow(fabs(f), power), 1e250);
       for (int d = 0; d < dim; ++d) { atomicAdd(&s_d[off[d] + iy[d]], f2); atomicAdd(&s_n[off[d] + iy[d]], 1); }
     }
   }
@@ -2965,9 +2920,10 @@ extern "C" int pb_detector_cut(pb_engine e, const pb_stack* st, int64_t first, i
   return PB_OK;
 }
 
-extern "C" int pb_train_accumulate(pb_engine e, int process, const double* grid, int nE, int dim, const int32_t* ninc,
-                                   const double* E_inc, int64_t n_points, uint64_t seed, double mT, double* d_out,
-                                   double* n_out, double* integral_out) {
+extern "C" int pb_train_accumulate_p(pb_engine e, int process, const double* grid, int nE, int dim, const int32_t* ninc,
+                                     const double* E_inc, int64_t n_points, uint64_t seed, double mT, double power, double* d_out,
+                                     double* n_out, double* integral_out) {
+  if (!(power > 0.0 && power <= 64.0)) return PB_ERR_ARG;
   if (!e || !grid || !ninc || !E_inc || !d_out || !n_out || !integral_out || nE < 1 || dim < 1 || dim > 4 || n_points < 1 ||
       process < 0 || process >= N_SAMPLED) return PB_ERR_ARG;
   PB_CUDA(e, cudaSetDevice(e->device));
@@ -2990,8 +2946,6 @@ extern "C" int pb_train_accumulate(pb_engine e, int process, const double* grid,
   if (c == cudaSuccess) c = cudaFuncSetAttribute(k_train, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (c == cudaSuccess) {
     int bx = (int)std::max<long long>(1, std::min<long long>(64, n_points / 4096));
-    double power = 2.0;
-    if (const char* g = getenv("PB_TRAIN_POW")) { power = atof(g); if (!(power > 0.0)) power = 2.0; }      // experiment knob (profiles/r02_summary.md 6)
     k_train<<<dim3(bx, nE), 256, smem, st>>>(m, process, dim, stride, make_int4(nn[0], nn[1], nn[2], nn[3]), d_grid, d_E, n_points, seed, d_d, d_n, d_I, power);
     c = cudaMemcpyAsync(d_out, d_d, sizeof(double) * rows, cudaMemcpyDeviceToHost, st);
   }
@@ -3001,6 +2955,12 @@ extern "C" int pb_train_accumulate(pb_engine e, int process, const double* grid,
   cudaFree(d);
   if (c != cudaSuccess) { e->err = cudaGetErrorString(c); return PB_ERR_CUDA; }
   return PB_OK;
+}
+
+extern "C" int pb_train_accumulate(pb_engine e, int process, const double* grid, int nE, int dim, const int32_t* ninc,
+                                   const double* E_inc, int64_t n_points, uint64_t seed, double mT, double* d_out,
+                                   double* n_out, double* integral_out) {
+  return pb_train_accumulate_p(e, process, grid, nE, dim, ninc, E_inc, n_points, seed, mT, 2.0, d_out, n_out, integral_out);
 }
 
 extern "C" int pb_set_profiling(pb_engine e, int on) {

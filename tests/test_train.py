@@ -31,8 +31,10 @@ def test_refine_concentrates_increments_where_the_integrand_is():
 @pytest.mark.gpu
 @pytest.mark.parametrize("process", ["PairProd", "Brem", "Comp"])
 def test_trained_maps_reproduce_shipped_cross_sections(process):
-    """Train on hydrogen as the reference does, then integrate graphite through the NEW maps: sigma must reproduce the
-    shipped sm_xsec rows, and the sampler's efficiency must be comparable to the shipped maps'."""
+    """Train on hydrogen as the reference does (default schedule, training weight |jac f|^8), then integrate graphite through the
+    NEW maps: sigma must reproduce the shipped sm_xsec rows, and the accept/reject efficiency sigma / (B max_F) must reach the shipped
+    maps' (row f-2; measured 2.3-2.8x for the 4-D processes, profiles/r03/exp_train_pow2.log).  The plain VEGAS criterion
+    (power = 2) is kept as the comparison: same sigma, lower efficiency."""
     from petite_b200.train import Trainer
     from petite_b200 import tables as tb
     from petite_b200.shower import Shower, process_code
@@ -40,7 +42,7 @@ def test_trained_maps_reproduce_shipped_cross_sections(process):
     rows = [30, 60, 80, 99]
     E = xs[rows, 0]
     tr = Trainer()
-    grids, ninc, I = tr.train(process, E, nitn=30, n_points=1_000_000, alpha=1.0)
+    grids, ninc, I = tr.train(process, E)
     assert np.all(np.isfinite(grids)) and np.all(I > 0)
     off = 0
     for n in ninc:
@@ -48,15 +50,28 @@ def test_trained_maps_reproduce_shipped_cross_sections(process):
         off += n + 1
     sh = Shower(DATA, "graphite", 0.010, seed=3)
     shipped = sh._maps[process]
-    mf_old, sg_old = sh.find_max(process, n_trials=400, seed=9)      # 1.2e5 points per row: MC error of sigma well below the 5 % bound
-    ms = tb.MapSet(process, E, ninc, grids, np.ones(len(E)), shipped.neval, shipped.Eg_min, shipped.Ee_min)
-    sh._upload_maps(process_code[process], ms)
-    sh._maps[process] = ms
-    mf, sg = sh.find_max(process, n_trials=400, seed=9)
-    assert np.all(np.abs(sg / xs[rows, 1] - 1) < 0.05), sg / xs[rows, 1]
-    eff_new = sg / (300 * mf)
+    mf_old, sg_old = sh.find_max(process, n_trials=2000, seed=9)     # 6e5 points per row: MC error of sigma well below the 5 % bound
     eff_old = (sg_old / (300 * mf_old))[rows]
-    assert np.all(eff_new > 0.12 * eff_old), (eff_new, eff_old)      # measured: 0.2-0.6 of the shipped maps' efficiency (max_F over 1.2e5 points)
+
+    def through(g):
+        ms = tb.MapSet(process, E, ninc, g, np.ones(len(E)), shipped.neval, shipped.Eg_min, shipped.Ee_min)
+        sh._upload_maps(process_code[process], ms)
+        sh._maps[process] = ms
+        mf, sg = sh.find_max(process, n_trials=2000, seed=9)
+        assert np.all(np.abs(sg / xs[rows, 1] - 1) < 0.05), sg / xs[rows, 1]
+        return sg / (300 * mf) / eff_old
+
+    r8 = through(grids)
+    gmean = float(np.exp(np.mean(np.log(r8))))
+    print(process, "efficiency / shipped, power 8:", r8.round(3), "geometric mean", round(gmean, 3))
+    if process in ("PairProd", "Brem"):
+        assert gmean > 1.0 and np.all(r8 > 0.4), r8                 # max_F is the maximum of a heavy-tailed sample: single rows scatter by 2x
+        g2, _, _ = tr.train(process, E, power=2.0)
+        r2 = through(g2)
+        print(process, "efficiency / shipped, power 2:", r2.round(3))
+        assert gmean > float(np.exp(np.mean(np.log(r2))))
+    else:
+        assert np.all(r8 > 0.12), r8
 
 
 @pytest.mark.gpu
@@ -68,7 +83,7 @@ def test_trained_dark_brem_maps_reproduce_shipped_dark_xsec():
     rows = [20, 50, 80, 99]
     E = xs[rows, 0]
     tr = Trainer(mT=200.0, mV=0.03)                      # the reference trains on hydrogen with mT = 200 GeV (map readme)
-    grids, ninc, _ = tr.train("DarkBrem", E, nitn=30, n_points=1_000_000)
+    grids, ninc, _ = tr.train("DarkBrem", E)
     ds = DarkShower(DATA, "graphite", 0.010, 0.03, active_processes=["DarkBrem", "DarkComp", "DarkAnn"], seed=2)
     old = ds._dark_maps["DarkBrem"]
     ms = tb.MapSet("DarkBrem", E, ninc, grids, np.ones(len(E)), old.neval, old.Eg_min, old.Ee_min)

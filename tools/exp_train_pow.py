@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Training-weight experiment: VEGAS refines its map on sum (jac f)^2 per increment; with vegas' adaptive stratified
 sampling (the reference trains with nstrat 60 x 50 x 50 x 50, beta 0.75) a hypercube holding n_h ~ sigma_h^beta samples contributes
-(jac f)^2 / n_h, i.e. the map effectively sees a LOWER power of the integrand.  PB_TRAIN_POW = p trains on |jac f|^p; this tool
+(jac f)^2 / n_h.  Trainer.train(power=p) trains on |jac f|^p (pb_train_accumulate_p); this tool
 reports the accept/reject efficiency sigma / (B max_F) of maps trained with several p relative to the shipped maps.
     python tools/exp_train_pow.py Brem PairProd"""
 import sys, time, json, os
@@ -21,10 +21,9 @@ for P in sys.argv[1:] or ["Brem"]:
     mf_old, sg_old = sh.find_max(P, n_trials=NT, seed=9)
     eff_old = (sg_old / (300 * mf_old))[rows]
     print(json.dumps({"process": P, "E": E.round(3).tolist(), "shipped_eff": eff_old.round(4).tolist()}), flush=True)
-    for power in (2.0, 1.5, 1.25, 1.0, 3.0):
-        os.environ["PB_TRAIN_POW"] = str(power)
+    for power in [float(v) for v in os.environ.get("EXP_POWERS", "2,1.5,1.25,1,3").split(",")]:
         tr = Trainer(); t = time.time()
-        grids, ninc, I = tr.train(P, E, schedule=SCHED)
+        grids, ninc, I = tr.train(P, E, schedule=SCHED, power=power)
         dt = time.time() - t
         ms = tb.MapSet(P, E, ninc, grids, np.ones(len(E)), shipped.neval, shipped.Eg_min, shipped.Ee_min)
         sh._upload_maps(process_code[P], ms); sh._maps[P] = ms

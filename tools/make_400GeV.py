@@ -13,7 +13,7 @@ import numpy as np
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 from petite_b200 import tables as tb
-from petite_b200.train import Trainer
+from petite_b200.train import Trainer, TRAIN_POWER
 
 
 def main():
@@ -21,9 +21,11 @@ def main():
     ap.add_argument("--dir", default=os.path.join(ROOT, "data_400GeV", ""))
     ap.add_argument("--materials", default="lead")
     ap.add_argument("--mV", type=float, default=0.01)
-    ap.add_argument("--nitn", type=int, default=30)
+    ap.add_argument("--nitn", type=int, default=0, help="0: petite_b200.train.TRAIN_SCHEDULE")
     ap.add_argument("--points", type=int, default=1_000_000)
+    ap.add_argument("--power", type=float, default=None, help="training weight |jac f|^p (default petite_b200.train.TRAIN_POWER = 8)")
     a = ap.parse_args()
+    power = TRAIN_POWER if a.power is None else a.power
     D = a.dir
     mats = a.materials.split(",")
     t0 = time.time()
@@ -33,7 +35,7 @@ def main():
     sig_h = {}
     for P in ("Brem", "PairProd", "MuonBrem"):
         E = xs[f"{P}/lead"][:, 0]
-        grids, ninc, I = tr.train(P, E, nitn=a.nitn, n_points=a.points)
+        grids, ninc, I = tr.train(P, E, nitn=a.nitn or None, n_points=a.points, power=power)
         sm[f"{P}/E"], sm[f"{P}/ninc"], sm[f"{P}/grid"], sm[f"{P}/meta"] = E, ninc, grids, np.array([300, 0.001, 0.005])
         sig_h[P] = I
         print(f"trained {P}: {len(E)} energies, {time.time() - t0:.1f} s", flush=True)
@@ -59,7 +61,7 @@ def main():
     trd = Trainer(mT=200.0, mV=a.mV)                       # the reference's training target: hydrogen with mT = 200 GeV
     for P in ("DarkBrem", "DarkMuonBrem"):
         E = dxs[f"{tag}/{P}/lead"][:, 0]
-        grids, ninc, I = trd.train(P, E, nitn=a.nitn, n_points=a.points)
+        grids, ninc, I = trd.train(P, E, nitn=a.nitn or None, n_points=a.points, power=power)
         dk[f"{P}/E"], dk[f"{P}/ninc"], dk[f"{P}/grid"], dk[f"{P}/meta"] = E, ninc, grids, np.array([300, 0.001, 0.005])
         print(f"trained {P}: {len(E)} energies, {time.time() - t0:.1f} s", flush=True)
     np.savez_compressed(D + f"dark_maps_mV{tag}.npz", **dk)
