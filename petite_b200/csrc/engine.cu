@@ -1750,24 +1750,37 @@ __global__ void __launch_bounds__(256) k_tally(Stack S, long long first, long lo
   double cnt[PB_TALLY_NSPECIES], ws[PB_TALLY_NSPECIES], wes[PB_TALLY_NSPECIES];
 #pragma unroll
   for (int k = 0; k < PB_TALLY_NSPECIES; ++k) { cnt[k] = 0.0; ws[k] = 0.0; wes[k] = 0.0; }
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    long long s = first + i;
+  // warp-uniform loop (every lane takes part in the match operations below; lanes past the end carry weight 0 into bin 0)
+  for (long long base = (blockIdx.x * (long long)blockDim.x + warp * 32); base < n; base += (long long)gridDim.x * blockDim.x) {
+    const long long i = base + lane;
+    const bool valid = i < n;
+    long long s = first + (valid ? i : 0);
     const double2* p0p = reinterpret_cast<const double2*>(S.p0 + 4 * s);
     double2 a0 = p0p[0], a1 = p0p[1];
     const int4 kw = ld_kw(S, s);                  // pid and weight sit in the record's one 32-byte ids sector (r0w is not touched)
-    double w = kw_weight(kw);
+    double w = valid ? kw_weight(kw) : 0.0;
     int sp = species_of(ld_meta(S, s).x);
+    if (valid) {
 #pragma unroll
-    for (int k = 0; k < PB_TALLY_NSPECIES; ++k)
-      if (sp == k) { cnt[k] += 1.0; ws[k] += w; wes[k] += w * a0.x; }
+      for (int k = 0; k < PB_TALLY_NSPECIES; ++k)
+        if (sp == k) { cnt[k] += 1.0; ws[k] += w; wes[k] += w * a0.x; }
+    }
     int eb = (int)floor((log10(a0.x) + 3.0) * (PB_TALLY_EBINS / 6.0));
     eb = min(max(eb, 0), PB_TALLY_EBINS - 1);
-    atomicAdd(&mine[PB_TALLY_EHIST + sp * PB_TALLY_EBINS + eb], w);    // (a warp-wide pre-sum per bin by shuffles was measured slower: 4.3 vs 3.0 ms per 7.5e7 records)
     double pt = sqrt(a0.y * a0.y + a1.x * a1.x);
     double th = atan2(pt, a1.y);
     int tb = (th > 0) ? (int)floor((log10(th) + 7.0) * (PB_TALLY_TBINS / 8.0)) : 0;
     tb = min(max(tb, 0), PB_TALLY_TBINS - 1);
-    atomicAdd(&mine[PB_TALLY_THIST + sp * PB_TALLY_TBINS + tb], w);
+    // Almost every record of a shower batch falls into the same handful of bins, and a shared-memory fp64 atomicAdd is a
+    // compare-and-swap loop: 32 lanes on one bin retry 32 times.  Lanes with the same (bin, weight) - weights are 1 except
+    // below a decay - elect a leader that adds weight x count once: a few atomics per warp instead of 32 serialised ones.
+    const unsigned same_w = __match_any_sync(0xffffffffu, __double_as_longlong(w));
+    const unsigned ge = __match_any_sync(0xffffffffu, sp * PB_TALLY_EBINS + eb) & same_w;
+    const unsigned gt = __match_any_sync(0xffffffffu, sp * PB_TALLY_TBINS + tb) & same_w;
+    if (w != 0.0) {
+      if (lane == __ffs(ge) - 1) atomicAdd(&mine[PB_TALLY_EHIST + sp * PB_TALLY_EBINS + eb], w * (double)__popc(ge));
+      if (lane == __ffs(gt) - 1) atomicAdd(&mine[PB_TALLY_THIST + sp * PB_TALLY_TBINS + tb], w * (double)__popc(gt));
+    }
   }
 #pragma unroll
   for (int k = 0; k < PB_TALLY_NSPECIES; ++k) {

@@ -761,6 +761,30 @@ class Shower:
         capi.check(self._engine, capi.lib.pb_find_max(self._engine, code, int(n_trials), int(seed), float(mT), capi.dptr(mf), capi.dptr(sg)))
         return mf, sg
 
+    def retrain_maps(self, processes=("Brem", "PairProd"), power=None, n_trials=100, seed=20261017, schedule=None):
+        """Rows f-2 + f-1 on this engine: retrain the VEGAS maps of ``processes`` on the GPU at the energies of the loaded set
+        (``petite_b200.train.Trainer``, training weight |jac f|^power, default 8: the accept/reject figure of merit), rebuild their
+        ``max_F`` for this target (``find_max``, utilities/find_maxes.py:55-119) and switch the sampler to them.  The sampled
+        distributions do not depend on the map (accept/reject is exact for any map whose ``max_F`` bounds jac f); the number of
+        trials per sample does: 10 GeV photons in lead need ~14 with the shipped maps.  -> {process: (sigma / shipped-map sigma,
+        efficiency / shipped-map efficiency)} per energy row."""
+        from .train import Trainer, TRAIN_POWER
+        tr = Trainer(device=self._device)
+        out = {}
+        for P in processes:
+            old = self._maps[P]
+            mf0, sg0 = self.find_max(P, n_trials=n_trials, seed=seed)
+            grids, ninc, _ = tr.train(P, old.E, power=TRAIN_POWER if power is None else power, schedule=schedule, seed=seed)
+            ms = tb.MapSet(P, old.E, ninc, grids, np.ones(len(old.E)), old.neval, old.Eg_min, old.Ee_min)
+            self._upload_maps(process_code[P], ms)
+            self._maps[P] = ms
+            mf, sg = self.find_max(P, n_trials=n_trials, seed=seed)
+            ms.max_F = mf
+            self._upload_maps(process_code[P], ms)
+            with np.errstate(all="ignore"):
+                out[P] = (sg / sg0, (sg / mf) / (sg0 / mf0))
+        return out
+
     def batch_from_particles(self, plist):
         """Upload an existing list of SM ``Particle`` objects as stack records (one pseudo-shower; fresh Philox keys)."""
         torch = self._torch
