@@ -205,7 +205,7 @@ int pb_train_accumulate(pb_engine e, int process, const double* grid, int n_ener
 /* The same with the training weight |jac*f|^power (0 < power <= 64) in d_out.  power = 2 is pb_train_accumulate, i.e. VEGAS'
  * variance criterion; the maps are USED for accept/reject sampling (shower.py:401-465), whose cost is max / mean of jac*f, and
  * a larger power trains for exactly that: power = 8 gives maps with 2.3-2.8x the accept rate of the shipped ones for Brem,
- * PairProd and MuonBrem (profiles/r03/exp_train_pow2.log); the integral through the map is unbiased for any power. */
+ * PairProd and MuonBrem (profiles/r02_final/exp_train_pow2.log); the integral through the map is unbiased for any power. */
 int pb_train_accumulate_p(pb_engine e, int process, const double* grid, int n_energy, int dim, const int32_t* ninc,
                           const double* E_inc, int64_t n_points, uint64_t seed, double mT, double power, double* d_out,
                           double* n_out, double* integral_out);

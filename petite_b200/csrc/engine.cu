@@ -479,12 +479,14 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   const int* __restrict__ order_c = W.list[2 * parity];
   const int* __restrict__ carry_in = W.carry[parity];
   int* __restrict__ carry_out = W.carry[parity ^ 1];
-  const unsigned cap_mask = W.loop_cap > 0 ? (unsigned)W.loop_cap - 1u : 0xffffffffu;
   // **Drain pause.**  When the list is dry a warp finishes the <= 32 tracks it holds at falling occupancy: the slowest of 32 geometric
   // sub-step counts takes ~30 iterations where the work is worth ~8 (a mid-size wave ran 23.6 of 32 lanes, profiles/r02z).  In a wave wide
   // enough to have filled every warp, a warp that is down to drain_lanes live tracks pauses them like tracks at the cap: the next
   // wave resumes them FIRST, packed into full warps.  Scheduling only (see the carry-over note above).
   const int drain_lanes = (W.drain_lanes > 0 && n_work >= 2 * (int)(gridDim.x * blockDim.x)) ? W.drain_lanes : 0;
+  // sub-step cap: in a wide wave the drain pause already removes the tail, and a cap of 2 K costs fewer extra waves (measured with
+  // K = 32: 129.8 -> 128.7 ms per config-2 step, 123 -> 114 waves); narrow waves, where the cap IS the critical path, keep K
+  const unsigned cap_mask = W.loop_cap > 0 ? (unsigned)(drain_lanes ? 2 * W.loop_cap : W.loop_cap) - 1u : 0xffffffffu;
   const int lane = threadIdx.x & 31;
   LoopBuf* buf = s_buf[threadIdx.x >> 5];
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -1721,7 +1723,7 @@ k_train(const __grid_constant__ Material M, int process, int dim, int stride, in
       acc += f;
       // training weight |jac f|^p.  p = 2 is Lepage's variance criterion (what vegas trains on); the SAMPLER's figure of merit is
       // mean / max of jac f, and a larger p flattens the peaks that set max_F (p = 8: 2.3-2.8x the accept rate of the shipped maps,
-      // profiles/r03/exp_train_pow2.log).  Only ratios within an axis matter to the refinement; the clamp keeps the sums finite.
+      // profiles/r02_final/exp_train_pow2.log).  Only ratios within an axis matter to the refinement; the clamp keeps the sums finite.
       double f2 = (power == 2.0) ? f * f : fmin(pow(fabs(f), power), 1e250);
       for (int d = 0; d < dim; ++d) { atomicAdd(&s_d[off[d] + iy[d]], f2); atomicAdd(&s_n[off[d] + iy[d]], 1); }
     }
@@ -2685,7 +2687,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     if (hws->status != 0) break;
     if (const char* lw = getenv("PB_LOG_WAVES")) {        // measurement aid: sizes of the waves the host sees
       if (FILE* f = fopen(lw, "a")) {
-        fprintf(f, "wave %d n %d n_charged %d", hws->waves, hws->n, hws->n_charged);
+        fprintf(f, "wave %d n %d n_charged %d n_new %d n_carry %d", hws->waves, hws->n, hws->n_charged, hws->n_new, hws->n_carry);
         if (plevel >= 2) { fprintf(f, " ms"); for (int k = 1; k < PB_K_N; ++k) fprintf(f, " %.4f", e->prof.ms[k] - ms_before[k]); }   // this wave's kernels
         fprintf(f, "\n");
         fclose(f);

@@ -33,7 +33,7 @@ def test_refine_concentrates_increments_where_the_integrand_is():
 def test_trained_maps_reproduce_shipped_cross_sections(process):
     """Train on hydrogen as the reference does (default schedule, training weight |jac f|^8), then integrate graphite through the
     NEW maps: sigma must reproduce the shipped sm_xsec rows, and the accept/reject efficiency sigma / (B max_F) must reach the shipped
-    maps' (row f-2; measured 2.3-2.8x for the 4-D processes, profiles/r03/exp_train_pow2.log).  The plain VEGAS criterion
+    maps' (row f-2; measured 2.3-2.8x for the 4-D processes, profiles/r02_final/exp_train_pow2.log).  The plain VEGAS criterion
     (power = 2) is kept as the comparison: same sigma, lower efficiency."""
     from petite_b200.train import Trainer
     from petite_b200 import tables as tb

@@ -17,6 +17,7 @@ DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "data", ""
 ap = argparse.ArgumentParser()
 ap.add_argument("--primaries", type=int, default=100_000)
 ap.add_argument("--dark", action="store_true")
+ap.add_argument("--profiling", type=int, default=0, help="2 with PB_LOG_WAVES=<file>: every wave's sizes and per-kernel times")
 a = ap.parse_args()
 n = a.primaries
 if a.dark:
@@ -27,6 +28,8 @@ if a.dark:
 else:
     sh = Shower(DATA, "lead", 0.010, seed=20261017)
     E0, pid, mass, per = 10.0, 22, 0.0, 1800
+if a.profiling:
+    sh.set_profiling(a.profiling)
 p = np.tile([E0, 0.0, 0.0, np.sqrt(E0 ** 2 - mass ** 2)], (n, 1))
 b = sh.run_arrays(p, np.zeros((n, 3)), np.ones(n), np.full(n, mass), np.full(n, pid, dtype=np.int32), np.zeros(n, dtype=np.int32),
                   capacity=n * per, first_shower_id=0)
