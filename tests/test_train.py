@@ -92,3 +92,37 @@ def test_trained_dark_brem_maps_reproduce_shipped_dark_xsec():
     mf, sg = ds.find_max("DarkBrem", n_trials=100, seed=4)
     assert np.all(np.abs(sg / xs[rows, 1] - 1) < 0.05), sg / xs[rows, 1]
     assert np.all(sg / (300 * mf) > 0.01)
+
+
+@pytest.mark.gpu
+def test_retrain_maps_same_showers_statistically_fewer_trials():
+    """Shower.retrain_maps (rows f-2 + f-1 on a live engine): accept/reject is exact for any map whose max_F bounds jac f, so the
+    showers must be the same PHYSICS (per-shower multiplicity and photon count distributions: two-sample KS; the means within
+    4 standard errors) while the sampler spends fewer trials per sample.  4 000 showers of 3 GeV photons in lead each way."""
+    from scipy import stats
+    import torch
+    from petite_b200.shower import Shower
+    from tests.gpu_util import primaries
+
+    def run(sh, first):
+        b = sh.generate_showers(primaries(22, 3.0, 4000), first_shower_id=first)
+        t, m = b._t, b.n
+        sid = t["meta"][:m, 3].long()
+        mult = torch.bincount(sid, minlength=4000).cpu().numpy()
+        phot = torch.bincount(sid, weights=(t["meta"][:m, 0] == 22).double(), minlength=4000).cpu().numpy()
+        return mult, phot, b.counters["n_trials"] / b.counters["n_samples"]
+
+    sh = Shower(DATA, "lead", 0.010, seed=31)
+    m0, g0, tps0 = run(sh, 0)
+    gain = sh.retrain_maps()
+    assert set(gain) == {"Brem", "PairProd"}
+    for P, (sig, eff) in gain.items():
+        ok = np.isfinite(sig) & (sig > 0)
+        assert abs(np.median(sig[ok]) - 1) < 0.02, (P, np.median(sig[ok]))           # same cross-sections through the new maps
+        assert np.exp(np.mean(np.log(eff[ok & np.isfinite(eff) & (eff > 0)]))) > 1.0, P
+    m1, g1, tps1 = run(sh, 100_000)                                                  # other shower ids: independent showers
+    print("trials per sample", tps0, "->", tps1, "multiplicity", m0.mean(), m1.mean())
+    assert tps1 < 0.9 * tps0
+    for a, b in ((m0, m1), (g0, g1)):
+        assert stats.ks_2samp(a, b).pvalue > 1e-3
+        assert abs(a.mean() - b.mean()) < 4 * np.sqrt(a.var() / len(a) + b.var() / len(b))
