@@ -38,10 +38,16 @@ class _NodeGrid:
 
 
 class _Unpickler(pickle.Unpickler):
+    """The reference's table pickles hold dicts / lists of NumPy arrays and ``vegas`` objects (replaced by ``_NodeGrid``); nothing
+    else is allowed to be constructed while loading one."""
+    _ALLOWED = ("numpy", "builtins", "collections", "copyreg", "_codecs")
+
     def find_class(self, module, name):
         if module.startswith("vegas"):
             return _NodeGrid
-        return super().find_class(module, name)
+        if module.split(".")[0] in self._ALLOWED and not (module == "builtins" and name in ("eval", "exec", "compile", "open", "__import__", "getattr")):
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"table pickle refers to {module}.{name}: only NumPy / builtin containers and vegas maps are expected")
 
 
 def load_reference_pickle(path):
