@@ -78,6 +78,7 @@ typedef struct pb_stack {
 } pb_stack;
 
 #define PB_FLAG_SHORT_LIVED 1   /* ids['stability'] == 'short-lived' */
+#define PB_FLAG_LONG_LIVED 4    /* ids['stability'] == 'long-lived': pi+-, K+- decay in flight (particle.py:410-422) */
 #define PB_FLAG_NO_SAMPLE 2     /* sampler exhausted */
 
 /* Primaries (host SoA): what the caller's loop over Particle objects feeds generate_shower with. */
@@ -87,7 +88,7 @@ typedef struct pb_primaries {
   const double* weight;   /* [host] n */
   const double* mass;     /* [host] n   ids['mass'] (particle.py:125-131 back-computed value if absent) */
   const int32_t* pid;     /* [host] n */
-  const int32_t* flags;   /* [host] n   PB_FLAG_SHORT_LIVED for pi0 etc. */
+  const int32_t* flags;   /* [host] n   PB_FLAG_SHORT_LIVED for pi0 etc., PB_FLAG_LONG_LIVED for pi+-, K+- */
   int64_t n;
   int64_t on_device;      /* 0: the six arrays are host memory (copied inside the call); 1: they are [dev] already */
 } pb_primaries;
@@ -262,7 +263,7 @@ int pb_probe(pb_engine e, int what, int process, const double* in, int64_t n, in
  *   photon:  random() (free path);
  *   then the process choice uniform, then per tested trial  y_0 .. y_{dim-1}, u_accept,  then the kinematics azimuth uniform
  *   (two uniforms for a short-lived decay instead of all of the above).
- * particles [host]: n x 10 doubles: pid, E, px, py, pz, x, y, z, mass, flags (1 = multiple scattering on, 2 = short-lived).
+ * particles [host]: n x 10 doubles: pid, E, px, py, pz, x, y, z, mass, flags (1 = multiple scattering on, 2 = short-lived, 4 = long-lived).
  * out [host]: n x 32 doubles: 0 status (0 ok, 1 tape ran out, 2 tape not used up, 3 no sample), 1 sub-steps, 2 process code,
  *   3 trials, 4-7 pf, 8-10 rf, 11 kept daughters (bit 0 / bit 1), 12 pid_a, 13-16 p_a, 17 pid_b, 18-21 p_b, 22-25 sampled x,
  *   26 tape entries consumed, 27 weight factor, 28 propagated (1) / below threshold (0). */

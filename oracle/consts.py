@@ -44,6 +44,11 @@ MASS = {11: m_electron, -11: m_electron, 12: 0.0, -12: 0.0, 22: 0.0,
         211: m_pi_pm, -211: m_pi_pm, 321: m_K_pm, -321: m_K_pm,
         221: m_eta, 331: m_eta_prime, 2212: m_proton, 223: m_omega}
 
+# particle.py:15-20 (interaction lengths and c tau of the long-lived mesons, metres; physical_constants.py:31-33)
+c_tau_pi_pm, c_tau_K_pm = 7.8045, 3.711
+INT_LENGTH = {211: 1.796e-1, -211: 1.796e-1, 321: 2.2875e-1, -321: 2.2875e-1}
+DECAY_LENGTH = {211: c_tau_pi_pm, -211: c_tau_pi_pm, 321: c_tau_K_pm, -321: c_tau_K_pm}
+
 # particle.py:40-47 (first = two-body branching ratio)
 MESON_DECAYS = {111: [[0.98823, [22, 22]]],
                 221: [[0.3936, [22, 22]], [0.3257, [111, 111, 111]]],

@@ -50,6 +50,10 @@ class StreamDraws:
     def decay(self, pc=12):
         return np.random.random(), np.random.random()
 
+    def decay_x(self, loop, i):
+        # particle.py:371-372: np.random.uniform(0, x_max), np.random.uniform(0, 1) per accept/reject iteration
+        return np.random.random(), np.random.random()
+
     def dbin(self, pc):
         return np.random.random()
 
@@ -121,6 +125,10 @@ class CounterDraws:
 
     def decay(self, pc=12):
         return self._d(0, ph.ST_DECAY, 0, pc)
+
+    def decay_x(self, loop, i):
+        # i-th (x, u) pair of accept/reject loop 1 (path length), 2, 3 (the daughters' weights) of a decay in flight
+        return self._d(i, ph.ST_DECAY, loop, 12)
 
     def dbin(self, pc):
         return self._d(0, ph.ST_DBIN, 0, pc)[0]

@@ -2,7 +2,7 @@
 
 Restates reference ``src/PETITE/shower.py``: table set-up :202-320, get_mfp :370-389, draw_sample :401-465,
 sample_scattering :467-507, propagate_particle :509-601, generate_shower :603-708, and
-``particle.py:391-409`` (short-lived two-body decays).  Reads this repo's ``data/*.npz`` tables (the same
+``particle.py:363-424`` (short-lived two-body decays; decay in flight of the long-lived pi+-, K+-).  Reads this repo's ``data/*.npz`` tables (the same
 numbers as the reference's pickles, repacked by tools/pack_reference_data.py) and the regenerated max_F.
 """
 import math
@@ -290,7 +290,27 @@ class OracleShower:
                 p.pf = self._mcs(p.pf, last, C.m_electron, d, MCS_FINAL_INDEX)
         p.ended = True
 
-    # ---- particle.py:391-409 (short-lived only) ----
+    # ---- particle.py:363-389 (draw_x_sample, prob_decay_b_int) ----
+    @staticmethod
+    def _decay_rates(p, int_length, ctau0):
+        E = p.p0[0]                                      # particle.py:358, 381: the energy at creation
+        gamma = E / p.mass
+        beta = np.sqrt(1 - 1 / gamma ** 2)
+        ctau = ctau0 * gamma * beta
+        return ctau, 1.0 / ctau + 1.0 / int_length
+
+    def _draw_x(self, p, loop, tot_rate):
+        c = tot_rate                                     # decay_int_prob(0)[0]
+        x_max = 4 / (tot_rate * np.exp(-tot_rate * 0))   # 4 / decay_int_prob(0)[1]
+        i = 0
+        while True:
+            u1, u2 = p.draws.decay_x(loop, i)
+            x = 0 + (x_max - 0) * u1                     # np.random.uniform(0, x_max)
+            if u2 < tot_rate * np.exp(-tot_rate * x) / c:
+                return x
+            i += 1
+
+    # ---- particle.py:391-424 ----
     def decay(self, p):
         if p.PID not in C.MESON_DECAYS:
             raise ValueError("Decay options for particle not specified.")
@@ -298,14 +318,25 @@ class OracleShower:
         if len(opts) != 1:
             raise NotImplementedError("multi-channel decays are outside the hot-path scope (SURVEY.md 2)")
         br, dec = opts[0]
-        if len(dec) != 2 or p.stability != "short-lived":
-            raise ValueError("only short-lived two-body decays are in scope")
+        if len(dec) != 2 or p.stability not in ("short-lived", "long-lived"):
+            raise ValueError("only two-body decays are in scope")
+        weights = [p.weight * br, p.weight * br]
+        if p.stability == "long-lived":                  # particle.py:410-422: decay in flight of pi+-, K+-
+            int_length, ctau0 = C.INT_LENGTH[p.PID], C.DECAY_LENGTH[p.PID]
+            ctau, tot_rate = self._decay_rates(p, int_length, ctau0)
+            delta_z = self._draw_x(p, 1, tot_rate)
+            pf0 = float(np.linalg.norm(p.pf[1:]))
+            if pf0 > 0.0:
+                p.rf = [p.rf[k] + p.pf[1 + k] / pf0 * delta_z for k in range(3)]
+            for bit in range(2):                         # prob_decay_b_int draws its own x for EACH daughter dictionary
+                x = self._draw_x(p, 2 + bit, tot_rate)
+                weights[bit] = p.weight * br * ((1 - np.exp(-tot_rate * x)) / (1 + ctau / int_length))
         uc, up = p.draws.decay()
         v1, v2 = phy.two_body_decay(p.pf, p.mass, C.MASS[dec[0]], C.MASS[dec[1]], uc, up)
         out = []
         for bit, (v, pid) in enumerate(zip((v1, v2), dec)):
             dd = OParticle(v, p.rf, PID=pid, ID=2 * p.ID + bit, gen=p.gen + 1, process="SMDecay",
-                           weight=p.weight * br, mass=C.MASS[pid])      # Q-10: parent_PID/parent_ID defaults
+                           weight=weights[bit], mass=C.MASS[pid])      # Q-10: parent_PID/parent_ID defaults
             dd.draws = p.draws.child(bit)
             out.append(dd)
         p.ended = True

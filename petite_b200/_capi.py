@@ -103,7 +103,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _f.argtypes = _args
 
 PB_OK, PB_ERR_CUDA, PB_ERR_ARG, PB_ERR_CAPACITY, PB_ERR_STATE, PB_ERR_NO_SAMPLE = 0, -1, -2, -3, -4, -5
-PB_FLAG_SHORT_LIVED, PB_FLAG_NO_SAMPLE = 1, 2
+PB_FLAG_SHORT_LIVED, PB_FLAG_NO_SAMPLE, PB_FLAG_LONG_LIVED = 1, 2, 4
 PROBE_DSIGMA, PROBE_NSIGMA, PROBE_MAP, PROBE_MCS, PROBE_KIN, PROBE_PHILOX, PROBE_HOTMATH, PROBE_MCS_FAST, PROBE_SUBSTEP, PROBE_DARKKIN, PROBE_PROPAGATE = range(11)
 
 

@@ -344,6 +344,7 @@ struct PhiloxDraws {
   __device__ __forceinline__ double choice_u() { return draw2(key, 0, ST_CHOICE).a; }
   __device__ __forceinline__ double kin_u(int proc) { return draw2(key, 0, ST_KIN, 0, proc).a; }
   __device__ __forceinline__ D2 decay_u(int proc) { return draw2(key, 0, ST_DECAY, 0, proc); }
+  __device__ __forceinline__ D2 decay_x(uint32_t loop, uint32_t i) { return draw2(key, i, ST_DECAY, loop, P_SMDECAY); }   // i-th (x, u) pair of accept/reject loop 1..3 of a decay in flight
 };
 struct TapeDraws {             // sequential reader; `over` is set if the tape runs out (a decision differed from the recording)
   const double* t; long long pos, end; bool over;
@@ -356,6 +357,7 @@ struct TapeDraws {             // sequential reader; `over` is set if the tape r
   __device__ __forceinline__ double choice_u() { return next(); }
   __device__ __forceinline__ double kin_u(int) { return next(); }
   __device__ __forceinline__ D2 decay_u(int) { double a = next(), b = next(); return D2{a, b}; }
+  __device__ __forceinline__ D2 decay_x(uint32_t, uint32_t) { double a = next(), b = next(); return D2{a, b}; }
 };
 
 // One iteration of the dE/dx + multiple-scattering loop (shower.py:559-581) on a track: true = the loop ends here (energy
@@ -658,8 +660,8 @@ __device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, 
       }
     }
   } else {
-    if (flags & PB_FLAG_SHORT_LIVED) {
-      bucket = P_SMDECAY * LU_MAX;                                      // particle.py:391-409, decays in k_emit
+    if (flags & (PB_FLAG_SHORT_LIVED | PB_FLAG_LONG_LIVED)) {
+      bucket = P_SMDECAY * LU_MAX;                                      // particle.py:391-424, decays in k_emit
     } else if (pid == 22) {
       double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
       if (!(p.E < pmin)) {                                              // shower.py:538-553 (MS_g is always False)
@@ -672,7 +674,7 @@ __device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, 
       }
     }
   }
-  if (cls >= 0 && !(flags & PB_FLAG_SHORT_LIVED)) {
+  if (cls >= 0 && !(flags & (PB_FLAG_SHORT_LIVED | PB_FLAG_LONG_LIVED))) {
     // process choice (shower.py:665-698) and the sample_scattering threshold (shower.py:469)
     double Ef = p.E;
     int cand[3]; double c[3]; int nc;
@@ -1247,15 +1249,53 @@ k_sample(const __grid_constant__ Material M, const __grid_constant__ Tables T_, 
 
 // Hard scatter or decay of ONE particle: sampled point -> two four-vectors in the parent frame (kinematics.py) -> lab frame
 // (particle.py:176-185, shower.py:471-480), PDG ids of the two products (shower.py:77-96) and the weight factor (decays).
+// Decay in flight of a long-lived meson, pi+- / K+- -> mu nu (particle.py:363-389 draw_x_sample / prob_decay_b_int, :410-422): the
+// distance to the decay point is drawn by accept/reject from tot_rate exp(-tot_rate x) on [0, 4 / tot_rate], and EACH daughter's
+// weight carries BR x P(decay before interaction) evaluated at its own, independently drawn x (the reference calls
+// prob_decay_b_int once per daughter dictionary).  One accept/reject loop: `loop` = 1 (path), 2, 3 (the two weights).
 template <class DS>
-__device__ __forceinline__ void scatter_products(int proc, int pid, V4 pf, double mass, const double* x, DS& ds,
-                                                 V4& da, V4& db, int& pid_a, int& pid_b, double& wfac) {
-  wfac = 1.0;
-  if (proc == P_SMDECAY) {                                     // pi0 -> gamma gamma (particle.py:391-409)
+__device__ __forceinline__ double decay_draw_x(DS& ds, uint32_t loop, double tot_rate) {
+  const double x_max = 4.0 / (tot_rate * 1.0);
+  double x = 0.0;
+  for (uint32_t i = 0; i < (1u << 20); ++i) {
+    D2 u = ds.decay_x(loop, i);
+    x = x_max * u.a;                                            // np.random.uniform(0, x_max)
+    if (u.b < (tot_rate * exp(-tot_rate * x)) / tot_rate) break;
+  }
+  return x;
+}
+// The three accept/reject loops of one decay in flight.  Only primaries can be long-lived (daughters are created 'stable'), so the
+// engine runs this once per primary in k_init_primaries and k_emit only reads the three numbers (PRE = true): the loops and their
+// exponentials stay out of k_emit's register budget.  The tape-driven replay (k_replay) draws in line, in the reference's order.
+template <class DS>
+__device__ __forceinline__ void decay_in_flight_draws(DS& ds, int pid, double E, double mass, double* dz, double* wfac, double* wfac_b) {
+  const bool kaon = pid == 321 || pid == -321;
+  const double int_len = kaon ? 2.2875e-1 : 1.796e-1, ctau0 = kaon ? 3.711 : 7.8045, br = kaon ? 0.6356 : 0.9998;     // particle.py:15-20, 44-47
+  const double gamma = E / mass;                                // the energy at creation (particle.py:358, 381)
+  const double beta = sqrt(1 - 1 / (gamma * gamma));
+  const double ctau = ctau0 * gamma * beta;
+  const double tot_rate = 1.0 / ctau + 1.0 / int_len;
+  *dz = decay_draw_x(ds, 1, tot_rate);
+  const double den = 1 + ctau / int_len;
+  *wfac = br * ((1 - exp(-tot_rate * decay_draw_x(ds, 2, tot_rate))) / den);
+  *wfac_b = br * ((1 - exp(-tot_rate * decay_draw_x(ds, 3, tot_rate))) / den);
+}
+template <bool PRE, class DS>
+__device__ __forceinline__ void scatter_products(int proc, int pid, int flags, V4 pf, double mass, const double* x, DS& ds,
+                                                 V4& da, V4& db, int& pid_a, int& pid_b, double& wfac, double& wfac_b, double& dz) {
+  wfac = 1.0; wfac_b = 1.0; dz = 0.0;
+  if (proc == P_SMDECAY) {
+    double m1 = 0.0;
+    if (flags & PB_FLAG_LONG_LIVED) {                          // pi+- / K+- -> mu nu in flight (particle.py:410-422)
+      pid_a = pid > 0 ? -13 : 13; pid_b = pid > 0 ? 14 : -14;
+      m1 = kMmu;
+      if (!PRE) decay_in_flight_draws(ds, pid, pf.E, mass, &dz, &wfac, &wfac_b);      // PRE: the caller applies the numbers k_init_primaries drew
+    } else {                                                   // pi0 -> gamma gamma (particle.py:391-409)
+      pid_a = 22; pid_b = 22;
+      wfac = wfac_b = 0.98823;                                 // particle.py:40 meson_decay_dict[111]
+    }
     D2 u = ds.decay_u(P_SMDECAY);
-    two_body_decay(pf, mass, 0.0, 0.0, u.a, u.b, &da, &db);
-    pid_a = 22; pid_b = 22;
-    wfac = 0.98823;                                            // particle.py:40 meson_decay_dict[111]
+    two_body_decay(pf, mass, m1, 0.0, u.a, u.b, &da, &db);
     return;
   }
   double u_az = ds.kin_u(proc);
@@ -1274,7 +1314,8 @@ __device__ __forceinline__ void scatter_products(int proc, int pid, V4 pf, doubl
 
 // Kinematics + rotation + daughter append, in bucket order (warps are process-coherent).
 __global__ void PB_EMIT_BOUNDS
-k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, int wave_order) {
+k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W, int wave_order,
+       const double* __restrict__ decay_aux) {
   const long long begin = W.ws->begin;
   const int n = W.ws->n, n_new = W.ws->n_new, parity = W.ws->parity;
   int* __restrict__ next_c = W.list[2 * (parity ^ 1)];
@@ -1320,8 +1361,8 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       int pid = meta.x;
       double x[4] = {x01.x, x01.y, x23.x, x23.y};
       PhiloxDraws ds{key};
-      double wfac;
-      scatter_products(proc, pid, pf, mass, x, ds, da, db, pid_a, pid_b, wfac);
+      double wfac, wfac_b, dz;
+      scatter_products<true>(proc, pid, (meta.z >> 8) & 0x7f, pf, mass, x, ds, da, db, pid_a, pid_b, wfac, wfac_b, dz);
       wgt *= wfac;
       keep_a = da.E > M.min_energy;                                // shower.py:704-706
       keep_b = db.E > M.min_energy;
@@ -1357,6 +1398,22 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
   }
   __syncthreads();
   const unsigned long long base = s_base[wid], lbase = s_lbase[wid];
+  // decay in flight of a long-lived primary (pi+-, K+-: particle.py:410-422): path and weight factors were drawn by k_init_primaries
+  // (decay_aux: dz, factor of the first daughter, of the second).  The parent ends where it decays, the daughters start there.
+  // Read here, late, so that the rare branch holds no registers across the kinematics above.
+  const bool in_flight = proc == P_SMDECAY && ((meta.z >> 8) & PB_FLAG_LONG_LIVED);
+  if (in_flight) {
+    const double dz = decay_aux[3 * slot];
+    const double2* pfp = reinterpret_cast<const double2*>(S.pf + 4 * slot);
+    const double2 q0 = pfp[0], q1 = pfp[1];
+    const double pn = sqrt(q0.y * q0.y + q1.x * q1.x + q1.y * q1.y);
+    if (pn > 0.0) {
+      rx += q0.y / pn * dz; ry += q1.x / pn * dz; rz += q1.y / pn * dz;
+      double2* rfo = reinterpret_cast<double2*>(S.rf + 4 * slot);
+      const double m = rfo[1].y;
+      rfo[0] = make_double2(rx, ry); rfo[1] = make_double2(rz, m);
+    }
+  }
   if (cnt) {
     long long dst = (long long)base + (incl - cnt);
     int ci = (int)(lbase & 0xffffffffu) + (inch - cch);
@@ -1371,8 +1428,9 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
       double2* p0p = reinterpret_cast<double2*>(S.p0 + 4 * dst);
       double2* r0p = reinterpret_cast<double2*>(S.r0w + 4 * dst);
       p0p[0] = make_double2(d.E, d.x); p0p[1] = make_double2(d.y, d.z);
-      r0p[0] = make_double2(rx, ry);   r0p[1] = make_double2(rz, wgt);
-      st_ids(S, dst, make_int4(bit ? pid_b : pid_a, (int)slot, pack_info(gen, bit, 0, proc), meta.w), child_key(key, bit), wgt);
+      const double wd = in_flight ? wgt * decay_aux[3 * slot + 1 + bit] : wgt;      // each daughter of a decay in flight has its own factor
+      r0p[0] = make_double2(rx, ry);   r0p[1] = make_double2(rz, wd);
+      st_ids(S, dst, make_int4(bit ? pid_b : pid_a, (int)slot, pack_info(gen, bit, 0, proc), meta.w), child_key(key, bit), wd);
       if (bit ? ch_b : ch_a) {
         next_c[ci++] = (int)(dst - next_begin);
         store_track_setup(M, T, S, dst, bit ? pid_b : pid_a, pid_mass(bit ? pid_b : pid_a), d.E, d.x, d.y, d.z);
@@ -1386,14 +1444,18 @@ k_emit(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
 __global__ void k_init_primaries(const __grid_constant__ Material M, const __grid_constant__ Tables T, Stack S, Work W,
                                  const double* __restrict__ p, const double* __restrict__ r, const double* __restrict__ w,
                                  const double* __restrict__ mass, const int* __restrict__ pid, const int* __restrict__ flags,
-                                 long long n, unsigned long long seed, unsigned long long first_id) {
+                                 long long n, unsigned long long seed, unsigned long long first_id, double* __restrict__ decay_aux) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (flags[i] & PB_FLAG_LONG_LIVED) {                     // decay in flight: the draws k_emit will apply (scatter_products<true>)
+    PhiloxDraws ds{root_key(seed, first_id + (unsigned long long)i)};
+    decay_in_flight_draws(ds, pid[i], p[4 * i], mass[i], decay_aux + 3 * i, decay_aux + 3 * i + 1, decay_aux + 3 * i + 2);
+  }
   for (int k = 0; k < 4; ++k) S.p0[4 * i + k] = p[4 * i + k];
   for (int k = 0; k < 3; ++k) S.r0w[4 * i + k] = r[3 * i + k];
   S.r0w[4 * i + 3] = w[i];
   st_ids(S, i, make_int4(pid[i], -1, pack_info(0, 0, flags[i], P_INPUT), (int)i), root_key(seed, first_id + (unsigned long long)i), w[i]);
-  const bool ch = is_charged(pid[i]) && !(flags[i] & PB_FLAG_SHORT_LIVED);
+  const bool ch = is_charged(pid[i]) && !(flags[i] & (PB_FLAG_SHORT_LIVED | PB_FLAG_LONG_LIVED));
   unsigned long long old = atomicAdd(&W.tail[1], ch ? 1ull : (1ull << 32));
   if (ch) {
     W.list[2][(int)(old & 0xffffffffu)] = (int)i;          // parity 1: the first k_wave_begin flips 0 -> 1
@@ -1862,7 +1924,7 @@ __global__ void k_replay(const __grid_constant__ Material M, const __grid_consta
   const int pid = (int)a[0];
   const double mass = a[8];
   const int fl = (int)a[9];
-  const int ms_e = fl & 1, flags = (fl & 2) ? PB_FLAG_SHORT_LIVED : 0;
+  const int ms_e = fl & 1, flags = ((fl & 2) ? PB_FLAG_SHORT_LIVED : 0) | ((fl & 4) ? PB_FLAG_LONG_LIVED : 0);
   const bool charged = is_charged(pid) && !flags;
   V4 p{a[1], a[2], a[3], a[4]};
   double rx = a[5], ry = a[6], rz = a[7], delta_z = 0.0;
@@ -1916,8 +1978,12 @@ __global__ void k_replay(const __grid_constant__ Material M, const __grid_consta
   }
   V4 da{0, 0, 0, 0}, db{0, 0, 0, 0};
   int pid_a = 0, pid_b = 0;
-  double wfac = 1.0;
-  if (proc != P_NONE && proc != P_INPUT) scatter_products(proc, pid, p, mass, x, ds, da, db, pid_a, pid_b, wfac);
+  double wfac = 1.0, wfac_b = 1.0, dz = 0.0;
+  if (proc != P_NONE && proc != P_INPUT) scatter_products<false>(proc, pid, flags, p, mass, x, ds, da, db, pid_a, pid_b, wfac, wfac_b, dz);
+  if (dz != 0.0) {
+    const double pn = sqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+    if (pn > 0.0) { rx += p.x / pn * dz; ry += p.y / pn * dz; rz += p.z / pn * dz; }
+  }
   if (ds.over) status = 1;
   else if (ds.pos != ds.end && status == 0) status = 2;
   o[0] = status; o[1] = nsub; o[2] = proc; o[3] = (double)ntr;
@@ -1927,6 +1993,7 @@ __global__ void k_replay(const __grid_constant__ Material M, const __grid_consta
   o[17] = pid_b; o[18] = db.E; o[19] = db.x; o[20] = db.y; o[21] = db.z;
   o[22] = x[0]; o[23] = x[1]; o[24] = x[2]; o[25] = x[3];
   o[26] = (double)(ds.pos - tape_off[i]); o[27] = wfac; o[28] = stepped ? 1.0 : 0.0;
+  o[29] = wfac_b;
 }
 
 // ------------------------------------------------------------------------------------------ dark set-up quadratures (row f-3)
@@ -2515,7 +2582,7 @@ static int ensure_wave_graph(pb_engine e, const Stack& S, int ms_flag) {
   SampleIO io{S.pf, reinterpret_cast<const uint2*>(S.ids), 4, 2, nullptr, reinterpret_cast<int*>(S.aux), 2, e->work.ws};
   k_bucket_fill<<<g_fill, 256, 0, cs>>>(e->work, io, -1);
   launch_sample(e, 1LL << 40, io, cs, true);
-  k_emit<<<g_emit, 128, 0, cs>>>(e->mat, e->tab, S, e->work, e->emit_wave_order);
+  k_emit<<<g_emit, 128, 0, cs>>>(e->mat, e->tab, S, e->work, e->emit_wave_order, e->prim_mass + e->prim_cap);
   cudaError_t ce = cudaStreamEndCapture(cs, nullptr);
   if (ce != cudaSuccess) { e->err = std::string("wave graph capture: ") + cudaGetErrorString(ce); return PB_ERR_CUDA; }
   PB_CUDA(e, cudaGraphInstantiate(&e->wave_exec, e->wave_graph, 0));
@@ -2546,7 +2613,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
   }
   if (n0 > e->prim_cap) {
     if (e->prim_mass) cudaFree(e->prim_mass);
-    PB_CUDA(e, cudaMalloc(&e->prim_mass, sizeof(double) * n0));
+    PB_CUDA(e, cudaMalloc(&e->prim_mass, sizeof(double) * 4 * n0));      // masses, then (decay path, two weight factors) per primary: k_init_primaries
     e->prim_cap = n0;
   }
   char* sp = (char*)e->prim_stage;
@@ -2606,7 +2673,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
     }
   };
   tick(PB_K_INIT, 0);
-  k_init_primaries<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(e->mat, e->tab, S, e->work, d_p, d_r, d_w, e->prim_mass, d_pid, d_fl, n0, seed, first_id);
+  k_init_primaries<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(e->mat, e->tab, S, e->work, d_p, d_r, d_w, e->prim_mass, d_pid, d_fl, n0, seed, first_id, e->prim_mass + e->prim_cap);
   tock(PB_K_INIT, 0);
   ++e->prof.launches[PB_K_INIT];
   ++launches;
@@ -2662,7 +2729,7 @@ extern "C" int pb_run_showers(pb_engine e, const pb_primaries* prim, uint64_t se
       tock(PB_K_FILL, j); tick(PB_K_SAMPLE, j);
       launch_sample(e, bound, io, stream, true);
       tock(PB_K_SAMPLE, j); tick(PB_K_EMIT, j);
-      k_emit<<<g128, 128, 0, stream>>>(e->mat, e->tab, S, e->work, e->emit_wave_order);
+      k_emit<<<g128, 128, 0, stream>>>(e->mat, e->tab, S, e->work, e->emit_wave_order, e->prim_mass + e->prim_cap);
       tock(PB_K_EMIT, j);
       launches += 7;
     }

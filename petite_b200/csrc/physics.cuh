@@ -14,6 +14,8 @@ constexpr double kMe = 510.998950 * 1e-6;
 constexpr double kMmu = 105.6583755 * 1e-3;
 constexpr double kMp = 938.272088 * 1e-3;
 constexpr double kMpi0 = 134.9768 * 1e-3;
+constexpr double kMpipm = 139.57039 * 1e-3;   // physical_constants.py:32-33
+constexpr double kMKpm = 493.677 * 1e-3;
 constexpr double kPi = 3.141592653589793;
 constexpr double kTwoPi = 2.0 * 3.141592653589793;
 constexpr double kCmToM = 0.01;
@@ -61,6 +63,8 @@ __host__ __device__ __forceinline__ double pid_mass(int pid) {  // particle.py:4
     case 11: case -11: return kMe;
     case 13: case -13: return kMmu;
     case 111: return kMpi0;
+    case 211: case -211: return kMpipm;
+    case 321: case -321: return kMKpm;
     default: return 0.0;
   }
 }

@@ -439,10 +439,15 @@ class Shower:
             r[i] = np.asarray(q.get_r0(), dtype=np.float64)
             w[i] = ids["weight"]; m[i] = ids["mass"]; pid[i] = ids["PID"]
             st = ids["stability"]
-            if st in ("short-lived", "long-lived"):
-                if st == "long-lived" or ids["PID"] != 111:
+            if st == "short-lived":
+                if ids["PID"] != 111:
+                    # eta / eta' pick a three-body channel at random and raise, omega's pi0 daughter is never ended (particle.py:391-409)
                     raise ValueError("only short-lived pi0 -> gamma gamma decays are handled on the GPU path")
                 fl[i] = capi.PB_FLAG_SHORT_LIVED
+            elif st == "long-lived":
+                if abs(ids["PID"]) not in (211, 321):
+                    raise ValueError("Decay options for particle not specified.")      # particle.py:392-393 / int_length_dict
+                fl[i] = capi.PB_FLAG_LONG_LIVED                                        # pi+-, K+- -> mu nu in flight (particle.py:410-422)
             elif ids["PID"] not in _STEPPING_PIDS and abs(ids["PID"]) != 14:
                 # the reference never ends such a particle and loops forever (SURVEY Q-20)
                 raise ValueError(f"stable PID {ids['PID']} cannot be showered")
@@ -734,7 +739,7 @@ class Shower:
         """Replay mode (``pb_replay``): run ``n`` independent particle-steps - propagation, process choice, accept/reject
         sampling, kinematics - through the wave kernels' own device functions with every random number taken from a TAPE
         recorded from a reference run (layout: include/petite_b200.h).  ``particles`` (n, 10): pid, p0[4], r0[3], mass, flags
-        (1 = multiple scattering on, 2 = short-lived); ``tape`` (m,) doubles; ``tape_off`` (n + 1,) segment offsets.
+        (1 = multiple scattering on, 2 = short-lived, 4 = long-lived); ``tape`` (m,) doubles; ``tape_off`` (n + 1,) segment offsets.
         -> dict of per-step results (status 0 = the step consumed exactly its tape segment)."""
         part = np.ascontiguousarray(particles, dtype=np.float64).reshape(-1, 10)
         tape = np.ascontiguousarray(tape, dtype=np.float64)
@@ -747,7 +752,7 @@ class Shower:
         return dict(status=out[:, 0].astype(int), nsub=out[:, 1].astype(int), process=out[:, 2].astype(int), ntrials=out[:, 3].astype(np.int64),
                     pf=out[:, 4:8], rf=out[:, 8:11], kept=out[:, 11].astype(int), pid_a=out[:, 12].astype(int), p_a=out[:, 13:17],
                     pid_b=out[:, 17].astype(int), p_b=out[:, 18:22], x=out[:, 22:26], consumed=out[:, 26].astype(np.int64),
-                    weight_factor=out[:, 27], propagated=out[:, 28].astype(int))
+                    weight_factor=out[:, 27], propagated=out[:, 28].astype(int), weight_factor_b=out[:, 29])
 
     def find_max(self, process, n_trials=100, seed=20261017, mT=None):
         """GPU ``do_find_max_work`` (utilities/find_maxes.py:55-119) for this target: -> (max_F (nE,), sigma (nE,))."""

@@ -28,7 +28,7 @@ def compare_with_oracle(batch, prims, material, min_energy, seed, **kw):
     h = batch.to_host()
     order, offs = batch.reference_order()
     rep = dict(showers=len(prims), structure_mismatch=0, particles=0, max_rel_p0=0.0, max_rel_pf=0.0, max_abs_rf=0.0,
-               first_mismatch=None)
+               max_rel_weight=0.0, first_mismatch=None)
     for i, olist in enumerate(ref):
         sl = order[offs[i]:offs[i + 1]]
         ok = len(sl) == len(olist)
@@ -46,6 +46,7 @@ def compare_with_oracle(batch, prims, material, min_energy, seed, **kw):
         for s, q in zip(sl, olist):
             rep["max_rel_p0"] = max(rep["max_rel_p0"], _relvec(q.p0, h["p0"][s]))
             rep["max_rel_pf"] = max(rep["max_rel_pf"], _relvec(q.pf, h["pf"][s]))
+            rep["max_rel_weight"] = max(rep["max_rel_weight"], abs(float(h["weight"][s]) - q.weight) / max(abs(q.weight), 1e-300))
             # positions relative to their own scale (at least 1 m): a track with n*sigma = 0 gets the reference's 1e12 m
             # mean free path (SURVEY Q-15) and ends ~1e10 m away
             rf = np.asarray(q.rf)

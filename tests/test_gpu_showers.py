@@ -31,6 +31,33 @@ def test_replay_parity_with_oracle(material, pid, E, Emin, n):
     assert rep["max_rel_p0"] < 1e-6 and rep["max_rel_pf"] < 1e-6 and rep["max_abs_rf"] < 1e-6, rep
 
 
+@pytest.mark.parametrize("material,pid,E,Emin,n", [("graphite", 211, 20.0, 0.030, 3), ("lead", -211, 5.0, 0.030, 3),
+                                                   ("graphite", 321, 30.0, 0.030, 2), ("lead", -321, 8.0, 0.010, 2)])
+def test_long_lived_decay_in_flight_parity_with_oracle(material, pid, E, Emin, n):
+    """Row f-5: pi+- / K+- primaries with stability 'long-lived' decay in flight to mu nu (particle.py:363-389, 410-422): decay
+    point drawn by accept/reject, the two daughters weighted by BR x P(decay before interaction) at independently drawn distances,
+    then the muon showers.  Counter-mode replay against the oracle, which reproduces the unmodified reference's own long-lived
+    showers in stream mode (tests/test_oracle_golden.py::test_stream_mode_long_lived_shower_equals_reference)."""
+    sh = shower(material, Emin, seed=21)
+    prims = primaries(pid, E, n, stability="long-lived")
+    batch = sh.generate_showers(prims, first_shower_id=40)
+    rep = compare_with_oracle(batch, prims, material, Emin, seed=21)
+    assert rep["structure_mismatch"] == 0, rep
+    assert rep["particles"] == batch.n and batch.n > 20 * n
+    assert rep["max_rel_p0"] < 1e-6 and rep["max_rel_pf"] < 1e-6 and rep["max_abs_rf"] < 1e-6 and rep["max_rel_weight"] < 1e-12, rep
+    out = batch.to_particles(prims)
+    for plist in out:
+        parent, mu, nu = plist[0], plist[1], plist[2]
+        assert mu.get_ids()["PID"] == (-13 if pid > 0 else 13) and nu.get_ids()["PID"] == (14 if pid > 0 else -14)
+        assert mu.get_ids()["generation_process"] == "SMDecay" and mu.get_ids()["parent_ID"] == -1                     # Q-10
+        br = 0.9998 if abs(pid) == 211 else 0.6356
+        assert 0 < mu.get_ids()["weight"] < br and 0 < nu.get_ids()["weight"] < br and mu.get_ids()["weight"] != nu.get_ids()["weight"]
+        assert parent.get_rf()[2] > 0 and np.allclose(mu.get_r0(), parent.get_rf(), rtol=0, atol=0)                    # daughters start at the decay point
+        assert abs(mu.get_p0()[0] + nu.get_p0()[0] - E) < 1e-9 * E
+    with pytest.raises(ValueError):
+        sh.generate_showers(primaries(111, 5.0, 1, stability="long-lived"))
+
+
 def test_pi0_primaries_and_q7_mass():
     sh = shower("graphite", 0.010, seed=3)
     from petite_b200 import Particle
@@ -173,7 +200,7 @@ def test_edge_cases_empty_ragged_and_invalid():
     with pytest.raises(ValueError):                                                           # Q-20: would loop forever
         sh.generate_showers([mk(2212, 5.0, 0.938)])
     with pytest.raises(ValueError):
-        sh.generate_showers([mk(211, 5.0, 0.1396, stability="long-lived")])
+        sh.generate_showers([mk(221, 5.0, 0.547862, stability="short-lived")])               # eta: a three-body channel may be drawn (particle.py:403-404)
     with pytest.raises(capi.EngineError) as ei:                                               # too small a stack fails loudly
         sh.generate_showers(primaries(11, 5.0, 64), capacity=200)
     assert ei.value.code == capi.PB_ERR_CAPACITY

@@ -136,6 +136,38 @@ def test_stream_mode_shower_equals_reference(golden, case):
         assert np.max(np.abs(arr - want) / scale) < 1e-6, name
 
 
+@pytest.mark.parametrize("case", range(6))
+def test_stream_mode_long_lived_shower_equals_reference(golden, case):
+    """Decay in flight of pi+- / K+- primaries (particle.py:363-389, 410-422; row f-5): whole generate_shower runs of the
+    unmodified reference (tests/golden/make_longlived.py) - decay point, the two independently drawn daughter weights, the
+    muon's shower - reproduced by the oracle on the reference's own uniform streams."""
+    from oracle import consts as OC
+    g = golden("longlived")
+    pid, E, Emin, seed, mass = g[f"{case}/case"]
+    pid, seed = int(pid), int(seed)
+    o = OracleShower(None, str(g[f"{case}/material"]), float(Emin), rng="stream")
+    np.random.seed(seed)
+    random.seed(seed)
+    assert mass == OC.MASS[pid]
+    p0 = OParticle([E, 0, 0, np.sqrt(E ** 2 - mass ** 2)], [0, 0, 0], PID=pid, ID=1, mass=float(mass), stability="long-lived")
+    got = o.generate_shower(p0)
+    assert len(got) == len(g[f"{case}/pid"]) and len(got) > 50
+    assert np.array_equal([q.PID for q in got], g[f"{case}/pid"])
+    assert got[1].PID == (-13 if pid > 0 else 13) and got[2].PID == (14 if pid > 0 else -14)
+    assert np.array_equal([PROC_CODE[q.process] for q in got], g[f"{case}/process"])
+    assert np.array_equal([q.gen for q in got], g[f"{case}/gen"])
+    assert np.array_equal([q.ID % (1 << 61) for q in got], g[f"{case}/ID_mod"])
+    w = np.array([q.weight for q in got])
+    assert np.allclose(w, g[f"{case}/weight"], rtol=1e-14) and w[1] != w[2]          # two draws of prob_decay_b_int
+    assert np.allclose([q.mass for q in got], g[f"{case}/mass"], rtol=0, atol=0)
+    assert np.allclose(got[0].rf, g[f"{case}/rf"][0], rtol=1e-15, atol=0) and got[0].rf[2] > 0       # the decay point
+    for name, arr in (("p0", [q.p0 for q in got]), ("pf", [q.pf for q in got]), ("r0", [q.r0 for q in got]), ("rf", [q.rf for q in got])):
+        want = g[f"{case}/{name}"]
+        arr = np.asarray(arr)
+        scale = np.maximum(np.max(np.abs(want), axis=1, keepdims=True), 1e-300)
+        assert np.max(np.abs(arr - want) / scale) < 1e-6, name
+
+
 def test_dark_kinematics(golden):
     """oracle.physics kin_darkbrem / kin_darkann / kin_compton_bound against l_to_lV_fourvecs, radiative_return_fourvecs and
     compton_fourvecs_boundelectron of the unmodified reference (tests/golden/make_golden.py golden_dark_kinematics)."""
