@@ -76,6 +76,9 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #ifndef PB_LOOP_NODE_CACHE
 #define PB_LOOP_NODE_CACHE 0             // 1: k_loop keeps the current n*sigma node in registers (nsigma_cached); measured SLOWER (48.6 vs 47.7 ms per config-2 step: six more live registers at the 80-register cap), kept as an option
 #endif
+#ifndef PB_LOOP_EARLY_MCS
+#define PB_LOOP_EARLY_MCS 1              // substep(): multiple-scattering draw issued at the top of the iteration (ILP)
+#endif
 #ifndef PB_LOOP_CG
 #define PB_LOOP_CG 1                     // k_loop's 16-byte record copies bypass L1 (cp.async.cg): the 23 KB of L1 stay with the tables (49.2 -> 48.6 ms per config-2 step)
 #endif
@@ -292,6 +295,31 @@ __device__ __forceinline__ double nsigma_c(const NSigmaTable& T, double E) {
   return __dadd_rn(__dmul_rn(nd.z, E - nd.x), nd.y);
 }
 
+// Up to three tables at the SAME energy (the species' processes in the final step and in the process choice).  K separate nsigma_c
+// calls are a chain of 2 K dependent look-ups (coarse table -> node, then the rare walk), and k_finalize spends half of its stall
+// samples waiting on such chains (profiles/r02f): here the K coarse look-ups are issued together, then the K node loads, then the
+// walks.  Same nodes, same two roundings per table as nsigma_c.  t[k] < 0: no table (result 0).
+__device__ __forceinline__ void nsigma_c3(const Tables& T, const int* t, int nt, double E, double* out) {
+  bool ok[3]; int h[3]; double4 nd[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    ok[k] = k < nt && t[k] >= 0 && T.ns[t[k] < 0 ? 0 : t[k]].n >= 2 && E >= T.ns[t[k] < 0 ? 0 : t[k]].xmin && E <= T.ns[t[k] < 0 ? 0 : t[k]].xmax;
+    h[k] = 1;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) if (ok[k]) h[k] = coarse_ub(T.ns[t[k]].c, E);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) nd[k] = ok[k] ? ld_node(&T.ns[t[k]].node[h[k] - 1]) : make_double4(0.0, 0.0, 0.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (ok[k]) {
+      const NSigmaTable& Tk = T.ns[t[k]];
+      while (h[k] > 1 && !(nd[k].x < E)) { --h[k]; nd[k] = ld_node(&Tk.node[h[k] - 1]); }
+      out[k] = __dadd_rn(__dmul_rn(nd[k].z, E - nd[k].x), nd[k].y);
+    } else out[k] = (k < nt && t[k] >= 0 && T.ns[t[k]].n >= 2 && !(E == E)) ? E : 0.0;      // out of range: 0; NaN stays NaN (scipy fill_value)
+  }
+}
+
 // SURVEY Q-1: argmin |E_i - E| + 1, clamped to the last row (shower.py:416-426).  lo = first row with E_row >= E comes from the
 // coarse table (upper bound) walked down.
 __device__ __forceinline__ int lookup_row(const MapInfo& m, double E) {
@@ -337,6 +365,7 @@ __device__ __forceinline__ void store_track_setup(const Material& M, const Table
 // the numbers a REFERENCE run consumed, in the reference's own order, so that the same device code can be
 // driven by the reference's uniform stream.
 struct PhiloxDraws {
+  static constexpr bool kOrderFree = true;      // draws are pure functions of (key, index): they may be computed early, or for nothing
   uint2 key;
   __device__ __forceinline__ D2 substep(uint32_t it) { D2 u = draw2(key, it, ST_SUBSTEP); return D2{u.a, 6.0 + 14.0 * u.b}; }   // u_hard, U(6, 20)
   __device__ __forceinline__ McsDraw mcs(uint32_t it, uint32_t pc) { return mcs_draw(key, it, pc); }
@@ -347,6 +376,7 @@ struct PhiloxDraws {
   __device__ __forceinline__ D2 decay_x(uint32_t loop, uint32_t i) { return draw2(key, i, ST_DECAY, loop, P_SMDECAY); }   // i-th (x, u) pair of accept/reject loop 1..3 of a decay in flight
 };
 struct TapeDraws {             // sequential reader; `over` is set if the tape runs out (a decision differed from the recording)
+  static constexpr bool kOrderFree = false;
   const double* t; long long pos, end; bool over;
   __device__ __forceinline__ double next() { if (pos >= end) { over = true; return 0.5; } return t[pos++]; }
   __device__ __forceinline__ D2 substep(uint32_t) { double a = next(), b = next(); return D2{a, b}; }                 // random(), uniform(6, 20)
@@ -365,6 +395,14 @@ struct TapeDraws {             // sequential reader; `over` is set if the tape r
 template <class DS>
 __device__ __forceinline__ bool substep(const Material& M, const Tables& T, Track& t, int ms_e, DS& ds) {
   if (!(t.p.E >= t.pmin)) return true;                                // loop condition (shower.py:559)
+#if PB_LOOP_EARLY_MCS
+  // the multiple-scattering draw of this sub-step, issued before the energy-loss chain instead of after it: its Philox rounds (integer
+  // pipe) and the log / sqrt of the radial variable overlap the dependent FP64 chain below (the loop is latency-bound at 5-6 warps
+  // per scheduler).  Wasted when the loop ends in this iteration (1 in ~9).  k_loop: 80 registers + 16 B spilled -> 74, no spill;
+  // 47.3 -> 46.5 ms per config-2 step.  (Resolving the hard-scatter branch after the energy-loss chain as well: no further gain.)
+  McsDraw d_early{0.0, 0.0, 0.0};
+  if (DS::kOrderFree && ms_e) d_early = ds.mcs((uint32_t)t.it, 0);
+#endif
 #if PB_LOOP_NODE_CACHE
   double ns = nsigma_cached(T.sp[t.sp], t.hint, t.nx, t.ny, t.nz, t.p.E);   // sum over the species' processes (shower.py:357-368)
 #else
@@ -388,7 +426,11 @@ __device__ __forceinline__ bool substep(const Material& M, const Tables& T, Trac
     double s = t.delta_z * inv;
     t.rx += t.p.x * s; t.ry += t.p.y * s; t.rz += t.p.z * s;
     if (ms_e) {
+#if PB_LOOP_EARLY_MCS
+      McsDraw d = DS::kOrderFree ? d_early : ds.mcs((uint32_t)t.it, 0);
+#else
       McsDraw d = ds.mcs((uint32_t)t.it, 0);
+#endif
       t.p = mcs_fast(M, t.p, p3f, inv, M.rho * (t.delta_z * (1.0 / kCmToM)), t.iKp, d.sign, d.radial, d.uphi);
     }
   } else {
@@ -440,7 +482,10 @@ __global__ void k_wave_begin_cond(Work W, cudaGraphConditionalHandle h) {
 // chunk cursor (atomic, consumed one chunk later) -> the chunk's list indices (register, consumed one chunk later) ->
 // the chunk's records copied asynchronously (cp.async / LDGSTS, no registers) into the idle half of a per-warp
 // double buffer in shared memory -> consumed with shared-memory reads.
-constexpr int LOOP_CHUNK = 32;
+#ifndef PB_LOOP_CHUNK
+#define PB_LOOP_CHUNK 32
+#endif
+constexpr int LOOP_CHUNK = PB_LOOP_CHUNK;      // entries per pipeline stage (<= 32: one per lane)
 struct LoopBuf {                 // one chunk of track records: p0, r0w, track set-up (rf), ids  (a carried track: pf, rf, -, ids, aux)
   double2 v[6][LOOP_CHUNK];
   int4 meta[LOOP_CHUNK];
@@ -642,8 +687,10 @@ __device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, 
       double last;
       if (p.E < pmin) last = distC * delta_z;
       else {
-        double ns = nsigma_c(T.ns[tb[0]], p.E) + nsigma_c(T.ns[tb[1]], p.E);
-        if (tb[2] >= 0) ns += nsigma_c(T.ns[tb[2]], p.E);
+        double v[3];
+        nsigma_c3(T, tb, 3, p.E, v);
+        double ns = v[0] + v[1];
+        if (tb[2] >= 0) ns += v[2];
         double mfp = mfp_from(ns);
         last = mfp * log(1.0 / (1.0 + (exp(-delta_z / mfp) - 1) * distC));
       }
@@ -666,7 +713,10 @@ __device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, 
       double pmin = fmax(fmax(M.min_calc[cls], M.min_energy), mass);
       if (!(p.E < pmin)) {                                              // shower.py:538-553 (MS_g is always False)
         stepped = true;
-        double mfp = mfp_from(nsigma_c(T.ns[P_PAIRPROD], p.E) + nsigma_c(T.ns[P_COMP], p.E));
+        const int tg[3] = {P_PAIRPROD, P_COMP, -1};
+        double v[3];
+        nsigma_c3(T, tg, 2, p.E, v);
+        double mfp = mfp_from(v[0] + v[1]);
         double distC = ds.final_u();
         double dist = mfp * log(1.0 / (1.0 - distC));
         double pn = norm3_nofma(p.x, p.y, p.z);
@@ -683,7 +733,9 @@ __device__ __forceinline__ int finalize_one(const Material& M, const Tables& T, 
     else if (pid == 22) { cand[0] = P_PAIRPROD; cand[1] = P_COMP; nc = 2; }
     else { cand[0] = P_MUONE; cand[1] = P_MUONBREM; nc = 2; }
     double SC = 0.0;
-    for (int k = 0; k < nc; ++k) { c[k] = nsigma_c(T.ns[cand[k]], Ef); SC += c[k]; }
+    if (nc == 2) cand[2] = -1;
+    nsigma_c3(T, cand, nc, Ef, c);
+    for (int k = 0; k < nc; ++k) SC += c[k];
     if (!(SC == 0.0 || SC != SC)) {
       double u = ds.choice_u();
       // np.random.choice: cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(u, 'right')
