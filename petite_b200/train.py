@@ -8,7 +8,10 @@ classic VEGAS refinement (Lepage 1978: smooth, damp with ``alpha``, re-bin to eq
 lines per iteration.  p = 2 is Lepage's variance criterion.  The maps are used for ACCEPT/REJECT sampling, whose cost is
 max / mean of jac f, so the default here is p = 8 (``TRAIN_POWER``): it flattens the peaks that set max_F and gives maps with
 2.3-2.8x the accept rate of the shipped ones (Brem, PairProd, MuonBrem; p = 2 reaches 0.3-0.5x because the reference's adaptive
-stratification is not reproduced - profiles/r02_final/exp_train_pow*.log); the integral through the map is unbiased for any p.  ``vegas`` itself is not available here, so this is the published algorithm, not a bit-level
+stratification is not reproduced - profiles/r02_final/exp_train_pow*.log); the integral through the map is unbiased for any p.  Training is not bit-reproducible: the fp64 atomics of the sums are
+unordered (1e-15 relative), the integrands have kinematic cuts, and twenty refinements amplify that to visibly different node
+positions (tools/check_train_determinism.py) - single rows scatter, sets of rows do not; table sets are therefore committed, not
+regenerated, where tests depend on them (data_400GeV/).  ``vegas`` itself is not available here, so this is the published algorithm, not a bit-level
 reproduction of the third-party package; the acceptance test is the one the shipped tables allow - the integral through
 the trained maps reproduces the shipped ``sm_xsec`` rows (tests/test_gpu_train.py).
 
