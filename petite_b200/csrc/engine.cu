@@ -73,9 +73,6 @@ constexpr int NBUCKET = 16 * LU_MAX;        // bucket = process * LU_MAX + row
 #define PB_LOOP_MINB 6
 #endif
 #ifndef PB_LOOP_CAP_DEFAULT
-#ifndef PB_LOOP_NODE_CACHE
-#define PB_LOOP_NODE_CACHE 0             // 1: k_loop keeps the current n*sigma node in registers (nsigma_cached); measured SLOWER (48.6 vs 47.7 ms per config-2 step: six more live registers at the 80-register cap), kept as an option
-#endif
 #ifndef PB_LOOP_EARLY_MCS
 #define PB_LOOP_EARLY_MCS 1              // substep(): multiple-scattering draw issued at the top of the iteration (ILP)
 #endif
@@ -262,21 +259,6 @@ __device__ __forceinline__ double nsigma_hinted(const NSigmaTable& T, int& hi, d
   return __dadd_rn(__dmul_rn(nd.z, E - nd.x), nd.y);
 }
 
-// The same with the node itself carried along the track: energy only decreases, so the node stays the right one until E drops to
-// its lower edge (a few per cent of the sub-steps); the others evaluate from registers instead of waiting on a dependent table
-// load (k_loop's L1 is the 23 KB the shared-memory carve-out leaves, and the record copies stream through it).  Same node, same
-// two roundings: bit-identical to nsigma_hinted.  nx = +Inf marks "not loaded yet".
-__device__ __forceinline__ double nsigma_cached(const NSigmaTable& T, int& hi, double& nx, double& ny, double& nz, double E) {
-  if (T.n < 2) return 0.0;
-  if (!(E >= T.xmin && E <= T.xmax)) return (E == E) ? 0.0 : E;
-  if (!(nx < E)) {
-    double4 nd = ld_node(&T.node[hi - 1]);
-    while (hi > 1 && !(nd.x < E)) { --hi; nd = ld_node(&T.node[hi - 1]); }
-    nx = nd.x; ny = nd.y; nz = nd.z;
-  }
-  return __dadd_rn(__dmul_rn(nz, E - nx), ny);
-}
-
 // tables entering the mean free path of a charged species, in the reference's summation order (shower.py:357-368)
 __device__ __forceinline__ void species_tables(int pid, int* t) {
   if (pid == 11) { t[0] = P_BREM; t[1] = P_MOLLER; t[2] = -1; }
@@ -342,9 +324,6 @@ struct Track {
   uint2 key;
   int sp, hint;    // species table (Tables::sp) and the look-up hint into it
   int it;          // loop iterations done == accepted sub-steps while the loop is alive
-#if PB_LOOP_NODE_CACHE
-  double nx = HUGE_VAL, ny = 0.0, nz = 0.0;   // the table node the hint points at (x, y, slope): valid while nx < E, so the common sub-step loads nothing
-#endif
 };
 
 // Track set-up computed where the particle is created (k_emit / k_init_primaries, all lanes busy) instead of at refill
@@ -403,11 +382,7 @@ __device__ __forceinline__ bool substep(const Material& M, const Tables& T, Trac
   McsDraw d_early{0.0, 0.0, 0.0};
   if (DS::kOrderFree && ms_e) d_early = ds.mcs((uint32_t)t.it, 0);
 #endif
-#if PB_LOOP_NODE_CACHE
-  double ns = nsigma_cached(T.sp[t.sp], t.hint, t.nx, t.ny, t.nz, t.p.E);   // sum over the species' processes (shower.py:357-368)
-#else
   double ns = nsigma_hinted(T.sp[t.sp], t.hint, t.p.E);                // sum over the species' processes (shower.py:357-368)
-#endif
   double mfp = (ns <= 0.0) ? 1.0e12 : kCmToM * fast_rcp(ns);          // shower.py:386-389
   D2 u = ds.substep((uint32_t)t.it);
   double iv = fast_rcp(u.b);                                          // delta_z = mfp / U(6, 20); delta_z / mfp = 1 / U
@@ -613,9 +588,6 @@ k_loop(const __grid_constant__ Material M, const __grid_constant__ Tables T, Sta
           t.iKp = t.mass / (1e3 * pid_mass(pid));
         }
         t.sp = species_index(pid);
-#if PB_LOOP_NODE_CACHE
-        t.nx = HUGE_VAL;     // node not loaded yet
-#endif
         if (cur < n_new) {         // fresh track: set-up stored at creation (store_track_setup)
           double2 s0 = B.v[4][e], s1 = B.v[5][e];
           t.pmin = s1.x;

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical record of how profiles/r02_final/ab_*.json were made; the nc0 variant needs the node-cache option that existed up to commit 39d01aa)
 # A/B of the k_loop changes (node cache, cp.async.cg, drain pause) and hot_cospi: full GPU suite on the default build, then
 # tools/sweep_sampler.py (digest of 2 000 showers + config-2 timing, per kernel and in graph mode) per variant, one process each
 O=gpurun_out/r3a; mkdir -p $O
