@@ -756,7 +756,9 @@ k_finalize(const __grid_constant__ Material M, const __grid_constant__ Tables T,
       delta_z = b1.y;
       const int2 ax = S.aux[s];
       nsub = ax.y;
-      E_start = S.p0[4 * s];
+      // "never propagated" (creation energy below the species threshold, shower.py:534-536) without gathering the p0 sector for it:
+      // a track that took no sub-step still has its creation energy, and one that took any started at or above the threshold
+      E_start = nsub == 0 ? a0.x : HUGE_VAL;
       paused = ax.x == AUX_PAUSED;     // sub-step loop paused in this wave (k_loop): nothing to finalize yet, the record stays as k_loop
                                        // left it.  (Tested AFTER finalize_one: the 2 % of wasted evaluations cost less than a branch that
                                        // every track would wait on with the latency of this load.)
