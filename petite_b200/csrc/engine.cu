@@ -1285,7 +1285,7 @@ __device__ __forceinline__ double decay_draw_x(DS& ds, uint32_t loop, double tot
   double x = 0.0;
   for (uint32_t i = 0; i < (1u << 20); ++i) {
     D2 u = ds.decay_x(loop, i);
-    x = x_max * u.a;                                            // np.random.uniform(0, x_max)
+    x = DS::kOrderFree ? x_max * u.a : u.a;                     // np.random.uniform(0, x_max); a tape holds the generator's output itself
     if (u.b < (tot_rate * exp(-tot_rate * x)) / tot_rate) break;
   }
   return x;
@@ -1321,6 +1321,7 @@ __device__ __forceinline__ void scatter_products(int proc, int pid, int flags, V
       wfac = wfac_b = 0.98823;                                 // particle.py:40 meson_decay_dict[111]
     }
     D2 u = ds.decay_u(P_SMDECAY);
+    if (!DS::kOrderFree) u.a = 0.5 * (u.a + 1.0);               // a tape holds cos(theta) = np.random.uniform(-1, 1) as drawn (particle.py:226)
     two_body_decay(pf, mass, m1, 0.0, u.a, u.b, &da, &db);
     return;
   }

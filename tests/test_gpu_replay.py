@@ -68,3 +68,43 @@ def test_replay_detects_a_wrong_tape(golden):
     tape[off[k + 1] - 2] = 1.0 - 2.0 ** -53          # segment = ..., trials x (y[dim], u), azimuth
     out = sh.replay(part, tape, off)
     assert out["status"][k] == 1 and np.all(np.delete(out["status"], k) == 0)
+
+
+def test_long_lived_decay_step_replays_a_tape():
+    """Tape mode of the decay in flight (row f-5): the tape holds what the reference's generators returned, in its order
+    (particle.py:371-372, 412, 420-421, 234-235) - per accept/reject iteration uniform(0, x_max) and uniform(0, 1) for the decay
+    point and for each daughter's weight, then cos(theta) = uniform(-1, 1) and the azimuth uniform.  The device step must consume
+    exactly that segment (incl. one rejected iteration) and reproduce the oracle's decay fed the same numbers."""
+    from oracle.shower import OracleShower, OParticle
+    from oracle import consts as OC
+    sh = shower("graphite", 0.030)
+    pid, E = -211, 12.0
+    m = OC.MASS[pid]
+    p0 = [E, 0.3, -0.2, np.sqrt(E * E - m * m - 0.13)]
+    o = OracleShower(None, "graphite", 0.030, rng="stream")
+    prim = OParticle(p0, [0.0, 0.01, 0.02], PID=pid, ID=1, mass=m, stability="long-lived")
+    ctau, tot = o._decay_rates(prim, OC.INT_LENGTH[pid], OC.DECAY_LENGTH[pid])
+    x_max = 4 / tot
+    loops = {1: [(0.9 * x_max, 0.9), (0.31 * x_max, 0.2)], 2: [(0.55 * x_max, 0.05)], 3: [(0.08 * x_max, 0.5)]}    # (x, u): loop 1 rejects once
+    assert 0.9 > np.exp(-tot * 0.9 * x_max) and 0.2 < np.exp(-tot * 0.31 * x_max)
+    cth, uphi = -0.37, 0.81
+    tape = [v for k in (1, 2, 3) for xu in loops[k] for v in xu] + [cth, uphi]
+
+    class Fixed:
+        def decay_x(self, loop, i):
+            x, u = loops[loop][i]
+            return x / x_max, u
+        def decay(self, pc=12):
+            return 0.5 * (cth + 1.0), uphi
+        def child(self, bit):
+            return self
+    prim.draws = Fixed()
+    mu, nu = o.decay(prim)
+    part = np.array([[pid, *p0, 0.0, 0.01, 0.02, m, 4.0]])
+    out = sh.replay(part, np.array(tape), np.array([0, len(tape)]))
+    assert out["status"][0] == 0 and out["consumed"][0] == len(tape) and out["process"][0] == 12
+    assert out["pid_a"][0] == 13 and out["pid_b"][0] == -14 and out["kept"][0] == 3
+    assert np.allclose(out["rf"][0], prim.rf, rtol=1e-13, atol=0) and prim.rf[2] > 0.02
+    assert abs(out["weight_factor"][0] - mu.weight) < 1e-13 * mu.weight and abs(out["weight_factor_b"][0] - nu.weight) < 1e-13 * nu.weight
+    assert mu.weight != nu.weight
+    assert np.allclose(out["p_a"][0], mu.p0, rtol=1e-11, atol=1e-13) and np.allclose(out["p_b"][0], nu.p0, rtol=1e-11, atol=1e-13)
