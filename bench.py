@@ -390,7 +390,7 @@ def ours(args):
             t_ms = float(t.item())
         return t_ms, tt, pm, pl, tr
 
-    # ---- timed region: K steps, device-resident primaries.  With --parts P > 1 (default 2) a step runs as P concurrent
+    # ---- timed region: K steps, device-resident primaries.  With --parts P > 1 (the default of configurations 1 and 5) a step runs as P concurrent
     # sub-batches and carries no per-kernel events; the single-stream pass after it (same K steps, same inputs) times the two
     # dominant kernels with CUDA events (level 1) while each launch owns the GPU: that is what the roofline is defined on.
     K = args.steps
