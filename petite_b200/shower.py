@@ -81,6 +81,16 @@ class ShowerBatch:
         self.n_primaries = int(n_primaries)
         self.first_shower_id = int(first_shower_id)
         self._host = None
+        # a batch is a VIEW of its owner's reusable stack: the next run on the same Shower overwrites it (copy what is needed with
+        # to_host() / to_particles() first, or step sub-batches on their own handles: run_arrays_split)
+        self._serial = getattr(owner, "_run_serial", 0)
+
+    def _check_live(self, device=False):
+        o = self._owner
+        if (device or self._host is None) and getattr(o, "_stack_tensors", None) is self._t and getattr(o, "_run_serial", 0) != self._serial:
+            import warnings
+            warnings.warn("this ShowerBatch was overwritten by a later run on the same Shower: its device records are those of the "
+                          "newer batch (call to_host() before the next run, or use run_arrays_split)", RuntimeWarning, stacklevel=3)
 
     def device(self, name):
         """Raw device column (torch tensor view over the first ``n`` records)."""
@@ -88,6 +98,7 @@ class ShowerBatch:
         return t[: self.n]
 
     def to_host(self):
+        self._check_live()
         if self._host is None:
             n = self.n
             t = {k: v[:n].cpu().numpy() for k, v in self._t.items() if k != "ids"}
@@ -493,6 +504,7 @@ class Shower:
         st = self._stack_struct()
         cnt = capi.pb_counters()
         stream = self._torch.cuda.current_stream(self._device).cuda_stream
+        self._run_serial = getattr(self, "_run_serial", 0) + 1           # earlier batches of this stack are stale from here on
         rc = capi.lib.pb_run_showers(self._engine, C.byref(prim), self._seed, int(first_shower_id), 1 if GlobalMS else 0,
                                      C.byref(st), C.byref(cnt), C.c_void_p(stream))
         if rc == capi.PB_ERR_CAPACITY and not on_device and auto:
@@ -611,6 +623,7 @@ class Shower:
         torch = self._torch
         if out is None:
             out = torch.zeros(capi.TALLY_SIZE, dtype=torch.float64, device=torch.device("cuda", self._device))
+        batch._check_live(device=True)
         st = stack_struct(batch._t)             # the batch's own stack (it may predate a regrow of this object's)
         stream = torch.cuda.current_stream(self._device).cuda_stream
         capi.check(self._engine, capi.lib.pb_tally(self._engine, C.byref(st), 0, batch.n, C.c_void_p(out.data_ptr()),

@@ -287,3 +287,22 @@ def test_sub_step_cap_does_not_change_the_showers(monkeypatch):
             assert np.array_equal(x, y), cap
         assert all(c[k] == c0[k] for k in ("n_particles", "n_steps", "n_substeps", "n_samples", "n_trials"))
     assert runs["4"][0]["n_waves"] > runs["0"][0]["n_waves"]       # the carried tracks did take extra waves
+
+
+def test_overwritten_batch_warns():
+    """A ShowerBatch is a view of its Shower's reusable stack: reading it after a later run on the same Shower warns (ADVICE, round 1)."""
+    import warnings
+    sh = shower("graphite", 0.010, seed=4)
+    b1 = sh.generate_showers(primaries(11, 1.0, 2), first_shower_id=0)
+    h1 = b1.to_host()                                   # copied in time: stays valid and silent
+    b2 = sh.generate_showers(primaries(11, 1.0, 3), first_shower_id=10)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert b1.to_host() is h1 and b2.to_host()["pid"].shape[0] == b2.n
+    b3 = sh.generate_showers(primaries(11, 1.0, 2), first_shower_id=20)
+    b4 = sh.generate_showers(primaries(11, 1.0, 2), first_shower_id=30)
+    with pytest.warns(RuntimeWarning):
+        b3.to_host()
+    with pytest.warns(RuntimeWarning):
+        sh.tally(b3)
+    assert b4.n > 0
